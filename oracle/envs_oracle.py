@@ -1,0 +1,278 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement (vectorised NumPy) of the four
+reference tasks on the hot path, plus the adapter / DummyVecEnv / Monitor
+semantics around them.  The product path never imports this module; only
+tests/, `__graft_entry__.smoke()` and bench.py's `cpu_baseline` leg do.
+
+Pinned (tests/test_oracle_cpu.py) against tests/golden/*.npz, which were made by
+running the UNMODIFIED reference classes (oracle/make_golden.py): 32 envs x 1000
+steps per task with state injection at every reset — bit-exact for all four
+tasks on the build container.
+
+Reference anchors (relative to /root/reference/backend):
+  basic      mlagents/envs.py:17-84
+  ball3d     examples/ball3d.py:10-113
+  gridworld  examples/gridworld.py:14-95
+  push       examples/push.py:10-125
+  adapter    mlagents/envs.py:87-159  (time-limit truncation, terminated/truncated split)
+  vec/auto-reset + Monitor: SB3 DummyVecEnv/Monitor semantics, SURVEY.md §8(a) A7
+Reset draws use this repo's Philox streams (oracle/philox.py), not MT19937.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import philox as px
+
+# ---- constants -----------------------------------------------------------------------
+# ball3d.py:10-37
+G = 9.81
+DT = 0.02
+MAX_TILT = float(np.deg2rad(25.0))      # 0x3fdbecde5da115a9
+TILT_DELTA = float(np.deg2rad(3.0))     # 0x3faacee9f37bebd6
+PLATFORM_HALF = 3.0
+BALL3D_DELTAS = np.array(
+    [[TILT_DELTA, 0.0], [-TILT_DELTA, 0.0], [0.0, TILT_DELTA], [0.0, -TILT_DELTA], [0.0, 0.0]],
+    dtype=np.float64,
+)
+# gridworld.py:19-25 and push.py:14-20 share the move table
+GRID_DELTAS = np.array([[0, 0], [0, 1], [0, -1], [-1, 0], [1, 0]], dtype=np.int32)
+
+TASKS = {
+    #            obs_dim n_actions max_steps
+    "basic":     (21, 3, 50),     # envs.py:17-44
+    "ball3d":    (6, 5, 200),     # ball3d.py:12,24,38 ; envs.py:169-175
+    "gridworld": (4, 5, 100),     # gridworld.py:14-30 ; envs.py:181-187
+    "push":      (4, 5, 120),     # push.py:10-24 ; envs.py:193-199
+}
+
+STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
+    "basic": np.dtype([("pos", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "ball3d": np.dtype([("rot", "<f8", (2,)), ("pos", "<f4", (2,)), ("vel", "<f4", (2,)),
+                        ("steps", "<i4"), ("ep_return", "<f4")]),
+    "gridworld": np.dtype([("agent", "<i4", (2,)), ("green", "<i4", (2,)), ("red", "<i4", (2,)),
+                           ("goal_type", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
+                      ("steps", "<i4"), ("ep_return", "<f4")]),
+}
+
+f32 = np.float32
+
+
+def push_reward_lut():
+    """18-entry LUT indexed [(d_ab+1)*6 + (d_bg+1)*2 + invalid], built with the
+    reference's own expression order in Python doubles, then rounded once to f32
+    (push.py:77,111-115)."""
+    lut = np.zeros(18, np.float32)
+    for dab in (-1, 0, 1):
+        for dbg in (-1, 0, 1):
+            for inv in (0, 1):
+                r = -0.01
+                r += 0.05 * dab
+                r += 0.3 * dbg
+                if inv:
+                    r -= 0.05
+                lut[(dab + 1) * 6 + (dbg + 1) * 2 + inv] = np.float32(r)
+    return lut
+
+
+def basic_reward_lut():
+    """envs.py:65-72: -0.01, (-0.01)+0.1, (-0.01)+1.0 in doubles -> f32."""
+    a = -0.01
+    b = -0.01
+    b += 0.1
+    c = -0.01
+    c += 1.0
+    return np.array([a, b, c], dtype=np.float32)
+
+
+PUSH_LUT = push_reward_lut()
+BASIC_LUT = basic_reward_lut()
+
+
+# ---- observations --------------------------------------------------------------------
+def observe(task, st):
+    n = st.shape[0]
+    if task == "basic":          # envs.py:24-27
+        obs = np.zeros((n, 21), np.float32)
+        obs[np.arange(n), np.clip(st["pos"], 0, 20)] = 1.0
+        return obs
+    if task == "ball3d":         # ball3d.py:61-72 : f32 of (rot f64|f32, pos, vel)
+        return np.concatenate([st["rot"].astype(np.float32), st["pos"], st["vel"]], axis=1)
+    if task == "gridworld":      # gridworld.py:55-64 ; quarters are exact in f32
+        goal = np.where(st["goal_type"][:, None] == 0, st["green"], st["red"])
+        d = (goal - st["agent"]).astype(np.float64) / 4.0
+        oh = np.stack([st["goal_type"] == 0, st["goal_type"] == 1], axis=1).astype(np.float64)
+        return np.concatenate([d, oh], axis=1).astype(np.float32)
+    if task == "push":           # push.py:53-59 ; f32(k/5.0) == f32(k)/f32(5) for |k|<=5
+        goal = np.stack([st["goal_x"], np.full(n, 5, np.int32)], axis=1)
+        ab = (st["box"] - st["agent"]).astype(np.float64) / 5.0
+        bg = (goal - st["box"]).astype(np.float64) / 5.0
+        return np.concatenate([ab, bg], axis=1).astype(np.float32)
+    raise KeyError(task)
+
+
+# ---- transitions (no reset) -------------------------------------------------------------
+def transition(task, st, actions):
+    """Advance `st` (structured array, modified in place) by one step.
+    Returns (obs, reward f32, terminated bool, truncated bool) as the adapter reports
+    them (envs.py:139-152; for basic envs.py:60-81) — BEFORE any auto-reset."""
+    a = np.asarray(actions).astype(np.int64)
+    n = st.shape[0]
+    max_steps = TASKS[task][2]
+    if task == "basic":
+        pos = np.clip(st["pos"] + (a - 1), 0, 20)                  # envs.py:61-62
+        st["pos"] = pos
+        st["steps"] += 1
+        small, large = pos == 7, pos == 17                          # envs.py:67-72
+        reward = np.where(small, BASIC_LUT[1], np.where(large, BASIC_LUT[2], BASIC_LUT[0])).astype(np.float32)
+        terminated = small | large
+        truncated = (st["steps"] >= max_steps) & ~terminated        # envs.py:74
+    elif task == "ball3d":
+        first = st["steps"] == 0
+        rot = st["rot"] + BALL3D_DELTAS[a]                          # ball3d.py:76-77 (f64 add)
+        # first step after a reset: rot is still the f32 array, `+=` rounds back to f32
+        rot = np.where(first[:, None], rot.astype(np.float32).astype(np.float64), rot)
+        rot = np.minimum(np.maximum(rot, -MAX_TILT), MAX_TILT)      # ball3d.py:78 -> f64 from here on
+        acc = G * np.sin(rot)                                       # ball3d.py:81-82 (f64)
+        vel = (st["vel"].astype(np.float64) + acc * DT).astype(np.float32)   # ball3d.py:83-84
+        vel = vel * f32(0.98)                                       # ball3d.py:87 (f32)
+        pos = st["pos"] + vel * f32(DT)                             # ball3d.py:90 (f32, no fma)
+        st["rot"], st["vel"], st["pos"] = rot, vel, pos
+        st["steps"] += 1
+        off = (np.abs(pos[:, 0]) > f32(3.0)) | (np.abs(pos[:, 1]) > f32(3.0))   # ball3d.py:96-98
+        timeout = st["steps"] >= 200                                # ball3d.py:99
+        done = off | timeout
+        sq = pos[:, 0] * pos[:, 0] + pos[:, 1] * pos[:, 1]          # np.linalg.norm: sqrt(x.dot(x)), f32
+        d = np.sqrt(sq).astype(np.float32)
+        reward = f32(1.0) - d / f32(3.0)                            # ball3d.py:104
+        reward = np.where(done, np.where(timeout & ~off, f32(1.0), f32(-1.0)), reward)  # :105-108
+        reward = (reward + f32(-0.02) * d).astype(np.float32)       # :110-111
+        hit = st["steps"] >= max_steps                              # envs.py:141-145
+        terminated, truncated = done & ~hit, hit
+    elif task == "gridworld":
+        agent = np.clip(st["agent"] + GRID_DELTAS[a], 0, 4)         # gridworld.py:68-71
+        st["agent"] = agent
+        st["steps"] += 1
+        on_green = np.all(agent == st["green"], axis=1)             # gridworld.py:79-90
+        on_red = np.all(agent == st["red"], axis=1) & ~on_green
+        gt = st["goal_type"]
+        reward = np.full(n, f32(-0.01), np.float32)
+        reward = np.where(on_green, np.where(gt == 0, f32(1.0), f32(-1.0)), reward)
+        reward = np.where(on_red, np.where(gt == 1, f32(1.0), f32(-1.0)), reward).astype(np.float32)
+        done = on_green | on_red | (st["steps"] >= 100)             # gridworld.py:92-93
+        hit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit, hit
+    elif task == "push":
+        d = GRID_DELTAS[a]
+        agent0, box0 = st["agent"].copy(), st["box"].copy()
+        goal = np.stack([st["goal_x"], np.full(n, 5, np.int32)], axis=1)
+        new_agent = np.clip(agent0 + d, 0, 5)                       # push.py:63-65
+        prev_bg = np.abs(goal - box0).sum(1)                        # push.py:70-75
+        prev_ab = np.abs(box0 - agent0).sum(1)
+        into_box = np.all(new_agent == box0, axis=1)                # push.py:83
+        tent = box0 + d
+        inb = np.all((tent >= 0) & (tent < 6), axis=1)              # push.py:87-90
+        new_box = np.where((into_box & inb)[:, None], tent, box0)
+        invalid = into_box & ~inb                                   # push.py:92-95
+        new_agent = np.where(invalid[:, None], agent0, new_agent)
+        st["agent"], st["box"] = new_agent, new_box
+        st["steps"] += 1
+        dist_bg = np.abs(goal - new_box).sum(1)                     # push.py:103-108
+        dist_ab = np.abs(new_box - new_agent).sum(1)
+        idx = (prev_ab - dist_ab + 1) * 6 + (prev_bg - dist_bg + 1) * 2 + invalid.astype(np.int64)
+        reward = PUSH_LUT[idx]
+        top = new_box[:, 1] == 5                                    # push.py:118-120
+        reward = np.where(top, f32(1.0), reward).astype(np.float32)
+        done = top | (st["steps"] >= 120)                           # push.py:122-123
+        hit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit, hit
+    else:
+        raise KeyError(task)
+    return observe(task, st), reward, terminated, truncated
+
+
+# ---- Philox resets (this repo's stream layout; distributions follow the reference) -----------
+def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET):
+    """Fresh episode state for global env ids `env_ids` at global step index `k`."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    n = env_ids.shape[0]
+    st = np.zeros(n, STATE_DTYPES[task])
+    if task == "basic":
+        st["pos"] = 10                                              # envs.py:21,55
+    elif task == "ball3d":                                          # ball3d.py:49-57
+        b0 = px.stream_block(seed, env_ids, k, tag, 0)
+        b1 = px.stream_block(seed, env_ids, k, tag, 1)
+        b2 = px.stream_block(seed, env_ids, k, tag, 2)
+        lo = -MAX_TILT * 0.5
+        rot = np.stack([lo + MAX_TILT * px.u53(b0[0], b0[1]), lo + MAX_TILT * px.u53(b0[2], b0[3])], 1)
+        pos = np.stack([-1.5 + 3.0 * px.u53(b1[0], b1[1]), -1.5 + 3.0 * px.u53(b1[2], b1[3])], 1)
+        vel = np.stack([-1.0 + 2.0 * px.u53(b2[0], b2[1]), -1.0 + 2.0 * px.u53(b2[2], b2[3])], 1)
+        st["rot"] = rot.astype(np.float32).astype(np.float64)       # `.astype(np.float32)` at reset
+        st["pos"] = pos.astype(np.float32)
+        st["vel"] = vel.astype(np.float32)
+    elif task == "gridworld":                                       # gridworld.py:42-50
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        a = px.bounded(b[0], 25)
+        g = px.bounded(b[1], 24)
+        g = g + (g >= a)
+        r = px.bounded(b[2], 23)
+        lo, hi = np.minimum(a, g), np.maximum(a, g)
+        r = r + (r >= lo)
+        r = r + (r >= hi)
+        st["agent"] = np.stack([a // 5, a % 5], 1)
+        st["green"] = np.stack([g // 5, g % 5], 1)
+        st["red"] = np.stack([r // 5, r % 5], 1)
+        st["goal_type"] = (b[3] >> np.uint32(31)).astype(np.int32)
+    elif task == "push":                                            # push.py:40-47
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        a = px.bounded(b[0], 36)
+        bx = px.bounded(b[1], 35)
+        bx = bx + (bx >= a)
+        st["agent"] = np.stack([a // 6, a % 6], 1)
+        st["box"] = np.stack([bx // 6, bx % 6], 1)
+        st["goal_x"] = px.bounded(b[2], 6)
+    return st
+
+
+def random_actions(task, seed, env_ids, step_index):
+    """Random-policy action of every env at global step `step_index` (TAG_ACTION stream)."""
+    n_act = TASKS[task][1]
+    b = px.stream_block(seed, env_ids, step_index // 4, px.TAG_ACTION, 0)
+    return px.bounded(b[step_index % 4], n_act)
+
+
+class OracleVecEnv:
+    """DummyVecEnv[Monitor[adapter]]-equivalent over the vectorised transitions above
+    with on-the-spot auto-reset; mirrors exactly what one `tmla_step` launch does."""
+
+    def __init__(self, task, n_envs, seed=1, env_id_base=0):
+        self.task, self.n, self.seed = task, int(n_envs), int(seed)
+        self.obs_dim, self.n_actions, self.max_steps = TASKS[task]
+        self.env_ids = np.arange(env_id_base, env_id_base + n_envs, dtype=np.uint64)
+        self.step_count = 0
+        self.state = np.zeros(n_envs, STATE_DTYPES[task])
+        self.reset()
+
+    def reset(self):
+        self.state = draw_reset(self.task, self.seed, self.env_ids, self.step_count, px.TAG_RESET_ALL)
+        return observe(self.task, self.state)
+
+    def step(self, actions):
+        st = self.state
+        obs, reward, terminated, truncated = transition(self.task, st, actions)
+        st["ep_return"] = (st["ep_return"] + reward).astype(np.float32)   # Monitor (f32 accumulator here)
+        self.step_count += 1
+        done = terminated | truncated
+        info = {
+            "terminal_obs": obs.copy(),
+            "episode_return": st["ep_return"].copy(),
+            "episode_length": st["steps"].copy(),
+            "terminated": terminated,
+        }
+        if done.any():
+            idx = np.nonzero(done)[0]
+            fresh = draw_reset(self.task, self.seed, self.env_ids[idx], self.step_count, px.TAG_RESET)
+            st[idx] = fresh
+            obs[idx] = observe(self.task, fresh)
+        # SB3: infos[i]["TimeLimit.truncated"] = truncated and not terminated
+        return obs, reward, done, truncated & ~terminated, info

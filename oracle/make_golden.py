@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY — golden-vector generator.
+
+Runs the UNMODIFIED reference environment code from /root/reference (its
+`mlagents.registry.make_env` -> `mlagents/envs.py` adapters -> `examples/*.py`
+dynamics) under the tiny `gymnasium` shim in `oracle/gym_shim/`, inside a
+DummyVecEnv-equivalent loop (step every env, on
+terminated|truncated keep the terminal observation and auto-reset), and records
+
+    (injected state, action) -> (obs, reward, terminated, truncated, reset state)
+
+for E environments x T steps per task into `tests/golden/<task>.npz`.
+The fixtures are data; this script is how they were made.  It can only run in
+the build container (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+Nothing in tests/, bench.py or the package imports this file.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BACKEND = "/root/reference/backend"
+OUT_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+E = 32      # environments per task
+T = 1000    # steps per environment (north_star: "over 1,000 steps")
+SEED = 20261017
+
+
+def _import_reference():
+    if not os.path.isdir(REF_BACKEND):
+        raise SystemExit("reference tree not present; golden vectors are committed under tests/golden/")
+    sys.path.insert(0, os.path.join(HERE, "gym_shim"))
+    sys.path.insert(0, REF_BACKEND)
+    from mlagents.registry import make_env  # reference code, unmodified
+
+    return make_env
+
+
+def _state_of(task, env):
+    """Read the reference object's private state (for injection on the other side)."""
+    if task == "basic":
+        return {"pos": np.int32(env.position)}
+    inner = env.env
+    if task == "ball3d":
+        return {
+            "rot": np.asarray(inner.rot, dtype=np.float64).copy(),
+            "pos": np.asarray(inner.pos, dtype=np.float32).copy(),
+            "vel": np.asarray(inner.vel, dtype=np.float32).copy(),
+        }
+    if task == "gridworld":
+        return {
+            "agent": np.asarray(inner.agent_pos, dtype=np.int32),
+            "green": np.asarray(inner.green_goals[0], dtype=np.int32),
+            "red": np.asarray(inner.red_goals[0], dtype=np.int32),
+            "goal_type": np.int32(inner.current_goal_type),
+        }
+    if task == "push":
+        return {
+            "agent": np.asarray(inner.agent_pos, dtype=np.int32),
+            "box": np.asarray(inner.box_pos, dtype=np.int32),
+            "goal_x": np.int32(inner.goal_pos[0]),
+        }
+    raise KeyError(task)
+
+
+def _actions(task, n_actions, rng):
+    """[T, E] action plan: a few constant-action envs (to reach clips, walls and
+    time-limit truncation) + uniform-random envs."""
+    acts = rng.integers(0, n_actions, size=(T, E), dtype=np.int64)
+    for j in range(min(2 * n_actions, E // 2)):
+        acts[:, j] = j % n_actions
+    # two envs alternate between opposite moves so they survive to the time limit
+    if n_actions >= 2:
+        acts[:, E - 1] = np.arange(T) % 2
+        acts[:, E - 2] = (np.arange(T) // 3) % n_actions
+    if task == "basic":
+        acts[:, 0] = 1   # stay put for 50 steps -> pure truncation episodes
+    if task == "ball3d":
+        acts[:, 4] = 4   # no-op forever
+    return acts.astype(np.int32)
+
+
+def record(task, make_env):
+    rng = np.random.default_rng(SEED + sum(map(ord, task)))
+    envs = [make_env(task) for _ in range(E)]
+    obs_dim = envs[0].observation_space.shape[0]
+    n_actions = envs[0].action_space.n
+    acts = _actions(task, n_actions, rng)
+
+    # seeding as make_vector_env does it: env i <- reset(seed=seed+i)  (training.py:80-84)
+    init_states, init_obs = [], []
+    for i, env in enumerate(envs):
+        o, _info = env.reset(seed=1 + i)
+        init_states.append(_state_of(task, env))
+        init_obs.append(o)
+
+    keys = list(init_states[0].keys())
+    out = {f"init_{k}": np.stack([s[k] for s in init_states]) for k in keys}
+    out["init_obs"] = np.stack(init_obs).astype(np.float32)
+    out["actions"] = acts
+    obs = np.zeros((T, E, obs_dim), np.float32)
+    rew = np.zeros((T, E), np.float32)
+    rew64 = np.zeros((T, E), np.float64)
+    term = np.zeros((T, E), np.bool_)
+    trunc = np.zeros((T, E), np.bool_)
+    reset_obs = np.zeros((T, E, obs_dim), np.float32)
+    resets = {k: np.zeros((T, E) + np.shape(init_states[0][k]), np.asarray(init_states[0][k]).dtype) for k in keys}
+
+    for t in range(T):
+        for i, env in enumerate(envs):
+            o, r, te, tr, _info = env.step(np.int64(acts[t, i]))
+            assert isinstance(te, bool) and isinstance(tr, bool)
+            obs[t, i] = o
+            rew64[t, i] = float(r)
+            rew[t, i] = np.float32(r)
+            term[t, i] = te
+            trunc[t, i] = tr
+            if te or tr:
+                ro, _ = env.reset()          # DummyVecEnv auto-reset: reset() without seed
+                reset_obs[t, i] = ro
+                st = _state_of(task, env)
+                for k in keys:
+                    resets[k][t, i] = st[k]
+    out.update(obs=obs, reward=rew, reward64=rew64, terminated=term, truncated=trunc, reset_obs=reset_obs)
+    out.update({f"reset_{k}": v for k, v in resets.items()})
+    for env in envs:
+        env.close()
+    return out
+
+
+def reset_samples(task, make_env, n=4096):
+    """Reset-state samples from the reference (global MT19937) for distributional checks."""
+    env = make_env(task)
+    env.reset(seed=777)
+    obs = []
+    states = []
+    for _ in range(n):
+        o, _ = env.reset()
+        obs.append(o)
+        states.append(_state_of(task, env))
+    env.close()
+    out = {"obs": np.stack(obs)}
+    for k in states[0]:
+        out[k] = np.stack([s[k] for s in states])
+    return out
+
+
+def main():
+    make_env = _import_reference()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for task in ("basic", "ball3d", "gridworld", "push"):
+        g = record(task, make_env)
+        path = os.path.join(OUT_DIR, f"{task}.npz")
+        np.savez_compressed(path, **g)
+        n_ep = int((g["terminated"] | g["truncated"]).sum())
+        print(f"{task}: {path}  episodes={n_ep} terminated={int(g['terminated'].sum())} "
+              f"truncated={int(g['truncated'].sum())}  size={os.path.getsize(path)/1024:.0f} KiB")
+    for task in ("ball3d", "gridworld", "push"):
+        s = reset_samples(task, make_env)
+        path = os.path.join(OUT_DIR, f"{task}_resets.npz")
+        np.savez_compressed(path, **s)
+        print(f"{task}: {path} size={os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""CPU tests: the oracle restatement against the reference-made golden vectors,
+Philox known-answer vectors, reset distributions against reference samples."""
+import numpy as np
+import pytest
+
+from oracle import envs_oracle as eo
+from oracle import philox as px
+import replay_util as _replay
+
+TASKS = ("basic", "ball3d", "gridworld", "push")
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = px.philox4x32_10([np.array([c]) for c in ctr], key)
+        assert tuple(int(x[0]) for x in got) == want
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_oracle_matches_reference_golden(task):
+    g = _replay.load(task)
+    acts = g["actions"]
+    T, E = acts.shape
+    st = _replay.initial_state(task, g, eo.STATE_DTYPES[task])
+    np.testing.assert_array_equal(eo.observe(task, st), g["init_obs"])
+    for t in range(T):
+        obs, rew, term, trunc = eo.transition(task, st, acts[t])
+        assert np.array_equal(term, g["terminated"][t]), (task, t)
+        assert np.array_equal(trunc, g["truncated"][t]), (task, t)
+        # bit-exact: integer tasks by construction, ball3d because the restatement
+        # reproduces NumPy's promotion/rounding order
+        assert np.array_equal(obs.view(np.uint32), g["obs"][t].view(np.uint32)), (task, t)
+        assert np.array_equal(rew.view(np.uint32), g["reward"][t].view(np.uint32)), (task, t)
+        done = term | trunc
+        st = _replay.inject_resets(task, g, t, st, done)
+        if done.any():
+            idx = np.nonzero(done)[0]
+            np.testing.assert_array_equal(eo.observe(task, st)[idx], g["reset_obs"][t][idx])
+
+
+def test_reward_luts_are_f32_of_double():
+    g = _replay.load("push")
+    assert np.array_equal(g["reward"], g["reward64"].astype(np.float32))
+    assert set(np.unique(g["reward"])).issubset(set(eo.PUSH_LUT.tolist()) | {np.float32(1.0)})
+    assert eo.BASIC_LUT.view(np.uint32).tolist() == [0xBC23D70A, 0x3DB851EC, 0x3F7D70A4]
+
+
+def test_reference_known_answer_basic():
+    # backend/tests/test_mlagents.py:32-45 — reset -> position 10; step(2) -> 11, not done
+    st = eo.draw_reset("basic", 1, np.arange(1), 0)
+    assert int(st["pos"][0]) == 10
+    obs, rew, term, trunc = eo.transition("basic", st, np.array([2]))
+    assert int(st["pos"][0]) == 11 and not term[0] and not trunc[0]
+    assert obs.shape == (1, 21) and obs[0, 11] == 1.0 and obs.sum() == 1.0
+
+
+@pytest.mark.parametrize("task", ("ball3d", "gridworld", "push"))
+def test_reset_distribution_matches_reference(task):
+    ref = np.load(_replay.GOLDEN + f"/{task}_resets.npz")
+    n = 200_000
+    st = eo.draw_reset(task, 7, np.arange(n), 3)
+    if task == "ball3d":
+        for key, half in (("rot", eo.MAX_TILT / 2), ("pos", 1.5), ("vel", 1.0)):
+            x = st[key].astype(np.float64)
+            assert np.abs(x).max() <= half * (1 + 1e-6) and np.abs(ref[key]).max() <= half * (1 + 1e-6)
+            assert abs(x.mean()) < 4 * half / np.sqrt(3 * n) * 2
+            assert abs(x.std() - half / np.sqrt(3)) < 0.01 * half
+            assert abs(ref[key].std() - half / np.sqrt(3)) < 0.05 * half
+            # both are f32-rounded doubles
+            assert np.array_equal(x.astype(np.float32).astype(np.float64), x)
+    elif task == "gridworld":
+        cells = lambda a: a[:, 0] * 5 + a[:, 1]
+        for s in (st, ref):
+            a, g_, r = cells(s["agent"]), cells(s["green"]), cells(s["red"])
+            assert ((a != g_) & (a != r) & (g_ != r)).all()
+            assert a.min() >= 0 and a.max() <= 24 and r.max() <= 24 and g_.max() <= 24
+        for key in ("agent", "green", "red"):
+            h = np.bincount(cells(st[key]), minlength=25) / n
+            assert np.abs(h - 1 / 25).max() < 0.003
+        assert abs(st["goal_type"].mean() - 0.5) < 0.01 and abs(ref["goal_type"].mean() - 0.5) < 0.05
+        # joint: red given (agent, green) is uniform over the 23 free cells
+        pair = cells(st["agent"]) * 25 + cells(st["green"])
+        sel = pair == pair[0]
+        assert len(np.unique(cells(st["red"])[sel])) == 23
+    else:
+        cells = lambda a: a[:, 0] * 6 + a[:, 1]
+        for s in (st, ref):
+            assert (cells(s["agent"]) != cells(s["box"])).all()
+            assert s["goal_x"].min() >= 0 and s["goal_x"].max() <= 5
+        for key in ("agent", "box"):
+            h = np.bincount(cells(st[key]), minlength=36) / n
+            assert np.abs(h - 1 / 36).max() < 0.003
+        h = np.bincount(st["goal_x"], minlength=6) / n
+        assert np.abs(h - 1 / 6).max() < 0.005
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_oracle_vecenv_autoreset_contract(task):
+    env = eo.OracleVecEnv(task, 64, seed=3)
+    rng = np.random.default_rng(0)
+    ep_ret = np.zeros(64, np.float64)
+    ep_len = np.zeros(64, np.int64)
+    seen_done = 0
+    for t in range(300):
+        a = rng.integers(0, env.n_actions, 64)
+        obs, rew, done, tl_trunc, info = env.step(a)
+        ep_ret += rew
+        ep_len += 1
+        assert obs.shape == (64, env.obs_dim) and obs.dtype == np.float32
+        if done.any():
+            i = np.nonzero(done)[0]
+            seen_done += i.size
+            assert np.allclose(info["episode_return"][i], ep_ret[i], rtol=1e-5, atol=1e-5)
+            assert np.array_equal(info["episode_length"][i], ep_len[i])
+            assert (env.state["steps"][i] == 0).all()
+            assert (ep_len[i] <= env.max_steps).all()
+            assert (tl_trunc[i] == (ep_len[i] == env.max_steps) & ~info["terminated"][i]).all()
+            ep_ret[i] = 0
+            ep_len[i] = 0
+    assert seen_done > 0
