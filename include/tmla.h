@@ -1,0 +1,189 @@
+/*
+ * tmla.h — C ABI of libtmla.so, the B200-native (sm_100a) hot path of three-mlagents.
+ *
+ * The reference (lukehollis/three-mlagents) has no FFI: its hot path is pure Python —
+ * `DummyVecEnv.step_wait` looping over `LegacySingleAgentGymAdapter.step`
+ * (backend/mlagents/envs.py:125-152) over `Ball3DEnv/GridWorldEnv/PushEnv.step`
+ * (backend/examples/ball3d.py:74-113, gridworld.py:67-95, push.py:62-125) and
+ * `BasicMoveToGoalEnv.step` (envs.py:60-81), then SB3's RolloutBuffer / PPO.train
+ * reached from backend/mlagents/training.py:150,166.  Every entry point below names the
+ * reference (or SB3-2.9.0) routine it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to bind them.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative TMLA_E* code; the message is
+ *     available from tmla_last_error() (thread-local).  No exceptions cross the ABI.
+ *   - Unless a name ends in `_host`, tensor pointers are DEVICE pointers owned by the
+ *     caller; the library owns only the packed structure-of-arrays environment state
+ *     inside a handle.  `stream` is a cudaStream_t passed as void*; calls enqueue on it
+ *     and never synchronise (the `_host` variants synchronise before returning because
+ *     they hand results back in host memory).
+ *   - A handle is bound to one (task, device); handles are independent; a handle is
+ *     not thread-safe.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef TMLA_H
+#define TMLA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMLA_VERSION 100          /* major*100 + minor */
+
+#define TMLA_OK            0
+#define TMLA_EINVAL       -1      /* bad argument (unknown task, null pointer, n<=0 ...) */
+#define TMLA_ECUDA        -2      /* a CUDA runtime call failed */
+#define TMLA_ENOMEM       -3
+#define TMLA_EACTION      -4      /* an out-of-range action was seen by a step kernel */
+
+typedef enum { TMLA_BASIC = 0, TMLA_BALL3D = 1, TMLA_GRIDWORLD = 2, TMLA_PUSH = 3 } tmla_task;
+
+typedef struct tmla_env tmla_env;     /* opaque handle: packed SoA state of n envs on one GPU */
+
+/* Wire format of tmla_get_state / tmla_set_state: array-of-structs, one per env, in DEVICE
+ * memory (state injection for parity tests; the resident layout is packed SoA). */
+typedef struct { int32_t pos, steps; float ep_return; } tmla_basic_state;                                /* envs.py:46-47 */
+typedef struct { double rot[2]; float pos[2]; float vel[2]; int32_t steps; float ep_return; } tmla_ball3d_state; /* ball3d.py:49-58 */
+typedef struct { int32_t agent[2], green[2], red[2], goal_type, steps; float ep_return; } tmla_gridworld_state;  /* gridworld.py:46-51 */
+typedef struct { int32_t agent[2], box[2], goal_x, steps; float ep_return; } tmla_push_state;                    /* push.py:42-49 */
+
+int         tmla_version(void);
+const char *tmla_last_error(void);
+
+/* task metadata — replaces the space declarations in make_*_env (envs.py:38-44,169-199) */
+int tmla_task_from_name(const char *name);            /* "basic"|"ball3d"|"gridworld"|"push" -> tmla_task or TMLA_EINVAL */
+int tmla_task_obs_dim(int task);                      /* 21 / 6 / 4 / 4 */
+int tmla_task_num_actions(int task);                  /* 3 / 5 / 5 / 5 */
+int tmla_task_max_steps(int task);                    /* 50 / 200 / 100 / 120 */
+int tmla_task_state_size(int task);                   /* sizeof(tmla_<task>_state) */
+
+/* make_vector_env (training.py:71-89): n_envs envs whose global ids are
+ * [env_id_base, env_id_base+n_envs); all randomness is Philox4x32-10 keyed by `seed`
+ * with the global env id as sub-sequence, so trajectories do not depend on sharding. */
+int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int device, tmla_env **out);
+int tmla_destroy(tmla_env *h);                        /* VecEnv.close (training.py:223) */
+int tmla_seed(tmla_env *h, uint64_t seed);            /* VecEnv.seed */
+int64_t  tmla_num_envs(const tmla_env *h);
+uint64_t tmla_step_count(const tmla_env *h);          /* global step index (host copy) */
+
+/* VecEnv.reset(): re-draw every env (adapter.reset, envs.py:110-123) and write obs[n,D]. */
+int tmla_reset(tmla_env *h, float *obs, void *stream);
+
+/* VecEnv.step() = DummyVecEnv.step_wait: one fused launch doing
+ * transition + reward + terminated/truncated + Monitor accumulation + terminal-obs capture +
+ * Philox auto-reset + observation write.
+ *   actions      int32[n]
+ *   obs          float[n,D]   observation AFTER auto-reset (what VecEnv.step returns)
+ *   reward       float[n]
+ *   done         uint8[n]     terminated|truncated
+ *   truncated    uint8[n]     infos[i]["TimeLimit.truncated"]
+ *   terminal_obs float[n,D]   written only where done (infos[i]["terminal_observation"])
+ *   ep_return    float[n]     written only where done (Monitor "r")
+ *   ep_length    int32[n]     written only where done (Monitor "l")
+ * terminal_obs / ep_return / ep_length may be NULL. */
+int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+              uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_length, void *stream);
+
+/* Same call with HOST buffers (the SB3 VecEnv contract is NumPy in / NumPy out): stages through
+ * pinned memory owned by the handle, H2D actions -> kernel -> D2H results, synchronises.
+ * *n_done receives the number of finished episodes (so callers only touch infos when >0). */
+int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                   uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_length,
+                   int64_t *n_done);
+int tmla_reset_host(tmla_env *h, float *obs);
+
+/* state injection / extraction (parity tests): `aos` is n structs of the task's wire type. */
+int tmla_get_state(tmla_env *h, void *aos, void *stream);
+int tmla_set_state(tmla_env *h, const void *aos, void *stream);
+/* out-of-range action flag, read back from the device (synchronises `stream`). */
+int tmla_check_actions(tmla_env *h, void *stream);
+
+/* Fused T-step random-policy rollout, ONE launch, state held in registers for all T steps
+ * (DummyVecEnv loop with `action_space.sample()`-style uniform actions from the TAG_ACTION
+ * Philox stream).  Buffers are [T,n,...] as SB3's RolloutBuffer lays them out:
+ *   obs_buf float[T,n,D] observation the action was taken on;  act_buf int32[T,n];
+ *   rew_buf float[T,n];  done_buf uint8[T,n].  Any of them may be NULL (not written). */
+int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, float *rew_buf,
+                        uint8_t *done_buf, void *stream);
+
+/* Policy-driven step of the PPO rollout (OnPolicyAlgorithm.collect_rollouts body):
+ * sample a ~ Categorical(logits) with the TAG_SAMPLE Philox stream (or argmax when
+ * deterministic!=0), log-prob, env step, auto-reset, rollout-row write.
+ *   logits float[n,A] ; obs_next float[n,D] (row t+1 of the obs buffer) ; act/logp/rew/done rows of
+ *   the [T,n] buffers ; truncation records (terminal obs + flat index) are appended to trunc_*;
+ *   step_base: optional DEVICE uint64 added to the handle's step index (CUDA-graph replay). */
+int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_t row_index,
+                     float *obs_next, int32_t *act, float *logp, float *rew, uint8_t *done,
+                     int32_t *trunc_count, int32_t *trunc_index, float *trunc_obs, int32_t trunc_capacity,
+                     float *ep_stats /* [4]: sum return, sum length, episodes, (unused) */,
+                     const uint64_t *step_base, void *stream);
+/* advance the handle's host step counter after a graph replay of T tmla_step_policy launches,
+ * and the matching device-side counter increment to put at the end of the captured graph */
+int tmla_advance_steps(tmla_env *h, uint64_t n);
+int tmla_counter_add(uint64_t *counter, uint64_t n, void *stream);
+
+/* rewards[idx] += gamma * values[i] for the truncation records (collect_rollouts timeout bootstrap) */
+int tmla_bootstrap_add(float *rew_buf, const int32_t *trunc_count, const int32_t *trunc_index,
+                       const float *trunc_values, double gamma, int32_t capacity, void *stream);
+
+/* RolloutBuffer.compute_returns_and_advantage (SB3 2.9.0), float32, same operation order:
+ * rewards/values float[T,n], dones uint8[T,n] (done after step t == episode_starts[t+1]),
+ * last_values float[n]  ->  advantages, returns float[T,n].  gamma/gae_lambda are doubles because
+ * NumPy multiplies the two Python floats in double before rounding to float32. */
+int tmla_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
+             double gamma, double gae_lambda, int T, int64_t n, float *advantages, float *returns, void *stream);
+
+/* RolloutBuffer.get: pseudo-random permutation of [0,total) (keyed Feistel + cycle walking), written
+ * as SB3's flat sample index env*T+t converted to buffer offset t*n+env.  out int32[total]. */
+int tmla_permutation(uint64_t seed, uint64_t epoch, int64_t total, int T, int64_t n, int32_t *out, void *stream);
+
+/* ---- policy / value network: MlpPolicy with net_arch dict(pi=[H,H], vf=[H,H]), tanh ------------
+ * Flat fp32 parameter vector in SB3's policy.parameters() order:
+ *   pi.W1[H,D] pi.b1[H] pi.W2[H,H] pi.b2[H] vf.W1[H,D] vf.b1[H] vf.W2[H,H] vf.b2[H] Wa[A,H] ba[A] Wv[1,H] bv[1]
+ */
+int64_t tmla_mlp_num_params(int obs_dim, int hidden, int n_actions);
+
+/* ActorCriticPolicy.forward / evaluate_actions / predict_values.
+ *   x float[rows,D] gathered through `index` (int32[rows], may be NULL = identity);
+ *   logits float[rows,A] (NULL: value tower only), values float[rows] (NULL: policy tower only);
+ *   act_cache: optional float[4,rows,H] (pi.h1, pi.h2, vf.h1, vf.h2) kept for tmla_mlp_backward;
+ *   rows_dev: optional DEVICE int32 row count overriding `rows` as an upper bound (rows<=capacity). */
+int tmla_mlp_forward(const float *params, int obs_dim, int hidden, int n_actions, const float *x,
+                     const int32_t *index, int64_t rows, const int32_t *rows_dev, float *logits,
+                     float *values, float *act_cache, void *stream);
+
+/* backward of the above: dlogits float[rows,A], dvalues float[rows] -> grads (flat, same order as
+ * params; OVERWRITTEN, not accumulated).  scratch: float[tmla_mlp_backward_scratch(...)] */
+int64_t tmla_mlp_backward_scratch(int obs_dim, int hidden, int n_actions, int64_t rows);
+int tmla_mlp_backward(const float *params, int obs_dim, int hidden, int n_actions, const float *x,
+                      const int32_t *index, int64_t rows, const float *act_cache, const float *dlogits,
+                      const float *dvalues, float *grads, float *scratch, void *stream);
+
+/* PPO.train, one minibatch, loss head (SB3 2.9.0 ppo.py): advantage normalisation statistics,
+ * then clipped surrogate + value MSE + entropy, forward and backward in one pass.
+ *   stats_out float[8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss, adv_mean, adv_std
+ *   adv_sums double[3] device scratch (sum, sum of squares, count) — filled by tmla_adv_stats;
+ *   with world_size>1 the caller all-reduces adv_sums between the two calls (global-minibatch
+ *   normalisation) and passes the global row count to tmla_ppo_loss. */
+int tmla_adv_stats(const float *advantages, const int32_t *index, int64_t rows, double *adv_sums, void *stream);
+int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actions, const float *advantages,
+                  const float *old_logp, const float *returns, const int32_t *index, int64_t rows,
+                  int64_t global_rows, int n_actions, const double *adv_sums, int normalize_advantage,
+                  float clip_range, float ent_coef, float vf_coef, float *dlogits, float *dvalues,
+                  float *stats_out, void *stream);
+
+/* clip_grad_norm_(max_norm) + Adam.step fused (after the gradient all-reduce).
+ *   grad_scale multiplies the gradient first (1/world_size); state m,v float[np]; step is the
+ *   1-based Adam step; norm_out float[1] receives the pre-clip global norm. */
+int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
+                   float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                   float *norm_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMLA_H */

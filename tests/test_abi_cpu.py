@@ -1,0 +1,87 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/tmla.h declares; metadata calls (no GPU needed) answer; compute calls fail loudly
+without a GPU instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "tmla.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tmla_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from three_mlagents_b200 import native
+
+    names = _declared()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(native.lib, name), f"{name} declared in tmla.h but not exported by libtmla.so"
+        assert name in native.SIGNATURES, f"{name} has no ctypes signature in native.py"
+    assert set(native.SIGNATURES) == set(names)
+
+
+def test_metadata_calls_match_reference_spaces():
+    from three_mlagents_b200 import native
+
+    lib = native.lib
+    assert lib.tmla_version() == 100
+    want = {"basic": (21, 3, 50, 12), "ball3d": (6, 5, 200, 40), "gridworld": (4, 5, 100, 36), "push": (4, 5, 120, 28)}
+    for name, (d, a, m, sz) in want.items():
+        t = lib.tmla_task_from_name(name.encode())
+        assert t == native.TASK_IDS[name]
+        assert (lib.tmla_task_obs_dim(t), lib.tmla_task_num_actions(t), lib.tmla_task_max_steps(t),
+                lib.tmla_task_state_size(t)) == (d, a, m, sz)
+    assert lib.tmla_task_from_name(b"walljump") == native.TMLA_EINVAL
+    assert b"walljump" in lib.tmla_last_error()
+    # parameter counts of SURVEY.md A8
+    assert lib.tmla_mlp_num_params(6, 256, 5) == 136710
+    assert lib.tmla_mlp_num_params(4, 256, 5) == 135686
+    assert lib.tmla_mlp_num_params(21, 256, 3) == 143876
+
+
+def test_wire_structs_match_numpy_dtypes():
+    from three_mlagents_b200 import native
+    from three_mlagents_b200.vec_env import STATE_DTYPES
+    from oracle.envs_oracle import STATE_DTYPES as ORACLE_DTYPES
+
+    for name, tid in native.TASK_IDS.items():
+        assert STATE_DTYPES[name].itemsize == native.lib.tmla_task_state_size(tid)
+        assert STATE_DTYPES[name] == ORACLE_DTYPES[name]
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from three_mlagents_b200 import native
+    from three_mlagents_b200.vec_env import CudaVecEnv
+
+    with pytest.raises(native.TmlaError):
+        CudaVecEnv("ball3d", 8)
+
+
+def test_registry_surface():
+    import three_mlagents_b200 as m
+    from three_mlagents_b200 import registry
+
+    assert len(registry.TASKS) == 19
+    assert registry.CUDA_TASKS == ("basic", "ball3d", "gridworld", "push")
+    assert m.get_task("brick-break").id == "brickbreak"            # tests/test_mlagents.py:47-49
+    assert m.get_task("self_driving_car").id == "self-driving-car"
+    with pytest.raises(KeyError):
+        m.get_task("nope")
+    with pytest.raises(ValueError):
+        m.make_env("fish")
+    card = m.get_task("basic").card()
+    assert card["trainable"] is True and "env_factory" not in card
+    assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["ball3d", "basic", "gridworld", "push"]
+    fams = [(t.family, t.id) for t in m.list_tasks()]
+    assert fams == sorted(fams)

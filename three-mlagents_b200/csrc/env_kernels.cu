@@ -1,0 +1,504 @@
+// env_kernels.cu — batched environment stepping for basic / ball3d / gridworld / push (sm_100a).
+//
+// Replaces SB3 `DummyVecEnv.step_wait` (a serial Python loop over envs) + `Monitor` + the reference's
+// `LegacySingleAgentGymAdapter.step/reset` (backend/mlagents/envs.py:110-152) and the task dynamics
+// (envs.cuh).  One thread per environment; state lives in packed structure-of-arrays planes in HBM
+// (128-bit loads/stores for ball3d, one 64-bit word per env for the integer tasks) and is kept in
+// registers for all T steps by the fused rollout kernel.  Observation rows are staged through shared
+// memory and leave the SM as coalesced 128-bit stores.
+//
+// These kernels are HBM-bound integer/byte/float32 work: no tensor cores, no GEMM reshaping.
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+#include "envs.cuh"
+
+// ------------------------------------------------------------------------------------------ handle
+struct tmla_env {
+    int task;
+    int64_t n;
+    uint64_t seed, env_id_base, step_count;
+    int device;
+    void *buf[4];             // packed SoA planes (device)
+    int *err_flag;            // device: set when a kernel saw an out-of-range action
+    // staging for the *_host entry points
+    void *d_stage, *h_stage;  // device / pinned host, same layout
+    size_t stage_bytes;
+    cudaStream_t own_stream;
+    int32_t *d_ndone;         // device counter of finished episodes in the last step
+};
+
+struct EnvPtrs { void *buf[4]; };
+
+static constexpr int kBlock = 128;
+
+// ------------------------------------------------------------------------- cooperative obs store
+// Threads of a block have written BLOCK*D floats (row-major [env][D]) to shared memory; write the
+// valid prefix to `dst` as 128-bit stores when the destination is 16-byte aligned.
+template <int D, int BLOCK, bool STREAMING>
+__device__ __forceinline__ void block_store_obs(const float *s_obs, float *dst, int valid_envs) {
+    const int total = valid_envs * D;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int nvec = total >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        for (int v = threadIdx.x; v < nvec; v += BLOCK) {
+            if (STREAMING) st_stream_f4(d4 + v, s4[v]);
+            else d4[v] = s4[v];
+        }
+        for (int e = (nvec << 2) + threadIdx.x; e < total; e += BLOCK) dst[e] = s_obs[e];
+    } else {
+        for (int e = threadIdx.x; e < total; e += BLOCK) dst[e] = s_obs[e];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void thread_store_obs(const float *o, float *dst) {   // rare paths (terminal obs)
+#pragma unroll
+    for (int j = 0; j < D; ++j) dst[j] = o[j];
+}
+
+// ---------------------------------------------------------------------------------- reset / state
+template <class Task>
+__global__ void __launch_bounds__(kBlock) reset_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base,
+                                                       uint64_t k, uint32_t tag, float *obs) {
+    __shared__ __align__(16) float s_obs[kBlock * Task::D];
+    const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    if (i < n) {
+        typename Task::State s;
+        Task::reset(s, seed, env_base + (uint64_t)i, k, tag);
+        Task::store(p.buf, i, s);
+        float o[Task::D];
+        Task::observe(s, o);
+#pragma unroll
+        for (int j = 0; j < Task::D; ++j) s_obs[threadIdx.x * Task::D + j] = o[j];
+    }
+    __syncthreads();
+    if (obs) block_store_obs<Task::D, kBlock, false>(s_obs, obs + i0 * Task::D, (int)min((int64_t)kBlock, n - i0));
+}
+
+template <class Task>
+__global__ void get_state_kernel(EnvPtrs p, int64_t n, typename Task::Wire *aos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) aos[i] = Task::to_wire(Task::load(p.buf, i));
+}
+template <class Task>
+__global__ void set_state_kernel(EnvPtrs p, int64_t n, const typename Task::Wire *aos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Task::store(p.buf, i, Task::from_wire(aos[i]));
+}
+
+// ------------------------------------------------------------------------------------ VecEnv.step
+template <class Task>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t step_index,
+            const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
+            uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
+            float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag) {
+    constexpr int D = Task::D;
+    __shared__ __align__(16) float s_obs[kBlock * D];
+    const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    if (i < n) {
+        typename Task::State s = Task::load(p.buf, i);
+        int a = actions[i];
+        if ((unsigned)a >= (unsigned)Task::A) { *err_flag = 1; a = min(max(a, 0), Task::A - 1); }
+        float r; bool term, trunc;
+        Task::step(s, a, r, term, trunc);
+        s.ep_ret = __fadd_rn(s.ep_ret, r);                       // Monitor: episode return
+        const bool d = term || trunc;
+        reward[i] = r;
+        done[i] = d ? 1 : 0;
+        truncated[i] = (trunc && !term) ? 1 : 0;                 // infos["TimeLimit.truncated"]
+        float o[D];
+        Task::observe(s, o);
+        if (d) {                                                 // DummyVecEnv: keep terminal obs, auto-reset
+            if (terminal_obs) thread_store_obs<D>(o, terminal_obs + i * D);
+            if (ep_return) ep_return[i] = s.ep_ret;
+            if (ep_length) ep_length[i] = s.steps;
+            if (n_done) atomicAdd(n_done, 1);
+            Task::reset(s, seed, env_base + (uint64_t)i, step_index + 1, TMLA_TAG_RESET);
+            Task::observe(s, o);
+        }
+        Task::store(p.buf, i, s);
+#pragma unroll
+        for (int j = 0; j < D; ++j) s_obs[threadIdx.x * D + j] = o[j];
+    }
+    __syncthreads();
+    block_store_obs<D, kBlock, false>(s_obs, obs + i0 * D, (int)min((int64_t)kBlock, n - i0));
+}
+
+// --------------------------------------------------------------- fused T-step random-policy rollout
+// State stays in registers for all T steps; per step and env the kernel writes obs (D floats, via the
+// double-buffered shared-memory stage -> st.global.cs.v4), action, reward and done: the [T,N] rollout
+// buffer is write-once streaming traffic, 33 B/env-step for ball3d.
+template <class Task>
+__global__ void __launch_bounds__(kBlock)
+rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t step0, int T,
+                      float *__restrict__ obs_buf, int32_t *__restrict__ act_buf, float *__restrict__ rew_buf,
+                      uint8_t *__restrict__ done_buf) {
+    constexpr int D = Task::D;
+    __shared__ __align__(16) float s_obs[2][kBlock * D];
+    const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    const bool active = i < n;
+    const int valid = (int)min((int64_t)kBlock, n - i0);
+    const uint64_t env_id = env_base + (uint64_t)i;
+    typename Task::State s;
+    if (active) s = Task::load(p.buf, i);
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    for (int t = 0; t < T; ++t) {
+        const uint64_t k = step0 + (uint64_t)t;
+        float *stage = s_obs[t & 1];
+        if (active) {
+            float o[D];
+            Task::observe(s, o);                                  // observation the action is taken on
+#pragma unroll
+            for (int j = 0; j < D; ++j) stage[threadIdx.x * D + j] = o[j];
+            const uint32_t lane = (uint32_t)(k & 3u);
+            if (lane == 0 || t == 0) blk = tmla_stream_block(seed, env_id, k >> 2, TMLA_TAG_ACTION, 0);
+            const uint32_t word = lane == 0 ? blk.x : (lane == 1 ? blk.y : (lane == 2 ? blk.z : blk.w));
+            const int a = tmla_bounded(word, Task::A);
+            float r; bool term, trunc;
+            Task::step(s, a, r, term, trunc);
+            s.ep_ret = __fadd_rn(s.ep_ret, r);
+            const bool d = term || trunc;
+            const int64_t off = (int64_t)t * n + i;
+            if (act_buf) __stcs(act_buf + off, a);
+            if (rew_buf) __stcs(rew_buf + off, r);
+            if (done_buf) __stcs(done_buf + off, (uint8_t)(d ? 1 : 0));
+            if (d) Task::reset(s, seed, env_id, k + 1, TMLA_TAG_RESET);
+        }
+        __syncthreads();
+        if (obs_buf) block_store_obs<D, kBlock, true>(stage, obs_buf + ((int64_t)t * n + i0) * D, valid);
+    }
+    if (active) Task::store(p.buf, i, s);
+}
+
+// ------------------------------------------------------------- policy-driven step (PPO rollout row)
+template <int A>
+__device__ __forceinline__ void categorical(const float *l, bool deterministic, float u, int &action, float &logp) {
+    float m = l[0];
+#pragma unroll
+    for (int j = 1; j < A; ++j) m = fmaxf(m, l[j]);
+    float e[A], sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < A; ++j) { e[j] = expf(l[j] - m); sum += e[j]; }
+    int a = 0;
+    if (deterministic) {                                   // argmax(probs), first maximum wins (torch.argmax)
+#pragma unroll
+        for (int j = 1; j < A; ++j) if (l[j] > l[a]) a = j;
+    } else {                                               // inverse CDF on the unnormalised weights
+        const float target = u * sum;
+        float c = 0.0f;
+        a = A - 1;                                         // guards against target == sum after rounding
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            c += e[j];
+            if (!found && target < c) { a = j; found = true; }
+        }
+    }
+    action = a;
+    logp = (l[a] - m) - logf(sum);                         // log_softmax(logits)[a]
+}
+
+template <class Task>
+__global__ void __launch_bounds__(kBlock)
+step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t step_index,
+                   const uint64_t *__restrict__ step_base, const float *__restrict__ logits, int deterministic,
+                   int64_t row_index, float *__restrict__ obs_next, int32_t *__restrict__ act, float *__restrict__ logp_out,
+                   float *__restrict__ rew, uint8_t *__restrict__ done, int32_t *trunc_count,
+                   int32_t *__restrict__ trunc_index, float *__restrict__ trunc_obs, int32_t trunc_capacity,
+                   float *ep_stats) {
+    constexpr int D = Task::D, A = Task::A;
+    __shared__ __align__(16) float s_obs[kBlock * D];
+    const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    const uint64_t k = step_base ? (*step_base + (uint64_t)row_index) : step_index;
+    if (i < n) {
+        const uint64_t env_id = env_base + (uint64_t)i;
+        typename Task::State s = Task::load(p.buf, i);
+        float l[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) l[j] = logits[i * A + j];
+        float u = 0.0f;
+        if (!deterministic) u = tmla_u24(tmla_stream_block(seed, env_id, k, TMLA_TAG_SAMPLE, 0).x);
+        int a; float lp;
+        categorical<A>(l, deterministic != 0, u, a, lp);
+        float r; bool term, trunc;
+        Task::step(s, a, r, term, trunc);
+        s.ep_ret = __fadd_rn(s.ep_ret, r);
+        const bool d = term || trunc;
+        if (act) act[i] = a;
+        if (logp_out) logp_out[i] = lp;
+        rew[i] = r;
+        done[i] = d ? 1 : 0;
+        float o[D];
+        Task::observe(s, o);
+        if (d) {
+            if (trunc && !term && trunc_count) {            // collect_rollouts: bootstrap with V(terminal_obs)
+                const int slot = atomicAdd(trunc_count, 1);
+                if (slot < trunc_capacity) {
+                    trunc_index[slot] = (int32_t)(row_index * n + i);
+                    thread_store_obs<D>(o, trunc_obs + (int64_t)slot * D);
+                }
+            }
+            if (ep_stats) {                                  // Monitor -> rollout/ep_rew_mean, ep_len_mean
+                atomicAdd(ep_stats + 0, s.ep_ret);
+                atomicAdd(ep_stats + 1, (float)s.steps);
+                atomicAdd(ep_stats + 2, 1.0f);
+            }
+            Task::reset(s, seed, env_id, k + 1, TMLA_TAG_RESET);
+            Task::observe(s, o);
+        }
+        Task::store(p.buf, i, s);
+#pragma unroll
+        for (int j = 0; j < D; ++j) s_obs[threadIdx.x * D + j] = o[j];
+    }
+    __syncthreads();
+    block_store_obs<D, kBlock, false>(s_obs, obs_next + i0 * D, (int)min((int64_t)kBlock, n - i0));
+}
+
+__global__ void counter_add_kernel(uint64_t *c, uint64_t n) { *c += n; }
+
+// ------------------------------------------------------------------------------------ dispatch
+#define TASK_SWITCH(task, CALL)                                   \
+    switch (task) {                                               \
+        case TMLA_BASIC: { using TaskT = BasicTask; CALL; } break;        \
+        case TMLA_BALL3D: { using TaskT = Ball3DTask; CALL; } break;      \
+        case TMLA_GRIDWORLD: { using TaskT = GridWorldTask; CALL; } break; \
+        case TMLA_PUSH: { using TaskT = PushTask; CALL; } break;          \
+        default: tmla_set_error("unknown task %d", task); return TMLA_EINVAL; \
+    }
+
+static EnvPtrs ptrs_of(const tmla_env *h) {
+    EnvPtrs p;
+    for (int b = 0; b < 4; ++b) p.buf[b] = h->buf[b];
+    return p;
+}
+static inline unsigned grid_for(int64_t n) { return (unsigned)ceil_div64(n, kBlock); }
+
+static const int kObsDim[4] = {BasicTask::D, Ball3DTask::D, GridWorldTask::D, PushTask::D};
+static const int kNumActions[4] = {BasicTask::A, Ball3DTask::A, GridWorldTask::A, PushTask::A};
+static const int kMaxSteps[4] = {BasicTask::MAX_STEPS, Ball3DTask::MAX_STEPS, GridWorldTask::MAX_STEPS, PushTask::MAX_STEPS};
+static const int kStateSize[4] = {(int)sizeof(tmla_basic_state), (int)sizeof(tmla_ball3d_state),
+                                  (int)sizeof(tmla_gridworld_state), (int)sizeof(tmla_push_state)};
+
+extern "C" {
+
+int tmla_task_from_name(const char *name) {
+    if (!name) { tmla_set_error("task name is NULL"); return TMLA_EINVAL; }
+    if (!strcmp(name, "basic")) return TMLA_BASIC;
+    if (!strcmp(name, "ball3d")) return TMLA_BALL3D;
+    if (!strcmp(name, "gridworld")) return TMLA_GRIDWORLD;
+    if (!strcmp(name, "push")) return TMLA_PUSH;
+    tmla_set_error("no CUDA backend for task '%s' (have: basic, ball3d, gridworld, push)", name);
+    return TMLA_EINVAL;
+}
+#define TASK_META(fn, table)                                                                   \
+    int fn(int task) {                                                                         \
+        if (task < 0 || task > 3) { tmla_set_error(#fn ": unknown task %d", task); return TMLA_EINVAL; } \
+        return table[task];                                                                    \
+    }
+TASK_META(tmla_task_obs_dim, kObsDim)
+TASK_META(tmla_task_num_actions, kNumActions)
+TASK_META(tmla_task_max_steps, kMaxSteps)
+TASK_META(tmla_task_state_size, kStateSize)
+
+int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int device, tmla_env **out) {
+    TMLA_REQUIRE(out != nullptr, "out is NULL");
+    TMLA_REQUIRE(task >= 0 && task <= 3, "unknown task");
+    TMLA_REQUIRE(n_envs > 0 && n_envs < (int64_t)1 << 31, "n_envs must be in (0, 2^31)");
+    int ndev = 0;
+    TMLA_CUDA(cudaGetDeviceCount(&ndev));
+    TMLA_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU path)");
+    TMLA_CUDA(cudaSetDevice(device));
+    tmla_env *h = new (std::nothrow) tmla_env();
+    if (!h) { tmla_set_error("out of host memory"); return TMLA_ENOMEM; }
+    memset(h, 0, sizeof(*h));
+    h->task = task; h->n = n_envs; h->seed = seed; h->env_id_base = env_id_base; h->device = device;
+    int nbuf = 0;
+    size_t pb[4] = {0, 0, 0, 0};
+    TASK_SWITCH(task, nbuf = TaskT::NBUF; for (int b = 0; b < nbuf; ++b) pb[b] = TaskT::plane_bytes(b));
+    for (int b = 0; b < nbuf; ++b) {
+        cudaError_t e = cudaMalloc(&h->buf[b], pb[b] * (size_t)n_envs);
+        if (e != cudaSuccess) { tmla_set_error("cudaMalloc(state plane %d): %s", b, cudaGetErrorString(e)); tmla_destroy(h); return TMLA_ENOMEM; }
+    }
+    const int D = kObsDim[task];
+    // staging layout: actions i32 | obs | reward | terminal_obs | ep_return | ep_length | done | truncated
+    h->stage_bytes = (size_t)n_envs * (4 + 4 * D + 4 + 4 * D + 4 + 4 + 1 + 1) + 64;
+    if (cudaMalloc(&h->d_stage, h->stage_bytes) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stage_bytes) != cudaSuccess ||
+        cudaMalloc((void **)&h->err_flag, sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->d_ndone, sizeof(int32_t)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        tmla_set_error("allocating staging buffers: %s", cudaGetErrorString(cudaGetLastError()));
+        tmla_destroy(h);
+        return TMLA_ENOMEM;
+    }
+    TMLA_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+    TMLA_CUDA(cudaMemset(h->d_ndone, 0, sizeof(int32_t)));
+    *out = h;
+    int rc = tmla_reset(h, nullptr, nullptr);
+    if (rc) return rc;
+    TMLA_CUDA(cudaStreamSynchronize(nullptr));
+    return TMLA_OK;
+}
+
+int tmla_destroy(tmla_env *h) {
+    if (!h) return TMLA_OK;
+    cudaSetDevice(h->device);
+    for (int b = 0; b < 4; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->err_flag) cudaFree(h->err_flag);
+    if (h->d_ndone) cudaFree(h->d_ndone);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return TMLA_OK;
+}
+
+int tmla_seed(tmla_env *h, uint64_t seed) { TMLA_REQUIRE(h, "handle is NULL"); h->seed = seed; return TMLA_OK; }
+int64_t tmla_num_envs(const tmla_env *h) { return h ? h->n : 0; }
+uint64_t tmla_step_count(const tmla_env *h) { return h ? h->step_count : 0; }
+int tmla_advance_steps(tmla_env *h, uint64_t n) { TMLA_REQUIRE(h, "handle is NULL"); h->step_count += n; return TMLA_OK; }
+
+int tmla_reset(tmla_env *h, float *obs, void *stream) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASK_SWITCH(h->task, (reset_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
+                             ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, TMLA_TAG_RESET_ALL, obs)));
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
+int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+              float *terminal_obs, float *ep_return, int32_t *ep_length, void *stream) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE(actions && obs && reward && done && truncated, "actions/obs/reward/done/truncated must be non-NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
+                             ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag)));
+    TMLA_LAUNCH_CHECK();
+    h->step_count += 1;
+    return TMLA_OK;
+}
+
+int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                   float *terminal_obs, float *ep_return, int32_t *ep_length, int64_t *n_done) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE(actions && obs && reward && done && truncated, "actions/obs/reward/done/truncated must be non-NULL");
+    TMLA_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    const int D = kObsDim[h->task];
+    // carve the staging block (device and pinned host share the layout)
+    size_t o_act = 0, o_obs = o_act + 4 * n, o_rew = o_obs + 4 * n * D, o_tobs = o_rew + 4 * n, o_ret = o_tobs + 4 * n * D,
+           o_len = o_ret + 4 * n, o_done = o_len + 4 * n, o_trunc = o_done + n, o_end = o_trunc + n;
+    char *d = (char *)h->d_stage, *p = (char *)h->h_stage;
+    cudaStream_t st = h->own_stream;
+    memcpy(p + o_act, actions, 4 * n);
+    TMLA_CUDA(cudaMemcpyAsync(d + o_act, p + o_act, 4 * n, cudaMemcpyHostToDevice, st));
+    TMLA_CUDA(cudaMemsetAsync(h->d_ndone, 0, sizeof(int32_t), st));
+    TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
+                             ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + o_act),
+                             (float *)(d + o_obs), (float *)(d + o_rew), (uint8_t *)(d + o_done), (uint8_t *)(d + o_trunc),
+                             (float *)(d + o_tobs), (float *)(d + o_ret), (int32_t *)(d + o_len), h->d_ndone, h->err_flag)));
+    TMLA_LAUNCH_CHECK();
+    h->step_count += 1;
+    // results every caller needs: obs | reward ... done | truncated  (two contiguous spans)
+    TMLA_CUDA(cudaMemcpyAsync(p + o_obs, d + o_obs, o_tobs - o_obs, cudaMemcpyDeviceToHost, st));
+    TMLA_CUDA(cudaMemcpyAsync(p + o_done, d + o_done, o_end - o_done, cudaMemcpyDeviceToHost, st));
+    int32_t nd = 0;
+    int err = 0;
+    TMLA_CUDA(cudaMemcpyAsync(&nd, h->d_ndone, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TMLA_CUDA(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TMLA_CUDA(cudaStreamSynchronize(st));
+    memcpy(obs, p + o_obs, 4 * n * D);
+    memcpy(reward, p + o_rew, 4 * n);
+    memcpy(done, p + o_done, n);
+    memcpy(truncated, p + o_trunc, n);
+    if (nd > 0 && (terminal_obs || ep_return || ep_length)) {   // episode-end payloads only when something finished
+        TMLA_CUDA(cudaMemcpyAsync(p + o_tobs, d + o_tobs, o_done - o_tobs, cudaMemcpyDeviceToHost, st));
+        TMLA_CUDA(cudaStreamSynchronize(st));
+        if (terminal_obs) memcpy(terminal_obs, p + o_tobs, 4 * n * D);
+        if (ep_return) memcpy(ep_return, p + o_ret, 4 * n);
+        if (ep_length) memcpy(ep_length, p + o_len, 4 * n);
+    }
+    if (n_done) *n_done = nd;
+    if (err) {
+        cudaMemsetAsync(h->err_flag, 0, sizeof(int), st);
+        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+        return TMLA_EACTION;
+    }
+    return TMLA_OK;
+}
+
+int tmla_reset_host(tmla_env *h, float *obs) {
+    TMLA_REQUIRE(h && obs, "handle/obs is NULL");
+    TMLA_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)4 * h->n * kObsDim[h->task];
+    int rc = tmla_reset(h, (float *)h->d_stage, h->own_stream);
+    if (rc) return rc;
+    TMLA_CUDA(cudaMemcpyAsync(h->h_stage, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->own_stream));
+    TMLA_CUDA(cudaStreamSynchronize(h->own_stream));
+    memcpy(obs, h->h_stage, bytes);
+    return TMLA_OK;
+}
+
+int tmla_get_state(tmla_env *h, void *aos, void *stream) {
+    TMLA_REQUIRE(h && aos, "handle/aos is NULL");
+    TASK_SWITCH(h->task, (get_state_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
+                             ptrs_of(h), h->n, (typename TaskT::Wire *)aos)));
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+int tmla_set_state(tmla_env *h, const void *aos, void *stream) {
+    TMLA_REQUIRE(h && aos, "handle/aos is NULL");
+    TASK_SWITCH(h->task, (set_state_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
+                             ptrs_of(h), h->n, (const typename TaskT::Wire *)aos)));
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+int tmla_check_actions(tmla_env *h, void *stream) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    int err = 0;
+    TMLA_CUDA(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TMLA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err) {
+        TMLA_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), (cudaStream_t)stream));
+        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+        return TMLA_EACTION;
+    }
+    return TMLA_OK;
+}
+
+int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, float *rew_buf, uint8_t *done_buf, void *stream) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE(T > 0, "T must be positive");
+    TASK_SWITCH(h->task, (rollout_random_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
+                             ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, T, obs_buf, act_buf, rew_buf, done_buf)));
+    TMLA_LAUNCH_CHECK();
+    h->step_count += (uint64_t)T;
+    return TMLA_OK;
+}
+
+int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_t row_index, float *obs_next,
+                     int32_t *act, float *logp, float *rew, uint8_t *done, int32_t *trunc_count, int32_t *trunc_index,
+                     float *trunc_obs, int32_t trunc_capacity, float *ep_stats, const uint64_t *step_base, void *stream) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE(logits && obs_next && rew && done, "logits/obs_next/rew/done must be non-NULL");
+    TMLA_REQUIRE(!trunc_count || (trunc_index && trunc_obs && trunc_capacity > 0), "truncation list is incomplete");
+    TASK_SWITCH(h->task, (step_policy_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
+                             ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, step_base, logits, deterministic,
+                             (int64_t)row_index, obs_next, act, logp, rew, done, trunc_count, trunc_index, trunc_obs,
+                             trunc_capacity, ep_stats)));
+    TMLA_LAUNCH_CHECK();
+    if (!step_base) h->step_count += 1;
+    return TMLA_OK;
+}
+
+int tmla_counter_add(uint64_t *counter, uint64_t n, void *stream) {
+    TMLA_REQUIRE(counter, "counter is NULL");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, n);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// envs.cuh — device-side dynamics of the four tasks, one environment per thread, state in registers.
+//
+// Each task is a struct with the same static interface so the kernels in env_kernels.cu are
+// written once and instantiated four times:
+//     D, A, MAX_STEPS, NBUF                 observation width, #actions, adapter time limit, #SoA planes
+//     State                                 register-resident episode state (+ Monitor accumulator)
+//     load / store                          packed structure-of-arrays planes in HBM <-> State
+//     from_wire / to_wire                   tmla_<task>_state (include/tmla.h) <-> State
+//     observe(State, float o[D])            the task's _get_obs
+//     step(State&, a, reward, term, trunc)  env.step + LegacySingleAgentGymAdapter.step flags
+//     reset(State&, seed, env_id, k, tag)   env.reset with this repo's Philox streams
+//
+// Reference being restated (relative to /root/reference/backend), all checked bit-for-bit on the
+// CPU side by oracle/envs_oracle.py against reference-made golden traces:
+//     basic      mlagents/envs.py:17-84        ball3d     examples/ball3d.py:10-113
+//     gridworld  examples/gridworld.py:14-95   push       examples/push.py:10-125
+//     adapter    mlagents/envs.py:125-152 (steps>=limit -> truncated; terminated = done && !truncated)
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// packed word shared by the three integer tasks: 3-bit cell coordinates, flags, 8-bit step counter
+//   bits  0..17 : up to six 3-bit coordinates        bit 18 : goal type (gridworld)
+//   bits 19..26 : steps (<= 120)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell3(uint32_t w, int slot) { return (int)((w >> (3 * slot)) & 7u); }
+__device__ __forceinline__ uint32_t put3(int v, int slot) { return ((uint32_t)v & 7u) << (3 * slot); }
+__device__ __forceinline__ int iclamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---------------------------------------------------------------------------- basic (envs.py:17-84)
+struct BasicTask {
+    static constexpr int D = 21, A = 3, MAX_STEPS = 50, NBUF = 1;
+    typedef tmla_basic_state Wire;
+    struct State { int pos, steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int) { return sizeof(uint2); }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        uint2 w = reinterpret_cast<const uint2 *>(buf[0])[i];
+        return State{(int)(w.x & 31u), (int)((w.x >> 19) & 255u), __uint_as_float(w.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        reinterpret_cast<uint2 *>(buf[0])[i] =
+            make_uint2((uint32_t)s.pos | ((uint32_t)s.steps << 19), __float_as_uint(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) { return State{iclamp(w.pos, 0, 20), w.steps, w.ep_return}; }
+    static __device__ Wire to_wire(const State &s) { return Wire{s.pos, s.steps, s.ep_ret}; }
+
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // position_to_onehot, envs.py:24-27
+#pragma unroll
+        for (int j = 0; j < D; ++j) o[j] = (j == s.pos) ? 1.0f : 0.0f;
+    }
+    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+        s.pos = iclamp(s.pos + a - 1, 0, 20);            // envs.py:61-62
+        s.steps += 1;
+        // envs.py:65-72: -0.01 (+0.1 | +1.0) evaluated in double, rounded once to f32
+        const bool small = s.pos == 7, large = s.pos == 17;
+        reward = __uint_as_float(small ? 0x3DB851ECu : (large ? 0x3F7D70A4u : 0xBC23D70Au));
+        term = small || large;
+        trunc = (s.steps >= MAX_STEPS) && !term;         // envs.py:74
+    }
+    static __device__ __forceinline__ void reset(State &s, uint64_t, uint64_t, uint64_t, uint32_t) {
+        s.pos = 10; s.steps = 0; s.ep_ret = 0.0f;        // envs.py:21,55-57 (no randomness)
+    }
+};
+
+// ------------------------------------------------------------------ ball3d (examples/ball3d.py:10-113)
+// sin on |x| <= MAX_TILT = 0.43633: odd Taylor/Horner through x^15, no range reduction.
+// Truncation error < 2.2e-21 (x^17/17!), evaluation error ~0.6 ulp: agrees with libm's double sin to
+// the last bit in the vast majority of cases; parity with the reference is tolerance-checked.
+__device__ __forceinline__ double sin_small(double x) {
+    const double z = x * x;
+    double p = -7.6471637318198164759e-13;        // -1/15!
+    p = fma(p, z, 1.6059043836821614599e-10);     //  1/13!
+    p = fma(p, z, -2.5052108385441718775e-08);    // -1/11!
+    p = fma(p, z, 2.7557319223985890653e-06);     //  1/9!
+    p = fma(p, z, -1.9841269841269841253e-04);    // -1/7!
+    p = fma(p, z, 8.3333333333333332177e-03);     //  1/5!
+    p = fma(p, z, -1.6666666666666665741e-01);    // -1/3!
+    return fma(x * z, p, x);
+}
+
+struct Ball3DTask {
+    static constexpr int D = 6, A = 5, MAX_STEPS = 200, NBUF = 3;
+    typedef tmla_ball3d_state Wire;
+    struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int b) { return b == 0 ? sizeof(double2) : (b == 1 ? sizeof(float4) : sizeof(int2)); }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const double2 r = reinterpret_cast<const double2 *>(buf[0])[i];     // 128-bit
+        const float4 pv = reinterpret_cast<const float4 *>(buf[1])[i];      // 128-bit
+        const int2 m = reinterpret_cast<const int2 *>(buf[2])[i];
+        return State{r.x, r.y, pv.x, pv.y, pv.z, pv.w, m.x, __int_as_float(m.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        reinterpret_cast<double2 *>(buf[0])[i] = make_double2(s.rx, s.rz);
+        reinterpret_cast<float4 *>(buf[1])[i] = make_float4(s.px, s.pz, s.vx, s.vz);
+        reinterpret_cast<int2 *>(buf[2])[i] = make_int2(s.steps, __float_as_int(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        return State{w.rot[0], w.rot[1], w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w; w.rot[0] = s.rx; w.rot[1] = s.rz; w.pos[0] = s.px; w.pos[1] = s.pz;
+        w.vel[0] = s.vx; w.vel[1] = s.vz; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+    }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // ball3d.py:61-72
+        o[0] = __double2float_rn(s.rx); o[1] = __double2float_rn(s.rz);
+        o[2] = s.px; o[3] = s.pz; o[4] = s.vx; o[5] = s.vz;
+    }
+    // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
+    // explicit (`__*_rn` never contracts into FMA) so the result does not depend on compiler flags.
+    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+        const double MAX_TILT = 0x1.becde5da115a9p-2;     // np.deg2rad(25.0), ball3d.py:18
+        const double TILT_DELTA = 0x1.acee9f37bebd6p-5;   // np.deg2rad(3.0),  ball3d.py:19
+        const double dx = (a == 0) ? TILT_DELTA : ((a == 1) ? -TILT_DELTA : 0.0);   // ball3d.py:31-37
+        const double dz = (a == 2) ? TILT_DELTA : ((a == 3) ? -TILT_DELTA : 0.0);
+        double rx = __dadd_rn(s.rx, dx), rz = __dadd_rn(s.rz, dz);                  // ball3d.py:77
+        if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back
+            rx = (double)__double2float_rn(rx);
+            rz = (double)__double2float_rn(rz);
+        }
+        rx = fmin(fmax(rx, -MAX_TILT), MAX_TILT);                                   // ball3d.py:78 (float64 from here)
+        rz = fmin(fmax(rz, -MAX_TILT), MAX_TILT);
+        const double ax = __dmul_rn(9.81, sin_small(rx));                           // ball3d.py:81-82
+        const double az = __dmul_rn(9.81, sin_small(rz));
+        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, 0.02))); // ball3d.py:83-84
+        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, 0.02)));
+        vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
+        vz = __fmul_rn(vz, 0.98f);
+        const float px = __fadd_rn(s.px, __fmul_rn(vx, 0.02f));                     // ball3d.py:90
+        const float pz = __fadd_rn(s.pz, __fmul_rn(vz, 0.02f));
+        s.rx = rx; s.rz = rz; s.vx = vx; s.vz = vz; s.px = px; s.pz = pz;
+        s.steps += 1;
+        const bool off = (fabsf(px) > 3.0f) || (fabsf(pz) > 3.0f);                  // ball3d.py:96-98
+        const bool timeout = s.steps >= 200;                                        // ball3d.py:99
+        const bool done = off || timeout;
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(pz, pz))); // np.linalg.norm (f32)
+        float r = __fsub_rn(1.0f, __fdiv_rn(d, 3.0f));                              // ball3d.py:104
+        if (done) r = (timeout && !off) ? 1.0f : -1.0f;                             // ball3d.py:105-108
+        reward = __fadd_rn(r, __fmul_rn(-0.02f, d));                                // ball3d.py:110-111
+        trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
+        term = done && !trunc;
+    }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const double MAX_TILT = 0x1.becde5da115a9p-2;
+        const uint4 b0 = tmla_stream_block(seed, env_id, k, tag, 0);
+        const uint4 b1 = tmla_stream_block(seed, env_id, k, tag, 1);
+        const uint4 b2 = tmla_stream_block(seed, env_id, k, tag, 2);
+        const double lo = -MAX_TILT * 0.5;     // np.random.uniform(lo, hi) = lo + (hi-lo)*u, ball3d.py:49-57
+        s.rx = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(MAX_TILT, tmla_u53(b0.x, b0.y))));
+        s.rz = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(MAX_TILT, tmla_u53(b0.z, b0.w))));
+        s.px = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, tmla_u53(b1.x, b1.y))));
+        s.pz = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, tmla_u53(b1.z, b1.w))));
+        s.vx = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, tmla_u53(b2.x, b2.y))));
+        s.vz = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, tmla_u53(b2.z, b2.w))));
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};
+
+// shared move table of gridworld.py:19-25 and push.py:14-20: 0 stay, 1 (0,+1), 2 (0,-1), 3 (-1,0), 4 (+1,0)
+__device__ __forceinline__ void grid_delta(int a, int &dx, int &dy) {
+    dx = (a == 4) - (a == 3);
+    dy = (a == 1) - (a == 2);
+}
+
+// ------------------------------------------------------------- gridworld (examples/gridworld.py:14-95)
+struct GridWorldTask {
+    static constexpr int D = 4, A = 5, MAX_STEPS = 100, NBUF = 1;
+    typedef tmla_gridworld_state Wire;
+    struct State { int ax, ay, gx, gy, rx, ry, type, steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int) { return sizeof(uint2); }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const uint2 w = reinterpret_cast<const uint2 *>(buf[0])[i];
+        return State{cell3(w.x, 0), cell3(w.x, 1), cell3(w.x, 2), cell3(w.x, 3), cell3(w.x, 4), cell3(w.x, 5),
+                     (int)((w.x >> 18) & 1u), (int)((w.x >> 19) & 255u), __uint_as_float(w.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        const uint32_t w = put3(s.ax, 0) | put3(s.ay, 1) | put3(s.gx, 2) | put3(s.gy, 3) | put3(s.rx, 4) |
+                           put3(s.ry, 5) | ((uint32_t)s.type << 18) | ((uint32_t)s.steps << 19);
+        reinterpret_cast<uint2 *>(buf[0])[i] = make_uint2(w, __float_as_uint(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        return State{w.agent[0], w.agent[1], w.green[0], w.green[1], w.red[0], w.red[1], w.goal_type & 1, w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w; w.agent[0] = s.ax; w.agent[1] = s.ay; w.green[0] = s.gx; w.green[1] = s.gy;
+        w.red[0] = s.rx; w.red[1] = s.ry; w.goal_type = s.type; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+    }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // gridworld.py:55-64
+        const int tx = s.type ? s.rx : s.gx, ty = s.type ? s.ry : s.gy;
+        o[0] = (float)(tx - s.ax) * 0.25f;      // k/4 is exact in f32
+        o[1] = (float)(ty - s.ay) * 0.25f;
+        o[2] = s.type ? 0.0f : 1.0f;
+        o[3] = s.type ? 1.0f : 0.0f;
+    }
+    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+        int dx, dy; grid_delta(a, dx, dy);
+        s.ax = iclamp(s.ax + dx, 0, 4);                                  // gridworld.py:68-71
+        s.ay = iclamp(s.ay + dy, 0, 4);
+        s.steps += 1;
+        const bool on_green = (s.ax == s.gx) && (s.ay == s.gy);          // gridworld.py:79-90 (if / elif)
+        const bool on_red = !on_green && (s.ax == s.rx) && (s.ay == s.ry);
+        reward = __uint_as_float(0xBC23D70Au);                           // f32(-0.01)
+        if (on_green) reward = (s.type == 0) ? 1.0f : -1.0f;
+        if (on_red) reward = (s.type == 1) ? 1.0f : -1.0f;
+        const bool done = on_green || on_red || (s.steps >= 100);        // gridworld.py:92-93
+        trunc = s.steps >= MAX_STEPS;                                    // envs.py:141-145
+        term = done && !trunc;
+    }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        // np.random.shuffle(cells)[:3] = uniform ordered triple of distinct cells; np.random.choice([0,1])
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);      // gridworld.py:42-50
+        const int a = tmla_bounded(b.x, 25);
+        int g = tmla_bounded(b.y, 24); g += (g >= a);
+        int r = tmla_bounded(b.z, 23);
+        const int lo = min(a, g), hi = max(a, g);
+        r += (r >= lo); r += (r >= hi);
+        s.ax = a / 5; s.ay = a % 5; s.gx = g / 5; s.gy = g % 5; s.rx = r / 5; s.ry = r % 5;
+        s.type = (int)(b.w >> 31);
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};
+
+// ---------------------------------------------------------------------- push (examples/push.py:10-125)
+// 18-entry reward table [(d_ab+1)*6 + (d_bg+1)*2 + invalid]: the reference evaluates
+// -0.01 + 0.05*d_ab + 0.3*d_bg (- 0.05) in Python doubles (push.py:77,111-115) and SB3 stores f32;
+// float32 arithmetic is 1-2 ulp off in 10 of 18 cases, so the f32(double) values are tabulated
+// (same table built at run time by oracle/envs_oracle.py:push_reward_lut and compared in tests).
+__device__ __constant__ uint32_t kPushRewardBits[18] = {
+    0xbeb851ecu, 0xbed1eb85u, 0xbd75c28fu, 0xbde147aeu, 0x3e75c28fu, 0x3e428f5cu,
+    0xbe9eb852u, 0xbeb851ecu, 0xbc23d70au, 0xbd75c28fu, 0x3e947ae1u, 0x3e75c28fu,
+    0xbe851eb8u, 0xbe9eb852u, 0x3d23d70au, 0xbc23d70au, 0x3eae147bu, 0x3e947ae1u};
+
+struct PushTask {
+    static constexpr int D = 4, A = 5, MAX_STEPS = 120, NBUF = 1;
+    typedef tmla_push_state Wire;
+    struct State { int ax, ay, bx, by, goal_x, steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int) { return sizeof(uint2); }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const uint2 w = reinterpret_cast<const uint2 *>(buf[0])[i];
+        return State{cell3(w.x, 0), cell3(w.x, 1), cell3(w.x, 2), cell3(w.x, 3), cell3(w.x, 4),
+                     (int)((w.x >> 19) & 255u), __uint_as_float(w.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        const uint32_t w = put3(s.ax, 0) | put3(s.ay, 1) | put3(s.bx, 2) | put3(s.by, 3) | put3(s.goal_x, 4) |
+                           ((uint32_t)s.steps << 19);
+        reinterpret_cast<uint2 *>(buf[0])[i] = make_uint2(w, __float_as_uint(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        return State{w.agent[0], w.agent[1], w.box[0], w.box[1], w.goal_x, w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w; w.agent[0] = s.ax; w.agent[1] = s.ay; w.box[0] = s.bx; w.box[1] = s.by;
+        w.goal_x = s.goal_x; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+    }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // push.py:53-59
+        // f32(k/5.0) == f32(k)/f32(5) for |k| <= 5 (checked in tests); IEEE division, not reciprocal-multiply
+        o[0] = __fdiv_rn((float)(s.bx - s.ax), 5.0f);
+        o[1] = __fdiv_rn((float)(s.by - s.ay), 5.0f);
+        o[2] = __fdiv_rn((float)(s.goal_x - s.bx), 5.0f);
+        o[3] = __fdiv_rn((float)(5 - s.by), 5.0f);
+    }
+    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+        int dx, dy; grid_delta(a, dx, dy);
+        int nax = iclamp(s.ax + dx, 0, 5), nay = iclamp(s.ay + dy, 0, 5);          // push.py:63-65
+        const int prev_bg = abs(s.goal_x - s.bx) + abs(5 - s.by);                  // push.py:70-75
+        const int prev_ab = abs(s.bx - s.ax) + abs(s.by - s.ay);
+        int nbx = s.bx, nby = s.by;
+        bool invalid = false;
+        if (nax == s.bx && nay == s.by) {                                          // push.py:83-95
+            const int tx = s.bx + dx, ty = s.by + dy;
+            if (tx >= 0 && tx < 6 && ty >= 0 && ty < 6) { nbx = tx; nby = ty; }
+            else { nax = s.ax; nay = s.ay; invalid = true; }
+        }
+        s.ax = nax; s.ay = nay; s.bx = nbx; s.by = nby;
+        s.steps += 1;
+        const int dist_bg = abs(s.goal_x - nbx) + abs(5 - nby);                    // push.py:103-108
+        const int dist_ab = abs(nbx - nax) + abs(nby - nay);
+        const int idx = (prev_ab - dist_ab + 1) * 6 + (prev_bg - dist_bg + 1) * 2 + (invalid ? 1 : 0);
+        reward = __uint_as_float(kPushRewardBits[idx]);                            // push.py:77,111-115
+        const bool top = nby == 5;                                                 // push.py:118-120
+        if (top) reward = 1.0f;
+        const bool done = top || (s.steps >= 120);                                 // push.py:122-123
+        trunc = s.steps >= MAX_STEPS;                                              // envs.py:141-145
+        term = done && !trunc;
+    }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                // push.py:40-47
+        const int a = tmla_bounded(b.x, 36);
+        int bx = tmla_bounded(b.y, 35); bx += (bx >= a);
+        s.ax = a / 6; s.ay = a % 6; s.bx = bx / 6; s.by = bx % 6;
+        s.goal_x = tmla_bounded(b.z, 6);
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};

@@ -1,0 +1,376 @@
+// mlp_kernels.cu — MlpPolicy (SB3 ActorCriticPolicy, net_arch dict(pi=[256,256], vf=[256,256]), tanh)
+// forward and backward in float32 on CUDA cores.
+//
+// Replaces ActorCriticPolicy.forward / evaluate_actions / predict_values and autograd's backward for
+// them (SB3 2.9.0, built in the reference at backend/mlagents/training.py:150 with policy_kwargs from
+// training.py:363-365).  This float32 path is the numerics reference on the device (it matches the
+// reference's fp32 CPU arithmetic to ~1e-6); the bf16 tcgen05/TMEM path in mlp_tc.cu is the fast one.
+//
+// Layout: flat fp32 parameter vector in policy.parameters() order (include/tmla.h), PyTorch Linear
+// weights [out,in].  Activations are [rows,256] row-major.
+#include <algorithm>
+#include "common.cuh"
+
+static constexpr int H = 256;   // hidden width (net_arch of training.py:363-365)
+
+struct MlpOffsets {
+    int64_t w1[2], b1[2], w2[2], b2[2], wh[2], bh[2], total;
+    int nout[2];
+};
+static MlpOffsets mlp_offsets(int D, int A) {
+    MlpOffsets o;
+    int64_t p = 0;
+    for (int t = 0; t < 2; ++t) {
+        o.w1[t] = p; p += (int64_t)H * D;
+        o.b1[t] = p; p += H;
+        o.w2[t] = p; p += (int64_t)H * H;
+        o.b2[t] = p; p += H;
+    }
+    o.wh[0] = p; p += (int64_t)A * H;
+    o.bh[0] = p; p += A;
+    o.wh[1] = p; p += H;
+    o.bh[1] = p; p += 1;
+    o.total = p;
+    o.nout[0] = A; o.nout[1] = 1;
+    return o;
+}
+
+__device__ __forceinline__ int64_t eff_rows(int64_t rows, const int32_t *rows_dev) {
+    return rows_dev ? min(rows, (int64_t)*rows_dev) : rows;
+}
+
+// ----------------------------------------------------------------------------- layer 1 (K = D tiny)
+// thread j owns hidden unit j: W1[j][:] in registers, x rows broadcast from shared memory.
+template <int D>
+__global__ void __launch_bounds__(H)
+l1_forward_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ x,
+                  const int32_t *__restrict__ index, int64_t rows, const int32_t *rows_dev, float *__restrict__ h1) {
+    constexpr int R = 32;
+    __shared__ float sx[R][D];
+    rows = eff_rows(rows, rows_dev);
+    const int64_t r0 = (int64_t)blockIdx.x * R;
+    if (r0 >= rows) return;
+    const int nr = (int)min((int64_t)R, rows - r0);
+    for (int e = threadIdx.x; e < nr * D; e += H) {
+        const int r = e / D, k = e % D;
+        const int64_t src = index ? index[r0 + r] : (r0 + r);
+        sx[r][k] = x[src * D + k];
+    }
+    float w[D];
+    const int j = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < D; ++k) w[k] = W1[j * D + k];
+    const float b = b1[j];
+    __syncthreads();
+    for (int r = 0; r < nr; ++r) {
+        float acc = b;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fmaf(sx[r][k], w[k], acc);
+        h1[(r0 + r) * H + j] = tanhf(acc);
+    }
+}
+
+// dW1[j][k] = sum_r dZ1[r][j] x[r][k], db1[j] = sum_r dZ1[r][j]
+template <int D>
+__global__ void __launch_bounds__(H)
+l1_backward_kernel(const float *__restrict__ dz1, const float *__restrict__ x, const int32_t *__restrict__ index,
+                   int64_t rows, int rows_per_block, float *__restrict__ dW1, float *__restrict__ db1) {
+    constexpr int R = 32;
+    __shared__ float sx[R][D];
+    const int j = threadIdx.x;
+    float acc[D], accb = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = 0.0f;
+    const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
+    for (int64_t r0 = rb; r0 < re; r0 += R) {
+        const int nr = (int)min((int64_t)R, re - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * D; e += H) {
+            const int r = e / D, k = e % D;
+            const int64_t src = index ? index[r0 + r] : (r0 + r);
+            sx[r][k] = x[src * D + k];
+        }
+        __syncthreads();
+        for (int r = 0; r < nr; ++r) {
+            const float g = dz1[(r0 + r) * H + j];
+            accb += g;
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) atomicAdd(dW1 + j * D + k, acc[k]);
+    atomicAdd(db1 + j, accb);
+}
+
+// ------------------------------------------------------------------------------------ output heads
+// one warp per row: lane holds 8 of the 256 hidden activations (two float4) and the matching weights.
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+head_forward_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, const float *__restrict__ h2,
+                    int64_t rows, const int32_t *rows_dev, float *__restrict__ out) {
+    rows = eff_rows(rows, rows_dev);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w[NOUT][8];      // scalar loads: the value head's weights are not 16-byte aligned in the flat vector
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[a][q] = Wh[a * H + (q < 4 ? lane * 4 + q : 128 + lane * 4 + (q - 4))];
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float4 x0 = reinterpret_cast<const float4 *>(h2 + r * H)[lane];
+        const float4 x1 = reinterpret_cast<const float4 *>(h2 + r * H)[32 + lane];
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) {
+            float s = x0.x * w[a][0] + x0.y * w[a][1] + x0.z * w[a][2] + x0.w * w[a][3] +
+                      x1.x * w[a][4] + x1.y * w[a][5] + x1.z * w[a][6] + x1.w * w[a][7];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) out[r * NOUT + a] = s + bh[a];
+        }
+    }
+}
+
+// thread j owns hidden column j over a chunk of rows:
+//   dZ2[r][j] = (sum_a dOut[r][a] Wh[a][j]) * (1 - h2[r][j]^2)
+//   dWh[a][j] += dOut[r][a] h2[r][j] ; db2[j] += dZ2[r][j] ; dbh[a] += dOut[r][a]
+template <int NOUT>
+__global__ void __launch_bounds__(H)
+head_backward_kernel(const float *__restrict__ Wh, const float *__restrict__ h2, const float *__restrict__ dout,
+                     int64_t rows, int rows_per_block, float *__restrict__ dz2, float *__restrict__ dWh,
+                     float *__restrict__ dbh, float *__restrict__ db2) {
+    constexpr int R = 64;
+    __shared__ float sd[R][NOUT];
+    const int j = threadIdx.x;
+    float w[NOUT], accw[NOUT], accb2 = 0.0f, accbh = 0.0f;
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) { w[a] = Wh[a * H + j]; accw[a] = 0.0f; }
+    const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
+    for (int64_t r0 = rb; r0 < re; r0 += R) {
+        const int nr = (int)min((int64_t)R, re - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * NOUT; e += H) sd[e / NOUT][e % NOUT] = dout[r0 * NOUT + e];
+        __syncthreads();
+        for (int r = 0; r < nr; ++r) {
+            const float h = h2[(r0 + r) * H + j];
+            float g = 0.0f;
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) { g = fmaf(sd[r][a], w[a], g); accw[a] = fmaf(sd[r][a], h, accw[a]); }
+            g *= (1.0f - h * h);
+            dz2[(r0 + r) * H + j] = g;
+            accb2 += g;
+        }
+        if (j < NOUT) for (int r = 0; r < nr; ++r) accbh += sd[r][j];
+    }
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) atomicAdd(dWh + a * H + j, accw[a]);
+    atomicAdd(db2 + j, accb2);
+    if (j < NOUT) atomicAdd(dbh + j, accbh);
+}
+
+// --------------------------------------------------------------------------- 128x128x8 SIMT SGEMM
+// C[M,N] = epi( sum_k A(m,k) B(k,n) ).  256 threads, 8x8 micro-tile per thread split as 2x2 blocks of
+// 4x4 (conflict-free float4 shared-memory reads), register prefetch of the next k-chunk.
+//   A_KMAJOR : A is stored [M][K] (k contiguous) else [K][M]
+//   B_KMAJOR : B is stored [N][K] (k contiguous) else [K][N]
+enum { EPI_BIAS_TANH = 0, EPI_DTANH = 1, EPI_ATOMIC = 2 };
+
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile(const float *__restrict__ P, int ld, int64_t mn0, int64_t MN, int64_t k0, int64_t Kend, float4 &v) {
+    // fetch this thread's float4 of a 128(mn) x 8(k) tile
+    const int tid = threadIdx.x;
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KMAJOR) {           // [MN][K]: 2 threads per row, float4 along k
+        const int64_t row = mn0 + (tid >> 1), k = k0 + (tid & 1) * 4;
+        if (row < MN) {
+            if (k + 3 < Kend) v = *reinterpret_cast<const float4 *>(P + row * ld + k);
+            else {
+                if (k + 0 < Kend) v.x = P[row * ld + k + 0];
+                if (k + 1 < Kend) v.y = P[row * ld + k + 1];
+                if (k + 2 < Kend) v.z = P[row * ld + k + 2];
+            }
+        }
+    } else {                // [K][MN]: 32 threads per k row, float4 along mn
+        const int64_t k = k0 + (tid >> 5), mn = mn0 + (tid & 31) * 4;
+        if (k < Kend) {
+            if (mn + 3 < MN) v = *reinterpret_cast<const float4 *>(P + k * ld + mn);
+            else {
+                if (mn + 0 < MN) v.x = P[k * ld + mn + 0];
+                if (mn + 1 < MN) v.y = P[k * ld + mn + 1];
+                if (mn + 2 < MN) v.z = P[k * ld + mn + 2];
+            }
+        }
+    }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void store_tile(float (*S)[128], const float4 &v) {
+    const int tid = threadIdx.x;
+    if (KMAJOR) {
+        const int mn = tid >> 1, k = (tid & 1) * 4;
+        S[k + 0][mn] = v.x; S[k + 1][mn] = v.y; S[k + 2][mn] = v.z; S[k + 3][mn] = v.w;
+    } else {
+        *reinterpret_cast<float4 *>(&S[tid >> 5][(tid & 31) * 4]) = v;
+    }
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int64_t M, int N, int64_t K,
+             int lda, int ldb, int ldc, int64_t k_per_split, const float *__restrict__ aux, const int32_t *rows_dev) {
+    __shared__ __align__(16) float As[8][128];
+    __shared__ __align__(16) float Bs[8][128];
+    if (rows_dev && EPI != EPI_ATOMIC) M = min(M, (int64_t)*rows_dev);
+    const int64_t m0 = (int64_t)blockIdx.x * 128;
+    const int n0 = blockIdx.y * 128;
+    if (m0 >= M) return;
+    const int64_t kb = (int64_t)blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    float4 ra, rb;
+    load_tile<A_KMAJOR>(A, lda, m0, M, kb, ke, ra);
+    load_tile<B_KMAJOR>(B, ldb, n0, N, kb, ke, rb);
+    for (int64_t k0 = kb; k0 < ke; k0 += 8) {
+        __syncthreads();
+        store_tile<A_KMAJOR>(As, ra);
+        store_tile<B_KMAJOR>(Bs, rb);
+        __syncthreads();
+        if (k0 + 8 < ke) {
+            load_tile<A_KMAJOR>(A, lda, m0, M, k0 + 8, ke, ra);
+            load_tile<B_KMAJOR>(B, ldb, n0, N, k0 + 8, ke, rb);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[k][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int n = n0 + (jh ? 64 : 0) + tx * 4;
+            float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            if (EPI == EPI_BIAS_TANH) {          // aux = bias[N]
+                const float4 b = *reinterpret_cast<const float4 *>(aux + n);
+                v.x = tanhf(v.x + b.x); v.y = tanhf(v.y + b.y); v.z = tanhf(v.z + b.z); v.w = tanhf(v.w + b.w);
+                *reinterpret_cast<float4 *>(C + m * ldc + n) = v;
+            } else if (EPI == EPI_DTANH) {       // aux = activation [M][N]: multiply by 1 - h^2
+                const float4 h = *reinterpret_cast<const float4 *>(aux + m * ldc + n);
+                v.x *= 1.0f - h.x * h.x; v.y *= 1.0f - h.y * h.y; v.z *= 1.0f - h.z * h.z; v.w *= 1.0f - h.w * h.w;
+                *reinterpret_cast<float4 *>(C + m * ldc + n) = v;
+            } else {                             // split-K accumulation
+                atomicAdd(C + m * ldc + n + 0, v.x); atomicAdd(C + m * ldc + n + 1, v.y);
+                atomicAdd(C + m * ldc + n + 2, v.z); atomicAdd(C + m * ldc + n + 3, v.w);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------- host API
+extern "C" {
+
+int64_t tmla_mlp_num_params(int obs_dim, int hidden, int n_actions) {
+    if (hidden != H || obs_dim <= 0 || n_actions <= 0) return TMLA_EINVAL;
+    return mlp_offsets(obs_dim, n_actions).total;
+}
+
+static int check_shape(int D, int hidden, int A) {
+    if (hidden != H) { tmla_set_error("hidden must be 256 (net_arch of training.py:363-365), got %d", hidden); return TMLA_EINVAL; }
+    if (!(D == 4 || D == 6 || D == 21)) { tmla_set_error("obs_dim must be 4, 6 or 21, got %d", D); return TMLA_EINVAL; }
+    if (!(A == 3 || A == 5)) { tmla_set_error("n_actions must be 3 or 5, got %d", A); return TMLA_EINVAL; }
+    return TMLA_OK;
+}
+
+int tmla_mlp_forward(const float *params, int obs_dim, int hidden, int n_actions, const float *x, const int32_t *index,
+                     int64_t rows, const int32_t *rows_dev, float *logits, float *values, float *act_cache, void *stream) {
+    TMLA_REQUIRE(params && x && act_cache, "params/x/act_cache must be non-NULL (act_cache is the activation workspace)");
+    TMLA_REQUIRE(rows > 0, "rows must be positive");
+    TMLA_REQUIRE(logits || values, "nothing to compute");
+    int rc = check_shape(obs_dim, hidden, n_actions);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+    for (int t = 0; t < 2; ++t) {
+        float *out = t == 0 ? logits : values;
+        if (!out) continue;
+        float *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
+        const unsigned g1 = (unsigned)ceil_div64(rows, 32);
+#define L1F(DD) l1_forward_kernel<DD><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
+        if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else L1F(21);
+#undef L1F
+        TMLA_LAUNCH_CHECK();
+        dim3 grid((unsigned)ceil_div64(rows, 128), H / 128, 1);
+        sgemm_kernel<true, true, EPI_BIAS_TANH><<<grid, 256, 0, st>>>(h1, params + o.w2[t], h2, rows, H, H, H, H, H, H,
+                                                                      params + o.b2[t], rows_dev);
+        TMLA_LAUNCH_CHECK();
+        const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
+        if (t == 1) head_forward_kernel<1><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
+        else if (n_actions == 3) head_forward_kernel<3><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        else head_forward_kernel<5><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        TMLA_LAUNCH_CHECK();
+    }
+    return TMLA_OK;
+}
+
+int64_t tmla_mlp_backward_scratch(int obs_dim, int hidden, int n_actions, int64_t rows) {
+    (void)obs_dim; (void)n_actions;
+    return 2 * rows * (int64_t)hidden;
+}
+
+int tmla_mlp_backward(const float *params, int obs_dim, int hidden, int n_actions, const float *x, const int32_t *index,
+                      int64_t rows, const float *act_cache, const float *dlogits, const float *dvalues, float *grads,
+                      float *scratch, void *stream) {
+    TMLA_REQUIRE(params && x && act_cache && dlogits && dvalues && grads && scratch, "NULL buffer");
+    TMLA_REQUIRE(rows > 0, "rows must be positive");
+    int rc = check_shape(obs_dim, hidden, n_actions);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+    TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
+    float *dz2 = scratch, *dz1 = scratch + rows * H;
+    // chunk rows so that ~4 blocks per SM share the reduction kernels
+    const int rpb = (int)std::max<int64_t>(64, ceil_div64(ceil_div64(rows, 148 * 4), 64) * 64);
+    const unsigned gr = (unsigned)ceil_div64(rows, rpb);
+    for (int t = 0; t < 2; ++t) {
+        const float *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
+        const float *dout = t == 0 ? dlogits : dvalues;
+        if (t == 1) head_backward_kernel<1><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
+        else if (n_actions == 3) head_backward_kernel<3><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        else head_backward_kernel<5><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        TMLA_LAUNCH_CHECK();
+        // dZ1 = (dZ2 . W2) * (1 - h1^2)      A = dZ2 [rows][H] (k-major), B = W2 [K=out][N=in]
+        dim3 gd((unsigned)ceil_div64(rows, 128), H / 128, 1);
+        sgemm_kernel<true, false, EPI_DTANH><<<gd, 256, 0, st>>>(dz2, params + o.w2[t], dz1, rows, H, H, H, H, H, H, h1, nullptr);
+        TMLA_LAUNCH_CHECK();
+        // dW2[j][i] = sum_r dZ2[r][j] h1[r][i]   A = dZ2 as [K=rows][M=H], B = h1 as [K=rows][N=H]; split-K + atomics
+        int64_t splits = std::min<int64_t>(std::max<int64_t>(1, ceil_div64(rows, 1024)), 148);
+        const int64_t kps = ceil_div64(ceil_div64(rows, splits), 8) * 8;
+        splits = ceil_div64(rows, kps);
+        dim3 gw(H / 128, H / 128, (unsigned)splits);
+        sgemm_kernel<false, false, EPI_ATOMIC><<<gw, 256, 0, st>>>(dz2, h1, grads + o.w2[t], H, H, rows, H, H, H, kps, nullptr, nullptr);
+        TMLA_LAUNCH_CHECK();
+#define L1B(DD) l1_backward_kernel<DD><<<gr, H, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t])
+        if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
+#undef L1B
+        TMLA_LAUNCH_CHECK();
+    }
+    return TMLA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Torch-tensor wrappers over the PPO entry points of libtmla.so (include/tmla.h).
+
+Each function takes CUDA tensors, checks dtype/contiguity/device, and enqueues the kernel on
+torch's current stream.  torch is plumbing here (memory + streams); the arithmetic is in csrc/.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import native
+from .native import lib, check, ptr
+
+HIDDEN = 256
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this backend has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _s():
+    return native.current_stream()
+
+
+def num_params(obs_dim: int, n_actions: int) -> int:
+    n = lib.tmla_mlp_num_params(obs_dim, HIDDEN, n_actions)
+    if n < 0:
+        raise ValueError("unsupported MLP shape")
+    return int(n)
+
+
+def gae(rewards, values, dones, last_values, gamma: float, gae_lambda: float, advantages=None, returns=None):
+    """RolloutBuffer.compute_returns_and_advantage on [T,n] buffers."""
+    T, n = rewards.shape
+    _chk(rewards, torch.float32, "rewards"); _chk(values, torch.float32, "values")
+    _chk(dones, torch.uint8, "dones"); _chk(last_values, torch.float32, "last_values")
+    if advantages is None:
+        advantages = torch.empty_like(rewards)
+    if returns is None:
+        returns = torch.empty_like(rewards)
+    check(lib.tmla_gae(ptr(rewards), ptr(values), ptr(dones), ptr(last_values), float(gamma), float(gae_lambda),
+                       int(T), int(n), ptr(advantages), ptr(returns), _s()))
+    return advantages, returns
+
+
+def permutation(seed: int, epoch: int, T: int, n: int, out=None, device="cuda"):
+    total = T * n
+    if out is None:
+        out = torch.empty(total, dtype=torch.int32, device=device)
+    _chk(out, torch.int32, "out")
+    check(lib.tmla_permutation(int(seed) & (2**64 - 1), int(epoch), total, int(T), int(n), ptr(out), _s()))
+    return out
+
+
+def mlp_forward(params, x, obs_dim, n_actions, *, index=None, rows=None, rows_dev=None, logits=None, values=None,
+                want_logits=True, want_values=True, act_cache=None):
+    _chk(params, torch.float32, "params"); _chk(x, torch.float32, "x"); _chk(index, torch.int32, "index")
+    if rows is None:
+        rows = index.numel() if index is not None else x.shape[0]
+    dev = params.device
+    if want_logits and logits is None:
+        logits = torch.empty((rows, n_actions), dtype=torch.float32, device=dev)
+    if want_values and values is None:
+        values = torch.empty(rows, dtype=torch.float32, device=dev)
+    if act_cache is None:
+        act_cache = torch.empty((4, rows, HIDDEN), dtype=torch.float32, device=dev)
+    check(lib.tmla_mlp_forward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(rows_dev),
+                               ptr(logits) if want_logits else None, ptr(values) if want_values else None,
+                               ptr(act_cache), _s()))
+    return logits, values, act_cache
+
+
+def mlp_backward(params, x, obs_dim, n_actions, act_cache, dlogits, dvalues, *, index=None, rows=None, grads=None,
+                 scratch=None):
+    if rows is None:
+        rows = index.numel() if index is not None else x.shape[0]
+    dev = params.device
+    if grads is None:
+        grads = torch.empty_like(params)
+    if scratch is None:
+        scratch = torch.empty(lib.tmla_mlp_backward_scratch(obs_dim, HIDDEN, n_actions, rows), dtype=torch.float32, device=dev)
+    _chk(dlogits, torch.float32, "dlogits"); _chk(dvalues, torch.float32, "dvalues")
+    check(lib.tmla_mlp_backward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(act_cache),
+                                ptr(dlogits), ptr(dvalues), ptr(grads), ptr(scratch), _s()))
+    return grads
+
+
+def adv_stats(advantages, index, rows, sums=None):
+    if sums is None:
+        sums = torch.empty(3, dtype=torch.float64, device=advantages.device)
+    check(lib.tmla_adv_stats(ptr(advantages), ptr(index), int(rows), ptr(sums), _s()))
+    return sums
+
+
+def ppo_loss(logits, values, actions, advantages, old_logp, returns, *, index=None, rows=None, global_rows=None,
+             adv_sums=None, normalize=True, clip_range=0.2, ent_coef=0.01, vf_coef=0.5, dlogits=None, dvalues=None,
+             stats=None):
+    if rows is None:
+        rows = logits.shape[0]
+    n_actions = logits.shape[1]
+    dev = logits.device
+    _chk(actions, torch.int32, "actions"); _chk(index, torch.int32, "index")
+    if dlogits is None:
+        dlogits = torch.empty_like(logits)
+    if dvalues is None:
+        dvalues = torch.empty(rows, dtype=torch.float32, device=dev)
+    if stats is None:
+        stats = torch.empty(8, dtype=torch.float32, device=dev)
+    if normalize and adv_sums is None:
+        adv_sums = adv_stats(advantages, index, rows)
+    check(lib.tmla_ppo_loss(ptr(logits), ptr(values), ptr(actions), ptr(advantages), ptr(old_logp), ptr(returns),
+                            ptr(index), int(rows), int(global_rows or rows), int(n_actions), ptr(adv_sums),
+                            1 if normalize else 0, float(clip_range), float(ent_coef), float(vf_coef), ptr(dlogits),
+                            ptr(dvalues), ptr(stats), _s()))
+    return dlogits, dvalues, stats
+
+
+def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
+              eps=1e-5, norm_out=None):
+    if norm_out is None:
+        norm_out = torch.empty(2, dtype=torch.float32, device=params.device)
+    check(lib.tmla_adam_clip(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
+                             float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                             ptr(norm_out), _s()))
+    return norm_out
+
+
+def bootstrap_add(rew_buf, trunc_count, trunc_index, trunc_values, gamma: float):
+    check(lib.tmla_bootstrap_add(ptr(rew_buf), ptr(trunc_count), ptr(trunc_index), ptr(trunc_values), float(gamma),
+                                 int(trunc_index.numel()), _s()))
+
+
+def step_policy(env, logits, row_index, obs_next, act, logp, rew, done, *, deterministic=False, trunc_count=None,
+                trunc_index=None, trunc_obs=None, ep_stats=None, step_base=None):
+    cap = 0 if trunc_index is None else int(trunc_index.numel())
+    check(lib.tmla_step_policy(env.handle, ptr(logits), 1 if deterministic else 0, int(row_index), ptr(obs_next),
+                               ptr(act), ptr(logp), ptr(rew), ptr(done), ptr(trunc_count), ptr(trunc_index),
+                               ptr(trunc_obs), cap, ptr(ep_stats), ptr(step_base), _s()))
