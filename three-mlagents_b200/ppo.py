@@ -1,0 +1,391 @@
+"""CudaPPO — SB3-compatible PPO front-end whose rollout, GAE and update all run in libtmla.so.
+
+Mirrors what the reference builds at backend/mlagents/training.py:150 (`PPO("MlpPolicy", vec_env,
+seed=seed, **kwargs)`) and drives at training.py:166-175 (`learn`, `save`), plus `predict`/`load`
+(training.py:269,278).  Algorithm = SB3 2.9.0 OnPolicyAlgorithm.collect_rollouts + RolloutBuffer +
+PPO.train, with these documented differences:
+  * all N envs advance in one kernel per step, sampling uses per-env Philox streams (not torch's
+    global generator), minibatch order is a keyed Feistel permutation (not np.random.permutation);
+  * callbacks fire per rollout, not per env step (SURVEY.md §7 "per-step host hooks");
+  * with world_size > 1, env shards are per rank, gradients are all-reduced (NCCL) once per
+    minibatch and advantage normalisation uses global-minibatch statistics.
+"""
+from __future__ import annotations
+
+import io
+import json
+import math
+import time
+import zipfile
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import ops
+from .vec_env import CudaVecEnv
+
+HIDDEN = 256
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def orthogonal_init(obs_dim: int, n_actions: int, seed: int) -> torch.Tensor:
+    """SB3 ActorCriticPolicy init: orthogonal weights with gain sqrt(2) (towers), 0.01 (action_net),
+    1.0 (value_net), zero biases; flat vector in policy.parameters() order (include/tmla.h)."""
+    g = torch.Generator().manual_seed(int(seed))
+    shapes = []
+    for _tower in range(2):
+        shapes += [((HIDDEN, obs_dim), math.sqrt(2.0)), ((HIDDEN,), None), ((HIDDEN, HIDDEN), math.sqrt(2.0)), ((HIDDEN,), None)]
+    shapes += [((n_actions, HIDDEN), 0.01), ((n_actions,), None), ((1, HIDDEN), 1.0), ((1,), None)]
+    chunks = []
+    for shape, gain in shapes:
+        t = torch.zeros(shape, dtype=torch.float32)
+        if gain is not None:
+            torch.nn.init.orthogonal_(t, gain=gain, generator=g)
+        chunks.append(t.reshape(-1))
+    return torch.cat(chunks)
+
+
+class CudaPPO:
+    def __init__(self, policy: str, env: CudaVecEnv, *, seed: int = 1, learning_rate: float = 3e-4, n_steps: int = 2048,
+                 batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
+                 normalize_advantage: bool = True, policy_kwargs: dict | None = None, tensorboard_log: str | None = None,
+                 verbose: int = 0, mlp_impl: str = "auto", _params: torch.Tensor | None = None):
+        if policy != "MlpPolicy":
+            raise ValueError("CudaPPO supports 'MlpPolicy' (vector observations) only")
+        arch = (policy_kwargs or {}).get("net_arch", {"pi": [256, 256], "vf": [256, 256]})
+        if arch != {"pi": [256, 256], "vf": [256, 256]}:
+            raise ValueError("CudaPPO implements net_arch dict(pi=[256,256], vf=[256,256]) (training.py:363-365)")
+        self.env = env
+        self.seed = int(seed)
+        self.lr, self.n_steps, self.batch_size, self.n_epochs = float(learning_rate), int(n_steps), int(batch_size), int(n_epochs)
+        self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
+        self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
+        self.normalize_advantage = bool(normalize_advantage)
+        self.verbose, self.tensorboard_log = int(verbose), tensorboard_log
+        self.mlp_impl = mlp_impl
+        self.obs_dim, self.n_actions, self.n_envs = env.obs_dim, env.n_actions, env.num_envs
+        self.device = torch.device("cuda", env.device_index)
+        self.num_timesteps = 0
+        self.n_updates = 0
+        self._adam_step = 0
+        self._epoch_counter = 0
+        self._dist, self.rank, self.world = _dist()
+        with torch.cuda.device(self.device):
+            p = orthogonal_init(self.obs_dim, self.n_actions, self.seed) if _params is None else _params.detach().float().cpu()
+            assert p.numel() == ops.num_params(self.obs_dim, self.n_actions)
+            self.params = p.to(self.device).contiguous()
+            self.m = torch.zeros_like(self.params)
+            self.v = torch.zeros_like(self.params)
+            self.grads = torch.zeros_like(self.params)
+        self._buffers_ready = False
+        self._last_obs_valid = False
+        self.logger_rows: list[dict[str, Any]] = []
+
+    # ------------------------------------------------------------------------------------- buffers
+    def _alloc(self):
+        if self._buffers_ready:
+            return
+        T, N, D, A, dev = self.n_steps, self.n_envs, self.obs_dim, self.n_actions, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.obs = torch.empty((T + 1, N, D), **f32)
+        self.act = torch.empty((T, N), dtype=torch.int32, device=dev)
+        self.logp = torch.empty((T, N), **f32)
+        self.rew = torch.empty((T, N), **f32)
+        self.val = torch.empty((T, N), **f32)
+        self.adv = torch.empty((T, N), **f32)
+        self.ret = torch.empty((T, N), **f32)
+        self.done = torch.empty((T, N), dtype=torch.uint8, device=dev)
+        self.last_values = torch.empty(N, **f32)
+        self.logits_roll = torch.empty((N, A), **f32)
+        self.cache_roll = torch.empty((4, N, HIDDEN), **f32)
+        # every env can hit its time limit at most floor(T/limit)+1 times per rollout
+        cap = N * (T // self.env.max_episode_steps + 1)
+        self.trunc_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.trunc_index = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.trunc_obs = torch.zeros((cap, D), **f32)
+        self.trunc_values = torch.zeros(cap, **f32)
+        self.cache_trunc = torch.empty((4, cap, HIDDEN), **f32) if cap != N else self.cache_roll
+        self.ep_stats = torch.zeros(4, **f32)
+        total = T * N
+        B = min(self.batch_size, total)
+        self.mb_rows = B
+        self.perm = torch.empty(total, dtype=torch.int32, device=dev)
+        self.logits_mb = torch.empty((B, A), **f32)
+        self.values_mb = torch.empty(B, **f32)
+        self.dlogits = torch.empty((B, A), **f32)
+        self.dvalues = torch.empty(B, **f32)
+        self.cache_mb = torch.empty((4, B, HIDDEN), **f32)
+        self.scratch_mb = torch.empty(2 * B * HIDDEN, **f32)
+        self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(8, **f32)
+        self.stats_acc = torch.zeros(8, **f32)
+        self.norm_out = torch.zeros(2, **f32)
+        self._buffers_ready = True
+
+    # ------------------------------------------------------------------------------------- rollout
+    def collect_rollouts(self):
+        """OnPolicyAlgorithm.collect_rollouts + compute_returns_and_advantage, no host round-trip per step."""
+        self._alloc()
+        T, N, D, A = self.n_steps, self.n_envs, self.obs_dim, self.n_actions
+        if not self._last_obs_valid:
+            self.obs[0].copy_(self.env.reset_tensor())
+            self._last_obs_valid = True
+        else:
+            self.obs[0].copy_(self.obs[T])
+        self.trunc_count.zero_()
+        self.ep_stats.zero_()
+        for t in range(T):
+            ops.mlp_forward(self.params, self.obs[t], D, A, rows=N, logits=self.logits_roll, values=self.val[t],
+                            act_cache=self.cache_roll)
+            ops.step_policy(self.env, self.logits_roll, t, self.obs[t + 1], self.act[t], self.logp[t], self.rew[t],
+                            self.done[t], trunc_count=self.trunc_count, trunc_index=self.trunc_index,
+                            trunc_obs=self.trunc_obs, ep_stats=self.ep_stats)
+        ops.mlp_forward(self.params, self.obs[T], D, A, rows=N, want_logits=False, values=self.last_values,
+                        act_cache=self.cache_roll)
+        # timeout bootstrap: rewards += gamma * V(terminal_obs) for time-limit truncations
+        cap = self.trunc_index.numel()
+        ops.mlp_forward(self.params, self.trunc_obs, D, A, rows=cap, rows_dev=self.trunc_count, want_logits=False,
+                        values=self.trunc_values, act_cache=self.cache_trunc)
+        ops.bootstrap_add(self.rew, self.trunc_count, self.trunc_index, self.trunc_values, self.gamma)
+        ops.gae(self.rew, self.val, self.done, self.last_values, self.gamma, self.gae_lambda, self.adv, self.ret)
+        self.num_timesteps += T * N * self.world
+
+    # -------------------------------------------------------------------------------------- update
+    def train(self):
+        """PPO.train: n_epochs passes over the rollout in minibatches of batch_size."""
+        T, N, D, A = self.n_steps, self.n_envs, self.obs_dim, self.n_actions
+        total = T * N
+        B = self.mb_rows
+        obs_flat = self.obs[:T].reshape(total, D)
+        self.stats_acc.zero_()
+        n_mb = 0
+        for _ in range(self.n_epochs):
+            ops.permutation(self.seed + 7919 * self.rank, self._epoch_counter, T, N, out=self.perm)
+            self._epoch_counter += 1
+            for start in range(0, total, B):
+                rows = min(B, total - start)
+                idx = self.perm[start:start + rows]
+                ops.mlp_forward(self.params, obs_flat, D, A, index=idx, rows=rows, logits=self.logits_mb,
+                                values=self.values_mb, act_cache=self.cache_mb)
+                sums = None
+                if self.normalize_advantage and rows * self.world > 1:
+                    sums = ops.adv_stats(self.adv, idx, rows, self.adv_sums)
+                    if self.world > 1:
+                        self._dist.all_reduce(sums)
+                ops.ppo_loss(self.logits_mb, self.values_mb, self.act, self.adv, self.logp, self.ret, index=idx,
+                             rows=rows, global_rows=rows * self.world, adv_sums=sums, normalize=sums is not None,
+                             clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
+                             dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
+                ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
+                                 rows=rows, grads=self.grads, scratch=self.scratch_mb)
+                if self.world > 1:
+                    self._dist.all_reduce(self.grads)     # the one collective on the path: NCCL sum over NVLink
+                self._adam_step += 1
+                ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
+                              lr=self.lr, eps=1e-5, norm_out=self.norm_out)
+                self.stats_acc += self.stats
+                n_mb += 1
+            self.n_updates += 1
+        return n_mb
+
+    def _log_row(self, n_mb: int, t_roll: float, t_train: float, t0: float) -> dict[str, Any]:
+        s = (self.stats_acc / max(n_mb, 1)).cpu().numpy()
+        if self.world > 1:
+            st = torch.from_numpy(s.copy()).to(self.device)
+            self._dist.all_reduce(st)
+            s = st.cpu().numpy()
+        ep = self.ep_stats.clone()
+        if self.world > 1:
+            self._dist.all_reduce(ep)
+        ep = ep.cpu().numpy()
+        var_y = float(self.ret.var())
+        ev = float("nan") if var_y == 0 else 1.0 - float((self.ret - self.val).var()) / var_y
+        row = {
+            "time/total_timesteps": self.num_timesteps, "time/iterations": len(self.logger_rows) + 1,
+            "time/time_elapsed": time.time() - t0,
+            "time/fps": self.n_steps * self.n_envs * self.world / max(t_roll + t_train, 1e-9),
+            "time/rollout_s": t_roll, "time/train_s": t_train,
+            "rollout/ep_rew_mean": float(ep[0] / ep[2]) if ep[2] > 0 else float("nan"),
+            "rollout/ep_len_mean": float(ep[1] / ep[2]) if ep[2] > 0 else float("nan"),
+            "rollout/episodes": int(ep[2]),
+            "train/policy_gradient_loss": float(s[0]), "train/value_loss": float(s[1]), "train/entropy_loss": float(s[2]),
+            "train/approx_kl": float(s[3]), "train/clip_fraction": float(s[4]), "train/loss": float(s[5]),
+            "train/explained_variance": ev, "train/learning_rate": self.lr, "train/clip_range": self.clip_range,
+            "train/n_updates": self.n_updates,
+        }
+        return row
+
+    def learn(self, total_timesteps: int, callback=None, progress_bar: bool = False, log_interval: int = 1):
+        t0 = time.time()
+        target = self.num_timesteps + int(total_timesteps)
+        it = 0
+        while self.num_timesteps < target:
+            ts = time.time()
+            self.collect_rollouts()
+            torch.cuda.synchronize(self.device)
+            tr = time.time()
+            n_mb = self.train()
+            torch.cuda.synchronize(self.device)
+            te = time.time()
+            row = self._log_row(n_mb, tr - ts, te - tr, t0)
+            self.logger_rows.append(row)
+            it += 1
+            if self.verbose and self.rank == 0 and it % log_interval == 0:
+                print(json.dumps({k: (round(v, 5) if isinstance(v, float) else v) for k, v in row.items()}), flush=True)
+            if self.tensorboard_log and self.rank == 0:
+                import os
+
+                os.makedirs(self.tensorboard_log, exist_ok=True)
+                with open(os.path.join(self.tensorboard_log, "progress.jsonl"), "a", encoding="utf-8") as f:
+                    f.write(json.dumps(row) + "\n")
+            if callback is not None:
+                keep = callback(self) if callable(callback) else callback.on_rollout(self)
+                if keep is False:
+                    break
+        return self
+
+    # ------------------------------------------------------------------------- predict / evaluate
+    def policy_logits(self, obs_dev: torch.Tensor) -> torch.Tensor:
+        rows = obs_dev.shape[0]
+        logits, _, _ = ops.mlp_forward(self.params, obs_dev.contiguous(), self.obs_dim, self.n_actions, rows=rows,
+                                       want_values=False)
+        return logits
+
+    def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
+        obs = np.asarray(observation, dtype=np.float32)
+        single = obs.ndim == 1
+        x = torch.from_numpy(obs.reshape(-1, self.obs_dim)).to(self.device)
+        logits = self.policy_logits(x)
+        if deterministic:
+            a = torch.argmax(logits, dim=1)
+        else:
+            a = torch.distributions.Categorical(logits=logits).sample()
+        a = a.cpu().numpy().astype(np.int64)
+        return (a[0] if single else a), state
+
+    def evaluate(self, n_episodes: int, seed: int, deterministic: bool = True):
+        """evaluate_policy equivalent, batched on the device: `n_episodes` envs run one episode each."""
+        env = CudaVecEnv(self.env.task_id, n_episodes, seed=seed, device=self.env.device_index)
+        try:
+            with torch.cuda.device(self.device):
+                obs = env.reset_tensor()
+                ret = torch.zeros(n_episodes, device=self.device)
+                length = torch.zeros(n_episodes, dtype=torch.int32, device=self.device)
+                finished = torch.zeros(n_episodes, dtype=torch.bool, device=self.device)
+                for _ in range(env.max_episode_steps):
+                    logits = self.policy_logits(obs)
+                    if deterministic:
+                        a = torch.argmax(logits, dim=1).to(torch.int32)
+                    else:
+                        a = torch.distributions.Categorical(logits=logits).sample().to(torch.int32)
+                    b = env.step_tensor(a.contiguous())
+                    new = b["done"].bool() & ~finished
+                    ret = torch.where(new, b["ret"], ret)
+                    length = torch.where(new, b["len"], length)
+                    finished |= new
+                    obs = b["obs"]
+                    if bool(finished.all()):
+                        break
+                return ret.cpu().numpy().astype(np.float64), length.cpu().numpy().astype(np.int64)
+        finally:
+            env.close()
+
+    # ------------------------------------------------------------------------------- persistence
+    def save(self, path) -> None:
+        path = str(path)
+        if not path.endswith(".zip"):
+            path += ".zip"
+        data = {
+            "format": "three-mlagents_b200/1", "algorithm": "ppo", "task_id": self.env.task_id, "obs_dim": self.obs_dim,
+            "n_actions": self.n_actions, "net_arch": {"pi": [256, 256], "vf": [256, 256]}, "seed": self.seed,
+            "num_timesteps": self.num_timesteps, "n_updates": self.n_updates, "adam_step": self._adam_step,
+            "hyper": {"learning_rate": self.lr, "n_steps": self.n_steps, "batch_size": self.batch_size,
+                      "n_epochs": self.n_epochs, "gamma": self.gamma, "gae_lambda": self.gae_lambda,
+                      "clip_range": self.clip_range, "ent_coef": self.ent_coef, "vf_coef": self.vf_coef,
+                      "max_grad_norm": self.max_grad_norm},
+        }
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data.json", json.dumps(data, indent=2))
+            for name, t in (("params", self.params), ("adam_m", self.m), ("adam_v", self.v)):
+                buf = io.BytesIO()
+                np.save(buf, t.cpu().numpy())
+                z.writestr(f"{name}.npy", buf.getvalue())
+
+    @classmethod
+    def load(cls, path, env: CudaVecEnv | None = None, device: int = 0):
+        with zipfile.ZipFile(str(path)) as z:
+            data = json.loads(z.read("data.json"))
+            arrs = {n: np.load(io.BytesIO(z.read(f"{n}.npy"))) for n in ("params", "adam_m", "adam_v")}
+        own_env = env is None
+        if own_env:
+            env = CudaVecEnv(data["task_id"], 1, seed=data["seed"], device=device)
+        model = cls("MlpPolicy", env, seed=data["seed"], _params=torch.from_numpy(arrs["params"]), **data["hyper"])
+        model.m.copy_(torch.from_numpy(arrs["adam_m"]))
+        model.v.copy_(torch.from_numpy(arrs["adam_v"]))
+        model.num_timesteps, model.n_updates, model._adam_step = data["num_timesteps"], data["n_updates"], data["adam_step"]
+        return model
+
+
+# ---------------------------------------------------------------------------------------- bench / smoke
+def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: int = 65536, n_steps: int = 128,
+              minibatches: int = 32, task: str = "ball3d") -> dict[str, Any]:
+    """BASELINE config 3: ball3d PPO end-to-end, 64K envs/GPU, 128-step rollouts, 2x256 MLP, 10 epochs,
+    32 minibatches per epoch (262 144 samples per GPU per optimizer step)."""
+    dist, _, _ = _dist()
+    env = CudaVecEnv(task, n_envs, seed=1, device=local_rank, env_id_base=rank * n_envs)
+    model = CudaPPO("MlpPolicy", env, seed=1, n_steps=n_steps, batch_size=n_envs * n_steps // minibatches, n_epochs=10,
+                    ent_coef=0.01)
+    dev = model.device
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    model.collect_rollouts(); model.train()           # warm-up iteration (allocations, NCCL setup)
+    sync()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roll_ms = train_ms = 0.0
+    for _ in range(iters):
+        e[0].record(); model.collect_rollouts(); e[1].record(); model.train(); e[2].record()
+        sync()
+        roll_ms += e[0].elapsed_time(e[1]); train_ms += e[1].elapsed_time(e[2])
+    tot = torch.tensor([roll_ms + train_ms, roll_ms, train_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, roll_ms, train_ms = (float(x) for x in tot)
+    samples = world * n_envs * n_steps * iters
+    flop_update = 807936.0 * n_envs * n_steps * 10 * iters          # SURVEY.md §8(d), ball3d fwd+bwd per sample
+    row = model._log_row(10 * minibatches, roll_ms / 1e3 / iters, train_ms / 1e3 / iters, time.time())
+    env.close()
+    return {
+        "value": samples / (tot_ms * 1e-3), "unit": "samples/s (env-steps consumed per second, rollout+GAE+update)",
+        "iters": iters, "ms_per_iter": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": train_ms / iters,
+        "config": {"task": task, "envs_per_gpu": n_envs, "n_steps": n_steps, "epochs": 10, "minibatches_per_epoch": minibatches,
+                   "minibatch_rows_per_gpu": n_envs * n_steps // minibatches, "mlp": "6-256-256-{5,1} tanh, separate towers",
+                   "mlp_impl": "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)"},
+        "update_tflops": flop_update / (train_ms * 1e-3) / 1e12,
+        "ep_rew_mean": row["rollout/ep_rew_mean"], "approx_kl": row["train/approx_kl"],
+    }
+
+
+def smoke_update() -> None:
+    """One tiny rollout + update on cuda:0 (called from __graft_entry__.smoke)."""
+    env = CudaVecEnv("ball3d", 256, seed=1)
+    model = CudaPPO("MlpPolicy", env, seed=1, n_steps=16, batch_size=1024, n_epochs=2, ent_coef=0.01)
+    before = model.params.clone()
+    model.learn(256 * 16)
+    torch.cuda.synchronize()
+    row = model.logger_rows[-1]
+    assert torch.isfinite(model.params).all() and not torch.equal(before, model.params)
+    assert math.isfinite(row["train/loss"]) and row["train/clip_fraction"] >= 0.0
+    env.close()
