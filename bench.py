@@ -187,6 +187,11 @@ def run_cuda(args):
     achieved = BYTES_PER_ENV_STEP * steps_per_launch / (launch_ms * 1e-3) / 1e9
     done_rate = float(done.float().mean().item())
 
+    if args.quick:      # profiling runs (ncu): only the fused rollout
+        if rank == 0:
+            print(json.dumps({"metric": "env_steps_per_sec", "value": value, "ms_per_step": launch_ms, "quick": True}))
+        env.close()
+        return
     # ---- per-launch VecEnv.step on device tensors (launch-bound; reported, not the headline) -------
     a_dev = torch.randint(0, 5, (N_ENVS,), dtype=torch.int32, device=dev)
     for _ in range(20):
@@ -264,6 +269,7 @@ def main():
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ppo-iters", type=int, default=3)
+    ap.add_argument("--quick", action="store_true", help="fused rollout only (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,3 +85,26 @@ def test_registry_surface():
     assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["ball3d", "basic", "gridworld", "push"]
     fams = [(t.family, t.id) for t in m.list_tasks()]
     assert fams == sorted(fams)
+
+
+def test_model_path_errors_match_reference(tmp_path, monkeypatch):
+    # backend/tests/test_mlagents.py:104-122
+    import numpy as np
+    from three_mlagents_b200 import training
+    from three_mlagents_b200.registry import get_task
+
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        training.predict_action("basic", np.zeros(21, np.float32), "missing.zip")
+    task = get_task("basic")
+    model_path = training.POLICIES_DIR / "resolver_regression_test.zip"
+    model_path.parent.mkdir(parents=True, exist_ok=True)
+    model_path.write_bytes(b"placeholder")
+    assert training._resolve_model_path(task, str(model_path)) == model_path
+    assert training._resolve_model_path(task, model_path.name) == model_path
+    with pytest.raises(ValueError):
+        training.train_task(training.TrainConfig("basic"))            # default algorithm dqn has no CUDA backend
+    with pytest.raises(ValueError):
+        training.train_task(training.TrainConfig("fish"))
+    with pytest.raises(KeyError):
+        training.train_task(training.TrainConfig("nope"))

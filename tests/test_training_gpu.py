@@ -1,0 +1,52 @@
+"""The reference's CLI/training boundary on the CUDA backend (BASELINE config 1:
+`three-mlagents train basic --algorithm ppo --timesteps 25000 --seed 1`)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cli_train_basic_ppo_config1(tmp_path, monkeypatch, capsys):
+    from three_mlagents_b200 import cli, training
+
+    monkeypatch.chdir(tmp_path)
+    cli.main(["train", "basic", "--algorithm", "ppo", "--timesteps", "25000", "--seed", "1", "--run-name", "t1", "--quiet"])
+    result = json.loads(capsys.readouterr().out)
+    # TrainResult fields of training.py:56-68
+    assert set(result) == {"task_id", "algorithm", "run_id", "model_filename", "model_path", "run_dir", "mean_reward",
+                           "std_reward", "eval_episodes", "total_timesteps", "metadata_path"}
+    assert result["task_id"] == "basic" and result["algorithm"] == "ppo" and result["eval_episodes"] == 50
+    assert result["model_filename"] == "basic_policy_t1.zip" and os.path.exists(result["model_path"])
+    meta = json.loads(open(result["metadata_path"]).read())
+    assert meta["task"]["id"] == "basic" and len(meta["episode_rewards"]) == 50 and meta["config"]["seed"] == 1
+    run_dir = result["run_dir"]
+    assert os.path.exists(os.path.join(run_dir, "eval", "evaluations.npz"))
+    assert os.path.exists(os.path.join(run_dir, "monitor", "0.monitor.csv"))
+    assert os.path.exists(os.path.join(run_dir, "tb", "progress.jsonl"))
+    # n_envs=1 (registry.py:63), n_steps=1024 -> 25 iterations of 1024 steps
+    rows = [json.loads(l) for l in open(os.path.join(run_dir, "tb", "progress.jsonl"))]
+    assert len(rows) == 25 and rows[-1]["time/total_timesteps"] == 25600
+    print("basic PPO 25k steps: mean_reward", result["mean_reward"])
+    assert result["mean_reward"] > 0.0
+
+    cli.main(["evaluate", "basic", result["model_filename"], "--episodes", "10"])
+    ev = json.loads(capsys.readouterr().out)
+    assert ev["episodes"] == 10 and len(ev["episode_rewards"]) == 10 and ev["task_id"] == "basic"
+    obs = np.zeros(21, np.float32); obs[10] = 1.0
+    assert training.predict_action("basic", obs, result["model_filename"]) in (0, 1, 2)
+    assert training.latest_model_filename("basic") == "basic_policy_t1.zip"
+
+    cli.main(["inspect", "ball3d"])
+    insp = json.loads(capsys.readouterr().out)
+    assert insp["task"] == "ball3d" and "Discrete(5)" in insp["action_space"]
+
+
+def test_train_task_ball3d_defaults_small(tmp_path, monkeypatch):
+    from three_mlagents_b200.training import TrainConfig, train_task
+
+    monkeypatch.chdir(tmp_path)
+    res = train_task(TrainConfig("ball3d", total_timesteps=8 * 1024 * 2, eval_episodes=8, verbose=0, run_name="b1"))
+    assert res.algorithm == "ppo" and res.total_timesteps == 16384 and np.isfinite(res.mean_reward)
