@@ -200,13 +200,13 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET):
     if task == "basic":
         st["pos"] = 10                                              # envs.py:21,55
     elif task == "ball3d":                                          # ball3d.py:49-57
+        # lo + (hi-lo)*u like np.random.uniform, u = (w + 0.5) * 2^-32 carries 32 random bits
         b0 = px.stream_block(seed, env_ids, k, tag, 0)
         b1 = px.stream_block(seed, env_ids, k, tag, 1)
-        b2 = px.stream_block(seed, env_ids, k, tag, 2)
         lo = -MAX_TILT * 0.5
-        rot = np.stack([lo + MAX_TILT * px.u53(b0[0], b0[1]), lo + MAX_TILT * px.u53(b0[2], b0[3])], 1)
-        pos = np.stack([-1.5 + 3.0 * px.u53(b1[0], b1[1]), -1.5 + 3.0 * px.u53(b1[2], b1[3])], 1)
-        vel = np.stack([-1.0 + 2.0 * px.u53(b2[0], b2[1]), -1.0 + 2.0 * px.u53(b2[2], b2[3])], 1)
+        rot = np.stack([lo + MAX_TILT * px.u32_unit(b0[0]), lo + MAX_TILT * px.u32_unit(b0[1])], 1)
+        pos = np.stack([-1.5 + 3.0 * px.u32_unit(b0[2]), -1.5 + 3.0 * px.u32_unit(b0[3])], 1)
+        vel = np.stack([-1.0 + 2.0 * px.u32_unit(b1[0]), -1.0 + 2.0 * px.u32_unit(b1[1])], 1)
         st["rot"] = rot.astype(np.float32).astype(np.float64)       # `.astype(np.float32)` at reset
         st["pos"] = pos.astype(np.float32)
         st["vel"] = vel.astype(np.float32)
@@ -235,10 +235,17 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET):
 
 
 def random_actions(task, seed, env_ids, step_index):
-    """Random-policy action of every env at global step `step_index` (TAG_ACTION stream)."""
-    n_act = TASKS[task][1]
-    b = px.stream_block(seed, env_ids, step_index // 4, px.TAG_ACTION, 0)
-    return px.bounded(b[step_index % 4], n_act)
+    """Random-policy action of every env at global step `step_index` (TAG_ACTION stream): Philox block
+    step>>4, word (step&15)>>2 read as a 32-bit fraction, base-A digit number step&3 (csrc/philox.cuh)."""
+    n_act = np.uint64(TASKS[task][1])
+    b = px.stream_block(seed, env_ids, step_index >> 4, px.TAG_ACTION, 0)
+    frac = b[(step_index & 15) >> 2].astype(np.uint64)
+    a = None
+    for _ in range((step_index & 3) + 1):
+        p = frac * n_act
+        a = (p >> np.uint64(32)).astype(np.int32)
+        frac = p & np.uint64(0xFFFFFFFF)
+    return a
 
 
 class OracleVecEnv:

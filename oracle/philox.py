@@ -74,3 +74,8 @@ def u53(a, b):
 def u24(a):
     """float32 in [0,1) from the top 24 bits of one word."""
     return ((np.asarray(a, dtype=np.uint32) >> np.uint32(8)).astype(np.float32)) * np.float32(1.0 / 16777216.0)
+
+
+def u32_unit(a):
+    """double in (0,1) with 32 random bits: (a + 0.5) * 2^-32 (exact)."""
+    return (np.asarray(a, dtype=np.uint64).astype(np.float64) + 0.5) * (1.0 / 4294967296.0)

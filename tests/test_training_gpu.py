@@ -29,7 +29,7 @@ def test_cli_train_basic_ppo_config1(tmp_path, monkeypatch, capsys):
     # n_envs=1 (registry.py:63), n_steps=1024 -> 25 iterations of 1024 steps
     rows = [json.loads(l) for l in open(os.path.join(run_dir, "tb", "progress.jsonl"))]
     assert len(rows) == 25 and rows[-1]["time/total_timesteps"] == 25600
-    print("basic PPO 25k steps: mean_reward", result["mean_reward"])
+    capsys.readouterr()
     assert result["mean_reward"] > 0.0
 
     cli.main(["evaluate", "basic", result["model_filename"], "--episodes", "10"])

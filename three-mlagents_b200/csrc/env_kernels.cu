@@ -131,44 +131,84 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
 // State stays in registers for all T steps; per step and env the kernel writes obs (D floats, via the
 // double-buffered shared-memory stage -> st.global.cs.v4), action, reward and done: the [T,N] rollout
 // buffer is write-once streaming traffic, 33 B/env-step for ball3d.
+// 64-thread blocks: 65 536 envs -> 1024 CTAs = 6.9 per SM (tail imbalance 1 %, vs 13 % with 128).
+static constexpr int kRollBlock = 64;
+
+template <int D>
+__device__ __forceinline__ void stage_obs(float *stage, const float *o) {     // row-major [env][D] in shared memory
+    if (D % 2 == 0) {                                                          // 64-bit stores: conflict-free for D=6
+        float2 *s2 = reinterpret_cast<float2 *>(stage + threadIdx.x * D);
+#pragma unroll
+        for (int j = 0; j < D / 2; ++j) s2[j] = make_float2(o[2 * j], o[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) stage[threadIdx.x * D + j] = o[j];
+    }
+}
+
 template <class Task>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kRollBlock)
 rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t step0, int T,
                       float *__restrict__ obs_buf, int32_t *__restrict__ act_buf, float *__restrict__ rew_buf,
                       uint8_t *__restrict__ done_buf) {
-    constexpr int D = Task::D;
-    __shared__ __align__(16) float s_obs[2][kBlock * D];
-    const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    constexpr int D = Task::D, BLOCK = kRollBlock;
+    constexpr bool STAGED = (D != 4);                     // D == 4: one float4 per env straight from registers
+    constexpr int NVEC = BLOCK * D / 4;                   // float4 per full block row
+    __shared__ __align__(16) float s_obs[STAGED ? 2 * BLOCK * D : 4];
+    const int64_t i0 = (int64_t)blockIdx.x * BLOCK, i = i0 + threadIdx.x;
     const bool active = i < n;
-    const int valid = (int)min((int64_t)kBlock, n - i0);
+    const int valid = (int)min((int64_t)BLOCK, n - i0);
     const uint64_t env_id = env_base + (uint64_t)i;
+    const int64_t row_floats = n * D;
+    // block-uniform fast path: full block, 16-byte aligned rows
+    const bool vec_ok = obs_buf && valid == BLOCK && ((reinterpret_cast<uintptr_t>(obs_buf + i0 * D) & 15u) == 0) &&
+                        ((row_floats & 3) == 0);
     typename Task::State s;
-    if (active) s = Task::load(p.buf, i);
-    uint4 blk = make_uint4(0, 0, 0, 0);
+    TmlaActionStream as;
+    if (active) {
+        s = Task::load(p.buf, i);
+        as.seek(seed, env_id, step0, Task::A);
+    }
+    float *orow = obs_buf ? obs_buf + i0 * D : nullptr;   // block's slice of row t
+    int64_t off = i;                                      // t*n + i
     for (int t = 0; t < T; ++t) {
         const uint64_t k = step0 + (uint64_t)t;
-        float *stage = s_obs[t & 1];
+        float *stage = STAGED ? s_obs + (t & 1) * BLOCK * D : s_obs;
         if (active) {
             float o[D];
-            Task::observe(s, o);                                  // observation the action is taken on
-#pragma unroll
-            for (int j = 0; j < D; ++j) stage[threadIdx.x * D + j] = o[j];
-            const uint32_t lane = (uint32_t)(k & 3u);
-            if (lane == 0 || t == 0) blk = tmla_stream_block(seed, env_id, k >> 2, TMLA_TAG_ACTION, 0);
-            const uint32_t word = lane == 0 ? blk.x : (lane == 1 ? blk.y : (lane == 2 ? blk.z : blk.w));
-            const int a = tmla_bounded(word, Task::A);
+            Task::observe(s, o);                          // observation the action is taken on
+            if (STAGED) stage_obs<D>(stage, o);
+            else if (obs_buf) {
+                float *dst = obs_buf + off * 4;
+                if ((reinterpret_cast<uintptr_t>(obs_buf) & 15u) == 0) st_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                else { dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; }
+            }
+            const int a = as.next(seed, env_id, k, Task::A, t == 0);
             float r; bool term, trunc;
             Task::step(s, a, r, term, trunc);
             s.ep_ret = __fadd_rn(s.ep_ret, r);
             const bool d = term || trunc;
-            const int64_t off = (int64_t)t * n + i;
             if (act_buf) __stcs(act_buf + off, a);
             if (rew_buf) __stcs(rew_buf + off, r);
             if (done_buf) __stcs(done_buf + off, (uint8_t)(d ? 1 : 0));
             if (d) Task::reset(s, seed, env_id, k + 1, TMLA_TAG_RESET);
         }
-        __syncthreads();
-        if (obs_buf) block_store_obs<D, kBlock, true>(stage, obs_buf + ((int64_t)t * n + i0) * D, valid);
+        if (STAGED) {
+            __syncthreads();
+            if (vec_ok) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+                float4 *d4 = reinterpret_cast<float4 *>(orow);
+#pragma unroll
+                for (int v = 0; v < (NVEC + BLOCK - 1) / BLOCK; ++v) {
+                    const int e = v * BLOCK + threadIdx.x;
+                    if ((v + 1) * BLOCK <= NVEC || e < NVEC) st_stream_f4(d4 + e, s4[e]);
+                }
+            } else if (obs_buf) {
+                block_store_obs<D, BLOCK, true>(stage, orow, valid);
+            }
+            if (orow) orow += row_floats;
+        }
+        off += n;
     }
     if (active) Task::store(p.buf, i, s);
 }
@@ -472,7 +512,7 @@ int tmla_check_actions(tmla_env *h, void *stream) {
 int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, float *rew_buf, uint8_t *done_buf, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
     TMLA_REQUIRE(T > 0, "T must be positive");
-    TASK_SWITCH(h->task, (rollout_random_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
+    TASK_SWITCH(h->task, (rollout_random_kernel<TaskT><<<(unsigned)ceil_div64(h->n, kRollBlock), kRollBlock, 0, (cudaStream_t)stream>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, T, obs_buf, act_buf, rew_buf, done_buf)));
     TMLA_LAUNCH_CHECK();
     h->step_count += (uint64_t)T;

@@ -65,20 +65,37 @@ struct BasicTask {
 };
 
 // ------------------------------------------------------------------ ball3d (examples/ball3d.py:10-113)
+// Double-precision constants live in constant memory so that DFMA/DMUL/DADD take them as c[bank][offset]
+// operands (64-bit literals cannot be encoded as immediates and would cost a UMOV pair each).
+struct Ball3DConst {
+    double max_tilt, tilt_delta, g, dt, half_lo;      // np.deg2rad(25), np.deg2rad(3), 9.81, 0.02, -max_tilt/2
+    double s15, s13, s11, s9, s7, s5, s3;            // sin Taylor coefficients -1/15! ... -1/3!
+    double inv32;                                    // 2^-32
+};
+__device__ __constant__ Ball3DConst kB3 = {
+    0x1.becde5da115a9p-2, 0x1.acee9f37bebd6p-5, 9.81, 0.02, -0x1.becde5da115a9p-3,
+    -7.6471637318198164759e-13, 1.6059043836821614599e-10, -2.5052108385441718775e-08, 2.7557319223985890653e-06,
+    -1.9841269841269841253e-04, 8.3333333333333332177e-03, -1.6666666666666665741e-01,
+    0x1p-32};
+
 // sin on |x| <= MAX_TILT = 0.43633: odd Taylor/Horner through x^15, no range reduction.
 // Truncation error < 2.2e-21 (x^17/17!), evaluation error ~0.6 ulp: agrees with libm's double sin to
 // the last bit in the vast majority of cases; parity with the reference is tolerance-checked.
 __device__ __forceinline__ double sin_small(double x) {
     const double z = x * x;
-    double p = -7.6471637318198164759e-13;        // -1/15!
-    p = fma(p, z, 1.6059043836821614599e-10);     //  1/13!
-    p = fma(p, z, -2.5052108385441718775e-08);    // -1/11!
-    p = fma(p, z, 2.7557319223985890653e-06);     //  1/9!
-    p = fma(p, z, -1.9841269841269841253e-04);    // -1/7!
-    p = fma(p, z, 8.3333333333333332177e-03);     //  1/5!
-    p = fma(p, z, -1.6666666666666665741e-01);    // -1/3!
+    double p = kB3.s15;
+    p = fma(p, z, kB3.s13);
+    p = fma(p, z, kB3.s11);
+    p = fma(p, z, kB3.s9);
+    p = fma(p, z, kB3.s7);
+    p = fma(p, z, kB3.s5);
+    p = fma(p, z, kB3.s3);
     return fma(x * z, p, x);
 }
+// np.clip(x, -m, m) for finite x
+__device__ __forceinline__ double clip_sym(double x, double m) { return fabs(x) > m ? copysign(m, x) : x; }
+// uniform double in (0,1) with 32 random bits: (w + 0.5) * 2^-32 (exact)
+__device__ __forceinline__ double u32_to_unit(uint32_t w) { return ((double)w + 0.5) * kB3.inv32; }
 
 struct Ball3DTask {
     static constexpr int D = 6, A = 5, MAX_STEPS = 200, NBUF = 3;
@@ -111,21 +128,21 @@ struct Ball3DTask {
     // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
     // explicit (`__*_rn` never contracts into FMA) so the result does not depend on compiler flags.
     static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
-        const double MAX_TILT = 0x1.becde5da115a9p-2;     // np.deg2rad(25.0), ball3d.py:18
-        const double TILT_DELTA = 0x1.acee9f37bebd6p-5;   // np.deg2rad(3.0),  ball3d.py:19
-        const double dx = (a == 0) ? TILT_DELTA : ((a == 1) ? -TILT_DELTA : 0.0);   // ball3d.py:31-37
-        const double dz = (a == 2) ? TILT_DELTA : ((a == 3) ? -TILT_DELTA : 0.0);
+        // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0)
+        const double td = kB3.tilt_delta;
+        const double dx = (a < 2) ? ((a == 0) ? td : -td) : 0.0;
+        const double dz = (a == 2) ? td : ((a == 3) ? -td : 0.0);
         double rx = __dadd_rn(s.rx, dx), rz = __dadd_rn(s.rz, dz);                  // ball3d.py:77
         if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back
             rx = (double)__double2float_rn(rx);
             rz = (double)__double2float_rn(rz);
         }
-        rx = fmin(fmax(rx, -MAX_TILT), MAX_TILT);                                   // ball3d.py:78 (float64 from here)
-        rz = fmin(fmax(rz, -MAX_TILT), MAX_TILT);
-        const double ax = __dmul_rn(9.81, sin_small(rx));                           // ball3d.py:81-82
-        const double az = __dmul_rn(9.81, sin_small(rz));
-        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, 0.02))); // ball3d.py:83-84
-        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, 0.02)));
+        rx = clip_sym(rx, kB3.max_tilt);                                            // ball3d.py:78 (float64 from here)
+        rz = clip_sym(rz, kB3.max_tilt);
+        const double ax = __dmul_rn(kB3.g, sin_small(rx));                          // ball3d.py:81-82
+        const double az = __dmul_rn(kB3.g, sin_small(rz));
+        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, kB3.dt))); // ball3d.py:83-84
+        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, kB3.dt)));
         vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
         vz = __fmul_rn(vz, 0.98f);
         const float px = __fadd_rn(s.px, __fmul_rn(vx, 0.02f));                     // ball3d.py:90
@@ -142,18 +159,18 @@ struct Ball3DTask {
         trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
         term = done && !trunc;
     }
+    // np.random.uniform(lo, hi) = lo + (hi-lo)*u (ball3d.py:49-57), `.astype(np.float32)`; u carries 32
+    // random bits here (the reference's 53-bit double is rounded to 24 bits anyway).
     static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
-        const double MAX_TILT = 0x1.becde5da115a9p-2;
         const uint4 b0 = tmla_stream_block(seed, env_id, k, tag, 0);
         const uint4 b1 = tmla_stream_block(seed, env_id, k, tag, 1);
-        const uint4 b2 = tmla_stream_block(seed, env_id, k, tag, 2);
-        const double lo = -MAX_TILT * 0.5;     // np.random.uniform(lo, hi) = lo + (hi-lo)*u, ball3d.py:49-57
-        s.rx = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(MAX_TILT, tmla_u53(b0.x, b0.y))));
-        s.rz = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(MAX_TILT, tmla_u53(b0.z, b0.w))));
-        s.px = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, tmla_u53(b1.x, b1.y))));
-        s.pz = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, tmla_u53(b1.z, b1.w))));
-        s.vx = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, tmla_u53(b2.x, b2.y))));
-        s.vz = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, tmla_u53(b2.z, b2.w))));
+        const double mt = kB3.max_tilt, lo = kB3.half_lo;
+        s.rx = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.x))));
+        s.rz = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.y))));
+        s.px = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.z))));
+        s.pz = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.w))));
+        s.vx = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.x))));
+        s.vz = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.y))));
         s.steps = 0; s.ep_ret = 0.0f;
     }
 };

@@ -48,3 +48,32 @@ __host__ __device__ __forceinline__ double tmla_u53(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 __host__ __device__ __forceinline__ float tmla_u24(uint32_t a) { return (float)(a >> 8) * (1.0f / 16777216.0f); }
+
+// Random-policy action stream (TAG_ACTION): one Philox block serves 16 consecutive steps.  Word w of the
+// block is read as a 32-bit fraction and expanded into 4 base-A digits by repeated multiply-shift
+// (digit = floor(frac*A), frac = frac*A mod 1); bias per digit <= A^4 / 2^32.
+//   step k -> block k>>4, word (k&15)>>2, digit k&3
+struct TmlaActionStream {
+    uint4 blk;
+    uint32_t frac;
+    __device__ __forceinline__ static uint32_t word_of(const uint4 &b, uint32_t w) {
+        return w == 0 ? b.x : (w == 1 ? b.y : (w == 2 ? b.z : b.w));
+    }
+    // position the stream so that the next call to next() yields the action of step k
+    __device__ __forceinline__ void seek(uint64_t seed, uint64_t env_id, uint64_t k, uint32_t n_actions) {
+        blk = tmla_stream_block(seed, env_id, k >> 4, TMLA_TAG_ACTION, 0);
+        frac = word_of(blk, (uint32_t)(k & 15u) >> 2);
+        for (uint32_t d = 0; d < (uint32_t)(k & 3u); ++d) frac = (uint32_t)((uint64_t)frac * n_actions);
+    }
+    // action of step k (k must advance by one per call after seek)
+    __device__ __forceinline__ int next(uint64_t seed, uint64_t env_id, uint64_t k, uint32_t n_actions, bool first) {
+        const uint32_t j = (uint32_t)(k & 15u);
+        if (!first) {
+            if (j == 0) blk = tmla_stream_block(seed, env_id, k >> 4, TMLA_TAG_ACTION, 0);
+            if ((j & 3u) == 0) frac = word_of(blk, j >> 2);
+        }
+        const uint64_t p = (uint64_t)frac * n_actions;
+        frac = (uint32_t)p;
+        return (int)(p >> 32);
+    }
+};
