@@ -125,6 +125,10 @@ int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_
  * and the matching device-side counter increment to put at the end of the captured graph */
 int tmla_advance_steps(tmla_env *h, uint64_t n);
 int tmla_counter_add(uint64_t *counter, uint64_t n, void *stream);
+/* test hook: exhaustive check of the kernels' hand-rolled correctly-rounded x/3, x/5 and the short double
+ * sin polynomial against the IEEE intrinsics; out3 = DEVICE uint64[3] {x/3 mismatches over [0,8),
+ * k/5 mismatches over k in [-5,5], max ulp distance of sin over [-25deg, 25deg]} */
+int tmla_selftest_arith(uint64_t *out3, void *stream);
 
 /* rewards[idx] += gamma * values[i] for the truncation records (collect_rollouts timeout bootstrap) */
 int tmla_bootstrap_add(float *rew_buf, const int32_t *trunc_count, const int32_t *trunc_index,

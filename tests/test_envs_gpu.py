@@ -219,3 +219,17 @@ def test_full_size_properties(task, n):
         acc = np.where(dn[t], np.float32(0), (acc + r[t]).astype(np.float32))
     assert np.array_equal(acc, st["ep_return"])
     env.close()
+
+
+def test_fast_arithmetic_is_exact():
+    """The kernels replace IEEE x/3 and k/5 by a 3-instruction Markstein sequence and libm sin by a short
+    polynomial: exhaustive check on the device over every input the tasks can produce."""
+    from three_mlagents_b200 import native
+
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    native.check(native.lib.tmla_selftest_arith(native.ptr(out), native.current_stream()))
+    bad3, bad5, sin_ulp = (int(x) for x in out.cpu())
+    assert bad3 == 0, f"{bad3} floats in [0,8) where div3_rn != IEEE division"
+    assert bad5 == 0
+    print("sin_small vs libdevice sin: max distance", sin_ulp, "ulp (double)")
+    assert sin_ulp <= 2

@@ -99,11 +99,12 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     __shared__ __align__(16) float s_obs[kBlock * D];
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
     if (i < n) {
+        const typename Task::Consts cst = Task::load_consts();
         typename Task::State s = Task::load(p.buf, i);
         int a = actions[i];
         if ((unsigned)a >= (unsigned)Task::A) { *err_flag = 1; a = min(max(a, 0), Task::A - 1); }
         float r; bool term, trunc;
-        Task::step(s, a, r, term, trunc);
+        Task::step(cst, s, a, r, term, trunc);
         s.ep_ret = __fadd_rn(s.ep_ret, r);                       // Monitor: episode return
         const bool d = term || trunc;
         reward[i] = r;
@@ -163,6 +164,7 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
     // block-uniform fast path: full block, 16-byte aligned rows
     const bool vec_ok = obs_buf && valid == BLOCK && ((reinterpret_cast<uintptr_t>(obs_buf + i0 * D) & 15u) == 0) &&
                         ((row_floats & 3) == 0);
+    const typename Task::Consts cst = Task::load_consts();
     typename Task::State s;
     TmlaActionStream as;
     if (active) {
@@ -185,7 +187,7 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
             }
             const int a = as.next(seed, env_id, k, Task::A, t == 0);
             float r; bool term, trunc;
-            Task::step(s, a, r, term, trunc);
+            Task::step(cst, s, a, r, term, trunc);
             s.ep_ret = __fadd_rn(s.ep_ret, r);
             const bool d = term || trunc;
             if (act_buf) __stcs(act_buf + off, a);
@@ -254,6 +256,7 @@ step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint6
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
     const uint64_t k = step_base ? (*step_base + (uint64_t)row_index) : step_index;
     if (i < n) {
+        const typename Task::Consts cst = Task::load_consts();
         const uint64_t env_id = env_base + (uint64_t)i;
         typename Task::State s = Task::load(p.buf, i);
         float l[A];
@@ -264,7 +267,7 @@ step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint6
         int a; float lp;
         categorical<A>(l, deterministic != 0, u, a, lp);
         float r; bool term, trunc;
-        Task::step(s, a, r, term, trunc);
+        Task::step(cst, s, a, r, term, trunc);
         s.ep_ret = __fadd_rn(s.ep_ret, r);
         const bool d = term || trunc;
         if (act) act[i] = a;
@@ -298,6 +301,33 @@ step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint6
 }
 
 __global__ void counter_add_kernel(uint64_t *c, uint64_t n) { *c += n; }
+
+// ---- arithmetic self-test (test hook): the hand-rolled correctly-rounded divisions and the short sin
+// polynomial against the IEEE intrinsics / libdevice over every input the tasks can produce.
+//   out[0] div3_rn != __fdiv_rn(x,3) count over all floats in [0, 8)      (ball3d |pos| <= ~4.3)
+//   out[1] div5_rn != __fdiv_rn(k,5) count over k in [-5,5]
+//   out[2] max ulp distance of sin_small vs sin() over 2^22 points of [-MAX_TILT, MAX_TILT]
+__global__ void selftest_arith_kernel(unsigned long long *out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned long long bad3 = 0;
+    for (uint32_t bits = tid; bits < 0x41000000u; bits += nth) {
+        const float x = __uint_as_float(bits);
+        bad3 += (__float_as_uint(div3_rn(x)) != __float_as_uint(__fdiv_rn(x, 3.0f)));
+    }
+    if (bad3) atomicAdd(out + 0, bad3);
+    if (tid < 11) {
+        const float k = (float)((int)tid - 5);
+        if (__float_as_uint(div5_rn(k)) != __float_as_uint(__fdiv_rn(k, 5.0f))) atomicAdd(out + 1, 1ull);
+    }
+    unsigned long long worst = 0;
+    for (uint32_t j = tid; j < (1u << 22); j += nth) {
+        const double x = kB3.max_tilt * (2.0 * ((double)j + 0.5) / 4194304.0 - 1.0);
+        const long long a = __double_as_longlong(sin_small(x)), b = __double_as_longlong(sin(x));
+        const unsigned long long d = (unsigned long long)(a > b ? a - b : b - a);
+        worst = d > worst ? d : worst;
+    }
+    atomicMax(out + 2, worst);
+}
 
 // ------------------------------------------------------------------------------------ dispatch
 #define TASK_SWITCH(task, CALL)                                   \
@@ -531,6 +561,14 @@ int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_
                              trunc_capacity, ep_stats)));
     TMLA_LAUNCH_CHECK();
     if (!step_base) h->step_count += 1;
+    return TMLA_OK;
+}
+
+int tmla_selftest_arith(uint64_t *out3, void *stream) {
+    TMLA_REQUIRE(out3, "out3 is NULL");
+    TMLA_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(uint64_t), (cudaStream_t)stream));
+    selftest_arith_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((unsigned long long *)out3);
+    TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
 

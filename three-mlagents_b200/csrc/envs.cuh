@@ -28,8 +28,25 @@ __device__ __forceinline__ int cell3(uint32_t w, int slot) { return (int)((w >> 
 __device__ __forceinline__ uint32_t put3(int v, int slot) { return ((uint32_t)v & 7u) << (3 * slot); }
 __device__ __forceinline__ int iclamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// Correctly rounded x/3 and x/5 without the generic division sequence (Markstein: q = RN(x*r), e = x - c*q
+// exactly by FMA, q' = RN(q + e*r), r = RN(1/c)).  Checked against __fdiv_rn over the whole input range the
+// tasks can produce by tmla_selftest_arith (tests/test_envs_gpu.py::test_fast_arithmetic_is_exact).
+__device__ __forceinline__ float div3_rn(float x) {
+    const float r = 0.333333343267440796f;           // RN(1/3) = 0x3eaaaaab
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-3.0f, q, x), r, q);
+}
+__device__ __forceinline__ float div5_rn(float x) {
+    const float r = 0.200000002980232239f;           // RN(1/5) = 0x3e4ccccd
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-5.0f, q, x), r, q);
+}
+struct NoConsts {};
+
 // ---------------------------------------------------------------------------- basic (envs.py:17-84)
 struct BasicTask {
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 21, A = 3, MAX_STEPS = 50, NBUF = 1;
     typedef tmla_basic_state Wire;
     struct State { int pos, steps; float ep_ret; };
@@ -50,7 +67,7 @@ struct BasicTask {
 #pragma unroll
         for (int j = 0; j < D; ++j) o[j] = (j == s.pos) ? 1.0f : 0.0f;
     }
-    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
         s.pos = iclamp(s.pos + a - 1, 0, 20);            // envs.py:61-62
         s.steps += 1;
         // envs.py:65-72: -0.01 (+0.1 | +1.0) evaluated in double, rounded once to f32
@@ -100,6 +117,22 @@ __device__ __forceinline__ double u32_to_unit(uint32_t w) { return ((double)w + 
 struct Ball3DTask {
     static constexpr int D = 6, A = 5, MAX_STEPS = 200, NBUF = 3;
     typedef tmla_ball3d_state Wire;
+    // loop-invariant double constants pinned in registers (the asm barrier stops the compiler from
+    // re-loading them from the constant bank on every iteration of the fused rollout loop)
+    struct Consts { double max_tilt, tilt_delta, g, dt, s15, s13, s11, s9, s7, s5, s3; };
+    static __device__ __forceinline__ Consts load_consts() {
+        Consts c{kB3.max_tilt, kB3.tilt_delta, kB3.g, kB3.dt, kB3.s15, kB3.s13, kB3.s11, kB3.s9, kB3.s7, kB3.s5, kB3.s3};
+        asm volatile("" : "+d"(c.max_tilt), "+d"(c.tilt_delta), "+d"(c.g), "+d"(c.dt), "+d"(c.s15), "+d"(c.s13),
+                          "+d"(c.s11), "+d"(c.s9), "+d"(c.s7), "+d"(c.s5), "+d"(c.s3));
+        return c;
+    }
+    static __device__ __forceinline__ double sin_small_c(const Consts &c, double x) {
+        const double z = x * x;
+        double p = c.s15;
+        p = fma(p, z, c.s13); p = fma(p, z, c.s11); p = fma(p, z, c.s9);
+        p = fma(p, z, c.s7); p = fma(p, z, c.s5); p = fma(p, z, c.s3);
+        return fma(x * z, p, x);
+    }
     struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; };
     static __host__ __device__ size_t plane_bytes(int b) { return b == 0 ? sizeof(double2) : (b == 1 ? sizeof(float4) : sizeof(int2)); }
 
@@ -127,22 +160,24 @@ struct Ball3DTask {
     }
     // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
     // explicit (`__*_rn` never contracts into FMA) so the result does not depend on compiler flags.
-    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
-        // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0)
-        const double td = kB3.tilt_delta;
-        const double dx = (a < 2) ? ((a == 0) ? td : -td) : 0.0;
-        const double dz = (a == 2) ? td : ((a == 3) ? -td : 0.0);
-        double rx = __dadd_rn(s.rx, dx), rz = __dadd_rn(s.rz, dz);                  // ball3d.py:77
+    static __device__ __forceinline__ void step(const Consts &c, State &s, int a, float &reward, bool &term, bool &trunc) {
+        // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0).  The sign is
+        // XOR-ed into the high word; adding the 0.0 entries is the identity (rot is never -0.0) and is skipped.
+        const int td_hi = __double2hiint(c.tilt_delta), td_lo = __double2loint(c.tilt_delta);
+        const double sd = __hiloint2double(td_hi ^ (int)((unsigned)a << 31), td_lo);   // a odd -> -delta
+        double rx = s.rx, rz = s.rz;
+        if (a < 2) rx = __dadd_rn(rx, sd);                                          // ball3d.py:77
+        else if (a < 4) rz = __dadd_rn(rz, sd);
         if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back
             rx = (double)__double2float_rn(rx);
             rz = (double)__double2float_rn(rz);
         }
-        rx = clip_sym(rx, kB3.max_tilt);                                            // ball3d.py:78 (float64 from here)
-        rz = clip_sym(rz, kB3.max_tilt);
-        const double ax = __dmul_rn(kB3.g, sin_small(rx));                          // ball3d.py:81-82
-        const double az = __dmul_rn(kB3.g, sin_small(rz));
-        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, kB3.dt))); // ball3d.py:83-84
-        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, kB3.dt)));
+        rx = clip_sym(rx, c.max_tilt);                                              // ball3d.py:78 (float64 from here)
+        rz = clip_sym(rz, c.max_tilt);
+        const double ax = __dmul_rn(c.g, sin_small_c(c, rx));                       // ball3d.py:81-82
+        const double az = __dmul_rn(c.g, sin_small_c(c, rz));
+        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, c.dt))); // ball3d.py:83-84
+        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, c.dt)));
         vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
         vz = __fmul_rn(vz, 0.98f);
         const float px = __fadd_rn(s.px, __fmul_rn(vx, 0.02f));                     // ball3d.py:90
@@ -153,7 +188,7 @@ struct Ball3DTask {
         const bool timeout = s.steps >= 200;                                        // ball3d.py:99
         const bool done = off || timeout;
         const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(pz, pz))); // np.linalg.norm (f32)
-        float r = __fsub_rn(1.0f, __fdiv_rn(d, 3.0f));                              // ball3d.py:104
+        float r = __fsub_rn(1.0f, div3_rn(d));                                      // ball3d.py:104 (IEEE d/3)
         if (done) r = (timeout && !off) ? 1.0f : -1.0f;                             // ball3d.py:105-108
         reward = __fadd_rn(r, __fmul_rn(-0.02f, d));                                // ball3d.py:110-111
         trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
@@ -183,6 +218,8 @@ __device__ __forceinline__ void grid_delta(int a, int &dx, int &dy) {
 
 // ------------------------------------------------------------- gridworld (examples/gridworld.py:14-95)
 struct GridWorldTask {
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 100, NBUF = 1;
     typedef tmla_gridworld_state Wire;
     struct State { int ax, ay, gx, gy, rx, ry, type, steps; float ep_ret; };
@@ -212,7 +249,7 @@ struct GridWorldTask {
         o[2] = s.type ? 0.0f : 1.0f;
         o[3] = s.type ? 1.0f : 0.0f;
     }
-    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
         int dx, dy; grid_delta(a, dx, dy);
         s.ax = iclamp(s.ax + dx, 0, 4);                                  // gridworld.py:68-71
         s.ay = iclamp(s.ay + dy, 0, 4);
@@ -251,6 +288,8 @@ __device__ __constant__ uint32_t kPushRewardBits[18] = {
     0xbe851eb8u, 0xbe9eb852u, 0x3d23d70au, 0xbc23d70au, 0x3eae147bu, 0x3e947ae1u};
 
 struct PushTask {
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 120, NBUF = 1;
     typedef tmla_push_state Wire;
     struct State { int ax, ay, bx, by, goal_x, steps; float ep_ret; };
@@ -274,13 +313,13 @@ struct PushTask {
         w.goal_x = s.goal_x; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
     }
     static __device__ __forceinline__ void observe(const State &s, float *o) {   // push.py:53-59
-        // f32(k/5.0) == f32(k)/f32(5) for |k| <= 5 (checked in tests); IEEE division, not reciprocal-multiply
-        o[0] = __fdiv_rn((float)(s.bx - s.ax), 5.0f);
-        o[1] = __fdiv_rn((float)(s.by - s.ay), 5.0f);
-        o[2] = __fdiv_rn((float)(s.goal_x - s.bx), 5.0f);
-        o[3] = __fdiv_rn((float)(5 - s.by), 5.0f);
+        // f32(k/5.0) == f32(k)/f32(5) for |k| <= 5 (checked in tests); correctly rounded division
+        o[0] = div5_rn((float)(s.bx - s.ax));
+        o[1] = div5_rn((float)(s.by - s.ay));
+        o[2] = div5_rn((float)(s.goal_x - s.bx));
+        o[3] = div5_rn((float)(5 - s.by));
     }
-    static __device__ __forceinline__ void step(State &s, int a, float &reward, bool &term, bool &trunc) {
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
         int dx, dy; grid_delta(a, dx, dy);
         int nax = iclamp(s.ax + dx, 0, 5), nay = iclamp(s.ay + dy, 0, 5);          // push.py:63-65
         const int prev_bg = abs(s.goal_x - s.bx) + abs(5 - s.by);                  // push.py:70-75

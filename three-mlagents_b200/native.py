@@ -58,6 +58,7 @@ SIGNATURES = {
     "tmla_step_policy": (_i, [vp, vp, _i, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "tmla_advance_steps": (_i, [vp, u64]),
     "tmla_counter_add": (_i, [vp, u64, vp]),
+    "tmla_selftest_arith": (_i, [vp, vp]),
     "tmla_bootstrap_add": (_i, [vp, vp, vp, vp, f64, i32, vp]),
     "tmla_gae": (_i, [vp, vp, vp, vp, f64, f64, _i, i64, vp, vp, vp]),
     "tmla_permutation": (_i, [u64, u64, i64, _i, i64, vp, vp]),
