@@ -47,7 +47,7 @@ typedef struct tmla_env tmla_env;     /* opaque handle: packed SoA state of n en
 /* Wire format of tmla_get_state / tmla_set_state: array-of-structs, one per env, in DEVICE
  * memory (state injection for parity tests; the resident layout is packed SoA). */
 typedef struct { int32_t pos, steps; float ep_return; } tmla_basic_state;                                /* envs.py:46-47 */
-typedef struct { double rot[2]; float pos[2]; float vel[2]; int32_t steps; float ep_return; } tmla_ball3d_state; /* ball3d.py:49-58 */
+typedef struct { double rot[2]; float pos[2]; float vel[2]; int32_t steps; float ep_return; int32_t episode, pad_; } tmla_ball3d_state; /* ball3d.py:49-58; episode = auto-reset stream index */
 typedef struct { int32_t agent[2], green[2], red[2], goal_type, steps; float ep_return; } tmla_gridworld_state;  /* gridworld.py:46-51 */
 typedef struct { int32_t agent[2], box[2], goal_x, steps; float ep_return; } tmla_push_state;                    /* push.py:42-49 */
 

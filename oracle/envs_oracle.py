@@ -48,7 +48,7 @@ TASKS = {
 STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
     "basic": np.dtype([("pos", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "ball3d": np.dtype([("rot", "<f8", (2,)), ("pos", "<f4", (2,)), ("vel", "<f4", (2,)),
-                        ("steps", "<i4"), ("ep_return", "<f4")]),
+                        ("steps", "<i4"), ("ep_return", "<f4"), ("episode", "<i4"), ("pad_", "<i4")]),
     "gridworld": np.dtype([("agent", "<i4", (2,)), ("green", "<i4", (2,)), ("red", "<i4", (2,)),
                            ("goal_type", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
@@ -192,8 +192,10 @@ def transition(task, st, actions):
 
 
 # ---- Philox resets (this repo's stream layout; distributions follow the reference) -----------
-def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET):
-    """Fresh episode state for global env ids `env_ids` at global step index `k`."""
+def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET, episode=None):
+    """Fresh episode state for global env ids `env_ids` at global step index `k`.
+    ball3d auto-resets (tag TAG_RESET) are indexed by the env's own episode counter instead of `k`
+    (`episode` = index of the episode being started), see csrc/envs.cuh:Ball3DTask::draw."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     n = env_ids.shape[0]
     st = np.zeros(n, STATE_DTYPES[task])
@@ -201,8 +203,12 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET):
         st["pos"] = 10                                              # envs.py:21,55
     elif task == "ball3d":                                          # ball3d.py:49-57
         # lo + (hi-lo)*u like np.random.uniform, u = (w + 0.5) * 2^-32 carries 32 random bits
-        b0 = px.stream_block(seed, env_ids, k, tag, 0)
-        b1 = px.stream_block(seed, env_ids, k, tag, 1)
+        ctr = k
+        if tag == px.TAG_RESET:
+            ctr = np.asarray(episode, dtype=np.uint64)
+            st["episode"] = ctr.astype(np.int32)
+        b0 = px.stream_block(seed, env_ids, ctr, tag, 0)
+        b1 = px.stream_block(seed, env_ids, ctr, tag, 1)
         lo = -MAX_TILT * 0.5
         rot = np.stack([lo + MAX_TILT * px.u32_unit(b0[0]), lo + MAX_TILT * px.u32_unit(b0[1])], 1)
         pos = np.stack([-1.5 + 3.0 * px.u32_unit(b0[2]), -1.5 + 3.0 * px.u32_unit(b0[3])], 1)
@@ -278,7 +284,8 @@ class OracleVecEnv:
         }
         if done.any():
             idx = np.nonzero(done)[0]
-            fresh = draw_reset(self.task, self.seed, self.env_ids[idx], self.step_count, px.TAG_RESET)
+            nxt = (st["episode"][idx] + 1) & 0xFFFFFF if self.task == "ball3d" else None
+            fresh = draw_reset(self.task, self.seed, self.env_ids[idx], self.step_count, px.TAG_RESET, episode=nxt)
             st[idx] = fresh
             obs[idx] = observe(self.task, fresh)
         # SB3: infos[i]["TimeLimit.truncated"] = truncated and not terminated

@@ -32,7 +32,7 @@ def test_metadata_calls_match_reference_spaces():
 
     lib = native.lib
     assert lib.tmla_version() == 100
-    want = {"basic": (21, 3, 50, 12), "ball3d": (6, 5, 200, 40), "gridworld": (4, 5, 100, 36), "push": (4, 5, 120, 28)}
+    want = {"basic": (21, 3, 50, 12), "ball3d": (6, 5, 200, 48), "gridworld": (4, 5, 100, 36), "push": (4, 5, 120, 28)}
     for name, (d, a, m, sz) in want.items():
         t = lib.tmla_task_from_name(name.encode())
         assert t == native.TASK_IDS[name]

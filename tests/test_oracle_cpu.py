@@ -65,7 +65,7 @@ def test_reference_known_answer_basic():
 def test_reset_distribution_matches_reference(task):
     ref = np.load(_replay.GOLDEN + f"/{task}_resets.npz")
     n = 200_000
-    st = eo.draw_reset(task, 7, np.arange(n), 3)
+    st = eo.draw_reset(task, 7, np.arange(n), 3, episode=np.full(n, 3))
     if task == "ball3d":
         for key, half in (("rot", eo.MAX_TILT / 2), ("pos", 1.5), ("vel", 1.0)):
             x = st[key].astype(np.float64)

@@ -185,7 +185,7 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
                 if ((reinterpret_cast<uintptr_t>(obs_buf) & 15u) == 0) st_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
                 else { dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; }
             }
-            const int a = as.next(seed, env_id, k, Task::A, t == 0);
+            const int a = as.next(seed, env_id, step0, (uint32_t)t, Task::A);
             float r; bool term, trunc;
             Task::step(cst, s, a, r, term, trunc);
             s.ep_ret = __fadd_rn(s.ep_ret, r);
@@ -213,6 +213,88 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
         off += n;
     }
     if (active) Task::store(p.buf, i, s);
+}
+
+// Fast path of the fused rollout (what bench.py times): every block full (n % 64 == 0), all four buffers
+// present, 16-byte aligned rows, 32-bit element offsets.  Same arithmetic as the generic kernel above (the
+// tests compare them bit for bit) with the loop bookkeeping stripped down: shared memory is indexed directly
+// (no generic pointers), offsets are running 32-bit counters, and for tasks with an episode-indexed reset
+// stream (ball3d) the next initial state is drawn ahead of time every 16 steps (`Spare`), so the two Philox
+// blocks of a reset no longer sit inside a divergent branch that ~23 % of the warps enter on every step.
+template <class Task>
+__global__ void __launch_bounds__(kRollBlock)
+rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uint64_t step0, int T,
+                    float4 *__restrict__ obs4, int32_t *__restrict__ act_buf, float *__restrict__ rew_buf,
+                    uint8_t *__restrict__ done_buf) {
+    constexpr int D = Task::D, BLOCK = kRollBlock, NVEC = BLOCK * D / 4;
+    constexpr bool STAGED = (D != 4);
+    static_assert((BLOCK * D) % 4 == 0, "block rows must be whole float4s");
+    __shared__ __align__(16) float s_stage[STAGED ? 2 * BLOCK * D : 4];
+    const uint32_t tid = threadIdx.x, i = blockIdx.x * BLOCK + tid;
+    const uint64_t env_id = env_base + (uint64_t)i;
+    const typename Task::Consts cst = Task::load_consts();
+    typename Task::State s = Task::load(p.buf, i);
+    TmlaActionStream as;
+    as.seek(seed, env_id, step0, Task::A);
+    uint32_t off = i;                                   // t*n + i, element offset into the [T,n] planes
+    uint32_t voff = blockIdx.x * NVEC + tid;            // float4 offset of this thread's first vector in row t
+    const uint32_t rowvec = n / 4 * D;                  // float4 per row (n % 64 == 0)
+    uint32_t sb = 0;                                    // stage buffer toggle: 0 / BLOCK*D
+    [[maybe_unused]] typename Task::Spare sp;
+    [[maybe_unused]] bool have_spare = false;
+    for (int t = 0; t < T; ++t) {
+        if constexpr (Task::HAS_SPARE) {
+            if ((t & 15) == 0 && !have_spare) {         // off the critical path: refill consumed spares
+                sp = Task::draw(seed, env_id, Task::next_episode(s), TMLA_TAG_RESET);
+                have_spare = true;
+            }
+        }
+        float o[D];
+        Task::observe(s, o);                            // observation the action is taken on
+        if constexpr (STAGED) {
+            if constexpr (D % 2 == 0) {
+                float2 *s2 = reinterpret_cast<float2 *>(s_stage + sb + tid * D);
+#pragma unroll
+                for (int j = 0; j < D / 2; ++j) s2[j] = make_float2(o[2 * j], o[2 * j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < D; ++j) s_stage[sb + tid * D + j] = o[j];
+            }
+        } else {
+            st_stream_f4(obs4 + off, make_float4(o[0], o[1], o[2], o[3]));
+        }
+        const int a = as.next(seed, env_id, step0, (uint32_t)t, Task::A);
+        float r; bool term, trunc;
+        Task::step(cst, s, a, r, term, trunc);
+        s.ep_ret = __fadd_rn(s.ep_ret, r);
+        const bool d = term || trunc;
+        __stcs(act_buf + off, a);
+        __stcs(rew_buf + off, r);
+        __stcs(done_buf + off, (uint8_t)(d ? 1 : 0));
+        if (d) {
+            if constexpr (Task::HAS_SPARE) {
+                const uint32_t e = Task::next_episode(s);
+                if (!have_spare) sp = Task::draw(seed, env_id, e, TMLA_TAG_RESET);   // second reset inside one window
+                Task::begin_episode(s, sp, e);
+                have_spare = false;
+            } else {
+                Task::reset(s, seed, env_id, step0 + (uint64_t)t + 1, TMLA_TAG_RESET);
+            }
+        }
+        if constexpr (STAGED) {
+            __syncthreads();
+            const float4 *s4 = reinterpret_cast<const float4 *>(s_stage + sb);
+#pragma unroll
+            for (int v = 0; v < (NVEC + BLOCK - 1) / BLOCK; ++v) {
+                const int e = v * BLOCK + tid;
+                if ((v + 1) * BLOCK <= NVEC || e < NVEC) st_stream_f4(obs4 + voff + v * BLOCK, s4[e]);
+            }
+            sb ^= BLOCK * D;
+            voff += rowvec;
+        }
+        off += n;
+    }
+    Task::store(p.buf, i, s);
 }
 
 // ------------------------------------------------------------- policy-driven step (PPO rollout row)
@@ -542,8 +624,18 @@ int tmla_check_actions(tmla_env *h, void *stream) {
 int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, float *rew_buf, uint8_t *done_buf, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
     TMLA_REQUIRE(T > 0, "T must be positive");
-    TASK_SWITCH(h->task, (rollout_random_kernel<TaskT><<<(unsigned)ceil_div64(h->n, kRollBlock), kRollBlock, 0, (cudaStream_t)stream>>>(
-                             ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, T, obs_buf, act_buf, rew_buf, done_buf)));
+    const int D = kObsDim[h->task];
+    const bool fast = obs_buf && act_buf && rew_buf && done_buf && (h->n % kRollBlock == 0) &&
+                      ((reinterpret_cast<uintptr_t>(obs_buf) & 15u) == 0) && ((int64_t)T * h->n * D / 4 < ((int64_t)1 << 31));
+    const unsigned grid = (unsigned)ceil_div64(h->n, kRollBlock);
+    if (fast) {
+        TASK_SWITCH(h->task, (rollout_fast_kernel<TaskT><<<grid, kRollBlock, 0, (cudaStream_t)stream>>>(
+                                 ptrs_of(h), (uint32_t)h->n, h->seed, h->env_id_base, h->step_count, T,
+                                 reinterpret_cast<float4 *>(obs_buf), act_buf, rew_buf, done_buf)));
+    } else {
+        TASK_SWITCH(h->task, (rollout_random_kernel<TaskT><<<grid, kRollBlock, 0, (cudaStream_t)stream>>>(
+                                 ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, T, obs_buf, act_buf, rew_buf, done_buf)));
+    }
     TMLA_LAUNCH_CHECK();
     h->step_count += (uint64_t)T;
     return TMLA_OK;

@@ -42,9 +42,12 @@ __device__ __forceinline__ float div5_rn(float x) {
     return __fmaf_rn(__fmaf_rn(-5.0f, q, x), r, q);
 }
 struct NoConsts {};
+struct NoSpare {};
 
 // ---------------------------------------------------------------------------- basic (envs.py:17-84)
 struct BasicTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 21, A = 3, MAX_STEPS = 50, NBUF = 1;
@@ -89,6 +92,11 @@ struct Ball3DConst {
     double s15, s13, s11, s9, s7, s5, s3;            // sin Taylor coefficients -1/15! ... -1/3!
     double inv32;                                    // 2^-32
 };
+#define TMLA_B3_INIT { \
+    0x1.becde5da115a9p-2, 0x1.acee9f37bebd6p-5, 9.81, 0.02, -0x1.becde5da115a9p-3, \
+    -7.6471637318198164759e-13, 1.6059043836821614599e-10, -2.5052108385441718775e-08, 2.7557319223985890653e-06, \
+    -1.9841269841269841253e-04, 8.3333333333333332177e-03, -1.6666666666666665741e-01, 0x1p-32}
+__device__ const Ball3DConst gB3 = TMLA_B3_INIT;      // same values in global memory (register-pinned loads)
 __device__ __constant__ Ball3DConst kB3 = {
     0x1.becde5da115a9p-2, 0x1.acee9f37bebd6p-5, 9.81, 0.02, -0x1.becde5da115a9p-3,
     -7.6471637318198164759e-13, 1.6059043836821614599e-10, -2.5052108385441718775e-08, 2.7557319223985890653e-06,
@@ -120,11 +128,15 @@ struct Ball3DTask {
     // loop-invariant double constants pinned in registers (the asm barrier stops the compiler from
     // re-loading them from the constant bank on every iteration of the fused rollout loop)
     struct Consts { double max_tilt, tilt_delta, g, dt, s15, s13, s11, s9, s7, s5, s3; };
+    static __device__ __forceinline__ double pinned(const double *p) {   // a load ptxas cannot rematerialise
+        double v;
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        return v;
+    }
     static __device__ __forceinline__ Consts load_consts() {
-        Consts c{kB3.max_tilt, kB3.tilt_delta, kB3.g, kB3.dt, kB3.s15, kB3.s13, kB3.s11, kB3.s9, kB3.s7, kB3.s5, kB3.s3};
-        asm volatile("" : "+d"(c.max_tilt), "+d"(c.tilt_delta), "+d"(c.g), "+d"(c.dt), "+d"(c.s15), "+d"(c.s13),
-                          "+d"(c.s11), "+d"(c.s9), "+d"(c.s7), "+d"(c.s5), "+d"(c.s3));
-        return c;
+        const Ball3DConst *g = &gB3;
+        return Consts{pinned(&g->max_tilt), pinned(&g->tilt_delta), pinned(&g->g), pinned(&g->dt), pinned(&g->s15),
+                      pinned(&g->s13), pinned(&g->s11), pinned(&g->s9), pinned(&g->s7), pinned(&g->s5), pinned(&g->s3)};
     }
     static __device__ __forceinline__ double sin_small_c(const Consts &c, double x) {
         const double z = x * x;
@@ -133,26 +145,26 @@ struct Ball3DTask {
         p = fma(p, z, c.s7); p = fma(p, z, c.s5); p = fma(p, z, c.s3);
         return fma(x * z, p, x);
     }
-    struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; };
+    struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; uint32_t episode; };
     static __host__ __device__ size_t plane_bytes(int b) { return b == 0 ? sizeof(double2) : (b == 1 ? sizeof(float4) : sizeof(int2)); }
 
     static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
         const double2 r = reinterpret_cast<const double2 *>(buf[0])[i];     // 128-bit
         const float4 pv = reinterpret_cast<const float4 *>(buf[1])[i];      // 128-bit
         const int2 m = reinterpret_cast<const int2 *>(buf[2])[i];
-        return State{r.x, r.y, pv.x, pv.y, pv.z, pv.w, m.x, __int_as_float(m.y)};
+        return State{r.x, r.y, pv.x, pv.y, pv.z, pv.w, m.x & 255, __int_as_float(m.y), (uint32_t)m.x >> 8};   // steps | episode<<8
     }
     static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
         reinterpret_cast<double2 *>(buf[0])[i] = make_double2(s.rx, s.rz);
         reinterpret_cast<float4 *>(buf[1])[i] = make_float4(s.px, s.pz, s.vx, s.vz);
-        reinterpret_cast<int2 *>(buf[2])[i] = make_int2(s.steps, __float_as_int(s.ep_ret));
+        reinterpret_cast<int2 *>(buf[2])[i] = make_int2((int)((uint32_t)s.steps | (s.episode << 8)), __float_as_int(s.ep_ret));
     }
     static __device__ State from_wire(const Wire &w) {
-        return State{w.rot[0], w.rot[1], w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.steps, w.ep_return};
+        return State{w.rot[0], w.rot[1], w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.steps, w.ep_return, (uint32_t)w.episode & 0xFFFFFFu};
     }
     static __device__ Wire to_wire(const State &s) {
         Wire w; w.rot[0] = s.rx; w.rot[1] = s.rz; w.pos[0] = s.px; w.pos[1] = s.pz;
-        w.vel[0] = s.vx; w.vel[1] = s.vz; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+        w.vel[0] = s.vx; w.vel[1] = s.vz; w.steps = s.steps; w.ep_return = s.ep_ret; w.episode = (int32_t)s.episode; w.pad_ = 0; return w;
     }
     static __device__ __forceinline__ void observe(const State &s, float *o) {   // ball3d.py:61-72
         o[0] = __double2float_rn(s.rx); o[1] = __double2float_rn(s.rz);
@@ -169,6 +181,7 @@ struct Ball3DTask {
         if (a < 2) rx = __dadd_rn(rx, sd);                                          // ball3d.py:77
         else if (a < 4) rz = __dadd_rn(rz, sd);
         if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back
+            asm volatile("");     // keep this a branch: 4 conversions on the XU pipe for <1 % of the lanes
             rx = (double)__double2float_rn(rx);
             rz = (double)__double2float_rn(rz);
         }
@@ -194,19 +207,38 @@ struct Ball3DTask {
         trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
         term = done && !trunc;
     }
-    // np.random.uniform(lo, hi) = lo + (hi-lo)*u (ball3d.py:49-57), `.astype(np.float32)`; u carries 32
-    // random bits here (the reference's 53-bit double is rounded to 24 bits anyway).
-    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
-        const uint4 b0 = tmla_stream_block(seed, env_id, k, tag, 0);
-        const uint4 b1 = tmla_stream_block(seed, env_id, k, tag, 1);
+    // Initial state of an episode.  np.random.uniform(lo, hi) = lo + (hi-lo)*u (ball3d.py:49-57) then
+    // `.astype(np.float32)`; u carries 32 random bits (the reference's 53-bit double is rounded to 24 bits
+    // anyway).  AUTO-RESET draws are indexed by the env's own episode counter (ctr = episode index, tag
+    // TAG_RESET), not by the global step, so the fused rollout kernel can draw the next initial state ahead
+    // of time, off the critical path (`Spare`); VecEnv.reset() draws use (global step, TAG_RESET_ALL).
+    struct Spare { float rx, rz, px, pz, vx, vz; };
+    static constexpr bool HAS_SPARE = true;
+    static __device__ __forceinline__ Spare draw(uint64_t seed, uint64_t env_id, uint64_t counter, uint32_t tag) {
+        const uint4 b0 = tmla_stream_block(seed, env_id, counter, tag, 0);
+        const uint4 b1 = tmla_stream_block(seed, env_id, counter, tag, 1);
         const double mt = kB3.max_tilt, lo = kB3.half_lo;
-        s.rx = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.x))));
-        s.rz = (double)__double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.y))));
-        s.px = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.z))));
-        s.pz = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.w))));
-        s.vx = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.x))));
-        s.vz = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.y))));
-        s.steps = 0; s.ep_ret = 0.0f;
+        Spare sp;
+        sp.rx = __double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.x))));
+        sp.rz = __double2float_rn(__dadd_rn(lo, __dmul_rn(mt, u32_to_unit(b0.y))));
+        sp.px = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.z))));
+        sp.pz = __double2float_rn(__dadd_rn(-1.5, __dmul_rn(3.0, u32_to_unit(b0.w))));
+        sp.vx = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.x))));
+        sp.vz = __double2float_rn(__dadd_rn(-1.0, __dmul_rn(2.0, u32_to_unit(b1.y))));
+        return sp;
+    }
+    static __device__ __forceinline__ void begin_episode(State &s, const Spare &sp, uint32_t episode) {
+        s.rx = (double)sp.rx; s.rz = (double)sp.rz; s.px = sp.px; s.pz = sp.pz; s.vx = sp.vx; s.vz = sp.vz;
+        s.steps = 0; s.ep_ret = 0.0f; s.episode = episode;
+    }
+    static __device__ __forceinline__ uint32_t next_episode(const State &s) { return (s.episode + 1u) & 0xFFFFFFu; }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        if (tag == TMLA_TAG_RESET) {
+            const uint32_t e = next_episode(s);
+            begin_episode(s, draw(seed, env_id, e, TMLA_TAG_RESET), e);
+        } else {
+            begin_episode(s, draw(seed, env_id, k, tag), 0u);
+        }
     }
 };
 
@@ -218,6 +250,8 @@ __device__ __forceinline__ void grid_delta(int a, int &dx, int &dy) {
 
 // ------------------------------------------------------------- gridworld (examples/gridworld.py:14-95)
 struct GridWorldTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 100, NBUF = 1;
@@ -288,6 +322,8 @@ __device__ __constant__ uint32_t kPushRewardBits[18] = {
     0xbe851eb8u, 0xbe9eb852u, 0x3d23d70au, 0xbc23d70au, 0x3eae147bu, 0x3e947ae1u};
 
 struct PushTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 120, NBUF = 1;

@@ -65,12 +65,13 @@ struct TmlaActionStream {
         frac = word_of(blk, (uint32_t)(k & 15u) >> 2);
         for (uint32_t d = 0; d < (uint32_t)(k & 3u); ++d) frac = (uint32_t)((uint64_t)frac * n_actions);
     }
-    // action of step k (k must advance by one per call after seek)
-    __device__ __forceinline__ int next(uint64_t seed, uint64_t env_id, uint64_t k, uint32_t n_actions, bool first) {
-        const uint32_t j = (uint32_t)(k & 15u);
-        if (!first) {
-            if (j == 0) blk = tmla_stream_block(seed, env_id, k >> 4, TMLA_TAG_ACTION, 0);
-            if ((j & 3u) == 0) frac = word_of(blk, j >> 2);
+    // action of step k = step0 + t (t must advance by one per call after seek(step0)).  Only the low bits of
+    // k are touched on the common path; the 64-bit counter is formed inside the 1-in-16 Philox branch.
+    __device__ __forceinline__ int next(uint64_t seed, uint64_t env_id, uint64_t step0, uint32_t t, uint32_t n_actions) {
+        const uint32_t j = ((uint32_t)step0 + t) & 15u;
+        if ((j & 3u) == 0) {
+            if (j == 0 && t != 0) blk = tmla_stream_block(seed, env_id, (step0 + t) >> 4, TMLA_TAG_ACTION, 0);
+            frac = word_of(blk, j >> 2);
         }
         const uint64_t p = (uint64_t)frac * n_actions;
         frac = (uint32_t)p;

@@ -24,7 +24,7 @@ from .spaces import spaces_for
 STATE_DTYPES = {   # wire structs of include/tmla.h
     "basic": np.dtype([("pos", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "ball3d": np.dtype([("rot", "<f8", (2,)), ("pos", "<f4", (2,)), ("vel", "<f4", (2,)),
-                        ("steps", "<i4"), ("ep_return", "<f4")]),
+                        ("steps", "<i4"), ("ep_return", "<f4"), ("episode", "<i4"), ("pad_", "<i4")]),
     "gridworld": np.dtype([("agent", "<i4", (2,)), ("green", "<i4", (2,)), ("red", "<i4", (2,)),
                            ("goal_type", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
