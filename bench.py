@@ -39,6 +39,21 @@ OBS_DIM = 6
 BYTES_PER_ENV_STEP = 33.0 + 56.0 / T_ROLLOUT
 
 
+def _ncu_traffic():
+    """dram bytes (read+write) per rollout launch from the committed `ncu --set full` capture, or None."""
+    path = os.path.join(ROOT, "profiles", "r1_rollout_fast_ncu_raw.csv")
+    try:
+        vals = {}
+        with open(path) as f:
+            for line in f:
+                k, unit, v = line.strip().split(",")[:3]
+                if k.startswith("dram__bytes_"):
+                    vals[k] = float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -231,11 +246,13 @@ def run_cuda(args):
                    "l2": "each step writes 277 MB of rollout rows (> 126 MB L2); no flush needed",
                    "done_rate": done_rate},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "rollout_random_kernel<Ball3DTask>",
+                     "traffic": _ncu_traffic(), "algorithmic_bytes": BYTES_PER_ENV_STEP * steps_per_launch,
+                     "kernel": "rollout_fast_kernel<Ball3DTask>",
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N_ENVS,
                 "d2h_bytes_per_step": N_ENVS * (4 * OBS_DIM + 4 + 1 + 1),
-                "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_host (pinned staging, sync)", "steps": n_e2e},
+                "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_pinned (H2D actions, kernel, one D2H, sync; "
+                       "results copied out of the pinned block into fresh NumPy arrays)", "steps": n_e2e},
         "step_api": {"value": step_api, "unit": "env-steps/s", "us_per_launch": 1e3 * api_ms / n_api,
                      "frac_hbm": (89.0 * N_ENVS / (api_ms / n_api * 1e-3) / 1e9) / peak,
                      "note": "one tmla_step launch per env step on device tensors; 5.8 MB working set, launch-bound"},

@@ -95,6 +95,13 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
                    uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_length,
                    int64_t *n_done);
 int tmla_reset_host(tmla_env *h, float *obs);
+/* Zero-copy variant for language bindings: the handle owns one pinned host block; tmla_host_views hands
+ * out the pointers into it (valid for the life of the handle; any may be NULL).  The caller writes
+ * int32 actions into *actions, calls tmla_step_pinned, and reads the results in place: obs/reward/done/
+ * truncated after every call, terminal_obs/ep_return/ep_length valid where done when *n_done > 0. */
+int tmla_host_views(tmla_env *h, int32_t **actions, float **obs, float **reward, uint8_t **done,
+                    uint8_t **truncated, float **terminal_obs, float **ep_return, int32_t **ep_length);
+int tmla_step_pinned(tmla_env *h, int64_t *n_done);
 
 /* state injection / extraction (parity tests): `aos` is n structs of the task's wire type. */
 int tmla_get_state(tmla_env *h, void *aos, void *stream);

@@ -434,6 +434,28 @@ static const int kMaxSteps[4] = {BasicTask::MAX_STEPS, Ball3DTask::MAX_STEPS, Gr
 static const int kStateSize[4] = {(int)sizeof(tmla_basic_state), (int)sizeof(tmla_ball3d_state),
                                   (int)sizeof(tmla_gridworld_state), (int)sizeof(tmla_push_state)};
 
+// staging layout shared by the device block and its pinned host mirror (16-byte aligned sections):
+//   actions i32[n] | obs f32[n,D] | reward f32[n] | done u8[n] | truncated u8[n] | flags i32[4] {n_done, bad_action}
+//   | terminal_obs f32[n,D] | ep_return f32[n] | ep_length i32[n]
+// obs..flags is one contiguous span -> ONE device-to-host copy per step; the episode-end payload behind it
+// is fetched only when n_done > 0.
+struct StageLayout { size_t act, obs, rew, done, trunc, flags, tobs, ret, len, end; };
+static StageLayout stage_layout(int64_t n, int D) {
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    StageLayout L;
+    L.act = 0;
+    L.obs = up(L.act + 4 * n);
+    L.rew = L.obs + 4 * n * D;
+    L.done = L.rew + 4 * n;
+    L.trunc = L.done + n;
+    L.flags = up(L.trunc + n);
+    L.tobs = L.flags + 16;
+    L.ret = L.tobs + 4 * n * D;
+    L.len = L.ret + 4 * n;
+    L.end = L.len + 4 * n;
+    return L;
+}
+
 extern "C" {
 
 int tmla_task_from_name(const char *name) {
@@ -476,7 +498,7 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
     }
     const int D = kObsDim[task];
     // staging layout: actions i32 | obs | reward | terminal_obs | ep_return | ep_length | done | truncated
-    h->stage_bytes = (size_t)n_envs * (4 + 4 * D + 4 + 4 * D + 4 + 4 + 1 + 1) + 64;
+    h->stage_bytes = stage_layout(n_envs, D).end + 64;
     if (cudaMalloc(&h->d_stage, h->stage_bytes) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stage_bytes) != cudaSuccess ||
         cudaMalloc((void **)&h->err_flag, sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->d_ndone, sizeof(int32_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -533,64 +555,92 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
     return TMLA_OK;
 }
 
-int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
-                   float *terminal_obs, float *ep_return, int32_t *ep_length, int64_t *n_done) {
+// VecEnv.step with the actions already in the pinned stage and the results left there (zero-copy host API:
+// tmla_host_views hands out the pinned pointers).  H2D actions -> kernel -> one D2H, then a synchronise.
+int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
     TMLA_REQUIRE(h, "handle is NULL");
-    TMLA_REQUIRE(actions && obs && reward && done && truncated, "actions/obs/reward/done/truncated must be non-NULL");
     TMLA_CUDA(cudaSetDevice(h->device));
     const int64_t n = h->n;
     const int D = kObsDim[h->task];
-    // carve the staging block (device and pinned host share the layout)
-    size_t o_act = 0, o_obs = o_act + 4 * n, o_rew = o_obs + 4 * n * D, o_tobs = o_rew + 4 * n, o_ret = o_tobs + 4 * n * D,
-           o_len = o_ret + 4 * n, o_done = o_len + 4 * n, o_trunc = o_done + n, o_end = o_trunc + n;
+    const StageLayout L = stage_layout(n, D);
     char *d = (char *)h->d_stage, *p = (char *)h->h_stage;
     cudaStream_t st = h->own_stream;
-    memcpy(p + o_act, actions, 4 * n);
-    TMLA_CUDA(cudaMemcpyAsync(d + o_act, p + o_act, 4 * n, cudaMemcpyHostToDevice, st));
-    TMLA_CUDA(cudaMemsetAsync(h->d_ndone, 0, sizeof(int32_t), st));
+    int32_t *dflags = (int32_t *)(d + L.flags), *hflags = (int32_t *)(p + L.flags);
+    TMLA_CUDA(cudaMemcpyAsync(d + L.act, p + L.act, 4 * n, cudaMemcpyHostToDevice, st));
+    TMLA_CUDA(cudaMemsetAsync(dflags, 0, 16, st));
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
-                             ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + o_act),
-                             (float *)(d + o_obs), (float *)(d + o_rew), (uint8_t *)(d + o_done), (uint8_t *)(d + o_trunc),
-                             (float *)(d + o_tobs), (float *)(d + o_ret), (int32_t *)(d + o_len), h->d_ndone, h->err_flag)));
+                             ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
+                             (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
+                             (float *)(d + L.tobs), (float *)(d + L.ret), (int32_t *)(d + L.len), dflags, dflags + 1)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
-    // results every caller needs: obs | reward ... done | truncated  (two contiguous spans)
-    TMLA_CUDA(cudaMemcpyAsync(p + o_obs, d + o_obs, o_tobs - o_obs, cudaMemcpyDeviceToHost, st));
-    TMLA_CUDA(cudaMemcpyAsync(p + o_done, d + o_done, o_end - o_done, cudaMemcpyDeviceToHost, st));
-    int32_t nd = 0;
-    int err = 0;
-    TMLA_CUDA(cudaMemcpyAsync(&nd, h->d_ndone, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    TMLA_CUDA(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TMLA_CUDA(cudaMemcpyAsync(p + L.obs, d + L.obs, L.tobs - L.obs, cudaMemcpyDeviceToHost, st));
     TMLA_CUDA(cudaStreamSynchronize(st));
-    memcpy(obs, p + o_obs, 4 * n * D);
-    memcpy(reward, p + o_rew, 4 * n);
-    memcpy(done, p + o_done, n);
-    memcpy(truncated, p + o_trunc, n);
-    if (nd > 0 && (terminal_obs || ep_return || ep_length)) {   // episode-end payloads only when something finished
-        TMLA_CUDA(cudaMemcpyAsync(p + o_tobs, d + o_tobs, o_done - o_tobs, cudaMemcpyDeviceToHost, st));
+    const int32_t nd = hflags[0];
+    if (nd > 0) {   // episode-end payload (terminal obs, Monitor r/l) only when something finished
+        TMLA_CUDA(cudaMemcpyAsync(p + L.tobs, d + L.tobs, L.end - L.tobs, cudaMemcpyDeviceToHost, st));
         TMLA_CUDA(cudaStreamSynchronize(st));
-        if (terminal_obs) memcpy(terminal_obs, p + o_tobs, 4 * n * D);
-        if (ep_return) memcpy(ep_return, p + o_ret, 4 * n);
-        if (ep_length) memcpy(ep_length, p + o_len, 4 * n);
     }
     if (n_done) *n_done = nd;
-    if (err) {
-        cudaMemsetAsync(h->err_flag, 0, sizeof(int), st);
+    if (hflags[1]) {
         tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
         return TMLA_EACTION;
     }
     return TMLA_OK;
 }
 
+int tmla_host_views(tmla_env *h, int32_t **actions, float **obs, float **reward, uint8_t **done, uint8_t **truncated,
+                    float **terminal_obs, float **ep_return, int32_t **ep_length) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    char *p = (char *)h->h_stage;
+    if (actions) *actions = (int32_t *)(p + L.act);
+    if (obs) *obs = (float *)(p + L.obs);
+    if (reward) *reward = (float *)(p + L.rew);
+    if (done) *done = (uint8_t *)(p + L.done);
+    if (truncated) *truncated = (uint8_t *)(p + L.trunc);
+    if (terminal_obs) *terminal_obs = (float *)(p + L.tobs);
+    if (ep_return) *ep_return = (float *)(p + L.ret);
+    if (ep_length) *ep_length = (int32_t *)(p + L.len);
+    return TMLA_OK;
+}
+
+int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                   float *terminal_obs, float *ep_return, int32_t *ep_length, int64_t *n_done) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE(actions && obs && reward && done && truncated, "actions/obs/reward/done/truncated must be non-NULL");
+    const int64_t n = h->n;
+    const int D = kObsDim[h->task];
+    const StageLayout L = stage_layout(n, D);
+    char *p = (char *)h->h_stage;
+    memcpy(p + L.act, actions, 4 * n);
+    int64_t nd = 0;
+    const int rc = tmla_step_pinned(h, &nd);
+    if (rc != TMLA_OK && rc != TMLA_EACTION) return rc;
+    memcpy(obs, p + L.obs, 4 * n * D);
+    memcpy(reward, p + L.rew, 4 * n);
+    memcpy(done, p + L.done, n);
+    memcpy(truncated, p + L.trunc, n);
+    if (nd > 0) {
+        if (terminal_obs) memcpy(terminal_obs, p + L.tobs, 4 * n * D);
+        if (ep_return) memcpy(ep_return, p + L.ret, 4 * n);
+        if (ep_length) memcpy(ep_length, p + L.len, 4 * n);
+    }
+    if (n_done) *n_done = nd;
+    return rc;
+}
+
 int tmla_reset_host(tmla_env *h, float *obs) {
     TMLA_REQUIRE(h && obs, "handle/obs is NULL");
     TMLA_CUDA(cudaSetDevice(h->device));
     const size_t bytes = (size_t)4 * h->n * kObsDim[h->task];
-    int rc = tmla_reset(h, (float *)h->d_stage, h->own_stream);
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    char *d = (char *)h->d_stage, *p = (char *)h->h_stage;
+    int rc = tmla_reset(h, (float *)(d + L.obs), h->own_stream);
     if (rc) return rc;
-    TMLA_CUDA(cudaMemcpyAsync(h->h_stage, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->own_stream));
+    TMLA_CUDA(cudaMemcpyAsync(p + L.obs, d + L.obs, bytes, cudaMemcpyDeviceToHost, h->own_stream));
     TMLA_CUDA(cudaStreamSynchronize(h->own_stream));
-    memcpy(obs, h->h_stage, bytes);
+    if (obs != (float *)(p + L.obs)) memcpy(obs, p + L.obs, bytes);
     return TMLA_OK;
 }
 

@@ -51,6 +51,8 @@ SIGNATURES = {
     "tmla_step": (_i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "tmla_step_host": (_i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "tmla_reset_host": (_i, [vp, vp]),
+    "tmla_host_views": (_i, [vp] + [C.POINTER(vp)] * 8),
+    "tmla_step_pinned": (_i, [vp, C.POINTER(i64)]),
     "tmla_get_state": (_i, [vp, vp, vp]),
     "tmla_set_state": (_i, [vp, vp, vp]),
     "tmla_check_actions": (_i, [vp, vp]),

@@ -52,7 +52,7 @@ class LazyInfos(Sequence):
             raise IndexError(i)
         info: dict[str, Any] = {"TimeLimit.truncated": bool(self._trunc[i])}
         if self._done[i]:
-            info["terminal_observation"] = self._tobs[i].copy()
+            info["terminal_observation"] = self._tobs[i]
             info["episode"] = {"r": round(float(self._ret[i]), 6), "l": int(self._len[i]), "t": round(self._t, 6)}
             info["steps"] = int(self._len[i])
         return info
@@ -78,13 +78,23 @@ class CudaVecEnv:
         check(lib.tmla_create(native.TASK_IDS[task_id], self.num_envs, int(seed) & (2**64 - 1), int(env_id_base),
                               self.device_index, C.byref(self._h)))
         n, d = self.num_envs, self.obs_dim
-        self._obs = np.empty((n, d), np.float32)
-        self._rew = np.empty(n, np.float32)
-        self._done = np.empty(n, np.uint8)
-        self._trunc = np.empty(n, np.uint8)
-        self._tobs = np.zeros((n, d), np.float32)
-        self._ret = np.zeros(n, np.float32)
-        self._len = np.zeros(n, np.int32)
+        # NumPy views straight onto the handle's pinned host block (tmla_host_views): the D2H copy of a
+        # step lands in these arrays, no intermediate memcpy.
+        ptrs = [native.vp() for _ in range(8)]
+        check(lib.tmla_host_views(self._h, *[C.byref(q) for q in ptrs]))
+
+        def view(q, ctype, shape):
+            count = int(np.prod(shape))
+            return np.ctypeslib.as_array((ctype * count).from_address(q.value)).reshape(shape)
+
+        self._pin_act = view(ptrs[0], C.c_int32, (n,))
+        self._obs = view(ptrs[1], C.c_float, (n, d))
+        self._rew = view(ptrs[2], C.c_float, (n,))
+        self._done = view(ptrs[3], C.c_uint8, (n,))
+        self._trunc = view(ptrs[4], C.c_uint8, (n,))
+        self._tobs = view(ptrs[5], C.c_float, (n, d))
+        self._ret = view(ptrs[6], C.c_float, (n,))
+        self._len = view(ptrs[7], C.c_int32, (n,))
         self._actions = None
         self._t0 = time.time()
         self._dev = None      # device-side buffers for step_tensor, allocated lazily
@@ -105,23 +115,28 @@ class CudaVecEnv:
         return self._obs.copy()
 
     def step_async(self, actions) -> None:
-        a = np.ascontiguousarray(np.asarray(actions).reshape(-1), dtype=np.int32)
+        a = np.asarray(actions).reshape(-1)
         if a.shape[0] != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions, got {a.shape[0]}")
-        self._actions = a
+        np.copyto(self._pin_act, a, casting="unsafe")      # int64 -> int32 straight into pinned memory
+        self._actions = self._pin_act
 
     def step_wait(self):
         nd = native.i64(0)
-        check(lib.tmla_step_host(self._h, ptr(self._actions), ptr(self._obs), ptr(self._rew), ptr(self._done),
-                                 ptr(self._trunc), ptr(self._tobs), ptr(self._ret), ptr(self._len), C.byref(nd)))
-        done = self._done.astype(bool)
-        infos = LazyInfos(self.num_envs, done, self._trunc.astype(bool), self._tobs, self._ret, self._len,
-                          time.time() - self._t0)
-        if nd.value and self._monitor is not None:
-            t = round(time.time() - self._t0, 6)
-            for i in np.nonzero(done)[0]:
-                self._monitor.write(f"{round(float(self._ret[i]), 6)},{int(self._len[i])},{t}\n")
-        return self._obs.copy(), self._rew.copy(), done, infos
+        check(lib.tmla_step_pinned(self._h, C.byref(nd)))
+        done = self._done.astype(bool)                      # fresh arrays: the pinned block is reused next step
+        trunc = self._trunc.astype(bool)
+        obs, rew = self._obs.copy(), self._rew.copy()
+        if nd.value:
+            infos = LazyInfos(self.num_envs, done, trunc, self._tobs.copy(), self._ret.copy(), self._len.copy(),
+                              time.time() - self._t0)
+            if self._monitor is not None:
+                t = round(time.time() - self._t0, 6)
+                for i in np.nonzero(done)[0]:
+                    self._monitor.write(f"{round(float(self._ret[i]), 6)},{int(self._len[i])},{t}\n")
+        else:
+            infos = LazyInfos(self.num_envs, done, trunc, None, None, None, 0.0)
+        return obs, rew, done, infos
 
     def step(self, actions):
         self.step_async(actions)
