@@ -194,6 +194,19 @@ int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_
                    float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                    float *norm_out, void *stream);
 
+/* ---- tensor-core building blocks (csrc/mlp_tc.cu: tcgen05.mma, TMEM accumulators), bf16 row-major device
+ * buffers.  Used by the bf16 MLP path; exported so the parity tests can exercise them in isolation.
+ *   tmla_tc_linear: out[M,256] = tanh(A . W^T + bias)            (epi 0; layer-2 forward of a tower)
+ *                   out[M,256] = (A . W^T) * (1 - aux^2)          (epi 1; dgrad through tanh, W = W2^T)
+ *                   A, aux, out bf16 [M,256]; W bf16 [256 out][256 in]; bias fp32[256]
+ *   tmla_tc_wgrad : G[256,256] (fp32, accumulated) += X[rows,256]^T . Y[rows,256]
+ *   tmla_f32_to_bf16: elementwise conversion;  tmla_tc_debug: descriptor-field experiment switch (tests only) */
+int tmla_tc_linear(int epi, const void *A, const void *W, const float *bias, const void *aux, void *out, int64_t M,
+                   const int32_t *rows_dev, void *stream);
+int tmla_tc_wgrad(const void *X, const void *Y, float *G, int64_t rows, void *stream);
+int tmla_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream);
+int tmla_tc_debug(int swap_lbo_sbo);
+
 #ifdef __cplusplus
 }
 #endif

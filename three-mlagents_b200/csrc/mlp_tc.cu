@@ -1,0 +1,391 @@
+// mlp_tc.cu — the 256x256 hidden-layer GEMMs of the policy/value MLP on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM), bf16 operands, fp32 accumulation.  sm_100a only.
+//
+// Replaces the three [rows x 256 x 256] matrix products per tower that SB3's ActorCriticPolicy / autograd
+// execute as torch CPU GEMMs (policy built at backend/mlagents/training.py:150, net_arch training.py:363-365):
+//     forward   H2  = tanh(H1 . W2^T + b2)                 tc_linear_kernel<EPI_BIAS_TANH>
+//     dgrad     dZ1 = (dZ2 . W2) * (1 - H1^2)              tc_linear_kernel<EPI_DTANH>   (with W2^T as weight)
+//     wgrad     dW2 = dZ2^T . H1   (reduction over rows)   tc_wgrad_kernel
+// The K=obs_dim first layer and the N<=5 heads stay on CUDA cores (mlp_kernels.cu, bf16 activation variants).
+//
+// Design (no TMA, no swizzle — operands are staged by the CTA's own threads):
+//   * Operand tiles live in shared memory in the canonical K-major SWIZZLE_NONE layout of the UMMA shared
+//     memory descriptor: 8-row x 16-byte "core matrices" stored as 128 contiguous bytes; LBO = byte stride
+//     between core matrices adjacent in K, SBO = byte stride between 8-row groups
+//     (element (r,k) at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2).
+//   * One thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16 per instruction) and
+//     tcgen05.commit -> mbarrier; everybody waits on the mbarrier, then the 8 warps drain TMEM with
+//     tcgen05.ld.32x32b.x16 (thread = accumulator row) and apply the fused epilogue.
+//   * The 256x256 weight stays resident in shared memory for the whole persistent CTA (one CTA per SM).
+//   * wgrad transposes its operands while staging them (8x8 bf16 blocks through PRMT) so that the same
+//     K-major descriptors apply, accumulates 256x256 fp32 in all 512 TMEM columns across the CTA's row
+//     chunks, and finishes with red.global.add.f32 into the flat gradient (split-K over CTAs).
+#include <algorithm>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+static constexpr int H = 256;
+
+// ------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *holder) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {   // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {   // 32 lanes x 16 consecutive columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | base_offset=0 | lbo_mode=0 | layout_type=SWIZZLE_NONE(0) [61,64)
+__device__ int g_desc_swap = 0;      // debug: exchange the LBO/SBO fields (tmla_tc_debug)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    if (g_desc_swap) { const uint32_t t = lbo; lbo = sbo; sbo = t; }
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4) | a=bf16 (1<<7) | b=bf16 (1<<10) |
+// K-major A and B (bits 15,16 = 0) | N>>3 at [17,23) | M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// -------------------------------------------------------------------- out = epi(A[M,256] . W[256,256]^T)
+enum { EPI_BIAS_TANH = 0, EPI_DTANH = 1 };
+
+static constexpr uint32_t kLBO = 128;                    // K-adjacent core matrices are contiguous
+static constexpr uint32_t kSBO = (H / 8) * kLBO;         // 4096 B per 8-row group (K = 256)
+static constexpr uint32_t kWBytes = (H / 8) * kSBO;      // 131072: 256 rows
+static constexpr uint32_t kABytes = (128 / 8) * kSBO;    // 65536: 128 rows
+static constexpr uint32_t kLinearSmem = kWBytes + kABytes + 64;
+
+// stage `nrows` (<= R) rows of a row-major bf16 [*,256] matrix into the K-major core-matrix layout.
+// chunk q (16 bytes): r = q%8 + 8*(q/(8*32)), kb = (q/8)%32  -> a quarter-warp writes 128 contiguous bytes.
+template <int R>
+__device__ __forceinline__ void stage_rows(uint8_t *dst, const __nv_bfloat16 *__restrict__ src, int64_t row0, int64_t nvalid) {
+    constexpr int KB = H / 8;
+    for (int q = threadIdx.x; q < R * KB; q += blockDim.x) {
+        const int rin = q & 7, kb = (q >> 3) & (KB - 1), rg = q >> 8;
+        const int r = rg * 8 + rin;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < nvalid) v = __ldg(reinterpret_cast<const uint4 *>(src + (row0 + r) * H + kb * 8));
+        *reinterpret_cast<uint4 *>(dst + rg * kSBO + kb * kLBO + rin * 16) = v;
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 1)
+tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ W, const float *__restrict__ bias,
+                 const __nv_bfloat16 *__restrict__ aux, __nv_bfloat16 *__restrict__ out, int64_t M, const int32_t *rows_dev) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *Ws = smem, *As = smem + kWBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kWBytes + kABytes);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kWBytes + kABytes + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (rows_dev) M = min(M, (int64_t)*rows_dev);
+    const int64_t ntiles = (M + 127) / 128;
+    if ((int64_t)blockIdx.x >= ntiles) return;            // whole CTA exits before any allocation
+
+    if (warp == 0) tmem_alloc<256>(tmem_holder);
+    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    stage_rows<H>(Ws, W, 0, H);                           // resident weight: W[n][k], K-major
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t idesc = make_idesc(128, 256);
+    const uint32_t a_addr = smem_u32(As), w_addr = smem_u32(Ws);
+    uint32_t phase = 0;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * 128;
+        stage_rows<128>(As, A, row0, M - row0);
+        fence_proxy_async();                              // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < H / 16; ++kk)           // 16 MMAs of K=16: two core matrices along K each
+                umma_bf16(tmem_base, make_desc(a_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc(w_addr + kk * 2 * kLBO, kLBO, kSBO),
+                          idesc, kk > 0 ? 1u : 0u);
+            umma_commit(bar);                             // arrives on `bar` when all MMAs above have finished
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // epilogue: warp w drains lanes 32*(w%4).. of columns (w/4)*128 .. +127; thread = one output row
+        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        const int colbase = (warp >> 2) * 128;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(taddr + c0, acc);
+            if (row < M) {
+                const int col = colbase + c0;
+                uint32_t o[8];
+                if (EPI == EPI_BIAS_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = pack_bf16(tanh_fast(__uint_as_float(acc[2 * j]) + __ldg(bias + col + 2 * j)),
+                                         tanh_fast(__uint_as_float(acc[2 * j + 1]) + __ldg(bias + col + 2 * j + 1)));
+                } else {
+                    const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(aux + row * H + col));
+                    const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(aux + row * H + col + 8));
+                    const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = bf16_lo(hw[j]), b = bf16_hi(hw[j]);
+                        o[j] = pack_bf16(__uint_as_float(acc[2 * j]) * (1.0f - a * a), __uint_as_float(acc[2 * j + 1]) * (1.0f - b * b));
+                    }
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(out + row * H + col);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                  // TMEM drained + As free before the next tile
+    }
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+// --------------------------------------------------------- G[256,256] += X[rows,256]^T . Y[rows,256]
+static constexpr uint32_t kgLBO = 128;
+static constexpr uint32_t kgSBO = 16 * kgLBO + 16;       // 2064: 16 k-blocks per 8-row group + 16 B pad (bank spread)
+static constexpr uint32_t kgTile = 32 * kgSBO;           // 66048 B: 256 rows x K=128
+static constexpr uint32_t kWgradSmem = 2 * kgTile + 64;
+
+// transpose-stage a [128 rows(k) x 256 cols(m)] row-major bf16 chunk into the K-major tile [256 (m) x 128 (k)]:
+// thread handles 8x8 blocks: 8 LDG.128 (coalesced: a warp reads 512 contiguous bytes per row), 32 PRMT, 8 STS.128
+__device__ __forceinline__ void stage_transposed(uint8_t *dst, const __nv_bfloat16 *__restrict__ src, int64_t row0, int64_t nvalid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int kb = it * 8 + warp;                     // 8-row block of the chunk (k direction)
+        const int mg = lane;                              // 8-column group (m direction)
+        uint4 in[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = kb * 8 + i;
+            in[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(src + (row0 + r) * H + mg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint8_t *base = dst + mg * kgSBO + kb * kgLBO;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                     // output row c = column mg*8+c over the 8 source rows
+            const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+            uint32_t w[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t a = (&in[2 * p].x)[c >> 1], b = (&in[2 * p + 1].x)[c >> 1];
+                w[p] = __byte_perm(a, b, sel);
+            }
+            *reinterpret_cast<uint4 *>(base + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ Y, float *__restrict__ G, int64_t rows) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *Xs = smem, *Ys = smem + kgTile;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * kgTile);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + 2 * kgTile + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t nchunks = (rows + 127) / 128;
+    if ((int64_t)blockIdx.x >= nchunks) return;
+
+    if (warp == 0) tmem_alloc<512>(tmem_holder);
+    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t idesc = make_idesc(128, 256);
+    const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
+    uint32_t phase = 0, first = 1;
+
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t row0 = chunk * 128;
+        stage_transposed(Xs, X, row0, rows - row0);
+        stage_transposed(Ys, Y, row0, rows - row0);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)                // output rows 0..127 / 128..255 -> TMEM columns 0..255 / 256..511
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(tmem_base + mh * 256, make_desc(x_addr + mh * 16 * kgSBO + kk * 2 * kgLBO, kgLBO, kgSBO),
+                              make_desc(y_addr + kk * 2 * kgLBO, kgLBO, kgSBO), idesc, (first && kk == 0) ? 0u : 1u);
+            umma_commit(bar);
+        }
+        first = 0;
+        mbar_wait(bar, phase);                            // operands may be overwritten once the MMAs are done
+        phase ^= 1u;
+        tc_fence_after();
+        __syncthreads();
+    }
+    // epilogue: split-K reduction over CTAs with fire-and-forget float atomics
+    const int colbase = (warp >> 2) * 128;
+#pragma unroll 1
+    for (int mh = 0; mh < 2; ++mh) {
+        const int m = mh * 128 + (warp & 3) * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mh * 256 + colbase);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(taddr + c0, acc);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(G + m * H + colbase + c0 + j, __uint_as_float(acc[j]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------- small helper kernels
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+// W2 [out][in] fp32 -> bf16 copy and bf16 transpose ([in][out]) for the dgrad GEMM
+__global__ void pack_w2_kernel(const float *__restrict__ w2, __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__restrict__ wt) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const float v = w2[(by + j) * H + bx + threadIdx.x];
+        tile[j][threadIdx.x] = v;
+        w[(by + j) * H + bx + threadIdx.x] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) wt[(bx + j) * H + by + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+}
+
+static int g_attr_done = 0;
+static int ensure_attrs() {
+    if (g_attr_done) return TMLA_OK;
+    TMLA_CUDA(cudaFuncSetAttribute(tc_linear_kernel<EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLinearSmem));
+    TMLA_CUDA(cudaFuncSetAttribute(tc_linear_kernel<EPI_DTANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLinearSmem));
+    TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmem));
+    g_attr_done = 1;
+    return TMLA_OK;
+}
+static int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+// launchers shared with mlp_kernels.cu
+int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, const void *aux, void *out, int64_t M,
+                     const int32_t *rows_dev, cudaStream_t st) {
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, sm_count());
+    if (epi == EPI_BIAS_TANH)
+        tc_linear_kernel<EPI_BIAS_TANH><<<grid, 256, kLinearSmem, st>>>((const __nv_bfloat16 *)A, (const __nv_bfloat16 *)W, bias,
+                                                                        (const __nv_bfloat16 *)aux, (__nv_bfloat16 *)out, M, rows_dev);
+    else
+        tc_linear_kernel<EPI_DTANH><<<grid, 256, kLinearSmem, st>>>((const __nv_bfloat16 *)A, (const __nv_bfloat16 *)W, bias,
+                                                                    (const __nv_bfloat16 *)aux, (__nv_bfloat16 *)out, M, rows_dev);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st) {
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<int64_t>((rows + 127) / 128, sm_count());
+    tc_wgrad_kernel<<<grid, 256, kWgradSmem, st>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)Y, G, rows);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st) {
+    pack_w2_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(w2, (__nv_bfloat16 *)w, (__nv_bfloat16 *)wt);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
+extern "C" {
+
+// Test hooks for the tensor-core building blocks (bf16 device buffers, row-major):
+//   tmla_tc_linear: out[M,256] = tanh(A.W^T + bias) (epi 0)  |  (A.W^T) * (1 - aux^2) (epi 1);  W is [256 out][256 in]
+//   tmla_tc_wgrad : G[256,256] (fp32) += X[rows,256]^T . Y[rows,256]
+int tmla_tc_linear(int epi, const void *A, const void *W, const float *bias, const void *aux, void *out, int64_t M,
+                   const int32_t *rows_dev, void *stream) {
+    TMLA_REQUIRE(A && W && out && M > 0, "bad arguments");
+    TMLA_REQUIRE((epi == EPI_BIAS_TANH && bias) || (epi == EPI_DTANH && aux), "epilogue operand missing");
+    return tc_linear_launch(epi, A, W, bias, aux, out, M, rows_dev, (cudaStream_t)stream);
+}
+int tmla_tc_wgrad(const void *X, const void *Y, float *G, int64_t rows, void *stream) {
+    TMLA_REQUIRE(X && Y && G && rows > 0, "bad arguments");
+    return tc_wgrad_launch(X, Y, G, rows, (cudaStream_t)stream);
+}
+int tmla_tc_debug(int swap_lbo_sbo) {
+    TMLA_CUDA(cudaMemcpyToSymbol(g_desc_swap, &swap_lbo_sbo, sizeof(int)));
+    return TMLA_OK;
+}
+int tmla_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream) {
+    TMLA_REQUIRE(src && dst && n > 0, "bad arguments");
+    f32_to_bf16_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16 *)dst, n);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
+}  // extern "C"
