@@ -174,6 +174,18 @@ int tmla_mlp_backward(const float *params, int obs_dim, int hidden, int n_action
                       const int32_t *index, int64_t rows, const float *act_cache, const float *dlogits,
                       const float *dvalues, float *grads, float *scratch, void *stream);
 
+/* bf16 / tensor-core variant of the same network (csrc/mlp_tc.cu): identical semantics, the 256x256 hidden
+ * layers run on tcgen05 with bf16 operands and fp32 accumulation, activations (act_cache, scratch) are bf16.
+ *   wpack: bf16[4][256][256] = {pi.W2, pi.W2^T, vf.W2, vf.W2^T}, refreshed by tmla_mlp_pack_bf16 after every
+ *   optimizer step.  act_cache: bf16[4,rows,256]; scratch: bf16[2,rows,256]. */
+int tmla_mlp_pack_bf16(const float *params, int obs_dim, int hidden, int n_actions, void *wpack, void *stream);
+int tmla_mlp_forward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
+                          const int32_t *index, int64_t rows, const int32_t *rows_dev, float *logits, float *values,
+                          void *act_cache, void *stream);
+int tmla_mlp_backward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
+                           const int32_t *index, int64_t rows, const void *act_cache, const float *dlogits,
+                           const float *dvalues, float *grads, void *scratch, void *stream);
+
 /* PPO.train, one minibatch, loss head (SB3 2.9.0 ppo.py): advantage normalisation statistics,
  * then clipped surrogate + value MSE + entropy, forward and backward in one pass.
  *   stats_out float[8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss, adv_mean, adv_std

@@ -22,7 +22,7 @@ def test_one_iteration_matches_sb3_restatement(task, n, T, B):
     from three_mlagents_b200.vec_env import CudaVecEnv
 
     env = CudaVecEnv(task, n, seed=3)
-    model = CudaPPO("MlpPolicy", env, seed=3, n_steps=T, batch_size=B, n_epochs=2, ent_coef=0.01)
+    model = CudaPPO("MlpPolicy", env, seed=3, n_steps=T, batch_size=B, n_epochs=2, ent_coef=0.01, mlp_impl="fp32")
     d, a = env.obs_dim, env.n_actions
     p0 = model.params.cpu().numpy().copy()
     np.testing.assert_array_equal(p0, po.init_params(d, a, 3))          # same orthogonal init
@@ -108,3 +108,39 @@ def test_learn_improves_basic_and_roundtrips(tmp_path):
     rows = model.logger_rows
     assert rows[-1]["rollout/ep_rew_mean"] > rows[0]["rollout/ep_rew_mean"]
     env.close(); loaded.env.close()
+
+
+@pytest.mark.parametrize("task,n,T,B", [("ball3d", 512, 32, 4096), ("gridworld", 300, 40, 1000)])
+def test_bf16_tensor_core_path_tracks_fp32(task, n, T, B):
+    """Same seeds, same rollout protocol: the tcgen05 bf16 path must stay close to the fp32 path.
+    Stated tolerance: logits/values 3e-2 abs (bf16 activations, 8-bit mantissa, over two 256-wide layers),
+    gradient cosine similarity > 0.999 on one minibatch."""
+    from three_mlagents_b200 import ops
+    from three_mlagents_b200.ppo import CudaPPO
+    from three_mlagents_b200.vec_env import CudaVecEnv
+
+    env = CudaVecEnv(task, n, seed=5)
+    m = CudaPPO("MlpPolicy", env, seed=5, n_steps=T, batch_size=B, n_epochs=1, ent_coef=0.01, mlp_impl="bf16")
+    d, a = env.obs_dim, env.n_actions
+    with torch.no_grad():
+        m.params += 0.05 * torch.randn_like(m.params)          # non-trivial biases / heads
+    m._repack()
+    m.collect_rollouts()
+    torch.cuda.synchronize()
+    obs_flat = m.obs[:T].reshape(T * n, d)
+    rows = min(B, T * n)
+    idx = ops.permutation(1, 0, T, n)[:rows].contiguous()
+    l16, v16, c16 = ops.mlp_forward(m.params, obs_flat, d, a, index=idx, wpack=m.wpack)
+    l32, v32, c32 = ops.mlp_forward(m.params, obs_flat, d, a, index=idx)
+    assert float((l16 - l32).abs().max()) < 3e-2 and float((v16 - v32).abs().max()) < 3e-2
+    dl, dv, _ = ops.ppo_loss(l32, v32, m.act, m.adv, m.logp, m.ret, index=idx)
+    g16 = ops.mlp_backward(m.params, obs_flat, d, a, c16, dl, dv, index=idx, wpack=m.wpack)
+    g32 = ops.mlp_backward(m.params, obs_flat, d, a, c32, dl, dv, index=idx)
+    cos = float(torch.nn.functional.cosine_similarity(g16, g32, dim=0))
+    rel = float((g16 - g32).norm() / g32.norm())
+    print(f"{task}: bf16 vs fp32 gradient cosine {cos:.6f}, relative error {rel:.4f}")
+    assert cos > 0.999 and rel < 0.05
+    m.train()
+    torch.cuda.synchronize()
+    assert torch.isfinite(m.params).all()
+    env.close()

@@ -9,9 +9,22 @@
 // Layout: flat fp32 parameter vector in policy.parameters() order (include/tmla.h), PyTorch Linear
 // weights [out,in].  Activations are [rows,256] row-major.
 #include <algorithm>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 static constexpr int H = 256;   // hidden width (net_arch of training.py:363-365)
+
+// activations are float (numerics-reference path) or bf16 (tensor-core path, mlp_tc.cu)
+__device__ __forceinline__ float act_load(const float *p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float act_load(const __nv_bfloat16 *p, int64_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void act_store(float *p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void act_store(__nv_bfloat16 *p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// launchers of the tcgen05 kernels (mlp_tc.cu)
+int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, const void *aux, void *out, int64_t M,
+                     const int32_t *rows_dev, cudaStream_t st);
+int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st);
+int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st);
 
 struct MlpOffsets {
     int64_t w1[2], b1[2], w2[2], b2[2], wh[2], bh[2], total;
@@ -41,10 +54,10 @@ __device__ __forceinline__ int64_t eff_rows(int64_t rows, const int32_t *rows_de
 
 // ----------------------------------------------------------------------------- layer 1 (K = D tiny)
 // thread j owns hidden unit j: W1[j][:] in registers, x rows broadcast from shared memory.
-template <int D>
+template <int D, typename AT>
 __global__ void __launch_bounds__(H)
 l1_forward_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ x,
-                  const int32_t *__restrict__ index, int64_t rows, const int32_t *rows_dev, float *__restrict__ h1) {
+                  const int32_t *__restrict__ index, int64_t rows, const int32_t *rows_dev, AT *__restrict__ h1) {
     constexpr int R = 32;
     __shared__ float sx[R][D];
     rows = eff_rows(rows, rows_dev);
@@ -66,14 +79,14 @@ l1_forward_kernel(const float *__restrict__ W1, const float *__restrict__ b1, co
         float acc = b;
 #pragma unroll
         for (int k = 0; k < D; ++k) acc = fmaf(sx[r][k], w[k], acc);
-        h1[(r0 + r) * H + j] = tanhf(acc);
+        act_store(h1, (r0 + r) * H + j, tanhf(acc));
     }
 }
 
 // dW1[j][k] = sum_r dZ1[r][j] x[r][k], db1[j] = sum_r dZ1[r][j]
-template <int D>
+template <int D, typename AT>
 __global__ void __launch_bounds__(H)
-l1_backward_kernel(const float *__restrict__ dz1, const float *__restrict__ x, const int32_t *__restrict__ index,
+l1_backward_kernel(const AT *__restrict__ dz1, const float *__restrict__ x, const int32_t *__restrict__ index,
                    int64_t rows, int rows_per_block, float *__restrict__ dW1, float *__restrict__ db1) {
     constexpr int R = 32;
     __shared__ float sx[R][D];
@@ -92,7 +105,7 @@ l1_backward_kernel(const float *__restrict__ dz1, const float *__restrict__ x, c
         }
         __syncthreads();
         for (int r = 0; r < nr; ++r) {
-            const float g = dz1[(r0 + r) * H + j];
+            const float g = act_load(dz1, (r0 + r) * H + j);
             accb += g;
 #pragma unroll
             for (int k = 0; k < D; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
@@ -105,25 +118,38 @@ l1_backward_kernel(const float *__restrict__ dz1, const float *__restrict__ x, c
 
 // ------------------------------------------------------------------------------------ output heads
 // one warp per row: lane holds 8 of the 256 hidden activations (two float4) and the matching weights.
-template <int NOUT>
+template <int NOUT, typename AT>
 __global__ void __launch_bounds__(256)
-head_forward_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, const float *__restrict__ h2,
+head_forward_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, const AT *__restrict__ h2,
                     int64_t rows, const int32_t *rows_dev, float *__restrict__ out) {
     rows = eff_rows(rows, rows_dev);
+    constexpr bool BF = sizeof(AT) == 2;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // lane's 8 hidden units: bf16 -> one 16-byte load (elements 8*lane..); f32 -> two float4 (4*lane.., 128+4*lane..)
     float w[NOUT][8];      // scalar loads: the value head's weights are not 16-byte aligned in the flat vector
 #pragma unroll
     for (int a = 0; a < NOUT; ++a)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) w[a][q] = Wh[a * H + (q < 4 ? lane * 4 + q : 128 + lane * 4 + (q - 4))];
+        for (int q = 0; q < 8; ++q)
+            w[a][q] = Wh[a * H + (BF ? lane * 8 + q : (q < 4 ? lane * 4 + q : 128 + lane * 4 + (q - 4)))];
     for (int64_t r = warp; r < rows; r += nwarps) {
-        const float4 x0 = reinterpret_cast<const float4 *>(h2 + r * H)[lane];
-        const float4 x1 = reinterpret_cast<const float4 *>(h2 + r * H)[32 + lane];
+        float x[8];
+        if constexpr (BF) {
+            const uint4 v = reinterpret_cast<const uint4 *>(h2 + r * H)[lane];
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { x[2 * q] = __uint_as_float(u[q] << 16); x[2 * q + 1] = __uint_as_float(u[q] & 0xFFFF0000u); }
+        } else {
+            const float4 x0 = reinterpret_cast<const float4 *>(h2 + r * H)[lane];
+            const float4 x1 = reinterpret_cast<const float4 *>(h2 + r * H)[32 + lane];
+            x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        }
 #pragma unroll
         for (int a = 0; a < NOUT; ++a) {
-            float s = x0.x * w[a][0] + x0.y * w[a][1] + x0.z * w[a][2] + x0.w * w[a][3] +
-                      x1.x * w[a][4] + x1.y * w[a][5] + x1.z * w[a][6] + x1.w * w[a][7];
+            float s = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s = fmaf(x[q], w[a][q], s);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) out[r * NOUT + a] = s + bh[a];
@@ -134,10 +160,10 @@ head_forward_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, 
 // thread j owns hidden column j over a chunk of rows:
 //   dZ2[r][j] = (sum_a dOut[r][a] Wh[a][j]) * (1 - h2[r][j]^2)
 //   dWh[a][j] += dOut[r][a] h2[r][j] ; db2[j] += dZ2[r][j] ; dbh[a] += dOut[r][a]
-template <int NOUT>
+template <int NOUT, typename AT>
 __global__ void __launch_bounds__(H)
-head_backward_kernel(const float *__restrict__ Wh, const float *__restrict__ h2, const float *__restrict__ dout,
-                     int64_t rows, int rows_per_block, float *__restrict__ dz2, float *__restrict__ dWh,
+head_backward_kernel(const float *__restrict__ Wh, const AT *__restrict__ h2, const float *__restrict__ dout,
+                     int64_t rows, int rows_per_block, AT *__restrict__ dz2, float *__restrict__ dWh,
                      float *__restrict__ dbh, float *__restrict__ db2) {
     constexpr int R = 64;
     __shared__ float sd[R][NOUT];
@@ -152,12 +178,12 @@ head_backward_kernel(const float *__restrict__ Wh, const float *__restrict__ h2,
         for (int e = threadIdx.x; e < nr * NOUT; e += H) sd[e / NOUT][e % NOUT] = dout[r0 * NOUT + e];
         __syncthreads();
         for (int r = 0; r < nr; ++r) {
-            const float h = h2[(r0 + r) * H + j];
+            const float h = act_load(h2, (r0 + r) * H + j);
             float g = 0.0f;
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) { g = fmaf(sd[r][a], w[a], g); accw[a] = fmaf(sd[r][a], h, accw[a]); }
             g *= (1.0f - h * h);
-            dz2[(r0 + r) * H + j] = g;
+            act_store(dz2, (r0 + r) * H + j, g);
             accb2 += g;
         }
         if (j < NOUT) for (int r = 0; r < nr; ++r) accbh += sd[r][j];
@@ -283,6 +309,88 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
 }
 
 // --------------------------------------------------------------------------------------- host API
+// shared body of the fp32 (AT=float, SIMT SGEMM) and bf16 (AT=__nv_bfloat16, tcgen05) paths
+template <typename AT>
+static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim, int n_actions, const float *x, const int32_t *index,
+                            int64_t rows, const int32_t *rows_dev, float *logits, float *values, AT *act_cache, cudaStream_t st) {
+    constexpr bool BF = sizeof(AT) == 2;
+    const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+    for (int t = 0; t < 2; ++t) {
+        float *out = t == 0 ? logits : values;
+        if (!out) continue;
+        AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
+        const unsigned g1 = (unsigned)ceil_div64(rows, 32);
+#define L1F(DD) l1_forward_kernel<DD, AT><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
+        if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else L1F(21);
+#undef L1F
+        TMLA_LAUNCH_CHECK();
+        if constexpr (BF) {
+            const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
+            int rc = tc_linear_launch(0, h1, w2, params + o.b2[t], nullptr, h2, rows, rows_dev, st);
+            if (rc) return rc;
+        } else {
+            dim3 grid((unsigned)ceil_div64(rows, 128), H / 128, 1);
+            sgemm_kernel<true, true, EPI_BIAS_TANH><<<grid, 256, 0, st>>>((const float *)h1, params + o.w2[t], (float *)h2, rows, H, H, H, H,
+                                                                          H, H, params + o.b2[t], rows_dev);
+            TMLA_LAUNCH_CHECK();
+        }
+        const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
+        if (t == 1) head_forward_kernel<1, AT><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
+        else if (n_actions == 3) head_forward_kernel<3, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        else head_forward_kernel<5, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        TMLA_LAUNCH_CHECK();
+    }
+    return TMLA_OK;
+}
+
+template <typename AT>
+static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim, int n_actions, const float *x, const int32_t *index,
+                             int64_t rows, const AT *act_cache, const float *dlogits, const float *dvalues, float *grads,
+                             AT *scratch, cudaStream_t st) {
+    constexpr bool BF = sizeof(AT) == 2;
+    const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+    TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
+    AT *dz2 = scratch, *dz1 = scratch + rows * H;
+    // chunk rows so that ~4 blocks per SM share the reduction kernels
+    const int rpb = (int)std::max<int64_t>(64, ceil_div64(ceil_div64(rows, 148 * 4), 64) * 64);
+    const unsigned gr = (unsigned)ceil_div64(rows, rpb);
+    for (int t = 0; t < 2; ++t) {
+        const AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
+        const float *dout = t == 0 ? dlogits : dvalues;
+        if (t == 1) head_backward_kernel<1, AT><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
+        else if (n_actions == 3) head_backward_kernel<3, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        else head_backward_kernel<5, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        TMLA_LAUNCH_CHECK();
+        if constexpr (BF) {
+            // dZ1 = (dZ2 . W2) * (1 - h1^2) with W2^T as the K-major weight;  dW2 += dZ2^T . h1  (tcgen05)
+            const __nv_bfloat16 *w2t = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(2 * t + 1) * H * H;
+            int rc = tc_linear_launch(1, dz2, w2t, nullptr, h1, dz1, rows, nullptr, st);
+            if (rc) return rc;
+            rc = tc_wgrad_launch(dz2, h1, grads + o.w2[t], rows, st);
+            if (rc) return rc;
+        } else {
+            // dZ1 = (dZ2 . W2) * (1 - h1^2)      A = dZ2 [rows][H] (k-major), B = W2 [K=out][N=in]
+            dim3 gd((unsigned)ceil_div64(rows, 128), H / 128, 1);
+            sgemm_kernel<true, false, EPI_DTANH><<<gd, 256, 0, st>>>((const float *)dz2, params + o.w2[t], (float *)dz1, rows, H, H, H, H, H, H,
+                                                                     (const float *)h1, nullptr);
+            TMLA_LAUNCH_CHECK();
+            // dW2[j][i] = sum_r dZ2[r][j] h1[r][i]   A = dZ2 as [K=rows][M=H], B = h1 as [K=rows][N=H]; split-K + atomics
+            int64_t splits = std::min<int64_t>(std::max<int64_t>(1, ceil_div64(rows, 1024)), 148);
+            const int64_t kps = ceil_div64(ceil_div64(rows, splits), 8) * 8;
+            splits = ceil_div64(rows, kps);
+            dim3 gw(H / 128, H / 128, (unsigned)splits);
+            sgemm_kernel<false, false, EPI_ATOMIC><<<gw, 256, 0, st>>>((const float *)dz2, (const float *)h1, grads + o.w2[t], H, H, rows, H, H, H,
+                                                                      kps, nullptr, nullptr);
+            TMLA_LAUNCH_CHECK();
+        }
+#define L1B(DD) l1_backward_kernel<DD, AT><<<gr, H, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t])
+        if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
+#undef L1B
+        TMLA_LAUNCH_CHECK();
+    }
+    return TMLA_OK;
+}
+
 extern "C" {
 
 int64_t tmla_mlp_num_params(int obs_dim, int hidden, int n_actions) {
@@ -304,28 +412,19 @@ int tmla_mlp_forward(const float *params, int obs_dim, int hidden, int n_actions
     TMLA_REQUIRE(logits || values, "nothing to compute");
     int rc = check_shape(obs_dim, hidden, n_actions);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
-    for (int t = 0; t < 2; ++t) {
-        float *out = t == 0 ? logits : values;
-        if (!out) continue;
-        float *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
-        const unsigned g1 = (unsigned)ceil_div64(rows, 32);
-#define L1F(DD) l1_forward_kernel<DD><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
-        if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else L1F(21);
-#undef L1F
-        TMLA_LAUNCH_CHECK();
-        dim3 grid((unsigned)ceil_div64(rows, 128), H / 128, 1);
-        sgemm_kernel<true, true, EPI_BIAS_TANH><<<grid, 256, 0, st>>>(h1, params + o.w2[t], h2, rows, H, H, H, H, H, H,
-                                                                      params + o.b2[t], rows_dev);
-        TMLA_LAUNCH_CHECK();
-        const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
-        if (t == 1) head_forward_kernel<1><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
-        else if (n_actions == 3) head_forward_kernel<3><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
-        else head_forward_kernel<5><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
-        TMLA_LAUNCH_CHECK();
-    }
-    return TMLA_OK;
+    return mlp_forward_impl<float>(params, nullptr, obs_dim, n_actions, x, index, rows, rows_dev, logits, values, act_cache, (cudaStream_t)stream);
+}
+
+int tmla_mlp_forward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
+                          const int32_t *index, int64_t rows, const int32_t *rows_dev, float *logits, float *values,
+                          void *act_cache, void *stream) {
+    TMLA_REQUIRE(params && wpack && x && act_cache, "params/wpack/x/act_cache must be non-NULL");
+    TMLA_REQUIRE(rows > 0, "rows must be positive");
+    TMLA_REQUIRE(logits || values, "nothing to compute");
+    int rc = check_shape(obs_dim, hidden, n_actions);
+    if (rc) return rc;
+    return mlp_forward_impl<__nv_bfloat16>(params, wpack, obs_dim, n_actions, x, index, rows, rows_dev, logits, values,
+                                           (__nv_bfloat16 *)act_cache, (cudaStream_t)stream);
 }
 
 int64_t tmla_mlp_backward_scratch(int obs_dim, int hidden, int n_actions, int64_t rows) {
@@ -340,35 +439,31 @@ int tmla_mlp_backward(const float *params, int obs_dim, int hidden, int n_action
     TMLA_REQUIRE(rows > 0, "rows must be positive");
     int rc = check_shape(obs_dim, hidden, n_actions);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
+    return mlp_backward_impl<float>(params, nullptr, obs_dim, n_actions, x, index, rows, act_cache, dlogits, dvalues, grads, scratch,
+                                    (cudaStream_t)stream);
+}
+
+int tmla_mlp_backward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
+                           const int32_t *index, int64_t rows, const void *act_cache, const float *dlogits,
+                           const float *dvalues, float *grads, void *scratch, void *stream) {
+    TMLA_REQUIRE(params && wpack && x && act_cache && dlogits && dvalues && grads && scratch, "NULL buffer");
+    TMLA_REQUIRE(rows > 0, "rows must be positive");
+    int rc = check_shape(obs_dim, hidden, n_actions);
+    if (rc) return rc;
+    return mlp_backward_impl<__nv_bfloat16>(params, wpack, obs_dim, n_actions, x, index, rows, (const __nv_bfloat16 *)act_cache,
+                                            dlogits, dvalues, grads, (__nv_bfloat16 *)scratch, (cudaStream_t)stream);
+}
+
+// bf16 copies of the two hidden-layer weights per tower: wpack = [pi.W2, pi.W2^T, vf.W2, vf.W2^T], each [256][256] bf16
+int tmla_mlp_pack_bf16(const float *params, int obs_dim, int hidden, int n_actions, void *wpack, void *stream) {
+    TMLA_REQUIRE(params && wpack, "NULL buffer");
+    int rc = check_shape(obs_dim, hidden, n_actions);
+    if (rc) return rc;
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
-    TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
-    float *dz2 = scratch, *dz1 = scratch + rows * H;
-    // chunk rows so that ~4 blocks per SM share the reduction kernels
-    const int rpb = (int)std::max<int64_t>(64, ceil_div64(ceil_div64(rows, 148 * 4), 64) * 64);
-    const unsigned gr = (unsigned)ceil_div64(rows, rpb);
     for (int t = 0; t < 2; ++t) {
-        const float *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
-        const float *dout = t == 0 ? dlogits : dvalues;
-        if (t == 1) head_backward_kernel<1><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
-        else if (n_actions == 3) head_backward_kernel<3><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
-        else head_backward_kernel<5><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
-        TMLA_LAUNCH_CHECK();
-        // dZ1 = (dZ2 . W2) * (1 - h1^2)      A = dZ2 [rows][H] (k-major), B = W2 [K=out][N=in]
-        dim3 gd((unsigned)ceil_div64(rows, 128), H / 128, 1);
-        sgemm_kernel<true, false, EPI_DTANH><<<gd, 256, 0, st>>>(dz2, params + o.w2[t], dz1, rows, H, H, H, H, H, H, h1, nullptr);
-        TMLA_LAUNCH_CHECK();
-        // dW2[j][i] = sum_r dZ2[r][j] h1[r][i]   A = dZ2 as [K=rows][M=H], B = h1 as [K=rows][N=H]; split-K + atomics
-        int64_t splits = std::min<int64_t>(std::max<int64_t>(1, ceil_div64(rows, 1024)), 148);
-        const int64_t kps = ceil_div64(ceil_div64(rows, splits), 8) * 8;
-        splits = ceil_div64(rows, kps);
-        dim3 gw(H / 128, H / 128, (unsigned)splits);
-        sgemm_kernel<false, false, EPI_ATOMIC><<<gw, 256, 0, st>>>(dz2, h1, grads + o.w2[t], H, H, rows, H, H, H, kps, nullptr, nullptr);
-        TMLA_LAUNCH_CHECK();
-#define L1B(DD) l1_backward_kernel<DD><<<gr, H, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t])
-        if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
-#undef L1B
-        TMLA_LAUNCH_CHECK();
+        __nv_bfloat16 *w = reinterpret_cast<__nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
+        rc = tc_pack_w2_launch(params + o.w2[t], w, w + H * H, (cudaStream_t)stream);
+        if (rc) return rc;
     }
     return TMLA_OK;
 }

@@ -58,36 +58,59 @@ def permutation(seed: int, epoch: int, T: int, n: int, out=None, device="cuda"):
     return out
 
 
+def mlp_pack(params, obs_dim, n_actions, wpack=None):
+    """bf16 copies {pi.W2, pi.W2^T, vf.W2, vf.W2^T} for the tensor-core path (refresh after every optimizer step)."""
+    if wpack is None:
+        wpack = torch.empty((4, HIDDEN, HIDDEN), dtype=torch.bfloat16, device=params.device)
+    _chk(wpack, torch.bfloat16, "wpack")
+    check(lib.tmla_mlp_pack_bf16(ptr(params), obs_dim, HIDDEN, n_actions, ptr(wpack), _s()))
+    return wpack
+
+
 def mlp_forward(params, x, obs_dim, n_actions, *, index=None, rows=None, rows_dev=None, logits=None, values=None,
-                want_logits=True, want_values=True, act_cache=None):
+                want_logits=True, want_values=True, act_cache=None, wpack=None):
+    """ActorCriticPolicy.forward.  wpack=None: float32 CUDA-core path; wpack=bf16 pack: tcgen05 path
+    (act_cache is then bf16 [4,rows,256])."""
     _chk(params, torch.float32, "params"); _chk(x, torch.float32, "x"); _chk(index, torch.int32, "index")
     if rows is None:
         rows = index.numel() if index is not None else x.shape[0]
     dev = params.device
+    act_dtype = torch.float32 if wpack is None else torch.bfloat16
     if want_logits and logits is None:
         logits = torch.empty((rows, n_actions), dtype=torch.float32, device=dev)
     if want_values and values is None:
         values = torch.empty(rows, dtype=torch.float32, device=dev)
     if act_cache is None:
-        act_cache = torch.empty((4, rows, HIDDEN), dtype=torch.float32, device=dev)
-    check(lib.tmla_mlp_forward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(rows_dev),
-                               ptr(logits) if want_logits else None, ptr(values) if want_values else None,
-                               ptr(act_cache), _s()))
+        act_cache = torch.empty((4, rows, HIDDEN), dtype=act_dtype, device=dev)
+    _chk(act_cache, act_dtype, "act_cache")
+    lg, vl = (ptr(logits) if want_logits else None), (ptr(values) if want_values else None)
+    if wpack is None:
+        check(lib.tmla_mlp_forward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(rows_dev),
+                                   lg, vl, ptr(act_cache), _s()))
+    else:
+        check(lib.tmla_mlp_forward_bf16(ptr(params), ptr(wpack), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows),
+                                        ptr(rows_dev), lg, vl, ptr(act_cache), _s()))
     return logits, values, act_cache
 
 
 def mlp_backward(params, x, obs_dim, n_actions, act_cache, dlogits, dvalues, *, index=None, rows=None, grads=None,
-                 scratch=None):
+                 scratch=None, wpack=None):
     if rows is None:
         rows = index.numel() if index is not None else x.shape[0]
     dev = params.device
+    act_dtype = torch.float32 if wpack is None else torch.bfloat16
     if grads is None:
         grads = torch.empty_like(params)
     if scratch is None:
-        scratch = torch.empty(lib.tmla_mlp_backward_scratch(obs_dim, HIDDEN, n_actions, rows), dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.tmla_mlp_backward_scratch(obs_dim, HIDDEN, n_actions, rows), dtype=act_dtype, device=dev)
     _chk(dlogits, torch.float32, "dlogits"); _chk(dvalues, torch.float32, "dvalues")
-    check(lib.tmla_mlp_backward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(act_cache),
-                                ptr(dlogits), ptr(dvalues), ptr(grads), ptr(scratch), _s()))
+    _chk(act_cache, act_dtype, "act_cache"); _chk(scratch, act_dtype, "scratch")
+    if wpack is None:
+        check(lib.tmla_mlp_backward(ptr(params), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows), ptr(act_cache),
+                                    ptr(dlogits), ptr(dvalues), ptr(grads), ptr(scratch), _s()))
+    else:
+        check(lib.tmla_mlp_backward_bf16(ptr(params), ptr(wpack), obs_dim, HIDDEN, n_actions, ptr(x), ptr(index), int(rows),
+                                         ptr(act_cache), ptr(dlogits), ptr(dvalues), ptr(grads), ptr(scratch), _s()))
     return grads
 
 

@@ -71,7 +71,9 @@ class CudaPPO:
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.normalize_advantage = bool(normalize_advantage)
         self.verbose, self.tensorboard_log = int(verbose), tensorboard_log
-        self.mlp_impl = mlp_impl
+        if mlp_impl not in ("auto", "bf16", "fp32"):
+            raise ValueError("mlp_impl must be 'auto', 'bf16' (tcgen05 tensor cores) or 'fp32' (CUDA cores)")
+        self.mlp_impl = "bf16" if mlp_impl == "auto" else mlp_impl
         self.obs_dim, self.n_actions, self.n_envs = env.obs_dim, env.n_actions, env.num_envs
         self.device = torch.device("cuda", env.device_index)
         self.num_timesteps = 0
@@ -86,9 +88,20 @@ class CudaPPO:
             self.m = torch.zeros_like(self.params)
             self.v = torch.zeros_like(self.params)
             self.grads = torch.zeros_like(self.params)
+            self.wpack = None
+            self._repack()
         self._buffers_ready = False
         self._last_obs_valid = False
         self.logger_rows: list[dict[str, Any]] = []
+
+    def _repack(self):
+        """bf16 copies of the hidden-layer weights for the tensor-core path (after every optimizer step)."""
+        if self.mlp_impl == "bf16":
+            self.wpack = ops.mlp_pack(self.params, self.obs_dim, self.n_actions, self.wpack)
+
+    @property
+    def _act_dtype(self):
+        return torch.bfloat16 if self.mlp_impl == "bf16" else torch.float32
 
     # ------------------------------------------------------------------------------------- buffers
     def _alloc(self):
@@ -106,14 +119,14 @@ class CudaPPO:
         self.done = torch.empty((T, N), dtype=torch.uint8, device=dev)
         self.last_values = torch.empty(N, **f32)
         self.logits_roll = torch.empty((N, A), **f32)
-        self.cache_roll = torch.empty((4, N, HIDDEN), **f32)
+        self.cache_roll = torch.empty((4, N, HIDDEN), dtype=self._act_dtype, device=dev)
         # every env can hit its time limit at most floor(T/limit)+1 times per rollout
         cap = N * (T // self.env.max_episode_steps + 1)
         self.trunc_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.trunc_index = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.trunc_obs = torch.zeros((cap, D), **f32)
         self.trunc_values = torch.zeros(cap, **f32)
-        self.cache_trunc = torch.empty((4, cap, HIDDEN), **f32) if cap != N else self.cache_roll
+        self.cache_trunc = torch.empty((4, cap, HIDDEN), dtype=self._act_dtype, device=dev) if cap != N else self.cache_roll
         self.ep_stats = torch.zeros(4, **f32)
         total = T * N
         B = min(self.batch_size, total)
@@ -123,8 +136,8 @@ class CudaPPO:
         self.values_mb = torch.empty(B, **f32)
         self.dlogits = torch.empty((B, A), **f32)
         self.dvalues = torch.empty(B, **f32)
-        self.cache_mb = torch.empty((4, B, HIDDEN), **f32)
-        self.scratch_mb = torch.empty(2 * B * HIDDEN, **f32)
+        self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
+        self.scratch_mb = torch.empty(2 * B * HIDDEN, dtype=self._act_dtype, device=dev)
         self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
@@ -145,16 +158,16 @@ class CudaPPO:
         self.ep_stats.zero_()
         for t in range(T):
             ops.mlp_forward(self.params, self.obs[t], D, A, rows=N, logits=self.logits_roll, values=self.val[t],
-                            act_cache=self.cache_roll)
+                            act_cache=self.cache_roll, wpack=self.wpack)
             ops.step_policy(self.env, self.logits_roll, t, self.obs[t + 1], self.act[t], self.logp[t], self.rew[t],
                             self.done[t], trunc_count=self.trunc_count, trunc_index=self.trunc_index,
                             trunc_obs=self.trunc_obs, ep_stats=self.ep_stats)
         ops.mlp_forward(self.params, self.obs[T], D, A, rows=N, want_logits=False, values=self.last_values,
-                        act_cache=self.cache_roll)
+                        act_cache=self.cache_roll, wpack=self.wpack)
         # timeout bootstrap: rewards += gamma * V(terminal_obs) for time-limit truncations
         cap = self.trunc_index.numel()
         ops.mlp_forward(self.params, self.trunc_obs, D, A, rows=cap, rows_dev=self.trunc_count, want_logits=False,
-                        values=self.trunc_values, act_cache=self.cache_trunc)
+                        values=self.trunc_values, act_cache=self.cache_trunc, wpack=self.wpack)
         ops.bootstrap_add(self.rew, self.trunc_count, self.trunc_index, self.trunc_values, self.gamma)
         ops.gae(self.rew, self.val, self.done, self.last_values, self.gamma, self.gae_lambda, self.adv, self.ret)
         self.num_timesteps += T * N * self.world
@@ -175,7 +188,7 @@ class CudaPPO:
                 rows = min(B, total - start)
                 idx = self.perm[start:start + rows]
                 ops.mlp_forward(self.params, obs_flat, D, A, index=idx, rows=rows, logits=self.logits_mb,
-                                values=self.values_mb, act_cache=self.cache_mb)
+                                values=self.values_mb, act_cache=self.cache_mb, wpack=self.wpack)
                 sums = None
                 if self.normalize_advantage and rows * self.world > 1:
                     sums = ops.adv_stats(self.adv, idx, rows, self.adv_sums)
@@ -186,12 +199,13 @@ class CudaPPO:
                              clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
                              dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
                 ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
-                                 rows=rows, grads=self.grads, scratch=self.scratch_mb)
+                                 rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
                 if self.world > 1:
                     self._dist.all_reduce(self.grads)     # the one collective on the path: NCCL sum over NVLink
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
                               lr=self.lr, eps=1e-5, norm_out=self.norm_out)
+                self._repack()
                 self.stats_acc += self.stats
                 n_mb += 1
             self.n_updates += 1
@@ -257,7 +271,7 @@ class CudaPPO:
     def policy_logits(self, obs_dev: torch.Tensor) -> torch.Tensor:
         rows = obs_dev.shape[0]
         logits, _, _ = ops.mlp_forward(self.params, obs_dev.contiguous(), self.obs_dim, self.n_actions, rows=rows,
-                                       want_values=False)
+                                       want_values=False, wpack=self.wpack)
         return logits
 
     def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
@@ -329,6 +343,7 @@ class CudaPPO:
         if own_env:
             env = CudaVecEnv(data["task_id"], 1, seed=data["seed"], device=device)
         model = cls("MlpPolicy", env, seed=data["seed"], _params=torch.from_numpy(arrs["params"]), **data["hyper"])
+        model._repack()
         model.m.copy_(torch.from_numpy(arrs["adam_m"]))
         model.v.copy_(torch.from_numpy(arrs["adam_v"]))
         model.num_timesteps, model.n_updates, model._adam_step = data["num_timesteps"], data["n_updates"], data["adam_step"]
@@ -337,13 +352,13 @@ class CudaPPO:
 
 # ---------------------------------------------------------------------------------------- bench / smoke
 def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: int = 65536, n_steps: int = 128,
-              minibatches: int = 32, task: str = "ball3d") -> dict[str, Any]:
+              minibatches: int = 32, task: str = "ball3d", mlp_impl: str = "bf16") -> dict[str, Any]:
     """BASELINE config 3: ball3d PPO end-to-end, 64K envs/GPU, 128-step rollouts, 2x256 MLP, 10 epochs,
     32 minibatches per epoch (262 144 samples per GPU per optimizer step)."""
     dist, _, _ = _dist()
     env = CudaVecEnv(task, n_envs, seed=1, device=local_rank, env_id_base=rank * n_envs)
     model = CudaPPO("MlpPolicy", env, seed=1, n_steps=n_steps, batch_size=n_envs * n_steps // minibatches, n_epochs=10,
-                    ent_coef=0.01)
+                    ent_coef=0.01, mlp_impl=mlp_impl)
     dev = model.device
 
     def sync():
@@ -372,7 +387,8 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
         "iters": iters, "ms_per_iter": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": train_ms / iters,
         "config": {"task": task, "envs_per_gpu": n_envs, "n_steps": n_steps, "epochs": 10, "minibatches_per_epoch": minibatches,
                    "minibatch_rows_per_gpu": n_envs * n_steps // minibatches, "mlp": "6-256-256-{5,1} tanh, separate towers",
-                   "mlp_impl": "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)"},
+                   "mlp_impl": ("bf16 tcgen05/TMEM hidden-layer GEMMs, fp32 accumulate (csrc/mlp_tc.cu)" if mlp_impl == "bf16"
+                                else "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)")},
         "update_tflops": flop_update / (train_ms * 1e-3) / 1e12,
         "ep_rew_mean": row["rollout/ep_rew_mean"], "approx_kl": row["train/approx_kl"],
     }
