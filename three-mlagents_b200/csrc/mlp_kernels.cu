@@ -194,6 +194,149 @@ head_backward_kernel(const float *__restrict__ Wh, const AT *__restrict__ h2, co
     if (j < NOUT) atomicAdd(dbh + j, accbh);
 }
 
+// ------------------------------------------------------- bf16-path CUDA-core kernels (lane = 8 columns)
+// Row-streaming versions of the first layer and the head backward for the tensor-core path: a warp owns a
+// row, a lane owns 8 consecutive hidden units, so activations move as 16-byte loads/stores (512 contiguous
+// bytes per warp) and the per-row inputs (obs row, dOut row) are warp-uniform broadcast loads.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void unpack8(const uint4 &v, float *f) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { f[2 * q] = __uint_as_float(u[q] << 16); f[2 * q + 1] = __uint_as_float(u[q] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float *f) {
+    uint32_t u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+        u[q] = *reinterpret_cast<uint32_t *>(&t);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+}
+// block-wide sum of one float per (warp, column): 8 warps x 256 columns -> 256 sums, then `emit(col, sum)`
+template <class F>
+__device__ __forceinline__ void reduce_planes(float (*sh)[H], const float *vals8, F emit) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sh[warp][lane * 8 + c] = vals8[c];
+    __syncthreads();
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+    emit(threadIdx.x, s);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+l1_forward_bf16_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ x,
+                       const int32_t *__restrict__ index, int64_t rows, const int32_t *rows_dev, __nv_bfloat16 *__restrict__ h1) {
+    rows = eff_rows(rows, rows_dev);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w[8][D], b[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        b[c] = b1[lane * 8 + c];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[c][k] = W1[(lane * 8 + c) * D + k];
+    }
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const int64_t src = index ? index[r] : r;
+        float xr[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xr[k] = __ldg(x + src * D + k);
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float acc = b[c];
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = fmaf(xr[k], w[c][k], acc);
+            o[c] = tanh_approx(acc);
+        }
+        reinterpret_cast<uint4 *>(h1 + r * H)[lane] = pack8(o);
+    }
+}
+
+// dW1[j][k] += sum_r dZ1[r][j] x[r][k],  db1[j] += sum_r dZ1[r][j]
+template <int D>
+__global__ void __launch_bounds__(256)
+l1_backward_bf16_kernel(const __nv_bfloat16 *__restrict__ dz1, const float *__restrict__ x, const int32_t *__restrict__ index,
+                        int64_t rows, int rows_per_block, float *__restrict__ dW1, float *__restrict__ db1) {
+    __shared__ float sh[8][H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[D + 1][8];
+#pragma unroll
+    for (int k = 0; k <= D; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[k][c] = 0.0f;
+    const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
+#pragma unroll 2
+    for (int64_t r = rb + warp; r < re; r += 8) {
+        const int64_t src = index ? index[r] : r;
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz1 + r * H) + lane), g);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float xk = __ldg(x + src * D + k);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(g[c], xk, acc[k][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[D][c] += g[c];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) reduce_planes(sh, acc[k], [&](int j, float s) { atomicAdd(dW1 + j * D + k, s); });
+    reduce_planes(sh, acc[D], [&](int j, float s) { atomicAdd(db1 + j, s); });
+}
+
+//   dZ2[r][j] = (sum_a dOut[r][a] Wh[a][j]) * (1 - h2[r][j]^2) ; dWh[a][j] += dOut[r][a] h2[r][j] ; db2[j] += dZ2[r][j] ; dbh[a] += dOut[r][a]
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+head_backward_bf16_kernel(const float *__restrict__ Wh, const __nv_bfloat16 *__restrict__ h2, const float *__restrict__ dout,
+                          int64_t rows, int rows_per_block, __nv_bfloat16 *__restrict__ dz2, float *__restrict__ dWh,
+                          float *__restrict__ dbh, float *__restrict__ db2) {
+    __shared__ float sh[8][H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float w[NOUT][8], accw[NOUT][8], accb2[8], accbh[NOUT];
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) {
+        accbh[a] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { w[a][c] = Wh[a * H + lane * 8 + c]; accw[a][c] = 0.0f; }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) accb2[c] = 0.0f;
+    const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
+#pragma unroll 2
+    for (int64_t r = rb + warp; r < re; r += 8) {
+        float h[8], d[NOUT], g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(h2 + r * H) + lane), h);
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) { d[a] = __ldg(dout + r * NOUT + a); accbh[a] += d[a]; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float t = 0.0f;
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) { t = fmaf(d[a], w[a][c], t); accw[a][c] = fmaf(d[a], h[c], accw[a][c]); }
+            g[c] = t * (1.0f - h[c] * h[c]);
+            accb2[c] += g[c];
+        }
+        reinterpret_cast<uint4 *>(dz2 + r * H)[lane] = pack8(g);
+    }
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) reduce_planes(sh, accw[a], [&](int j, float s) { atomicAdd(dWh + a * H + j, s); });
+    reduce_planes(sh, accb2, [&](int j, float s) { atomicAdd(db2 + j, s); });
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) atomicAdd(dbh + a, accbh[a]);
+    }
+}
+
 // --------------------------------------------------------------------------- 128x128x8 SIMT SGEMM
 // C[M,N] = epi( sum_k A(m,k) B(k,n) ).  256 threads, 8x8 micro-tile per thread split as 2x2 blocks of
 // 4x4 (conflict-free float4 shared-memory reads), register prefetch of the next k-chunk.
@@ -321,7 +464,14 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
         AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
         const unsigned g1 = (unsigned)ceil_div64(rows, 32);
 #define L1F(DD) l1_forward_kernel<DD, AT><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
-        if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else L1F(21);
+        const unsigned gs = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);      // warp-per-row streaming kernels
+        if constexpr (BF) {
+            if (obs_dim == 4) l1_forward_bf16_kernel<4><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
+            else if (obs_dim == 6) l1_forward_bf16_kernel<6><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
+            else L1F(21);
+        } else {
+            if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else L1F(21);
+        }
 #undef L1F
         TMLA_LAUNCH_CHECK();
         if constexpr (BF) {
@@ -357,9 +507,15 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
     for (int t = 0; t < 2; ++t) {
         const AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
         const float *dout = t == 0 ? dlogits : dvalues;
-        if (t == 1) head_backward_kernel<1, AT><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
-        else if (n_actions == 3) head_backward_kernel<3, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
-        else head_backward_kernel<5, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        if constexpr (BF) {
+            if (t == 1) head_backward_bf16_kernel<1><<<gr, 256, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
+            else if (n_actions == 3) head_backward_bf16_kernel<3><<<gr, 256, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            else head_backward_bf16_kernel<5><<<gr, 256, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        } else {
+            if (t == 1) head_backward_kernel<1, AT><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
+            else if (n_actions == 3) head_backward_kernel<3, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            else head_backward_kernel<5, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+        }
         TMLA_LAUNCH_CHECK();
         if constexpr (BF) {
             // dZ1 = (dZ2 . W2) * (1 - h1^2) with W2^T as the K-major weight;  dW2 += dZ2^T . h1  (tcgen05)
@@ -384,7 +540,13 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
             TMLA_LAUNCH_CHECK();
         }
 #define L1B(DD) l1_backward_kernel<DD, AT><<<gr, H, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t])
-        if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
+        if constexpr (BF) {
+            if (obs_dim == 4) l1_backward_bf16_kernel<4><<<gr, 256, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
+            else if (obs_dim == 6) l1_backward_bf16_kernel<6><<<gr, 256, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
+            else L1B(21);
+        } else {
+            if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
+        }
 #undef L1B
         TMLA_LAUNCH_CHECK();
     }

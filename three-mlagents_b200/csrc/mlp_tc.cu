@@ -127,6 +127,9 @@ __device__ __forceinline__ void stage_rows(uint8_t *dst, const __nv_bfloat16 *__
     }
 }
 
+// The A tile of the NEXT row block is prefetched into registers (16 x 16 B per thread) right after the MMAs of
+// the current block have been issued, so global-load latency overlaps the tensor-core work and the epilogue;
+// the dgrad epilogue's 1-h^2 operand is prefetched the same way before waiting on the MMA barrier.
 template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ W, const float *__restrict__ bias,
@@ -139,6 +142,19 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
     if (rows_dev) M = min(M, (int64_t)*rows_dev);
     const int64_t ntiles = (M + 127) / 128;
     if ((int64_t)blockIdx.x >= ntiles) return;            // whole CTA exits before any allocation
+
+    // this thread's 16 staging chunks: q = tid + 256*i -> row r = 8*i' + (q&7) ..., see stage_rows
+    uint4 pre[16];
+    auto prefetch = [&](int64_t tile) {
+        const int64_t row0 = tile * 128, nvalid = M - row0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int q = tid + i * 256;
+            const int rin = q & 7, kb = (q >> 3) & 31, r = (q >> 8) * 8 + rin;
+            pre[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(A + (row0 + r) * H + kb * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    prefetch(blockIdx.x);
 
     if (warp == 0) tmem_alloc<256>(tmem_holder);
     if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
@@ -153,7 +169,11 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * 128;
-        stage_rows<128>(As, A, row0, M - row0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int q = tid + i * 256;
+            *reinterpret_cast<uint4 *>(As + (q >> 8) * kSBO + ((q >> 3) & 31) * kLBO + (q & 7) * 16) = pre[i];
+        }
         fence_proxy_async();                              // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -164,35 +184,41 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
                           idesc, kk > 0 ? 1u : 0u);
             umma_commit(bar);                             // arrives on `bar` when all MMAs above have finished
         }
+        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the MMAs and the epilogue
+        // epilogue mapping: warp w drains lanes 32*(w%4).. of columns (w/4)*128 .. +127; thread = one output row
+        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        const int colbase = (warp >> 2) * 128;
+        uint4 hx[EPI == EPI_DTANH ? 16 : 1];
+        if (EPI == EPI_DTANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                hx[i] = (row < M) ? __ldg(reinterpret_cast<const uint4 *>(aux + row * H + colbase) + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // epilogue: warp w drains lanes 32*(w%4).. of columns (w/4)*128 .. +127; thread = one output row
-        const int64_t row = row0 + (warp & 3) * 32 + lane;
-        const int colbase = (warp >> 2) * 128;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
             uint32_t acc[16];
-            tmem_ld16(taddr + c0, acc);
-            if (row < M) {
-                const int col = colbase + c0;
-                uint32_t o[8];
-                if (EPI == EPI_BIAS_TANH) {
+            tmem_ld16(taddr + c * 16, acc);
+            const int col = colbase + c * 16;
+            uint32_t o[8];
+            if (EPI == EPI_BIAS_TANH) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = pack_bf16(tanh_fast(__uint_as_float(acc[2 * j]) + __ldg(bias + col + 2 * j)),
-                                         tanh_fast(__uint_as_float(acc[2 * j + 1]) + __ldg(bias + col + 2 * j + 1)));
-                } else {
-                    const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(aux + row * H + col));
-                    const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(aux + row * H + col + 8));
-                    const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                for (int j = 0; j < 8; ++j)
+                    o[j] = pack_bf16(tanh_fast(__uint_as_float(acc[2 * j]) + __ldg(bias + col + 2 * j)),
+                                     tanh_fast(__uint_as_float(acc[2 * j + 1]) + __ldg(bias + col + 2 * j + 1)));
+            } else {
+                const uint32_t hw[8] = {hx[2 * c].x, hx[2 * c].y, hx[2 * c].z, hx[2 * c].w,
+                                        hx[2 * c + 1].x, hx[2 * c + 1].y, hx[2 * c + 1].z, hx[2 * c + 1].w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float a = bf16_lo(hw[j]), b = bf16_hi(hw[j]);
-                        o[j] = pack_bf16(__uint_as_float(acc[2 * j]) * (1.0f - a * a), __uint_as_float(acc[2 * j + 1]) * (1.0f - b * b));
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float a = bf16_lo(hw[j]), b = bf16_hi(hw[j]);
+                    o[j] = pack_bf16(__uint_as_float(acc[2 * j]) * (1.0f - a * a), __uint_as_float(acc[2 * j + 1]) * (1.0f - b * b));
                 }
+            }
+            if (row < M) {
                 uint4 *dst = reinterpret_cast<uint4 *>(out + row * H + col);
                 dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -205,82 +231,89 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
 }
 
 // --------------------------------------------------------- G[256,256] += X[rows,256]^T . Y[rows,256]
+// 64-row chunks, two shared-memory stages: while the tensor core works on stage s the threads load,
+// transpose and stage the next chunk into stage s^1 (per-stage mbarriers signal "MMAs done reading").
+static constexpr int kgRows = 64;                        // rows (= K) per chunk
 static constexpr uint32_t kgLBO = 128;
-static constexpr uint32_t kgSBO = 16 * kgLBO + 16;       // 2064: 16 k-blocks per 8-row group + 16 B pad (bank spread)
-static constexpr uint32_t kgTile = 32 * kgSBO;           // 66048 B: 256 rows x K=128
-static constexpr uint32_t kWgradSmem = 2 * kgTile + 64;
+static constexpr uint32_t kgSBO = (kgRows / 8) * kgLBO + 16;   // 1040: 8 k-blocks per 8-row group + 16 B pad (bank spread)
+static constexpr uint32_t kgTile = 32 * kgSBO;           // 33280 B: 256 rows x K=64
+static constexpr uint32_t kgStage = 2 * kgTile;          // X and Y tiles
+static constexpr uint32_t kWgradSmem = 2 * kgStage + 64;
 
-// transpose-stage a [128 rows(k) x 256 cols(m)] row-major bf16 chunk into the K-major tile [256 (m) x 128 (k)]:
-// thread handles 8x8 blocks: 8 LDG.128 (coalesced: a warp reads 512 contiguous bytes per row), 32 PRMT, 8 STS.128
-__device__ __forceinline__ void stage_transposed(uint8_t *dst, const __nv_bfloat16 *__restrict__ src, int64_t row0, int64_t nvalid) {
+// transpose-stage a [64 rows(k) x 256 cols(m)] row-major bf16 chunk into the K-major tile [256 (m) x 64 (k)]:
+// thread = one 8x8 block (k-block = warp, m-group = lane): 8 LDG.128 (a warp reads 512 contiguous bytes per
+// row), 32 PRMT, 8 STS.128
+__device__ __forceinline__ void load_block(uint4 (&in)[8], const __nv_bfloat16 *__restrict__ src, int64_t row0, int64_t nvalid) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int kb = it * 8 + warp;                     // 8-row block of the chunk (k direction)
-        const int mg = lane;                              // 8-column group (m direction)
-        uint4 in[8];
+    for (int i = 0; i < 8; ++i) {
+        const int r = warp * 8 + i;
+        in[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(src + (row0 + r) * H + lane * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ void store_block_transposed(uint8_t *dst, const uint4 (&in)[8]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *base = dst + lane * kgSBO + warp * kgLBO;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = kb * 8 + i;
-            in[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(src + (row0 + r) * H + mg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    for (int c = 0; c < 8; ++c) {                         // output row c = column lane*8+c over the 8 source rows
+        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+        uint32_t w[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t a = (c >> 1) == 0 ? in[2 * p].x : ((c >> 1) == 1 ? in[2 * p].y : ((c >> 1) == 2 ? in[2 * p].z : in[2 * p].w));
+            const uint32_t b = (c >> 1) == 0 ? in[2 * p + 1].x : ((c >> 1) == 1 ? in[2 * p + 1].y : ((c >> 1) == 2 ? in[2 * p + 1].z : in[2 * p + 1].w));
+            w[p] = __byte_perm(a, b, sel);
         }
-        uint8_t *base = dst + mg * kgSBO + kb * kgLBO;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {                     // output row c = column mg*8+c over the 8 source rows
-            const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
-            uint32_t w[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const uint32_t a = (&in[2 * p].x)[c >> 1], b = (&in[2 * p + 1].x)[c >> 1];
-                w[p] = __byte_perm(a, b, sel);
-            }
-            *reinterpret_cast<uint4 *>(base + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        *reinterpret_cast<uint4 *>(base + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ Y, float *__restrict__ G, int64_t rows) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *Xs = smem, *Ys = smem + kgTile;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * kgTile);
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + 2 * kgTile + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * kgStage);        // bar[0], bar[1]
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + 2 * kgStage + 32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t nchunks = (rows + 127) / 128;
+    const int64_t nchunks = (rows + kgRows - 1) / kgRows;
     if ((int64_t)blockIdx.x >= nchunks) return;
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
-    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (tid == 32) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t idesc = make_idesc(128, 256);
-    const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
-    uint32_t phase = 0, first = 1;
-
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const int64_t row0 = chunk * 128;
-        stage_transposed(Xs, X, row0, rows - row0);
-        stage_transposed(Ys, Y, row0, rows - row0);
+    uint32_t ph[2] = {0u, 0u};
+    int it = 0;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int64_t row0 = chunk * kgRows, nvalid = rows - row0;
+        uint4 xin[8], yin[8];
+        load_block(xin, X, row0, nvalid);                 // global loads first (independent of the barrier wait)
+        load_block(yin, Y, row0, nvalid);
+        if (it >= 2) { mbar_wait(bar + s, ph[s]); ph[s] ^= 1u; }   // MMAs of chunk it-2 have finished reading stage s
+        uint8_t *Xs = smem + s * kgStage, *Ys = Xs + kgTile;
+        store_block_transposed(Xs, xin);
+        store_block_transposed(Ys, yin);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
+            const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
 #pragma unroll
             for (int mh = 0; mh < 2; ++mh)                // output rows 0..127 / 128..255 -> TMEM columns 0..255 / 256..511
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
+                for (int kk = 0; kk < kgRows / 16; ++kk)
                     umma_bf16(tmem_base + mh * 256, make_desc(x_addr + mh * 16 * kgSBO + kk * 2 * kgLBO, kgLBO, kgSBO),
-                              make_desc(y_addr + kk * 2 * kgLBO, kgLBO, kgSBO), idesc, (first && kk == 0) ? 0u : 1u);
-            umma_commit(bar);
+                              make_desc(y_addr + kk * 2 * kgLBO, kgLBO, kgSBO), idesc, (it == 0 && kk == 0) ? 0u : 1u);
+            umma_commit(bar + s);
         }
-        first = 0;
-        mbar_wait(bar, phase);                            // operands may be overwritten once the MMAs are done
-        phase ^= 1u;
-        tc_fence_after();
-        __syncthreads();
     }
+    // the last commit covers every MMA this CTA issued
+    const int last = (it - 1) & 1;                        // every commit on bar[last] but the newest has been waited for
+    mbar_wait(bar + last, ph[last]);
+    tc_fence_after();
     // epilogue: split-K reduction over CTAs with fire-and-forget float atomics
     const int colbase = (warp >> 2) * 128;
 #pragma unroll 1
@@ -351,7 +384,7 @@ int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, c
 int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st) {
     int rc = ensure_attrs();
     if (rc) return rc;
-    const unsigned grid = (unsigned)std::min<int64_t>((rows + 127) / 128, sm_count());
+    const unsigned grid = (unsigned)std::min<int64_t>((rows + kgRows - 1) / kgRows, sm_count());
     tc_wgrad_kernel<<<grid, 256, kWgradSmem, st>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)Y, G, rows);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
