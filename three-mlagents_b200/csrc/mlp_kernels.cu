@@ -133,26 +133,45 @@ head_forward_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, 
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             w[a][q] = Wh[a * H + (BF ? lane * 8 + q : (q < 4 ? lane * 4 + q : 128 + lane * 4 + (q - 4)))];
-    for (int64_t r = warp; r < rows; r += nwarps) {
-        float x[8];
-        if constexpr (BF) {
-            const uint4 v = reinterpret_cast<const uint4 *>(h2 + r * H)[lane];
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    constexpr int RB = 4;                                  // rows in flight per warp
+    for (int64_t r0 = warp * RB; r0 < rows; r0 += nwarps * RB) {
+        float x[RB][8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { x[2 * q] = __uint_as_float(u[q] << 16); x[2 * q + 1] = __uint_as_float(u[q] & 0xFFFF0000u); }
-        } else {
-            const float4 x0 = reinterpret_cast<const float4 *>(h2 + r * H)[lane];
-            const float4 x1 = reinterpret_cast<const float4 *>(h2 + r * H)[32 + lane];
-            x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        for (int u = 0; u < RB; ++u) {
+            const int64_t r = min(r0 + u, rows - 1);
+            if constexpr (BF) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(h2 + r * H) + lane);
+                const uint32_t w32[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { x[u][2 * q] = __uint_as_float(w32[q] << 16); x[u][2 * q + 1] = __uint_as_float(w32[q] & 0xFFFF0000u); }
+            } else {
+                const float4 x0 = reinterpret_cast<const float4 *>(h2 + r * H)[lane];
+                const float4 x1 = reinterpret_cast<const float4 *>(h2 + r * H)[32 + lane];
+                x[u][0] = x0.x; x[u][1] = x0.y; x[u][2] = x0.z; x[u][3] = x0.w; x[u][4] = x1.x; x[u][5] = x1.y; x[u][6] = x1.z; x[u][7] = x1.w;
+            }
         }
+        float s[RB][NOUT];
 #pragma unroll
-        for (int a = 0; a < NOUT; ++a) {
-            float s = 0.0f;
+        for (int u = 0; u < RB; ++u)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) s = fmaf(x[q], w[a][q], s);
+            for (int a = 0; a < NOUT; ++a) {
+                float t = 0.0f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) out[r * NOUT + a] = s + bh[a];
+                for (int q = 0; q < 8; ++q) t = fmaf(x[u][q], w[a][q], t);
+                s[u][a] = t;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)                   // RB*NOUT independent butterflies interleaved
+#pragma unroll
+            for (int u = 0; u < RB; ++u)
+#pragma unroll
+                for (int a = 0; a < NOUT; ++a) s[u][a] += __shfl_xor_sync(0xffffffffu, s[u][a], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < RB; ++u)
+                if (r0 + u < rows)
+#pragma unroll
+                    for (int a = 0; a < NOUT; ++a) out[(r0 + u) * NOUT + a] = s[u][a] + bh[a];
         }
     }
 }
@@ -245,20 +264,29 @@ l1_forward_bf16_kernel(const float *__restrict__ W1, const float *__restrict__ b
 #pragma unroll
         for (int k = 0; k < D; ++k) w[c][k] = W1[(lane * 8 + c) * D + k];
     }
-    for (int64_t r = warp; r < rows; r += nwarps) {
-        const int64_t src = index ? index[r] : r;
-        float xr[D];
+    constexpr int RB = 4;                                  // rows in flight per warp (latency hiding)
+    for (int64_t r0 = warp * RB; r0 < rows; r0 += nwarps * RB) {
+        int64_t src[RB];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xr[k] = __ldg(x + src * D + k);
-        float o[8];
+        for (int u = 0; u < RB; ++u) src[u] = (r0 + u < rows) ? (index ? (int64_t)__ldg(index + r0 + u) : r0 + u) : 0;
+        float xr[RB][D];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float acc = b[c];
+        for (int u = 0; u < RB; ++u)
 #pragma unroll
-            for (int k = 0; k < D; ++k) acc = fmaf(xr[k], w[c][k], acc);
-            o[c] = tanh_approx(acc);
+            for (int k = 0; k < D; ++k) xr[u][k] = __ldg(x + src[u] * D + k);
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            if (r0 + u >= rows) break;
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float acc = b[c];
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(xr[u][k], w[c][k], acc);
+                o[c] = tanh_approx(acc);
+            }
+            reinterpret_cast<uint4 *>(h1 + (r0 + u) * H)[lane] = pack8(o);
         }
-        reinterpret_cast<uint4 *>(h1 + r * H)[lane] = pack8(o);
     }
 }
 
@@ -275,19 +303,30 @@ l1_backward_bf16_kernel(const __nv_bfloat16 *__restrict__ dz1, const float *__re
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[k][c] = 0.0f;
     const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
-#pragma unroll 2
-    for (int64_t r = rb + warp; r < re; r += 8) {
-        const int64_t src = index ? index[r] : r;
-        float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz1 + r * H) + lane), g);
+    constexpr int RB = 4;                                  // rows in flight per warp
+    for (int64_t r0 = rb + warp; r0 < re; r0 += 8 * RB) {
+        uint4 gv[RB];
+        float xr[RB][D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const float xk = __ldg(x + src * D + k);
+        for (int u = 0; u < RB; ++u) {
+            const int64_t r = r0 + 8 * u;
+            const bool ok = r < re;
+            gv[u] = ok ? __ldg(reinterpret_cast<const uint4 *>(dz1 + r * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
+            const int64_t src = ok ? (index ? (int64_t)__ldg(index + r) : r) : 0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(g[c], xk, acc[k][c]);
+            for (int k = 0; k < D; ++k) xr[u][k] = ok ? __ldg(x + src * D + k) : 0.0f;
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[D][c] += g[c];
+        for (int u = 0; u < RB; ++u) {
+            float g[8];
+            unpack8(gv[u], g);
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(g[c], xr[u][k], acc[k][c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[D][c] += g[c];
+        }
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) reduce_planes(sh, acc[k], [&](int j, float s) { atomicAdd(dW1 + j * D + k, s); });
@@ -312,21 +351,36 @@ head_backward_bf16_kernel(const float *__restrict__ Wh, const __nv_bfloat16 *__r
 #pragma unroll
     for (int c = 0; c < 8; ++c) accb2[c] = 0.0f;
     const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
-#pragma unroll 2
-    for (int64_t r = rb + warp; r < re; r += 8) {
-        float h[8], d[NOUT], g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(h2 + r * H) + lane), h);
+    constexpr int RB = 4;                                  // rows in flight per warp
+    for (int64_t r0 = rb + warp; r0 < re; r0 += 8 * RB) {
+        uint4 hv[RB];
+        float d[RB][NOUT];
 #pragma unroll
-        for (int a = 0; a < NOUT; ++a) { d[a] = __ldg(dout + r * NOUT + a); accbh[a] += d[a]; }
+        for (int u = 0; u < RB; ++u) {
+            const int64_t r = r0 + 8 * u;
+            const bool ok = r < re;
+            hv[u] = ok ? __ldg(reinterpret_cast<const uint4 *>(h2 + r * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float t = 0.0f;
-#pragma unroll
-            for (int a = 0; a < NOUT; ++a) { t = fmaf(d[a], w[a][c], t); accw[a][c] = fmaf(d[a], h[c], accw[a][c]); }
-            g[c] = t * (1.0f - h[c] * h[c]);
-            accb2[c] += g[c];
+            for (int a = 0; a < NOUT; ++a) d[u][a] = ok ? __ldg(dout + r * NOUT + a) : 0.0f;
         }
-        reinterpret_cast<uint4 *>(dz2 + r * H)[lane] = pack8(g);
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int64_t r = r0 + 8 * u;
+            if (r >= re) break;
+            float h[8], g[8];
+            unpack8(hv[u], h);
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) accbh[a] += d[u][a];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t = 0.0f;
+#pragma unroll
+                for (int a = 0; a < NOUT; ++a) { t = fmaf(d[u][a], w[a][c], t); accw[a][c] = fmaf(d[u][a], h[c], accw[a][c]); }
+                g[c] = t * (1.0f - h[c] * h[c]);
+                accb2[c] += g[c];
+            }
+            reinterpret_cast<uint4 *>(dz2 + r * H)[lane] = pack8(g);
+        }
     }
 #pragma unroll
     for (int a = 0; a < NOUT; ++a) reduce_planes(sh, accw[a], [&](int j, float s) { atomicAdd(dWh + a * H + j, s); });

@@ -107,10 +107,16 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // -------------------------------------------------------------------- out = epi(A[M,256] . W[256,256]^T)
 enum { EPI_BIAS_TANH = 0, EPI_DTANH = 1 };
 
-static constexpr uint32_t kLBO = 128;                    // K-adjacent core matrices are contiguous
+// resident weight tile: 256 rows, K-adjacent core matrices contiguous
+static constexpr uint32_t kLBO = 128;
 static constexpr uint32_t kSBO = (H / 8) * kLBO;         // 4096 B per 8-row group (K = 256)
-static constexpr uint32_t kWBytes = (H / 8) * kSBO;      // 131072: 256 rows
-static constexpr uint32_t kABytes = (128 / 8) * kSBO;    // 65536: 128 rows
+static constexpr uint32_t kWBytes = (H / 8) * kSBO;      // 131072
+// activation tile: 128 rows; core matrices along K are 144 B apart (16 B pad) so that a warp whose lanes
+// hold the 32 consecutive 16-byte chunks of ONE row (a fully coalesced 512-byte global load) stores them
+// without shared-memory bank conflicts
+static constexpr uint32_t kaLBO = 144;
+static constexpr uint32_t kaSBO = (H / 8) * kaLBO;       // 4608
+static constexpr uint32_t kABytes = (128 / 8) * kaSBO;   // 73728 (also reused as the 64 KB epilogue stage)
 static constexpr uint32_t kLinearSmem = kWBytes + kABytes + 64;
 
 // stage `nrows` (<= R) rows of a row-major bf16 [*,256] matrix into the K-major core-matrix layout.
@@ -127,9 +133,22 @@ __device__ __forceinline__ void stage_rows(uint8_t *dst, const __nv_bfloat16 *__
     }
 }
 
-// The A tile of the NEXT row block is prefetched into registers (16 x 16 B per thread) right after the MMAs of
-// the current block have been issued, so global-load latency overlaps the tensor-core work and the epilogue;
-// the dgrad epilogue's 1-h^2 operand is prefetched the same way before waiting on the MMA barrier.
+__device__ __forceinline__ uint4 mul_dtanh(const uint4 &v, const uint4 &h) {   // v * (1 - h^2), 8 bf16 lanes
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w}, hh[4] = {h.x, h.y, h.z, h.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(hh[j]), b = bf16_hi(hh[j]);
+        o[j] = pack_bf16(bf16_lo(vv[j]) * (1.0f - a * a), bf16_hi(vv[j]) * (1.0f - b * b));
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Per 128-row tile:  registers(prefetched A) -> smem (K-major) -> 16 x tcgen05.mma -> TMEM -> registers ->
+// smem stage (XOR-swizzled rows) -> coalesced 512-byte row stores.  The A tile of the NEXT row block (and the
+// dgrad epilogue's 1-h^2 operand) are prefetched into registers right after the MMAs have been issued, so
+// global-load latency overlaps the tensor-core work and the epilogue.  All global traffic is issued as full
+// 512-byte rows per warp (4 L1 wavefronts per request).
 template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ W, const float *__restrict__ bias,
@@ -143,15 +162,14 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
     const int64_t ntiles = (M + 127) / 128;
     if ((int64_t)blockIdx.x >= ntiles) return;            // whole CTA exits before any allocation
 
-    // this thread's 16 staging chunks: q = tid + 256*i -> row r = 8*i' + (q&7) ..., see stage_rows
+    // this thread's 16 chunks of a tile: row r = warp + 8*i, 16-byte chunk `lane` of that row
     uint4 pre[16];
     auto prefetch = [&](int64_t tile) {
         const int64_t row0 = tile * 128, nvalid = M - row0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int q = tid + i * 256;
-            const int rin = q & 7, kb = (q >> 3) & 31, r = (q >> 8) * 8 + rin;
-            pre[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(A + (row0 + r) * H + kb * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            const int r = warp + 8 * i;
+            pre[i] = (r < nvalid) ? __ldg(reinterpret_cast<const uint4 *>(A + (row0 + r) * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
         }
     };
     prefetch(blockIdx.x);
@@ -171,8 +189,8 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
         const int64_t row0 = tile * 128;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int q = tid + i * 256;
-            *reinterpret_cast<uint4 *>(As + (q >> 8) * kSBO + ((q >> 3) & 31) * kLBO + (q & 7) * 16) = pre[i];
+            const int r = warp + 8 * i;
+            *reinterpret_cast<uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16) = pre[i];
         }
         fence_proxy_async();                              // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
@@ -180,69 +198,76 @@ tc_linear_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__res
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)           // 16 MMAs of K=16: two core matrices along K each
-                umma_bf16(tmem_base, make_desc(a_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc(w_addr + kk * 2 * kLBO, kLBO, kSBO),
+                umma_bf16(tmem_base, make_desc(a_addr + kk * 2 * kaLBO, kaLBO, kaSBO), make_desc(w_addr + kk * 2 * kLBO, kLBO, kSBO),
                           idesc, kk > 0 ? 1u : 0u);
             umma_commit(bar);                             // arrives on `bar` when all MMAs above have finished
         }
         if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the MMAs and the epilogue
-        // epilogue mapping: warp w drains lanes 32*(w%4).. of columns (w/4)*128 .. +127; thread = one output row
-        const int64_t row = row0 + (warp & 3) * 32 + lane;
-        const int colbase = (warp >> 2) * 128;
         uint4 hx[EPI == EPI_DTANH ? 16 : 1];
-        if (EPI == EPI_DTANH) {
+        if (EPI == EPI_DTANH) {                           // same (row, chunk) mapping as the copy-out below
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                hx[i] = (row < M) ? __ldg(reinterpret_cast<const uint4 *>(aux + row * H + colbase) + i) : make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < 16; ++i) {
+                const int64_t r = row0 + warp + 8 * i;
+                hx[i] = (r < M) ? __ldg(reinterpret_cast<const uint4 *>(aux + r * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
+        // TMEM -> registers -> stage.  warp w drains lanes 32*(w%4).. of columns (w/4)*128..+127; thread = one row.
+        // stage layout: row-major 512 B rows, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
+        {
+            const int rt = (warp & 3) * 32 + lane;        // row inside the tile
+            const int colbase = (warp >> 2) * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
+            uint8_t *srow = As + rt * 512;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t acc[16];
-            tmem_ld16(taddr + c * 16, acc);
-            const int col = colbase + c * 16;
-            uint32_t o[8];
-            if (EPI == EPI_BIAS_TANH) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    o[j] = pack_bf16(tanh_fast(__uint_as_float(acc[2 * j]) + __ldg(bias + col + 2 * j)),
-                                     tanh_fast(__uint_as_float(acc[2 * j + 1]) + __ldg(bias + col + 2 * j + 1)));
-            } else {
-                const uint32_t hw[8] = {hx[2 * c].x, hx[2 * c].y, hx[2 * c].z, hx[2 * c].w,
-                                        hx[2 * c + 1].x, hx[2 * c + 1].y, hx[2 * c + 1].z, hx[2 * c + 1].w};
+            for (int c = 0; c < 8; ++c) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + c * 16, acc);
+                const int col = colbase + c * 16;
+                uint32_t o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float a = bf16_lo(hw[j]), b = bf16_hi(hw[j]);
-                    o[j] = pack_bf16(__uint_as_float(acc[2 * j]) * (1.0f - a * a), __uint_as_float(acc[2 * j + 1]) * (1.0f - b * b));
+                    float v0 = __uint_as_float(acc[2 * j]), v1 = __uint_as_float(acc[2 * j + 1]);
+                    if (EPI == EPI_BIAS_TANH) {
+                        v0 = tanh_fast(v0 + __ldg(bias + col + 2 * j));
+                        v1 = tanh_fast(v1 + __ldg(bias + col + 2 * j + 1));
+                    }
+                    o[j] = pack_bf16(v0, v1);
                 }
-            }
-            if (row < M) {
-                uint4 *dst = reinterpret_cast<uint4 *>(out + row * H + col);
-                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                const int ch = col >> 3;                  // first of two 16-byte chunks
+                *reinterpret_cast<uint4 *>(srow + ((ch ^ (rt & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(srow + (((ch + 1) ^ (rt & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
         tc_fence_before();
-        __syncthreads();                                  // TMEM drained + As free before the next tile
+        __syncthreads();                                  // stage complete, TMEM drained
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                    // coalesced copy-out: a warp writes one full 512-byte row
+            const int r = warp + 8 * i;
+            uint4 v = *reinterpret_cast<const uint4 *>(As + r * 512 + ((lane ^ (r & 7)) << 4));
+            if (EPI == EPI_DTANH) v = mul_dtanh(v, hx[i]);
+            if (row0 + r < M) reinterpret_cast<uint4 *>(out + (row0 + r) * H)[lane] = v;
+        }
+        __syncthreads();                                  // As free for the next tile
     }
     if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 // --------------------------------------------------------- G[256,256] += X[rows,256]^T . Y[rows,256]
-// 64-row chunks, two shared-memory stages: while the tensor core works on stage s the threads load,
-// transpose and stage the next chunk into stage s^1 (per-stage mbarriers signal "MMAs done reading").
+// 64-row chunks, two shared-memory stages and two chunks of register prefetch: while the tensor core works on
+// stage s the threads transpose and stage the next chunk into stage s^1, and the loads of the chunk after that
+// are already in flight (per-stage mbarriers signal "MMAs done reading").
 static constexpr int kgRows = 64;                        // rows (= K) per chunk
 static constexpr uint32_t kgLBO = 128;
 static constexpr uint32_t kgSBO = (kgRows / 8) * kgLBO + 16;   // 1040: 8 k-blocks per 8-row group + 16 B pad (bank spread)
 static constexpr uint32_t kgTile = 32 * kgSBO;           // 33280 B: 256 rows x K=64
 static constexpr uint32_t kgStage = 2 * kgTile;          // X and Y tiles
-static constexpr uint32_t kWgradSmem = 2 * kgStage + 64;
+static constexpr uint32_t kWgradSmem = 2 * kgStage + 64; // 133184 (>= 128 KB epilogue stage)
 
-// transpose-stage a [64 rows(k) x 256 cols(m)] row-major bf16 chunk into the K-major tile [256 (m) x 64 (k)]:
-// thread = one 8x8 block (k-block = warp, m-group = lane): 8 LDG.128 (a warp reads 512 contiguous bytes per
-// row), 32 PRMT, 8 STS.128
+// thread = one 8x8 block of the chunk (k-block = warp, m-group = lane): 8 LDG.128 (a warp reads 512 contiguous
+// bytes per row), 32 PRMT, 8 STS.128 into the K-major tile [256 (m) x 64 (k)]
 __device__ __forceinline__ void load_block(uint4 (&in)[8], const __nv_bfloat16 *__restrict__ src, int64_t row0, int64_t nvalid) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -285,17 +310,23 @@ tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__rest
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t idesc = make_idesc(128, 256);
     uint32_t ph[2] = {0u, 0u};
+    // software pipeline: (xa,ya) = chunk being staged now, (xb,yb) = the one after (loads in flight)
+    uint4 xa[8], ya[8], xb[8], yb[8];
+    const int64_t stride = gridDim.x;
+    int64_t chunk = blockIdx.x;
+    load_block(xa, X, chunk * kgRows, rows - chunk * kgRows);
+    load_block(ya, Y, chunk * kgRows, rows - chunk * kgRows);
+    if (chunk + stride < nchunks) {
+        load_block(xb, X, (chunk + stride) * kgRows, rows - (chunk + stride) * kgRows);
+        load_block(yb, Y, (chunk + stride) * kgRows, rows - (chunk + stride) * kgRows);
+    }
     int it = 0;
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+    for (; chunk < nchunks; chunk += stride, ++it) {
         const int s = it & 1;
-        const int64_t row0 = chunk * kgRows, nvalid = rows - row0;
-        uint4 xin[8], yin[8];
-        load_block(xin, X, row0, nvalid);                 // global loads first (independent of the barrier wait)
-        load_block(yin, Y, row0, nvalid);
         if (it >= 2) { mbar_wait(bar + s, ph[s]); ph[s] ^= 1u; }   // MMAs of chunk it-2 have finished reading stage s
         uint8_t *Xs = smem + s * kgStage, *Ys = Xs + kgTile;
-        store_block_transposed(Xs, xin);
-        store_block_transposed(Ys, yin);
+        store_block_transposed(Xs, xa);
+        store_block_transposed(Ys, ya);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -309,23 +340,49 @@ tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__rest
                               make_desc(y_addr + kk * 2 * kgLBO, kgLBO, kgSBO), idesc, (it == 0 && kk == 0) ? 0u : 1u);
             umma_commit(bar + s);
         }
+        // rotate the register pipeline and launch the loads two chunks ahead
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xa[i] = xb[i]; ya[i] = yb[i]; }
+        const int64_t nxt = chunk + 2 * stride;
+        if (nxt < nchunks) {
+            load_block(xb, X, nxt * kgRows, rows - nxt * kgRows);
+            load_block(yb, Y, nxt * kgRows, rows - nxt * kgRows);
+        }
     }
-    // the last commit covers every MMA this CTA issued
     const int last = (it - 1) & 1;                        // every commit on bar[last] but the newest has been waited for
     mbar_wait(bar + last, ph[last]);
     tc_fence_after();
-    // epilogue: split-K reduction over CTAs with fire-and-forget float atomics
-    const int colbase = (warp >> 2) * 128;
+    // epilogue: TMEM -> registers -> smem stage (fp32 [128][256], 16-byte chunks XOR-swizzled by row) ->
+    // coalesced red.global.add.v4.f32 (split-K reduction over CTAs): a warp adds one 1 KB row in two requests
 #pragma unroll 1
     for (int mh = 0; mh < 2; ++mh) {
-        const int m = mh * 128 + (warp & 3) * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mh * 256 + colbase);
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-            uint32_t acc[16];
-            tmem_ld16(taddr + c0, acc);
+        __syncthreads();                                  // previous half fully flushed / MMAs done with smem
+        {
+            const int rt = (warp & 3) * 32 + lane;
+            const int colbase = (warp >> 2) * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mh * 256 + colbase);
+            uint8_t *srow = smem + rt * 1024;
+#pragma unroll 2
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + c0, acc);
+                const int ch = (colbase + c0) >> 2;       // first of four 16-byte chunks (4 floats each)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(G + m * H + colbase + c0 + j, __uint_as_float(acc[j]));
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4 *>(srow + (((ch + q) ^ (rt & 7)) << 4)) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int r = warp + 8 * i;
+            float *grow = G + (int64_t)(mh * 128 + r) * H;
+#pragma unroll
+            for (int hseg = 0; hseg < 2; ++hseg) {
+                const int ch = hseg * 32 + lane;
+                const float4 v = *reinterpret_cast<const float4 *>(smem + r * 1024 + ((ch ^ (r & 7)) << 4));
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + ch * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
         }
     }
     tc_fence_before();
