@@ -250,52 +250,98 @@ __device__ __forceinline__ void reduce_planes(float (*sh)[H], const float *vals8
     emit(threadIdx.x, s);
 }
 
+// ---- per-warp cp.async row pipeline: DEPTH rows of 512 B (+ up to 8 aux floats) in flight per warp at zero
+// register cost.  Every iteration commits exactly one group (possibly empty), so wait_group<DEPTH-1> always
+// means "the oldest row has landed".
+template <int DEPTH>
+struct WarpRowPipe {
+    static constexpr int SLOT = 512 + 32;
+    uint8_t *base;
+    int lane;
+    __device__ __forceinline__ WarpRowPipe(uint8_t *smem_block) : base(smem_block + (threadIdx.x >> 5) * DEPTH * SLOT), lane(threadIdx.x & 31) {}
+    __device__ __forceinline__ void issue(int slot, const void *row512, const float *aux, int naux) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + slot * SLOT);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"((const uint8_t *)row512 + lane * 16) : "memory");
+        if (lane < naux) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 512 + lane * 4), "l"(aux + lane) : "memory");
+    }
+    __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void wait_oldest() {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ uint4 row(int slot) const { return *reinterpret_cast<const uint4 *>(base + slot * SLOT + lane * 16); }
+    __device__ __forceinline__ float aux(int slot, int j) const { return *reinterpret_cast<const float *>(base + slot * SLOT + 512 + j * 4); }
+};
+static constexpr int kPipeDepth = 12;
+static constexpr int kPipeSmem = 8 * kPipeDepth * (512 + 32);      // 52224 B per 256-thread block
+
+// h1 = tanh(x W1^T + b1): W1 staged once per block through shared memory (coalesced), persistent grid,
+// the obs gather is lane-parallel over windows of 32 rows (lane l fetches index and the D floats of row l,
+// values are broadcast with shuffles) and the next window is prefetched while the current one is computed.
 template <int D>
 __global__ void __launch_bounds__(256)
 l1_forward_bf16_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ x,
                        const int32_t *__restrict__ index, int64_t rows, const int32_t *rows_dev, __nv_bfloat16 *__restrict__ h1) {
+    __shared__ float sw[H * D + H];
     rows = eff_rows(rows, rows_dev);
+    for (int e = threadIdx.x; e < H * D + H; e += 256) sw[e] = e < H * D ? W1[e] : b1[e - H * D];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float w[8][D], b[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        b[c] = b1[lane * 8 + c];
+        b[c] = sw[H * D + lane * 8 + c];
 #pragma unroll
-        for (int k = 0; k < D; ++k) w[c][k] = W1[(lane * 8 + c) * D + k];
+        for (int k = 0; k < D; ++k) w[c][k] = sw[(lane * 8 + c) * D + k];
     }
-    constexpr int RB = 4;                                  // rows in flight per warp (latency hiding)
-    for (int64_t r0 = warp * RB; r0 < rows; r0 += nwarps * RB) {
-        int64_t src[RB];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nwin = (rows + 31) / 32;
+    auto fetch = [&](int64_t win, float *xv) {
+        const int64_t r = win * 32 + lane;
+        if (win < nwin && r < rows) {
+            const int64_t src = index ? (int64_t)__ldg(index + r) : r;
 #pragma unroll
-        for (int u = 0; u < RB; ++u) src[u] = (r0 + u < rows) ? (index ? (int64_t)__ldg(index + r0 + u) : r0 + u) : 0;
-        float xr[RB][D];
+            for (int k = 0; k < D; ++k) xv[k] = __ldg(x + src * D + k);
+        } else {
 #pragma unroll
-        for (int u = 0; u < RB; ++u)
+            for (int k = 0; k < D; ++k) xv[k] = 0.0f;
+        }
+    };
+    float cur[D], nxt[D];
+    fetch(warp, cur);
+    for (int64_t win = warp; win < nwin; win += nwarps) {
+        fetch(win + nwarps, nxt);                          // in flight while this window is computed
+        const int64_t r0 = win * 32;
+        const int nr = (int)min((int64_t)32, rows - r0);
+#pragma unroll 4
+        for (int j = 0; j < nr; ++j) {
+            float xr[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) xr[u][k] = __ldg(x + src[u] * D + k);
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            if (r0 + u >= rows) break;
+            for (int k = 0; k < D; ++k) xr[k] = __shfl_sync(0xffffffffu, cur[k], j);
             float o[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float acc = b[c];
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc = fmaf(xr[u][k], w[c][k], acc);
+                for (int k = 0; k < D; ++k) acc = fmaf(xr[k], w[c][k], acc);
                 o[c] = tanh_approx(acc);
             }
-            reinterpret_cast<uint4 *>(h1 + (r0 + u) * H)[lane] = pack8(o);
+            reinterpret_cast<uint4 *>(h1 + (r0 + j) * H)[lane] = pack8(o);
         }
+#pragma unroll
+        for (int k = 0; k < D; ++k) cur[k] = nxt[k];
     }
 }
 
 // dW1[j][k] += sum_r dZ1[r][j] x[r][k],  db1[j] += sum_r dZ1[r][j]
+// dZ1 rows stream through the cp.async pipe; the gathered obs row rides along as the slot's aux floats.
 template <int D>
 __global__ void __launch_bounds__(256)
 l1_backward_bf16_kernel(const __nv_bfloat16 *__restrict__ dz1, const float *__restrict__ x, const int32_t *__restrict__ index,
                         int64_t rows, int rows_per_block, float *__restrict__ dW1, float *__restrict__ db1) {
-    __shared__ float sh[8][H];
+    extern __shared__ __align__(16) uint8_t dyn[];
+    float (*sh)[H] = reinterpret_cast<float (*)[H]>(dyn);            // reduce_planes scratch (8 KB), after the loop
+    WarpRowPipe<kPipeDepth> pipe(dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[D + 1][8];
 #pragma unroll
@@ -303,43 +349,61 @@ l1_backward_bf16_kernel(const __nv_bfloat16 *__restrict__ dz1, const float *__re
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[k][c] = 0.0f;
     const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
-    constexpr int RB = 4;                                  // rows in flight per warp
-    for (int64_t r0 = rb + warp; r0 < re; r0 += 8 * RB) {
-        uint4 gv[RB];
-        float xr[RB][D];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int64_t r = r0 + 8 * u;
-            const bool ok = r < re;
-            gv[u] = ok ? __ldg(reinterpret_cast<const uint4 *>(dz1 + r * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
-            const int64_t src = ok ? (index ? (int64_t)__ldg(index + r) : r) : 0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) xr[u][k] = ok ? __ldg(x + src * D + k) : 0.0f;
+    const int n = re > rb + warp ? (int)((re - rb - warp + 7) / 8) : 0;      // rows of this warp: rb + warp + 8*i
+    // indices of the warp's rows, 32 at a time, lane-parallel (window w covers i in [32w, 32w+32))
+    auto load_idx = [&](int win) -> int64_t {
+        const int i = win * 32 + lane;
+        if (i >= n) return 0;
+        const int64_t r = rb + warp + 8 * (int64_t)i;
+        return index ? (int64_t)__ldg(index + r) : r;
+    };
+    int64_t idx_cur = load_idx(0), idx_nxt = load_idx(1);
+    auto issue_row = [&](int i) {                          // i-th row of this warp into slot i % DEPTH
+        if (i < n) {
+            const int64_t r = rb + warp + 8 * (int64_t)i;
+            const int64_t src = __shfl_sync(0xffffffffu, ((i >> 5) & 1) == 0 ? idx_cur : idx_nxt, i & 31);
+            pipe.issue(i % kPipeDepth, dz1 + r * H, x + src * D, D);
         }
+        pipe.commit();
+    };
+    // windows alternate between idx_cur (even) and idx_nxt (odd); refresh the one just finished
+    for (int p = 0; p < kPipeDepth; ++p) issue_row(p);
+    for (int i = 0; i < n; ++i) {
+        pipe.wait_oldest();
+        const int slot = i % kPipeDepth;
+        float g[8], xr[D];
+        unpack8(pipe.row(slot), g);
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            float g[8];
-            unpack8(gv[u], g);
-#pragma unroll
-            for (int k = 0; k < D; ++k)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(g[c], xr[u][k], acc[k][c]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[D][c] += g[c];
+        for (int k = 0; k < D; ++k) xr[k] = pipe.aux(slot, k);
+        __syncwarp();
+        const int ni = i + kPipeDepth;
+        if ((ni & 31) == 0) {                              // entering a new window at issue side: reload the stale register
+            if (((ni >> 5) & 1) == 0) idx_cur = load_idx(ni >> 5); else idx_nxt = load_idx(ni >> 5);
         }
+        issue_row(ni);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(g[c], xr[k], acc[k][c]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[D][c] += g[c];
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < D; ++k) reduce_planes(sh, acc[k], [&](int j, float s) { atomicAdd(dW1 + j * D + k, s); });
     reduce_planes(sh, acc[D], [&](int j, float s) { atomicAdd(db1 + j, s); });
 }
 
 //   dZ2[r][j] = (sum_a dOut[r][a] Wh[a][j]) * (1 - h2[r][j]^2) ; dWh[a][j] += dOut[r][a] h2[r][j] ; db2[j] += dZ2[r][j] ; dbh[a] += dOut[r][a]
+// h2 rows (and the dOut row as aux) stream through the cp.async pipe.
 template <int NOUT>
 __global__ void __launch_bounds__(256)
 head_backward_bf16_kernel(const float *__restrict__ Wh, const __nv_bfloat16 *__restrict__ h2, const float *__restrict__ dout,
                           int64_t rows, int rows_per_block, __nv_bfloat16 *__restrict__ dz2, float *__restrict__ dWh,
                           float *__restrict__ dbh, float *__restrict__ db2) {
-    __shared__ float sh[8][H];
+    extern __shared__ __align__(16) uint8_t dyn[];
+    float (*sh)[H] = reinterpret_cast<float (*)[H]>(dyn);
+    WarpRowPipe<kPipeDepth> pipe(dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float w[NOUT][8], accw[NOUT][8], accb2[8], accbh[NOUT];
 #pragma unroll
@@ -351,37 +415,37 @@ head_backward_bf16_kernel(const float *__restrict__ Wh, const __nv_bfloat16 *__r
 #pragma unroll
     for (int c = 0; c < 8; ++c) accb2[c] = 0.0f;
     const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
-    constexpr int RB = 4;                                  // rows in flight per warp
-    for (int64_t r0 = rb + warp; r0 < re; r0 += 8 * RB) {
-        uint4 hv[RB];
-        float d[RB][NOUT];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int64_t r = r0 + 8 * u;
-            const bool ok = r < re;
-            hv[u] = ok ? __ldg(reinterpret_cast<const uint4 *>(h2 + r * H) + lane) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int a = 0; a < NOUT; ++a) d[u][a] = ok ? __ldg(dout + r * NOUT + a) : 0.0f;
+    const int n = re > rb + warp ? (int)((re - rb - warp + 7) / 8) : 0;
+    auto issue_row = [&](int i) {
+        if (i < n) {
+            const int64_t r = rb + warp + 8 * (int64_t)i;
+            pipe.issue(i % kPipeDepth, h2 + r * H, dout + r * NOUT, NOUT);
         }
+        pipe.commit();
+    };
+    for (int p = 0; p < kPipeDepth; ++p) issue_row(p);
+    for (int i = 0; i < n; ++i) {
+        pipe.wait_oldest();
+        const int slot = i % kPipeDepth;
+        float h[8], d[NOUT], g[8];
+        unpack8(pipe.row(slot), h);
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int64_t r = r0 + 8 * u;
-            if (r >= re) break;
-            float h[8], g[8];
-            unpack8(hv[u], h);
+        for (int a = 0; a < NOUT; ++a) d[a] = pipe.aux(slot, a);
+        __syncwarp();
+        issue_row(i + kPipeDepth);
 #pragma unroll
-            for (int a = 0; a < NOUT; ++a) accbh[a] += d[u][a];
+        for (int a = 0; a < NOUT; ++a) accbh[a] += d[a];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float t = 0.0f;
+        for (int c = 0; c < 8; ++c) {
+            float t = 0.0f;
 #pragma unroll
-                for (int a = 0; a < NOUT; ++a) { t = fmaf(d[u][a], w[a][c], t); accw[a][c] = fmaf(d[u][a], h[c], accw[a][c]); }
-                g[c] = t * (1.0f - h[c] * h[c]);
-                accb2[c] += g[c];
-            }
-            reinterpret_cast<uint4 *>(dz2 + r * H)[lane] = pack8(g);
+            for (int a = 0; a < NOUT; ++a) { t = fmaf(d[a], w[a][c], t); accw[a][c] = fmaf(d[a], h[c], accw[a][c]); }
+            g[c] = t * (1.0f - h[c] * h[c]);
+            accb2[c] += g[c];
         }
+        reinterpret_cast<uint4 *>(dz2 + (rb + warp + 8 * (int64_t)i) * H)[lane] = pack8(g);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int a = 0; a < NOUT; ++a) reduce_planes(sh, accw[a], [&](int j, float s) { atomicAdd(dWh + a * H + j, s); });
     reduce_planes(sh, accb2, [&](int j, float s) { atomicAdd(db2 + j, s); });
@@ -389,6 +453,59 @@ head_backward_bf16_kernel(const float *__restrict__ Wh, const __nv_bfloat16 *__r
 #pragma unroll
         for (int a = 0; a < NOUT; ++a) atomicAdd(dbh + a, accbh[a]);
     }
+}
+
+// out[r][a] = h2[r] . Wh[a] + bh[a] for the tensor-core path: h2 rows stream through the cp.async pipe,
+// weights come from shared memory (staged once per block), NOUT butterflies are interleaved.
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+head_forward_bf16_kernel(const float *__restrict__ Wh, const float *__restrict__ bh, const __nv_bfloat16 *__restrict__ h2,
+                         int64_t rows, const int32_t *rows_dev, float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ float sw[NOUT * H];
+    rows = eff_rows(rows, rows_dev);
+    for (int e = threadIdx.x; e < NOUT * H; e += 256) sw[e] = Wh[e];
+    __syncthreads();
+    WarpRowPipe<kPipeDepth> pipe(dyn);
+    const int lane = threadIdx.x & 31;
+    float w[NOUT][8];
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[a][q] = sw[a * H + lane * 8 + q];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n = rows > warp ? (int)((rows - warp + nwarps - 1) / nwarps) : 0;   // rows warp + nwarps*i
+    auto issue_row = [&](int i) {
+        if (i < n) pipe.issue(i % kPipeDepth, h2 + (warp + nwarps * (int64_t)i) * H, nullptr, 0);
+        pipe.commit();
+    };
+    for (int p = 0; p < kPipeDepth; ++p) issue_row(p);
+    for (int i = 0; i < n; ++i) {
+        pipe.wait_oldest();
+        float x[8];
+        unpack8(pipe.row(i % kPipeDepth), x);
+        __syncwarp();
+        issue_row(i + kPipeDepth);
+        float s[NOUT];
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) {
+            float t = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t = fmaf(x[q], w[a][q], t);
+            s[a] = t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) s[a] += __shfl_xor_sync(0xffffffffu, s[a], o);
+        if (lane < NOUT) {
+            float v = s[0];
+#pragma unroll
+            for (int a = 1; a < NOUT; ++a) v = lane == a ? s[a] : v;
+            out[(warp + nwarps * (int64_t)i) * NOUT + lane] = v + bh[lane];
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // --------------------------------------------------------------------------- 128x128x8 SIMT SGEMM
@@ -506,11 +623,24 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
 }
 
 // --------------------------------------------------------------------------------------- host API
+static int ensure_pipe_attrs() {
+    static int done = 0;
+    if (done) return TMLA_OK;
+#define PIPE_ATTR(K) TMLA_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem))
+    PIPE_ATTR(head_forward_bf16_kernel<1>); PIPE_ATTR(head_forward_bf16_kernel<3>); PIPE_ATTR(head_forward_bf16_kernel<5>);
+    PIPE_ATTR(head_backward_bf16_kernel<1>); PIPE_ATTR(head_backward_bf16_kernel<3>); PIPE_ATTR(head_backward_bf16_kernel<5>);
+    PIPE_ATTR(l1_backward_bf16_kernel<4>); PIPE_ATTR(l1_backward_bf16_kernel<6>);
+#undef PIPE_ATTR
+    done = 1;
+    return TMLA_OK;
+}
+
 // shared body of the fp32 (AT=float, SIMT SGEMM) and bf16 (AT=__nv_bfloat16, tcgen05) paths
 template <typename AT>
 static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim, int n_actions, const float *x, const int32_t *index,
                             int64_t rows, const int32_t *rows_dev, float *logits, float *values, AT *act_cache, cudaStream_t st) {
     constexpr bool BF = sizeof(AT) == 2;
+    if (BF) { int rc = ensure_pipe_attrs(); if (rc) return rc; }
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
     for (int t = 0; t < 2; ++t) {
         float *out = t == 0 ? logits : values;
@@ -518,7 +648,7 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
         AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
         const unsigned g1 = (unsigned)ceil_div64(rows, 32);
 #define L1F(DD) l1_forward_kernel<DD, AT><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
-        const unsigned gs = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);      // warp-per-row streaming kernels
+        const unsigned gs = (unsigned)std::min<int64_t>(ceil_div64(rows, 256), 148 * 2);    // persistent: 32-row windows per warp
         if constexpr (BF) {
             if (obs_dim == 4) l1_forward_bf16_kernel<4><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
             else if (obs_dim == 6) l1_forward_bf16_kernel<6><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
@@ -538,10 +668,17 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
                                                                           H, H, params + o.b2[t], rows_dev);
             TMLA_LAUNCH_CHECK();
         }
-        const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
-        if (t == 1) head_forward_kernel<1, AT><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
-        else if (n_actions == 3) head_forward_kernel<3, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
-        else head_forward_kernel<5, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        if constexpr (BF) {
+            const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8 * kPipeDepth), 148 * 4);
+            if (t == 1) head_forward_bf16_kernel<1><<<gh, 256, kPipeSmem, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
+            else if (n_actions == 3) head_forward_bf16_kernel<3><<<gh, 256, kPipeSmem, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+            else head_forward_bf16_kernel<5><<<gh, 256, kPipeSmem, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        } else {
+            const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
+            if (t == 1) head_forward_kernel<1, AT><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
+            else if (n_actions == 3) head_forward_kernel<3, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+            else head_forward_kernel<5, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+        }
         TMLA_LAUNCH_CHECK();
     }
     return TMLA_OK;
@@ -552,6 +689,7 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
                              int64_t rows, const AT *act_cache, const float *dlogits, const float *dvalues, float *grads,
                              AT *scratch, cudaStream_t st) {
     constexpr bool BF = sizeof(AT) == 2;
+    if (BF) { int rc = ensure_pipe_attrs(); if (rc) return rc; }
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
     TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
     AT *dz2 = scratch, *dz1 = scratch + rows * H;
@@ -562,9 +700,9 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
         const AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
         const float *dout = t == 0 ? dlogits : dvalues;
         if constexpr (BF) {
-            if (t == 1) head_backward_bf16_kernel<1><<<gr, 256, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
-            else if (n_actions == 3) head_backward_bf16_kernel<3><<<gr, 256, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
-            else head_backward_bf16_kernel<5><<<gr, 256, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            if (t == 1) head_backward_bf16_kernel<1><<<gr, 256, kPipeSmem, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
+            else if (n_actions == 3) head_backward_bf16_kernel<3><<<gr, 256, kPipeSmem, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            else head_backward_bf16_kernel<5><<<gr, 256, kPipeSmem, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
         } else {
             if (t == 1) head_backward_kernel<1, AT><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
             else if (n_actions == 3) head_backward_kernel<3, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
@@ -595,8 +733,8 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
         }
 #define L1B(DD) l1_backward_kernel<DD, AT><<<gr, H, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t])
         if constexpr (BF) {
-            if (obs_dim == 4) l1_backward_bf16_kernel<4><<<gr, 256, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
-            else if (obs_dim == 6) l1_backward_bf16_kernel<6><<<gr, 256, 0, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
+            if (obs_dim == 4) l1_backward_bf16_kernel<4><<<gr, 256, kPipeSmem, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
+            else if (obs_dim == 6) l1_backward_bf16_kernel<6><<<gr, 256, kPipeSmem, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
             else L1B(21);
         } else {
             if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else L1B(21);
