@@ -1,0 +1,66 @@
+"""Multi-GPU protocol of the hot path: one process per GPU, environments sharded by global
+env id, ONE data-path collective — a sum all-reduce of the flat fp32 gradient per minibatch — plus a 24-byte
+all-reduce of the advantage statistics so that normalisation and the loss mean keep global-minibatch
+semantics.  The reference is single-process (no torch.distributed anywhere); this module is
+new surface, kept tiny so the same functions run under gloo on CPU (tests) and NCCL on GPUs.
+"""
+from __future__ import annotations
+
+import os
+
+
+def dist_state():
+    """(dist module or None, rank, world_size) of the initialised default process group."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def init_from_env(backend: str = "nccl", device_index: int | None = None):
+    """Initialise the default process group from torchrun's environment (RANK/WORLD_SIZE/MASTER_*)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return dist_state()
+    kwargs = {}
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0")) if device_index is None else device_index
+        torch.cuda.set_device(local)
+        kwargs["device_id"] = torch.device("cuda", local)
+    dist.init_process_group(backend, **kwargs)
+    return dist_state()
+
+
+def env_shard(rank: int, world: int, envs_per_rank: int) -> tuple[int, int]:
+    """[first, last) global env ids owned by `rank`; the Philox sub-sequence of an env is its global id,
+    so trajectories do not depend on `world`."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    return rank * envs_per_rank, (rank + 1) * envs_per_rank
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over ranks (no-op for a single process). Gradients are produced already scaled by
+    1/global_rows, so the SUM is the exact global-minibatch gradient."""
+    dist, _, world = dist_state()
+    if world > 1:
+        dist.all_reduce(tensor)
+    return tensor
+
+
+def global_rows(local_rows: int) -> int:
+    """Rows of the global minibatch when every rank contributes `local_rows` (equal shards)."""
+    return local_rows * dist_state()[2]
+
+
+def adv_mean_std(sums):
+    """(mean, unbiased std) from the all-reduced (sum, sum of squares, count) triple — what
+    csrc/ppo_kernels.cu:ppo_loss_kernel computes on the device."""
+    s, ss, n = (float(x) for x in sums)
+    mean = s / n
+    var = max((ss - s * mean) / (n - 1.0), 0.0)
+    return mean, var ** 0.5

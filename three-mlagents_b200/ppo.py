@@ -23,17 +23,13 @@ import numpy as np
 import torch
 
 from . import ops
+from .distributed import allreduce_sum_, dist_state
 from .vec_env import CudaVecEnv
 
 HIDDEN = 256
 
 
-def _dist():
-    import torch.distributed as dist
-
-    if dist.is_available() and dist.is_initialized():
-        return dist, dist.get_rank(), dist.get_world_size()
-    return None, 0, 1
+_dist = dist_state
 
 
 def orthogonal_init(obs_dim: int, n_actions: int, seed: int) -> torch.Tensor:
@@ -192,16 +188,14 @@ class CudaPPO:
                 sums = None
                 if self.normalize_advantage and rows * self.world > 1:
                     sums = ops.adv_stats(self.adv, idx, rows, self.adv_sums)
-                    if self.world > 1:
-                        self._dist.all_reduce(sums)
+                    allreduce_sum_(sums)
                 ops.ppo_loss(self.logits_mb, self.values_mb, self.act, self.adv, self.logp, self.ret, index=idx,
                              rows=rows, global_rows=rows * self.world, adv_sums=sums, normalize=sums is not None,
                              clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
                              dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
                 ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
                                  rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
-                if self.world > 1:
-                    self._dist.all_reduce(self.grads)     # the one collective on the path: NCCL sum over NVLink
+                allreduce_sum_(self.grads)                # the one collective on the path: NCCL sum over NVLink
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
                               lr=self.lr, eps=1e-5, norm_out=self.norm_out)
