@@ -209,7 +209,10 @@ ppo_loss_kernel(const float *__restrict__ logits, const float *__restrict__ valu
 }
 
 // ----------------------------------------------------------------- clip_grad_norm_ + Adam (fused)
-__global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__ g, int64_t np, float scale, float *normsq) {
+// The squared norm is reduced in a FIXED order (per-block partials, then every block of the Adam kernel sums
+// the partials identically), so data-parallel replicas that all-reduced the same gradient stay bit-identical.
+static constexpr int kNormBlocks = 128;
+__global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__ g, int64_t np, float scale, float *partial) {
     __shared__ float sh[8];
     float s = 0.0f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
@@ -219,17 +222,26 @@ __global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0f;
-        s = warp_sum(s);
-        if (threadIdx.x == 0) atomicAdd(normsq, s);
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        partial[blockIdx.x] = t;
     }
 }
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t np,
             float scale, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-            const float *normsq, float *norm_out) {
-    const float norm = sqrtf(*normsq);
+            const float *__restrict__ partial, float *norm_out) {
+    __shared__ float s_norm;
+    if (threadIdx.x < 32) {                                // same summation order in every block and on every rank
+        float t = 0.0f;
+        for (int j = threadIdx.x; j < kNormBlocks; j += 32) t += partial[j];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) s_norm = sqrtf(t);
+    }
+    __syncthreads();
+    const float norm = s_norm;
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
     const float coef = max_norm > 0.0f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,10 +323,8 @@ int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer (norm_out doubles as scratch)");
     TMLA_REQUIRE(num_params > 0 && step >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    // norm_out[0] = norm, norm_out[1] = scratch for the squared norm
-    TMLA_CUDA(cudaMemsetAsync(norm_out + 1, 0, sizeof(float), st));
-    const unsigned g1 = (unsigned)std::min<int64_t>(ceil_div64(num_params, 256 * 4), 148);
-    gradnorm_kernel<<<g1, 256, 0, st>>>(grads, num_params, grad_scale, norm_out + 1);
+    // norm_out[0] = norm, norm_out[1 .. 1+kNormBlocks) = per-block partial sums of squares
+    gradnorm_kernel<<<kNormBlocks, 256, 0, st>>>(grads, num_params, grad_scale, norm_out + 1);
     TMLA_LAUNCH_CHECK();
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<(unsigned)ceil_div64(num_params, 256), 256, 0, st>>>(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr,

@@ -147,7 +147,7 @@ def ppo_loss(logits, values, actions, advantages, old_logp, returns, *, index=No
 def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
               eps=1e-5, norm_out=None):
     if norm_out is None:
-        norm_out = torch.empty(2, dtype=torch.float32, device=params.device)
+        norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
     check(lib.tmla_adam_clip(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
                              float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
                              ptr(norm_out), _s()))

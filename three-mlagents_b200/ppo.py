@@ -137,7 +137,7 @@ class CudaPPO:
         self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
-        self.norm_out = torch.zeros(2, **f32)
+        self.norm_out = torch.zeros(129, **f32)
         self._buffers_ready = True
 
     # ------------------------------------------------------------------------------------- rollout
