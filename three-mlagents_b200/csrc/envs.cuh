@@ -48,6 +48,11 @@ struct NoSpare {};
 struct BasicTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 21, A = 3, MAX_STEPS = 50, NBUF = 1;
@@ -172,7 +177,8 @@ struct Ball3DTask {
     }
     // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
     // explicit (`__*_rn` never contracts into FMA) so the result does not depend on compiler flags.
-    static __device__ __forceinline__ void step(const Consts &c, State &s, int a, float &reward, bool &term, bool &trunc) {
+    struct Pending { float sq; uint32_t flags; };
+    static __device__ __forceinline__ void advance(const Consts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
         // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0).  The sign is
         // XOR-ed into the high word; adding the 0.0 entries is the identity (rot is never -0.0) and is skipped.
         const int td_hi = __double2hiint(c.tilt_delta), td_lo = __double2loint(c.tilt_delta);
@@ -200,12 +206,23 @@ struct Ball3DTask {
         const bool off = (fabsf(px) > 3.0f) || (fabsf(pz) > 3.0f);                  // ball3d.py:96-98
         const bool timeout = s.steps >= 200;                                        // ball3d.py:99
         const bool done = off || timeout;
-        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(pz, pz))); // np.linalg.norm (f32)
-        float r = __fsub_rn(1.0f, div3_rn(d));                                      // ball3d.py:104 (IEEE d/3)
-        if (done) r = (timeout && !off) ? 1.0f : -1.0f;                             // ball3d.py:105-108
-        reward = __fadd_rn(r, __fmul_rn(-0.02f, d));                                // ball3d.py:110-111
+        pend.sq = __fadd_rn(__fmul_rn(px, px), __fmul_rn(pz, pz));                  // np.linalg.norm: x.dot(x) in f32
+        pend.flags = (done ? 1u : 0u) | ((timeout && !off) ? 2u : 0u);
         trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
         term = done && !trunc;
+    }
+    // second half of step(): the reward (ball3d.py:103-111).  It depends only on `Pending`, so the fused rollout
+    // kernel evaluates it one iteration late, interleaved with the next step's physics (more ILP per warp).
+    static __device__ __forceinline__ float finish(const Pending &pend) {
+        const float d = __fsqrt_rn(pend.sq);
+        float r = __fsub_rn(1.0f, div3_rn(d));                                      // ball3d.py:104 (IEEE d/3)
+        if (pend.flags & 1u) r = (pend.flags & 2u) ? 1.0f : -1.0f;                  // ball3d.py:105-108
+        return __fadd_rn(r, __fmul_rn(-0.02f, d));                                  // ball3d.py:110-111
+    }
+    static __device__ __forceinline__ void step(const Consts &c, State &s, int a, float &reward, bool &term, bool &trunc) {
+        Pending pend;
+        advance(c, s, a, pend, term, trunc);
+        reward = finish(pend);
     }
     // Initial state of an episode.  np.random.uniform(lo, hi) = lo + (hi-lo)*u (ball3d.py:49-57) then
     // `.astype(np.float32)`; u carries 32 random bits (the reference's 53-bit double is rounded to 24 bits
@@ -252,6 +269,11 @@ __device__ __forceinline__ void grid_delta(int a, int &dx, int &dy) {
 struct GridWorldTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 100, NBUF = 1;
@@ -324,6 +346,11 @@ __device__ __constant__ uint32_t kPushRewardBits[18] = {
 struct PushTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 120, NBUF = 1;
