@@ -48,11 +48,6 @@ struct NoSpare {};
 struct BasicTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
-    struct Pending { float r; };
-    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
-        step(c, s, a, pend.r, term, trunc);
-    }
-    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 21, A = 3, MAX_STEPS = 50, NBUF = 1;
@@ -84,6 +79,11 @@ struct BasicTask {
         term = small || large;
         trunc = (s.steps >= MAX_STEPS) && !term;         // envs.py:74
     }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     static __device__ __forceinline__ void reset(State &s, uint64_t, uint64_t, uint64_t, uint32_t) {
         s.pos = 10; s.steps = 0; s.ep_ret = 0.0f;        // envs.py:21,55-57 (no randomness)
     }
@@ -269,11 +269,6 @@ __device__ __forceinline__ void grid_delta(int a, int &dx, int &dy) {
 struct GridWorldTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
-    struct Pending { float r; };
-    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
-        step(c, s, a, pend.r, term, trunc);
-    }
-    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 100, NBUF = 1;
@@ -319,6 +314,11 @@ struct GridWorldTask {
         trunc = s.steps >= MAX_STEPS;                                    // envs.py:141-145
         term = done && !trunc;
     }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
         // np.random.shuffle(cells)[:3] = uniform ordered triple of distinct cells; np.random.choice([0,1])
         const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);      // gridworld.py:42-50
@@ -346,11 +346,6 @@ __device__ __constant__ uint32_t kPushRewardBits[18] = {
 struct PushTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
-    struct Pending { float r; };
-    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
-        step(c, s, a, pend.r, term, trunc);
-    }
-    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     typedef NoConsts Consts;
     static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
     static constexpr int D = 4, A = 5, MAX_STEPS = 120, NBUF = 1;
@@ -406,6 +401,11 @@ struct PushTask {
         trunc = s.steps >= MAX_STEPS;                                              // envs.py:141-145
         term = done && !trunc;
     }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
     static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
         const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                // push.py:40-47
         const int a = tmla_bounded(b.x, 36);
