@@ -242,11 +242,6 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
     uint32_t sb = 0;                                    // stage buffer toggle: 0 / BLOCK*D
     [[maybe_unused]] typename Task::Spare sp;
     [[maybe_unused]] bool have_spare = false;
-    // The reward of step t-1 (`Task::finish`) is evaluated inside iteration t, in the same basic block as the
-    // physics of step t: the two are independent, so the scheduler interleaves them and the sqrt/divide tail
-    // no longer sits at the end of every step's dependency chain.
-    typename Task::Pending pend{};
-    bool done_prev = true;                              // iteration 0 has nothing pending
     for (int t = 0; t < T; ++t) {
         if constexpr (Task::HAS_SPARE) {
             if ((t & 15) == 0 && !have_spare) {         // off the critical path: refill consumed spares
@@ -269,13 +264,12 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
             st_stream_f4(obs4 + off, make_float4(o[0], o[1], o[2], o[3]));
         }
         const int a = as.next(seed, env_id, step0, (uint32_t)t, Task::A);
-        const float r_prev = Task::finish(pend);        // reward of step t-1 (garbage-in/ignored at t == 0)
-        if (t > 0) __stcs(rew_buf + (off - n), r_prev);
-        if (!done_prev) s.ep_ret = __fadd_rn(s.ep_ret, r_prev);
-        bool term, trunc;
-        Task::advance(cst, s, a, pend, term, trunc);
+        float r; bool term, trunc;
+        Task::step(cst, s, a, r, term, trunc);
+        s.ep_ret = __fadd_rn(s.ep_ret, r);
         const bool d = term || trunc;
         __stcs(act_buf + off, a);
+        __stcs(rew_buf + off, r);
         __stcs(done_buf + off, (uint8_t)(d ? 1 : 0));
         if (d) {
             if constexpr (Task::HAS_SPARE) {
@@ -287,7 +281,6 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
                 Task::reset(s, seed, env_id, step0 + (uint64_t)t + 1, TMLA_TAG_RESET);
             }
         }
-        done_prev = d;
         if constexpr (STAGED) {
             __syncthreads();
             const float4 *s4 = reinterpret_cast<const float4 *>(s_stage + sb);
@@ -300,11 +293,6 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
             voff += rowvec;
         }
         off += n;
-    }
-    {
-        const float r_last = Task::finish(pend);
-        __stcs(rew_buf + (off - n), r_last);
-        if (!done_prev) s.ep_ret = __fadd_rn(s.ep_ret, r_last);
     }
     Task::store(p.buf, i, s);
 }
