@@ -132,8 +132,9 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
 // State stays in registers for all T steps; per step and env the kernel writes obs (D floats, via the
 // double-buffered shared-memory stage -> st.global.cs.v4), action, reward and done: the [T,N] rollout
 // buffer is write-once streaming traffic, 33 B/env-step for ball3d.
-// 64-thread blocks: 65 536 envs -> 1024 CTAs = 6.9 per SM (tail imbalance 1 %, vs 13 % with 128).
-static constexpr int kRollBlock = 64;
+// One warp per CTA: 65 536 envs -> 2048 CTAs = 13.8 per SM (tail imbalance < 2 %); the obs stage is
+// private to the warp, so __syncwarp() replaces the CTA barrier (measured 78.6 -> 73.1 us vs 64-thread CTAs).
+static constexpr int kRollBlock = 32;
 
 template <int D>
 __device__ __forceinline__ void stage_obs(float *stage, const float *o) {     // row-major [env][D] in shared memory
@@ -242,6 +243,7 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
     uint32_t sb = 0;                                    // stage buffer toggle: 0 / BLOCK*D
     [[maybe_unused]] typename Task::Spare sp;
     [[maybe_unused]] bool have_spare = false;
+#pragma unroll 2   // measured: 73.2 us (no unroll) / 70.8 us (2) / 72.1 us (4)
     for (int t = 0; t < T; ++t) {
         if constexpr (Task::HAS_SPARE) {
             if ((t & 15) == 0 && !have_spare) {         // off the critical path: refill consumed spares
@@ -282,7 +284,7 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
             }
         }
         if constexpr (STAGED) {
-            __syncthreads();
+            if constexpr (BLOCK == 32) __syncwarp(); else __syncthreads();   // one warp per CTA: no CTA barrier needed
             const float4 *s4 = reinterpret_cast<const float4 *>(s_stage + sb);
 #pragma unroll
             for (int v = 0; v < (NVEC + BLOCK - 1) / BLOCK; ++v) {
