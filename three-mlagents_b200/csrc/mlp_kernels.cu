@@ -25,6 +25,9 @@ int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, c
                      const int32_t *rows_dev, cudaStream_t st);
 int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st);
 int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st);
+int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
+                            const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
+                            void *h1, void *h2, cudaStream_t st);
 
 struct MlpOffsets {
     int64_t w1[2], b1[2], w2[2], b2[2], wh[2], bh[2], total;
@@ -638,7 +641,8 @@ static int ensure_pipe_attrs() {
 // shared body of the fp32 (AT=float, SIMT SGEMM) and bf16 (AT=__nv_bfloat16, tcgen05) paths
 template <typename AT>
 static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim, int n_actions, const float *x, const int32_t *index,
-                            int64_t rows, const int32_t *rows_dev, float *logits, float *values, AT *act_cache, cudaStream_t st) {
+                            int64_t rows, const int32_t *rows_dev, float *logits, float *values, AT *act_cache, cudaStream_t st,
+                            bool keep_act = true) {
     constexpr bool BF = sizeof(AT) == 2;
     if (BF) { int rc = ensure_pipe_attrs(); if (rc) return rc; }
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
@@ -646,6 +650,16 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
         float *out = t == 0 ? logits : values;
         if (!out) continue;
         AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
+        if constexpr (BF) {
+            if (obs_dim <= 6) {      // fused tower: gather + layer 1 + tcgen05 layer 2 + head in one persistent kernel
+                const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
+                int rc = tc_tower_forward_launch(obs_dim, o.nout[t], params + o.w1[t], params + o.b1[t], w2, params + o.b2[t],
+                                                 params + o.wh[t], params + o.bh[t], x, index, rows, rows_dev, out,
+                                                 keep_act ? (void *)h1 : nullptr, keep_act ? (void *)h2 : nullptr, st);
+                if (rc) return rc;
+                continue;
+            }
+        }
         const unsigned g1 = (unsigned)ceil_div64(rows, 32);
 #define L1F(DD) l1_forward_kernel<DD, AT><<<g1, H, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1)
         const unsigned gs = (unsigned)std::min<int64_t>(ceil_div64(rows, 256), 148 * 2);    // persistent: 32-row windows per warp
@@ -772,13 +786,14 @@ int tmla_mlp_forward(const float *params, int obs_dim, int hidden, int n_actions
 int tmla_mlp_forward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
                           const int32_t *index, int64_t rows, const int32_t *rows_dev, float *logits, float *values,
                           void *act_cache, void *stream) {
-    TMLA_REQUIRE(params && wpack && x && act_cache, "params/wpack/x/act_cache must be non-NULL");
+    TMLA_REQUIRE(params && wpack && x, "params/wpack/x must be non-NULL");
+    TMLA_REQUIRE(act_cache || obs_dim <= 6, "act_cache may be NULL (inference, activations not kept) only for the fused path (obs_dim <= 6)");
     TMLA_REQUIRE(rows > 0, "rows must be positive");
     TMLA_REQUIRE(logits || values, "nothing to compute");
     int rc = check_shape(obs_dim, hidden, n_actions);
     if (rc) return rc;
     return mlp_forward_impl<__nv_bfloat16>(params, wpack, obs_dim, n_actions, x, index, rows, rows_dev, logits, values,
-                                           (__nv_bfloat16 *)act_cache, (cudaStream_t)stream);
+                                           (__nv_bfloat16 *)act_cache, (cudaStream_t)stream, act_cache != nullptr);
 }
 
 int64_t tmla_mlp_backward_scratch(int obs_dim, int hidden, int n_actions, int64_t rows) {

@@ -390,6 +390,195 @@ tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__rest
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------- fused forward of one tower
+//   out[r] = head( tanh( tanh(x[r] W1^T + b1) W2^T + b2 ) )          (ActorCriticPolicy.forward, one tower)
+// Per 128-row tile: gather obs rows -> layer 1 on CUDA cores straight into the K-major shared-memory operand
+// (H1 never round-trips HBM for the GEMM) -> 16 x tcgen05.mma against the resident W2 -> TMEM -> epilogue
+// (bias, tanh, head dot products from registers) -> logits/values; H1/H2 are written out (coalesced) only
+// when the caller keeps them for the backward pass.  The next tile's obs rows are prefetched into registers
+// while the MMAs run.
+template <int D, int NOUT>
+struct TowerSmem {
+    static constexpr uint32_t w = 0;                                   // W2 bf16, K-major (kLBO/kSBO)
+    static constexpr uint32_t a = kWBytes;                             // H1 tile, K-major padded (kaLBO/kaSBO); H2 stage
+    static constexpr uint32_t w1 = a + kABytes;                        // float [256][D]
+    static constexpr uint32_t b1 = w1 + H * D * 4;                     // float [256]
+    static constexpr uint32_t b2 = b1 + H * 4;                         // float [256]
+    static constexpr uint32_t wh = b2 + H * 4;                         // float [NOUT][256]
+    static constexpr uint32_t xs = wh + NOUT * H * 4;                  // float [128][D]
+    static constexpr uint32_t part = xs + 128 * D * 4;                 // float [128][NOUT] partial head sums (cols 128..255)
+    static constexpr uint32_t bar = (part + 128 * NOUT * 4 + 15) & ~15u;
+    static constexpr uint32_t total = bar + 64;
+};
+
+template <int D, int NOUT>
+__global__ void __launch_bounds__(256, 1)
+tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ B1, const __nv_bfloat16 *__restrict__ W2,
+                        const float *__restrict__ B2, const float *__restrict__ Wh, const float *__restrict__ Bh,
+                        const float *__restrict__ x, const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev,
+                        float *__restrict__ out, __nv_bfloat16 *__restrict__ h1_out, __nv_bfloat16 *__restrict__ h2_out) {
+    using L = TowerSmem<D, NOUT>;
+    constexpr int XPT = (128 * D + 255) / 256;             // gathered obs elements per thread per tile
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *Ws = smem + L::w, *As = smem + L::a;
+    float *w1s = reinterpret_cast<float *>(smem + L::w1), *b1s = reinterpret_cast<float *>(smem + L::b1);
+    float *b2s = reinterpret_cast<float *>(smem + L::b2), *whs = reinterpret_cast<float *>(smem + L::wh);
+    float *xs = reinterpret_cast<float *>(smem + L::xs), *part = reinterpret_cast<float *>(smem + L::part);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::bar);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (rows_dev) M = min(M, (int64_t)*rows_dev);
+    const int64_t ntiles = (M + 127) / 128;
+    if ((int64_t)blockIdx.x >= ntiles) return;
+
+    float xpre[XPT];
+    auto prefetch_x = [&](int64_t tile) {                  // element e = tid + 256*i of the [128][D] obs tile
+        const int64_t row0 = tile * 128;
+#pragma unroll
+        for (int i = 0; i < XPT; ++i) {
+            const int e = tid + 256 * i, r = e / D, k = e - r * D;
+            float v = 0.0f;
+            if (e < 128 * D && row0 + r < M) {
+                const int64_t src = index ? (int64_t)__ldg(index + row0 + r) : row0 + r;
+                v = __ldg(x + src * D + k);
+            }
+            xpre[i] = v;
+        }
+    };
+    prefetch_x(blockIdx.x);
+
+    if (warp == 0) tmem_alloc<256>(tmem_holder);
+    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    stage_rows<H>(Ws, W2, 0, H);
+    for (int e = tid; e < H * D; e += 256) w1s[e] = W1[e];
+    for (int e = tid; e < NOUT * H; e += 256) whs[e] = Wh[e];
+    b1s[tid] = B1[tid];
+    b2s[tid] = B2[tid];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t idesc = make_idesc(128, 256);
+    const uint32_t a_addr = smem_u32(As), w_addr = smem_u32(Ws);
+    uint32_t phase = 0;
+    // layer-1 weights of this thread's 8 hidden units (k-block `lane`)
+    float w1r[8][D], b1r[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        b1r[c] = b1s[lane * 8 + c];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w1r[c][k] = w1s[(lane * 8 + c) * D + k];
+    }
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * 128;
+#pragma unroll
+        for (int i = 0; i < XPT; ++i) { const int e = tid + 256 * i; if (e < 128 * D) xs[e] = xpre[i]; }
+        __syncthreads();                                   // obs tile staged; previous tile's stage fully copied out
+        // ---- layer 1: rows warp+8i, hidden units 8*lane..8*lane+7 -> bf16 chunk (r, kb=lane) of the K-major tile
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int r = warp + 8 * i;
+            float xr[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) xr[k] = xs[r * D + k];
+            uint32_t o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v0 = b1r[2 * c], v1 = b1r[2 * c + 1];
+#pragma unroll
+                for (int k = 0; k < D; ++k) { v0 = fmaf(xr[k], w1r[2 * c][k], v0); v1 = fmaf(xr[k], w1r[2 * c + 1][k], v1); }
+                o[c] = pack_bf16(tanh_fast(v0), tanh_fast(v1));
+            }
+            *reinterpret_cast<uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < H / 16; ++kk)
+                umma_bf16(tmem_base, make_desc(a_addr + kk * 2 * kaLBO, kaLBO, kaSBO), make_desc(w_addr + kk * 2 * kLBO, kLBO, kSBO),
+                          idesc, kk > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        if (tile + gridDim.x < ntiles) prefetch_x(tile + gridDim.x);
+        if (h1_out) {                                      // keep H1 for the backward pass: coalesced rows, overlaps the MMAs
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp + 8 * i;
+                const uint4 v = *reinterpret_cast<const uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16);
+                if (row0 + r < M) reinterpret_cast<uint4 *>(h1_out + (row0 + r) * H)[lane] = v;
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: thread = row rt, column half (warp>>2): bias + tanh, head partial dots, H2 stage
+        const int rt = (warp & 3) * 32 + lane;
+        const int colbase = (warp >> 2) * 128;
+        float hsum[NOUT];
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) hsum[a] = 0.0f;
+        {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
+            uint8_t *srow = As + rt * 512;
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + c * 16, acc);
+                const int col = colbase + c * 16;
+                float hv[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(b2s + col + 4 * q);
+                    hv[4 * q + 0] = tanh_fast(__uint_as_float(acc[4 * q + 0]) + bb.x);
+                    hv[4 * q + 1] = tanh_fast(__uint_as_float(acc[4 * q + 1]) + bb.y);
+                    hv[4 * q + 2] = tanh_fast(__uint_as_float(acc[4 * q + 2]) + bb.z);
+                    hv[4 * q + 3] = tanh_fast(__uint_as_float(acc[4 * q + 3]) + bb.w);
+                }
+#pragma unroll
+                for (int a = 0; a < NOUT; ++a)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 ww = *reinterpret_cast<const float4 *>(whs + a * H + col + 4 * q);
+                        hsum[a] = fmaf(hv[4 * q + 0], ww.x, hsum[a]); hsum[a] = fmaf(hv[4 * q + 1], ww.y, hsum[a]);
+                        hsum[a] = fmaf(hv[4 * q + 2], ww.z, hsum[a]); hsum[a] = fmaf(hv[4 * q + 3], ww.w, hsum[a]);
+                    }
+                if (h2_out) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = pack_bf16(hv[2 * j], hv[2 * j + 1]);
+                    const int ch = col >> 3;
+                    *reinterpret_cast<uint4 *>(srow + ((ch ^ (rt & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(srow + (((ch + 1) ^ (rt & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        }
+        if (warp >= 4) {
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) part[rt * NOUT + a] = hsum[a];
+        }
+        tc_fence_before();
+        __syncthreads();                                   // stage + partial sums complete, TMEM drained
+        if (warp < 4 && row0 + rt < M) {
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) out[(row0 + rt) * NOUT + a] = hsum[a] + part[rt * NOUT + a] + __ldg(Bh + a);
+        }
+        if (h2_out) {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp + 8 * i;
+                const uint4 v = *reinterpret_cast<const uint4 *>(As + r * 512 + ((lane ^ (r & 7)) << 4));
+                if (row0 + r < M) reinterpret_cast<uint4 *>(h2_out + (row0 + r) * H)[lane] = v;
+            }
+        }
+        // the __syncthreads at the top of the next iteration orders these stage reads before the next H1 stores
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------- small helper kernels
 __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,6 +635,33 @@ int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaSt
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
+template <int D, int NOUT>
+static int tower_forward_launch_t(const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh, const float *Bh,
+                                  const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out, void *h1,
+                                  void *h2, cudaStream_t st) {
+    static int attr_done = 0;
+    constexpr uint32_t smem = TowerSmem<D, NOUT>::total;
+    static_assert(smem <= 232448, "fused tower kernel exceeds the 227 KB shared-memory limit");
+    if (!attr_done) {
+        TMLA_CUDA(cudaFuncSetAttribute(tc_tower_forward_kernel<D, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = 1;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, sm_count());
+    tc_tower_forward_kernel<D, NOUT><<<grid, 256, smem, st>>>(W1, B1, (const __nv_bfloat16 *)W2, B2, Wh, Bh, x, index, M, rows_dev, out,
+                                                              (__nv_bfloat16 *)h1, (__nv_bfloat16 *)h2);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+// fused tower forward for the shapes of the four tasks; returns TMLA_EINVAL for an unsupported (D, NOUT)
+int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
+                            const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
+                            void *h1, void *h2, cudaStream_t st) {
+#define TF(DD, NN) if (D == DD && nout == NN) return tower_forward_launch_t<DD, NN>(W1, B1, W2, B2, Wh, Bh, x, index, M, rows_dev, out, h1, h2, st)
+    TF(6, 5); TF(6, 1); TF(4, 5); TF(4, 1);
+#undef TF
+    return TMLA_EINVAL;
+}
+
 int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st) {
     pack_w2_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(w2, (__nv_bfloat16 *)w, (__nv_bfloat16 *)wt);
     TMLA_LAUNCH_CHECK();

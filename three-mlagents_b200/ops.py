@@ -68,7 +68,7 @@ def mlp_pack(params, obs_dim, n_actions, wpack=None):
 
 
 def mlp_forward(params, x, obs_dim, n_actions, *, index=None, rows=None, rows_dev=None, logits=None, values=None,
-                want_logits=True, want_values=True, act_cache=None, wpack=None):
+                want_logits=True, want_values=True, act_cache=None, wpack=None, keep_act=True):
     """ActorCriticPolicy.forward.  wpack=None: float32 CUDA-core path; wpack=bf16 pack: tcgen05 path
     (act_cache is then bf16 [4,rows,256])."""
     _chk(params, torch.float32, "params"); _chk(x, torch.float32, "x"); _chk(index, torch.int32, "index")
@@ -80,7 +80,9 @@ def mlp_forward(params, x, obs_dim, n_actions, *, index=None, rows=None, rows_de
         logits = torch.empty((rows, n_actions), dtype=torch.float32, device=dev)
     if want_values and values is None:
         values = torch.empty(rows, dtype=torch.float32, device=dev)
-    if act_cache is None:
+    if wpack is not None and not keep_act and obs_dim <= 6:
+        act_cache = None            # fused tower kernel, inference only: no activation workspace
+    elif act_cache is None:
         act_cache = torch.empty((4, rows, HIDDEN), dtype=act_dtype, device=dev)
     _chk(act_cache, act_dtype, "act_cache")
     lg, vl = (ptr(logits) if want_logits else None), (ptr(values) if want_values else None)

@@ -154,16 +154,16 @@ class CudaPPO:
         self.ep_stats.zero_()
         for t in range(T):
             ops.mlp_forward(self.params, self.obs[t], D, A, rows=N, logits=self.logits_roll, values=self.val[t],
-                            act_cache=self.cache_roll, wpack=self.wpack)
+                            act_cache=self.cache_roll, wpack=self.wpack, keep_act=False)
             ops.step_policy(self.env, self.logits_roll, t, self.obs[t + 1], self.act[t], self.logp[t], self.rew[t],
                             self.done[t], trunc_count=self.trunc_count, trunc_index=self.trunc_index,
                             trunc_obs=self.trunc_obs, ep_stats=self.ep_stats)
         ops.mlp_forward(self.params, self.obs[T], D, A, rows=N, want_logits=False, values=self.last_values,
-                        act_cache=self.cache_roll, wpack=self.wpack)
+                        act_cache=self.cache_roll, wpack=self.wpack, keep_act=False)
         # timeout bootstrap: rewards += gamma * V(terminal_obs) for time-limit truncations
         cap = self.trunc_index.numel()
         ops.mlp_forward(self.params, self.trunc_obs, D, A, rows=cap, rows_dev=self.trunc_count, want_logits=False,
-                        values=self.trunc_values, act_cache=self.cache_trunc, wpack=self.wpack)
+                        values=self.trunc_values, act_cache=self.cache_trunc, wpack=self.wpack, keep_act=False)
         ops.bootstrap_add(self.rew, self.trunc_count, self.trunc_index, self.trunc_values, self.gamma)
         ops.gae(self.rew, self.val, self.done, self.last_values, self.gamma, self.gae_lambda, self.adv, self.ret)
         self.num_timesteps += T * N * self.world
@@ -265,7 +265,7 @@ class CudaPPO:
     def policy_logits(self, obs_dev: torch.Tensor) -> torch.Tensor:
         rows = obs_dev.shape[0]
         logits, _, _ = ops.mlp_forward(self.params, obs_dev.contiguous(), self.obs_dim, self.n_actions, rows=rows,
-                                       want_values=False, wpack=self.wpack)
+                                       want_values=False, wpack=self.wpack, keep_act=False)
         return logits
 
     def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
