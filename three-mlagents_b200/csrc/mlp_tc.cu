@@ -397,6 +397,7 @@ tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__rest
 // (bias, tanh, head dot products from registers) -> logits/values; H1/H2 are written out (coalesced) only
 // when the caller keeps them for the backward pass.  The next tile's obs rows are prefetched into registers
 // while the MMAs run.
+static constexpr int kTowerThreads = 512;                 // 16 warps: 4 per SM sub-partition (latency hiding)
 template <int D, int NOUT>
 struct TowerSmem {
     static constexpr uint32_t w = 0;                                   // W2 bf16, K-major (kLBO/kSBO)
@@ -406,19 +407,21 @@ struct TowerSmem {
     static constexpr uint32_t b2 = b1 + H * 4;                         // float [256]
     static constexpr uint32_t wh = b2 + H * 4;                         // float [NOUT][256]
     static constexpr uint32_t xs = wh + NOUT * H * 4;                  // float [128][D]
-    static constexpr uint32_t part = xs + 128 * D * 4;                 // float [128][NOUT] partial head sums (cols 128..255)
-    static constexpr uint32_t bar = (part + 128 * NOUT * 4 + 15) & ~15u;
+    static constexpr uint32_t part = xs + 128 * D * 4;                 // float [3][128][NOUT] partial head sums of column quarters 1..3
+    static constexpr uint32_t bar = (part + 3 * 128 * NOUT * 4 + 15) & ~15u;
     static constexpr uint32_t total = bar + 64;
 };
 
 template <int D, int NOUT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kTowerThreads, 1)
 tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ B1, const __nv_bfloat16 *__restrict__ W2,
                         const float *__restrict__ B2, const float *__restrict__ Wh, const float *__restrict__ Bh,
                         const float *__restrict__ x, const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev,
                         float *__restrict__ out, __nv_bfloat16 *__restrict__ h1_out, __nv_bfloat16 *__restrict__ h2_out) {
     using L = TowerSmem<D, NOUT>;
-    constexpr int XPT = (128 * D + 255) / 256;             // gathered obs elements per thread per tile
+    constexpr int NT = kTowerThreads, NW = NT / 32;        // 16 warps
+    constexpr int RPW = 128 / NW;                          // rows per warp in the row-parallel phases (8)
+    constexpr int XPT = (128 * D + NT - 1) / NT;           // gathered obs elements per thread per tile
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *Ws = smem + L::w, *As = smem + L::a;
     float *w1s = reinterpret_cast<float *>(smem + L::w1), *b1s = reinterpret_cast<float *>(smem + L::b1);
@@ -432,11 +435,11 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     if ((int64_t)blockIdx.x >= ntiles) return;
 
     float xpre[XPT];
-    auto prefetch_x = [&](int64_t tile) {                  // element e = tid + 256*i of the [128][D] obs tile
+    auto prefetch_x = [&](int64_t tile) {                  // element e = tid + NT*i of the [128][D] obs tile
         const int64_t row0 = tile * 128;
 #pragma unroll
         for (int i = 0; i < XPT; ++i) {
-            const int e = tid + 256 * i, r = e / D, k = e - r * D;
+            const int e = tid + NT * i, r = e / D, k = e - r * D;
             float v = 0.0f;
             if (e < 128 * D && row0 + r < M) {
                 const int64_t src = index ? (int64_t)__ldg(index + row0 + r) : row0 + r;
@@ -450,10 +453,9 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     if (warp == 0) tmem_alloc<256>(tmem_holder);
     if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
     stage_rows<H>(Ws, W2, 0, H);
-    for (int e = tid; e < H * D; e += 256) w1s[e] = W1[e];
-    for (int e = tid; e < NOUT * H; e += 256) whs[e] = Wh[e];
-    b1s[tid] = B1[tid];
-    b2s[tid] = B2[tid];
+    for (int e = tid; e < H * D; e += NT) w1s[e] = W1[e];
+    for (int e = tid; e < NOUT * H; e += NT) whs[e] = Wh[e];
+    if (tid < H) { b1s[tid] = B1[tid]; b2s[tid] = B2[tid]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -473,12 +475,12 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * 128;
 #pragma unroll
-        for (int i = 0; i < XPT; ++i) { const int e = tid + 256 * i; if (e < 128 * D) xs[e] = xpre[i]; }
+        for (int i = 0; i < XPT; ++i) { const int e = tid + NT * i; if (e < 128 * D) xs[e] = xpre[i]; }
         __syncthreads();                                   // obs tile staged; previous tile's stage fully copied out
-        // ---- layer 1: rows warp+8i, hidden units 8*lane..8*lane+7 -> bf16 chunk (r, kb=lane) of the K-major tile
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int r = warp + 8 * i;
+        // ---- layer 1: rows warp+NW*i, hidden units 8*lane..8*lane+7 -> bf16 chunk (r, kb=lane) of the K-major tile
+#pragma unroll 2
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + NW * i;
             float xr[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) xr[k] = xs[r * D + k];
@@ -504,9 +506,9 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
         }
         if (tile + gridDim.x < ntiles) prefetch_x(tile + gridDim.x);
         if (h1_out) {                                      // keep H1 for the backward pass: coalesced rows, overlaps the MMAs
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = warp + 8 * i;
+#pragma unroll 2
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + NW * i;
                 const uint4 v = *reinterpret_cast<const uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16);
                 if (row0 + r < M) reinterpret_cast<uint4 *>(h1_out + (row0 + r) * H)[lane] = v;
             }
@@ -514,17 +516,18 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- epilogue: thread = row rt, column half (warp>>2): bias + tanh, head partial dots, H2 stage
+        // ---- epilogue: thread = row rt, column quarter (warp>>2): bias + tanh, head partial dots, H2 stage
         const int rt = (warp & 3) * 32 + lane;
-        const int colbase = (warp >> 2) * 128;
+        const int cq = warp >> 2;
+        const int colbase = cq * 64;
         float hsum[NOUT];
 #pragma unroll
         for (int a = 0; a < NOUT; ++a) hsum[a] = 0.0f;
         {
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colbase;
             uint8_t *srow = As + rt * 512;
-#pragma unroll 2
-            for (int c = 0; c < 8; ++c) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
                 uint32_t acc[16];
                 tmem_ld16(taddr + c * 16, acc);
                 const int col = colbase + c * 16;
@@ -555,20 +558,21 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
                 }
             }
         }
-        if (warp >= 4) {
+        if (cq > 0) {
 #pragma unroll
-            for (int a = 0; a < NOUT; ++a) part[rt * NOUT + a] = hsum[a];
+            for (int a = 0; a < NOUT; ++a) part[((cq - 1) * 128 + rt) * NOUT + a] = hsum[a];
         }
         tc_fence_before();
         __syncthreads();                                   // stage + partial sums complete, TMEM drained
-        if (warp < 4 && row0 + rt < M) {
+        if (cq == 0 && row0 + rt < M) {
 #pragma unroll
-            for (int a = 0; a < NOUT; ++a) out[(row0 + rt) * NOUT + a] = hsum[a] + part[rt * NOUT + a] + __ldg(Bh + a);
+            for (int a = 0; a < NOUT; ++a)
+                out[(row0 + rt) * NOUT + a] = ((hsum[a] + part[rt * NOUT + a]) + (part[(128 + rt) * NOUT + a] + part[(256 + rt) * NOUT + a])) + __ldg(Bh + a);
         }
         if (h2_out) {
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = warp + 8 * i;
+#pragma unroll 2
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + NW * i;
                 const uint4 v = *reinterpret_cast<const uint4 *>(As + r * 512 + ((lane ^ (r & 7)) << 4));
                 if (row0 + r < M) reinterpret_cast<uint4 *>(h2_out + (row0 + r) * H)[lane] = v;
             }
@@ -647,7 +651,7 @@ static int tower_forward_launch_t(const float *W1, const float *B1, const void *
         attr_done = 1;
     }
     const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, sm_count());
-    tc_tower_forward_kernel<D, NOUT><<<grid, 256, smem, st>>>(W1, B1, (const __nv_bfloat16 *)W2, B2, Wh, Bh, x, index, M, rows_dev, out,
+    tc_tower_forward_kernel<D, NOUT><<<grid, kTowerThreads, smem, st>>>(W1, B1, (const __nv_bfloat16 *)W2, B2, Wh, Bh, x, index, M, rows_dev, out,
                                                               (__nv_bfloat16 *)h1, (__nv_bfloat16 *)h2);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
