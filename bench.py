@@ -264,6 +264,10 @@ def run_cuda(args):
             from three_mlagents_b200.ppo import bench_ppo
 
             out["ppo"] = bench_ppo(local_rank, rank, world, iters=args.ppo_iters)
+            if world == 1:
+                from three_mlagents_b200.ppo import bench_kernels
+
+                out["ppo"]["kernels"] = bench_kernels(local_rank)
         except Exception as e:  # noqa: BLE001 - the env-step headline must still print
             out["ppo"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

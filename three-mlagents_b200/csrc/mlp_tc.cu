@@ -504,7 +504,6 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
                           idesc, kk > 0 ? 1u : 0u);
             umma_commit(bar);
         }
-        if (tile + gridDim.x < ntiles) prefetch_x(tile + gridDim.x);
         if (h1_out) {                                      // keep H1 for the backward pass: coalesced rows, overlaps the MMAs
 #pragma unroll 2
             for (int i = 0; i < RPW; ++i) {
@@ -513,6 +512,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
                 if (row0 + r < M) reinterpret_cast<uint4 *>(h1_out + (row0 + r) * H)[lane] = v;
             }
         }
+        if (tile + gridDim.x < ntiles) prefetch_x(tile + gridDim.x);   // dependent index->obs loads, hidden behind the MMAs
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();

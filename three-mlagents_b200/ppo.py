@@ -388,6 +388,63 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
     }
 
 
+def bench_kernels(device: int = 0, n_envs: int = 65536, n_steps: int = 128) -> dict[str, Any]:
+    """Per-kernel roofline evidence for the PPO side at BASELINE config-3 sizes (CUDA events, 20 launches each):
+    GAE scan and loss head against the measured HBM peak, the tcgen05 GEMMs in TFLOP/s."""
+    from . import native as nat
+
+    dev = torch.device("cuda", device)
+    T, N, A = n_steps, n_envs, 5
+    g = torch.Generator(device=dev).manual_seed(0)
+    rew = torch.randn((T, N), device=dev, generator=g)
+    val = torch.randn((T, N), device=dev, generator=g)
+    done = (torch.rand((T, N), device=dev, generator=g) < 0.01).to(torch.uint8)
+    lastv = torch.randn(N, device=dev, generator=g)
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    B = T * N // 32
+    logits = torch.randn((B, A), device=dev, generator=g)
+    values = torch.randn(B, device=dev, generator=g)
+    act = torch.randint(0, A, (T, N), device=dev, dtype=torch.int32)
+    logp = -torch.rand((T, N), device=dev, generator=g)
+    idx = ops.permutation(1, 0, T, N)[:B].contiguous()
+    dl, dv, st = torch.empty_like(logits), torch.empty_like(values), torch.zeros(8, device=dev)
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    Abf = (torch.randn((B, HIDDEN), device=dev, generator=g) * 0.5).to(torch.bfloat16)
+    Hbf = torch.tanh(torch.randn((B, HIDDEN), device=dev, generator=g)).to(torch.bfloat16)
+    Wbf = (torch.randn((HIDDEN, HIDDEN), device=dev, generator=g) / 16).to(torch.bfloat16)
+    out = torch.empty_like(Abf)
+    G = torch.zeros((HIDDEN, HIDDEN), device=dev)
+    s = nat.current_stream()
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e3 / reps            # us per launch
+
+    res = {}
+    us = timed(lambda: ops.gae(rew, val, done, lastv, 0.99, 0.95, adv, ret))
+    res["gae"] = {"us": us, "GB/s": 17.0 * T * N / us / 1e3, "bytes_per_element": 17,
+                  "note": "r,V f32 + done u8 read, A,R f32 written (SURVEY's 20 B counts episode_start as f32)"}
+    us = timed(lambda: ops.ppo_loss(logits, values, act, adv, logp, ret, index=idx, adv_sums=ops.adv_stats(adv, idx, B, sums),
+                                    dlogits=dl, dvalues=dv, stats=st))
+    res["adv_stats+ppo_loss"] = {"us": us, "GB/s": (64.0 + 8.0) * B / us / 1e3, "rows": B}
+    flop = 2.0 * B * HIDDEN * HIDDEN
+    us = timed(lambda: nat.check(nat.lib.tmla_tc_linear(0, nat.ptr(Abf), nat.ptr(Wbf), nat.ptr(lastv), None, nat.ptr(out), B, None, s)))
+    res["tc_linear_fwd"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1024.0 * B / us / 1e3}
+    us = timed(lambda: nat.check(nat.lib.tmla_tc_linear(1, nat.ptr(Abf), nat.ptr(Wbf), None, nat.ptr(Hbf), nat.ptr(out), B, None, s)))
+    res["tc_linear_dgrad"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1536.0 * B / us / 1e3}
+    us = timed(lambda: nat.check(nat.lib.tmla_tc_wgrad(nat.ptr(Abf), nat.ptr(Hbf), nat.ptr(G), B, s)))
+    res["tc_wgrad"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1024.0 * B / us / 1e3}
+    return res
+
+
 def smoke_update() -> None:
     """One tiny rollout + update on cuda:0 (called from __graft_entry__.smoke)."""
     env = CudaVecEnv("ball3d", 256, seed=1)
