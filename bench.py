@@ -188,12 +188,26 @@ def run_cuda(args):
         env.rollout_random(T_ROLLOUT, obs, act, rew, done)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The timed region is only K x ~70 us long; nvidia-smi needs ~100 ms per sample.  The sampler therefore
+    # brackets the timed region with the same kernel running back to back (load before, during and after):
+    # untimed launches first, then the K timed launches, then untimed launches until >= 5 samples exist.
     with ClockSampler(local_rank) as clocks:
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.4:
+            for _ in range(50):
+                env.rollout_random(T_ROLLOUT, obs, act, rew, done)
+            torch.cuda.synchronize()
+        barrier()
         e0.record()
         for _ in range(K):
             env.rollout_random(T_ROLLOUT, obs, act, rew, done)
         e1.record()
         barrier()
+        t_load = time.perf_counter()
+        while len(clocks.rows) < 5 and time.perf_counter() - t_load < 3.0:
+            for _ in range(50):
+                env.rollout_random(T_ROLLOUT, obs, act, rew, done)
+            torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1))
     steps_per_launch = N_ENVS * T_ROLLOUT
     value = world * steps_per_launch * K / (ms * 1e-3)
