@@ -125,3 +125,46 @@ def test_oracle_vecenv_autoreset_contract(task):
             ep_ret[i] = 0
             ep_len[i] = 0
     assert seen_done > 0
+
+
+@pytest.mark.parametrize("task", ("ball3d", "gridworld", "push", "basic"))
+def test_scalar_port_matches_reference_golden(task):
+    """oracle/ref_port.py (the timed CPU baseline) reproduces the reference transitions bit for bit."""
+    from oracle import ref_port
+
+    g = _replay.load(task)
+    T, E = 300, 6
+    envs = []
+    for i in range(E):
+        e = ref_port.TASKS[task]()
+        if task == "basic":
+            e.p = int(g["init_pos"][i])
+        elif task == "ball3d":
+            e.rot, e.pos, e.vel = g["init_rot"][i].astype(np.float32), g["init_pos"][i].copy(), g["init_vel"][i].copy()
+        elif task == "gridworld":
+            e.agent, e.green, e.red, e.kind = tuple(g["init_agent"][i]), tuple(g["init_green"][i]), tuple(g["init_red"][i]), int(g["init_goal_type"][i])
+        else:
+            e.agent, e.box, e.goal = tuple(g["init_agent"][i]), tuple(g["init_box"][i]), (int(g["init_goal_x"][i]), 5)
+        e.t = 0
+        envs.append(e)
+    steps = [0] * E
+    for t in range(T):
+        for i, e in enumerate(envs):
+            obs, r, done = e.step(int(g["actions"][t, i]))
+            steps[i] += 1
+            hit = steps[i] >= e.limit
+            term, trunc = (done, hit and not done) if task == "basic" else (bool(done and not hit), bool(hit))
+            assert term == g["terminated"][t, i] and trunc == g["truncated"][t, i], (task, t, i)
+            assert np.array_equal(np.asarray(obs, np.float32).view(np.uint32), g["obs"][t, i].view(np.uint32)), (task, t, i)
+            assert np.float32(r).view(np.uint32) == g["reward"][t, i].view(np.uint32), (task, t, i)
+            if term or trunc:
+                steps[i] = 0
+                e.t = 0
+                if task == "basic":
+                    e.p = int(g["reset_pos"][t, i])
+                elif task == "ball3d":
+                    e.rot, e.pos, e.vel = g["reset_rot"][t, i].astype(np.float32), g["reset_pos"][t, i].copy(), g["reset_vel"][t, i].copy()
+                elif task == "gridworld":
+                    e.agent, e.green, e.red, e.kind = tuple(g["reset_agent"][t, i]), tuple(g["reset_green"][t, i]), tuple(g["reset_red"][t, i]), int(g["reset_goal_type"][t, i])
+                else:
+                    e.agent, e.box, e.goal = tuple(g["reset_agent"][t, i]), tuple(g["reset_box"][t, i]), (int(g["reset_goal_x"][t, i]), 5)
