@@ -309,38 +309,44 @@ class CudaPPO:
 
     # ------------------------------------------------------------------------------- persistence
     def save(self, path) -> None:
+        """`model.save` (training.py:172-175): a zip in Stable-Baselines3's archive layout (see sb3_zip.py)."""
+        from . import sb3_zip
+
         path = str(path)
         if not path.endswith(".zip"):
             path += ".zip"
-        data = {
-            "format": "three-mlagents_b200/1", "algorithm": "ppo", "task_id": self.env.task_id, "obs_dim": self.obs_dim,
-            "n_actions": self.n_actions, "net_arch": {"pi": [256, 256], "vf": [256, 256]}, "seed": self.seed,
-            "num_timesteps": self.num_timesteps, "n_updates": self.n_updates, "adam_step": self._adam_step,
-            "hyper": {"learning_rate": self.lr, "n_steps": self.n_steps, "batch_size": self.batch_size,
-                      "n_epochs": self.n_epochs, "gamma": self.gamma, "gae_lambda": self.gae_lambda,
-                      "clip_range": self.clip_range, "ent_coef": self.ent_coef, "vf_coef": self.vf_coef,
-                      "max_grad_norm": self.max_grad_norm},
-        }
-        with zipfile.ZipFile(path, "w") as z:
-            z.writestr("data.json", json.dumps(data, indent=2))
-            for name, t in (("params", self.params), ("adam_m", self.m), ("adam_v", self.v)):
-                buf = io.BytesIO()
-                np.save(buf, t.cpu().numpy())
-                z.writestr(f"{name}.npy", buf.getvalue())
+        sb3_zip.write_zip(path, self)
 
     @classmethod
-    def load(cls, path, env: CudaVecEnv | None = None, device: int = 0):
-        with zipfile.ZipFile(str(path)) as z:
-            data = json.loads(z.read("data.json"))
-            arrs = {n: np.load(io.BytesIO(z.read(f"{n}.npy"))) for n in ("params", "adam_m", "adam_v")}
-        own_env = env is None
-        if own_env:
-            env = CudaVecEnv(data["task_id"], 1, seed=data["seed"], device=device)
-        model = cls("MlpPolicy", env, seed=data["seed"], _params=torch.from_numpy(arrs["params"]), **data["hyper"])
+    def load(cls, path, env: CudaVecEnv | None = None, device: int = 0, task_id: str | None = None):
+        """`PPO.load` (training.py:269): accepts zips written by this backend and SB3-written zips of the same
+        architecture (pass `task_id` for those; it is inferred from the shapes when unambiguous)."""
+        from . import sb3_zip
+
+        z = sb3_zip.read_zip(str(path))
+        meta = z["meta"] or {}
+        data = z["data"]
+        task = task_id or meta.get("task_id") or sb3_zip.TASK_BY_SHAPE.get((z["obs_dim"], z["n_actions"]))
+        if task is None:
+            raise ValueError("cannot infer the task from the policy shapes; pass task_id=")
+        seed = int(meta.get("seed", data.get("seed", 0) or 0))
+        if env is None:
+            env = CudaVecEnv(task, 1, seed=seed, device=device)
+        if (env.obs_dim, env.n_actions) != (z["obs_dim"], z["n_actions"]):
+            raise ValueError(f"policy is {z['obs_dim']}->{z['n_actions']} but task '{task}' is {env.obs_dim}->{env.n_actions}")
+        keys = ("learning_rate", "n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "clip_range", "ent_coef",
+                "vf_coef", "max_grad_norm")
+        hyper = dict(meta.get("hyper", {}))
+        for k in keys:
+            if k not in hyper and isinstance(data.get(k), (int, float)):
+                hyper[k] = data[k]
+        model = cls("MlpPolicy", env, seed=seed, _params=z["params"], **hyper)
         model._repack()
-        model.m.copy_(torch.from_numpy(arrs["adam_m"]))
-        model.v.copy_(torch.from_numpy(arrs["adam_v"]))
-        model.num_timesteps, model.n_updates, model._adam_step = data["num_timesteps"], data["n_updates"], data["adam_step"]
+        model.m.copy_(z["adam_m"])
+        model.v.copy_(z["adam_v"])
+        model._adam_step = int(meta.get("adam_step", z["adam_step"]))
+        model.num_timesteps = int(meta.get("num_timesteps", data.get("num_timesteps", 0) or 0))
+        model.n_updates = int(meta.get("n_updates", data.get("_n_updates", 0) or 0))
         return model
 
 

@@ -216,7 +216,7 @@ def load_model(task: TaskSpec, model_filename_or_path: str | None = None):
     algorithm_name = _infer_algorithm_from_metadata(task, model_path) or "ppo"
     if algorithm_name not in ALGORITHMS:
         raise ValueError(f"Model '{model_path}' was trained with '{algorithm_name}', which has no CUDA backend.")
-    return ALGORITHMS[algorithm_name].load(model_path)
+    return ALGORITHMS[algorithm_name].load(model_path, task_id=task.id)
 
 
 def predict_action(task_id: str, obs: np.ndarray, model_filename: str | None = None) -> int | list[float]:
