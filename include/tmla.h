@@ -222,6 +222,38 @@ int tmla_tc_wgrad(const void *X, const void *Y, float *G, int64_t rows, void *st
 int tmla_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream);
 int tmla_tc_debug(int swap_lbo_sbo);
 
+/* ---- PPO.train, one minibatch, fully fused (csrc/mlp_train.cu) ------------------------------------------------
+ * Replaces, per minibatch of SB3's PPO.train (reached from backend/mlagents/training.py:166; hyper-parameters
+ * training.py:379-389; policy built at training.py:150 with net_arch training.py:363-365), the sequence
+ *     evaluate_actions -> advantage normalisation -> clipped surrogate + value MSE + entropy -> loss.backward()
+ * i.e. tmla_mlp_forward_bf16 + tmla_ppo_loss + tmla_mlp_backward_bf16 with identical semantics, but as one
+ * persistent kernel per tower (forward, loss and backward on chip; tcgen05 for the 256x256 layers) plus one
+ * split-K weight-gradient GEMM per tower.  Arguments as in those three calls:
+ *   obs float[total,D], index int32[rows] (NULL = identity) selects the minibatch rows of obs AND of the
+ *   [T*N] buffers actions/advantages/old_logp/returns;  adv_sums from tmla_adv_stats (all-reduced by the caller
+ *   when world_size>1), global_rows = rows summed over ranks;
+ *   grads float[num_params] OVERWRITTEN;  scratch bf16[tmla_ppo_minibatch_scratch(hidden, rows)];
+ *   stats_out float[8] as tmla_ppo_loss;  logits_out float[rows,A] / values_out float[rows]: optional (NULL).
+ * tmla_ppo_minibatch_supported: 1 when the fused path covers (obs_dim, hidden, n_actions) — ball3d, gridworld,
+ * push; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
+int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions);
+int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows);
+int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *obs,
+                            const int32_t *index, int64_t rows, int64_t global_rows, const int32_t *actions,
+                            const float *advantages, const float *old_logp, const float *returns, const double *adv_sums,
+                            int normalize_advantage, float clip_range, float ent_coef, float vf_coef, float *grads,
+                            void *scratch, float *stats_out, float *logits_out, float *values_out, void *stream);
+
+/* test hooks of csrc/mlp_train.cu:
+ *   tmla_tc_wgrad_mn: same contract as tmla_tc_wgrad, operands read through MN-major UMMA descriptors (no
+ *                     transposing stage), cp.async ring;  tmla_tc_wgrad_select(impl): which of the two the fused
+ *                     minibatch uses (1 = MN-major, default; 0 = transposing);
+ *   tmla_tc_probe   : one-CTA descriptor check, A bf16[128,256], B bf16[256,256]:
+ *                     mode 0 out[128,256] = A.B^T | mode 1 out[128,256] = A.B | mode 2 out[256,256] = A^T.B[0:128] */
+int tmla_tc_wgrad_mn(const void *X, const void *Y, float *G, int64_t rows, void *stream);
+int tmla_tc_wgrad_select(int impl);
+int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,163 @@
+"""Fused PPO minibatch (csrc/mlp_train.cu: forward + loss + backward in one kernel per tower, MN-major UMMA
+descriptors) against the unfused bf16 path (same arithmetic, different kernels) and the fp32 path.
+
+Stated tolerances:
+  * descriptor probe / wgrad: fp32 accumulation of exact bf16 products -> |d| <= 2e-3 * max(1, |ref|)
+  * head outputs (logits, values) fused vs unfused bf16: 2e-3 abs (same bf16 pipeline, other summation order)
+  * gradients fused vs unfused bf16: cosine > 0.9999, relative L2 error < 1e-2 (one extra bf16 rounding of dH1)
+  * gradients fused vs fp32: cosine > 0.999, relative L2 error < 5e-2 (the bf16-path tolerance of test_trainer_gpu)
+  * loss statistics: 1e-4 abs/rel
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _nat():
+    from three_mlagents_b200 import native
+
+    return native
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_mn_major_descriptor_probe(mode):
+    nat = _nat()
+    g = torch.Generator(device="cuda").manual_seed(11 + mode)
+    A = _bf16(torch.randn((128, 256), device="cuda", generator=g) * 0.5)
+    B = _bf16(torch.randn((256, 256), device="cuda", generator=g) * 0.25)
+    rows_out = 256 if mode == 2 else 128
+    out = torch.full((rows_out, 256), float("nan"), device="cuda")
+    nat.check(nat.lib.tmla_tc_probe(nat.ptr(A), nat.ptr(B), nat.ptr(out), mode, nat.current_stream()))
+    torch.cuda.synchronize()
+    Af, Bf = A.float(), B.float()
+    ref = {0: Af @ Bf.t(), 1: Af @ Bf, 2: Af.t() @ Bf[:128]}[mode]
+    err = (out - ref).abs()
+    tol = 2e-3 * torch.clamp(ref.abs(), min=1.0)
+    assert bool((err <= tol).all()), f"mode {mode}: max err {float(err.max())}, nan {int(torch.isnan(out).sum())}"
+
+
+@pytest.mark.parametrize("rows", [64, 100, 1000, 64 * 148 * 3 + 17, 64 * 148 * 4 + 64])
+def test_wgrad_mn_matches_torch(rows):
+    nat = _nat()
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    X = _bf16(torch.randn((rows, 256), device="cuda", generator=g) * 0.1)
+    Y = _bf16(torch.randn((rows, 256), device="cuda", generator=g))
+    G = torch.zeros((256, 256), device="cuda")
+    nat.check(nat.lib.tmla_tc_wgrad_mn(nat.ptr(X), nat.ptr(Y), nat.ptr(G), rows, nat.current_stream()))
+    torch.cuda.synchronize()
+    ref = X.float().t() @ Y.float()
+    err = (G - ref).abs()
+    scale = float(ref.abs().max())
+    assert float(err.max()) <= 2e-3 * max(1.0, scale), f"rows {rows}: max err {float(err.max())} (scale {scale})"
+    # accumulates (+=) like tmla_tc_wgrad
+    nat.check(nat.lib.tmla_tc_wgrad_mn(nat.ptr(X), nat.ptr(Y), nat.ptr(G), rows, nat.current_stream()))
+    torch.cuda.synchronize()
+    assert float((G - 2 * ref).abs().max()) <= 4e-3 * max(1.0, scale)
+
+
+def _setup(task, n, T, seed=5):
+    from three_mlagents_b200.ppo import CudaPPO
+    from three_mlagents_b200.vec_env import CudaVecEnv
+
+    env = CudaVecEnv(task, n, seed=seed)
+    m = CudaPPO("MlpPolicy", env, seed=seed, n_steps=T, batch_size=n * T, n_epochs=1, ent_coef=0.01, mlp_impl="bf16")
+    with torch.no_grad():
+        m.params += 0.05 * torch.randn_like(m.params)          # non-trivial biases / heads
+    m._repack()
+    m.collect_rollouts()
+    torch.cuda.synchronize()
+    return env, m
+
+
+@pytest.mark.parametrize("task,n,T,rows,wgrad_impl", [
+    ("ball3d", 64, 8, 100, 1),                # one partial tile
+    ("ball3d", 512, 32, 4096, 1),
+    ("gridworld", 300, 40, 1000, 1),
+    ("push", 512, 90, 128 * 148 * 2 + 77, 1),  # several tiles per CTA + ragged tail
+    ("ball3d", 512, 32, 4096, 0),             # transposing wgrad kernel under the fused tower kernel
+])
+def test_fused_minibatch_matches_unfused(task, n, T, rows, wgrad_impl):
+    from three_mlagents_b200 import ops
+
+    nat = _nat()
+    env, m = _setup(task, n, T)
+    d, a = env.obs_dim, env.n_actions
+    assert ops.ppo_minibatch_supported(d, a)
+    obs_flat = m.obs[:T].reshape(T * n, d)
+    idx = ops.permutation(1, 0, T, n)[:rows].contiguous()
+    sums = ops.adv_stats(m.adv, idx, rows)
+    # unfused bf16 reference path
+    l16, v16, c16 = ops.mlp_forward(m.params, obs_flat, d, a, index=idx, wpack=m.wpack)
+    dl, dv, st_ref = ops.ppo_loss(l16, v16, m.act, m.adv, m.logp, m.ret, index=idx, adv_sums=sums)
+    g_ref = ops.mlp_backward(m.params, obs_flat, d, a, c16, dl, dv, index=idx, wpack=m.wpack).clone()
+    # fp32 path
+    l32, v32, c32 = ops.mlp_forward(m.params, obs_flat, d, a, index=idx)
+    dl32, dv32, _ = ops.ppo_loss(l32, v32, m.act, m.adv, m.logp, m.ret, index=idx, adv_sums=sums)
+    g32 = ops.mlp_backward(m.params, obs_flat, d, a, c32, dl32, dv32, index=idx)
+    # fused
+    nat.check(nat.lib.tmla_tc_wgrad_select(wgrad_impl))
+    try:
+        logits = torch.full((rows, a), float("nan"), device="cuda")
+        values = torch.full((rows,), float("nan"), device="cuda")
+        g_f, st_f = ops.ppo_minibatch(m.params, m.wpack, obs_flat, d, a, m.act, m.adv, m.logp, m.ret, index=idx, rows=rows,
+                                      adv_sums=sums, logits=logits, values=values)
+        torch.cuda.synchronize()
+    finally:
+        nat.check(nat.lib.tmla_tc_wgrad_select(1))
+    assert float((logits - l16).abs().max()) < 2e-3 and float((values - v16).abs().max()) < 2e-3
+    assert torch.allclose(st_f[:6], st_ref[:6], rtol=1e-4, atol=1e-4), (st_f, st_ref)
+    assert torch.allclose(st_f[6:], st_ref[6:], rtol=1e-6, atol=1e-7)
+    off = 0
+    names = []
+    for t in ("pi", "vf"):
+        for nm, sz in (("W1", 256 * d), ("b1", 256), ("W2", 65536), ("b2", 256)):
+            names.append((f"{t}.{nm}", off, off + sz)); off += sz
+    for nm, sz in (("Wa", a * 256), ("ba", a), ("Wv", 256), ("bv", 1)):
+        names.append((nm, off, off + sz)); off += sz
+    assert off == g_f.numel()
+    for nm, lo, hi in names:
+        x, y = g_f[lo:hi], g_ref[lo:hi]
+        rel = float((x - y).norm() / (y.norm() + 1e-12))
+        assert rel < 2e-2, f"{task} {nm}: fused vs unfused-bf16 relative error {rel}"
+    cos = float(torch.nn.functional.cosine_similarity(g_f, g_ref, dim=0))
+    rel = float((g_f - g_ref).norm() / g_ref.norm())
+    cos32 = float(torch.nn.functional.cosine_similarity(g_f, g32, dim=0))
+    rel32 = float((g_f - g32).norm() / g32.norm())
+    print(f"{task} rows={rows}: fused vs bf16 cos {cos:.7f} rel {rel:.5f}; vs fp32 cos {cos32:.6f} rel {rel32:.4f}")
+    assert cos > 0.9999 and rel < 1e-2
+    assert cos32 > 0.999 and rel32 < 5e-2
+    env.close()
+
+
+def test_fused_training_tracks_unfused_and_learns():
+    """Same seeds: one train() with the fused update lands next to the unfused update; ball3d returns improve."""
+    from three_mlagents_b200.ppo import CudaPPO
+    from three_mlagents_b200.vec_env import CudaVecEnv
+
+    deltas = []
+    for fused in (True, False):
+        env = CudaVecEnv("ball3d", 1024, seed=2)
+        m = CudaPPO("MlpPolicy", env, seed=2, n_steps=32, batch_size=8192, n_epochs=1, ent_coef=0.01, fused_update=fused)
+        assert m.fused_update == fused
+        p0 = m.params.clone()
+        m.collect_rollouts()
+        m.train()
+        torch.cuda.synchronize()
+        assert torch.isfinite(m.params).all()
+        deltas.append((m.params - p0).clone())
+        env.close()
+    cos = float(torch.nn.functional.cosine_similarity(deltas[0], deltas[1], dim=0))
+    print(f"parameter-update cosine fused vs unfused after 4 Adam steps: {cos:.5f}")
+    assert cos > 0.98
+    env = CudaVecEnv("ball3d", 4096, seed=1)
+    m = CudaPPO("MlpPolicy", env, seed=1, n_steps=64, batch_size=32768, n_epochs=4, ent_coef=0.01)
+    m.learn(4096 * 64 * 10)
+    rows = m.logger_rows
+    print("ball3d ep_rew_mean:", [round(r["rollout/ep_rew_mean"], 2) for r in rows])
+    assert rows[-1]["rollout/ep_rew_mean"] > rows[0]["rollout/ep_rew_mean"] + 5.0
+    env.close()

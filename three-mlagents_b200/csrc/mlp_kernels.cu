@@ -29,27 +29,7 @@ int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, c
                             const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
                             void *h1, void *h2, cudaStream_t st);
 
-struct MlpOffsets {
-    int64_t w1[2], b1[2], w2[2], b2[2], wh[2], bh[2], total;
-    int nout[2];
-};
-static MlpOffsets mlp_offsets(int D, int A) {
-    MlpOffsets o;
-    int64_t p = 0;
-    for (int t = 0; t < 2; ++t) {
-        o.w1[t] = p; p += (int64_t)H * D;
-        o.b1[t] = p; p += H;
-        o.w2[t] = p; p += (int64_t)H * H;
-        o.b2[t] = p; p += H;
-    }
-    o.wh[0] = p; p += (int64_t)A * H;
-    o.bh[0] = p; p += A;
-    o.wh[1] = p; p += H;
-    o.bh[1] = p; p += 1;
-    o.total = p;
-    o.nout[0] = A; o.nout[1] = 1;
-    return o;
-}
+#include "mlp_common.cuh"
 
 __device__ __forceinline__ int64_t eff_rows(int64_t rows, const int32_t *rows_dev) {
     return rows_dev ? min(rows, (int64_t)*rows_dev) : rows;

@@ -146,6 +146,37 @@ def ppo_loss(logits, values, actions, advantages, old_logp, returns, *, index=No
     return dlogits, dvalues, stats
 
 
+def ppo_minibatch_supported(obs_dim: int, n_actions: int) -> bool:
+    return bool(lib.tmla_ppo_minibatch_supported(obs_dim, HIDDEN, n_actions))
+
+
+def ppo_minibatch(params, wpack, obs, obs_dim, n_actions, actions, advantages, old_logp, returns, *, index=None, rows=None,
+                  global_rows=None, adv_sums=None, normalize=True, clip_range=0.2, ent_coef=0.01, vf_coef=0.5, grads=None,
+                  scratch=None, stats=None, logits=None, values=None):
+    """One PPO.train minibatch, forward + loss + backward fused (tmla_ppo_minibatch_bf16): returns (grads, stats)."""
+    _chk(params, torch.float32, "params"); _chk(wpack, torch.bfloat16, "wpack"); _chk(obs, torch.float32, "obs")
+    _chk(index, torch.int32, "index"); _chk(actions, torch.int32, "actions"); _chk(advantages, torch.float32, "advantages")
+    _chk(old_logp, torch.float32, "old_logp"); _chk(returns, torch.float32, "returns")
+    if rows is None:
+        rows = index.numel() if index is not None else obs.shape[0]
+    dev = params.device
+    if grads is None:
+        grads = torch.empty_like(params)
+    if scratch is None:
+        scratch = torch.empty(lib.tmla_ppo_minibatch_scratch(HIDDEN, rows), dtype=torch.bfloat16, device=dev)
+    if stats is None:
+        stats = torch.empty(8, dtype=torch.float32, device=dev)
+    _chk(scratch, torch.bfloat16, "scratch"); _chk(grads, torch.float32, "grads"); _chk(stats, torch.float32, "stats")
+    _chk(logits, torch.float32, "logits"); _chk(values, torch.float32, "values")
+    if normalize and adv_sums is None:
+        adv_sums = adv_stats(advantages, index, rows)
+    check(lib.tmla_ppo_minibatch_bf16(ptr(params), ptr(wpack), obs_dim, HIDDEN, n_actions, ptr(obs), ptr(index), int(rows),
+                                      int(global_rows or rows), ptr(actions), ptr(advantages), ptr(old_logp), ptr(returns),
+                                      ptr(adv_sums), 1 if normalize else 0, float(clip_range), float(ent_coef),
+                                      float(vf_coef), ptr(grads), ptr(scratch), ptr(stats), ptr(logits), ptr(values), _s()))
+    return grads, stats
+
+
 def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
               eps=1e-5, norm_out=None):
     if norm_out is None:

@@ -54,7 +54,8 @@ class CudaPPO:
                  batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  normalize_advantage: bool = True, policy_kwargs: dict | None = None, tensorboard_log: str | None = None,
-                 verbose: int = 0, mlp_impl: str = "auto", _params: torch.Tensor | None = None):
+                 verbose: int = 0, mlp_impl: str = "auto", fused_update: bool = True,
+                 _params: torch.Tensor | None = None):
         if policy != "MlpPolicy":
             raise ValueError("CudaPPO supports 'MlpPolicy' (vector observations) only")
         arch = (policy_kwargs or {}).get("net_arch", {"pi": [256, 256], "vf": [256, 256]})
@@ -71,6 +72,8 @@ class CudaPPO:
             raise ValueError("mlp_impl must be 'auto', 'bf16' (tcgen05 tensor cores) or 'fp32' (CUDA cores)")
         self.mlp_impl = "bf16" if mlp_impl == "auto" else mlp_impl
         self.obs_dim, self.n_actions, self.n_envs = env.obs_dim, env.n_actions, env.num_envs
+        # one fused forward+loss+backward kernel per tower and minibatch (csrc/mlp_train.cu) where the shape allows
+        self.fused_update = bool(fused_update) and self.mlp_impl == "bf16" and ops.ppo_minibatch_supported(self.obs_dim, self.n_actions)
         self.device = torch.device("cuda", env.device_index)
         self.num_timesteps = 0
         self.n_updates = 0
@@ -128,11 +131,12 @@ class CudaPPO:
         B = min(self.batch_size, total)
         self.mb_rows = B
         self.perm = torch.empty(total, dtype=torch.int32, device=dev)
-        self.logits_mb = torch.empty((B, A), **f32)
-        self.values_mb = torch.empty(B, **f32)
-        self.dlogits = torch.empty((B, A), **f32)
-        self.dvalues = torch.empty(B, **f32)
-        self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
+        if not self.fused_update:
+            self.logits_mb = torch.empty((B, A), **f32)
+            self.values_mb = torch.empty(B, **f32)
+            self.dlogits = torch.empty((B, A), **f32)
+            self.dvalues = torch.empty(B, **f32)
+            self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
         self.scratch_mb = torch.empty(2 * B * HIDDEN, dtype=self._act_dtype, device=dev)
         self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(8, **f32)
@@ -183,18 +187,24 @@ class CudaPPO:
             for start in range(0, total, B):
                 rows = min(B, total - start)
                 idx = self.perm[start:start + rows]
-                ops.mlp_forward(self.params, obs_flat, D, A, index=idx, rows=rows, logits=self.logits_mb,
-                                values=self.values_mb, act_cache=self.cache_mb, wpack=self.wpack)
                 sums = None
                 if self.normalize_advantage and rows * self.world > 1:
                     sums = ops.adv_stats(self.adv, idx, rows, self.adv_sums)
                     allreduce_sum_(sums)
-                ops.ppo_loss(self.logits_mb, self.values_mb, self.act, self.adv, self.logp, self.ret, index=idx,
-                             rows=rows, global_rows=rows * self.world, adv_sums=sums, normalize=sums is not None,
-                             clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
-                             dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
-                ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
-                                 rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
+                if self.fused_update:
+                    ops.ppo_minibatch(self.params, self.wpack, obs_flat, D, A, self.act, self.adv, self.logp, self.ret,
+                                      index=idx, rows=rows, global_rows=rows * self.world, adv_sums=sums,
+                                      normalize=sums is not None, clip_range=self.clip_range, ent_coef=self.ent_coef,
+                                      vf_coef=self.vf_coef, grads=self.grads, scratch=self.scratch_mb, stats=self.stats)
+                else:
+                    ops.mlp_forward(self.params, obs_flat, D, A, index=idx, rows=rows, logits=self.logits_mb,
+                                    values=self.values_mb, act_cache=self.cache_mb, wpack=self.wpack)
+                    ops.ppo_loss(self.logits_mb, self.values_mb, self.act, self.adv, self.logp, self.ret, index=idx,
+                                 rows=rows, global_rows=rows * self.world, adv_sums=sums, normalize=sums is not None,
+                                 clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
+                                 dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
+                    ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
+                                     rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
                 allreduce_sum_(self.grads)                # the one collective on the path: NCCL sum over NVLink
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
@@ -352,13 +362,13 @@ class CudaPPO:
 
 # ---------------------------------------------------------------------------------------- bench / smoke
 def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: int = 65536, n_steps: int = 128,
-              minibatches: int = 32, task: str = "ball3d", mlp_impl: str = "bf16") -> dict[str, Any]:
+              minibatches: int = 32, task: str = "ball3d", mlp_impl: str = "bf16", fused_update: bool = True) -> dict[str, Any]:
     """BASELINE config 3: ball3d PPO end-to-end, 64K envs/GPU, 128-step rollouts, 2x256 MLP, 10 epochs,
     32 minibatches per epoch (262 144 samples per GPU per optimizer step)."""
     dist, _, _ = _dist()
     env = CudaVecEnv(task, n_envs, seed=1, device=local_rank, env_id_base=rank * n_envs)
     model = CudaPPO("MlpPolicy", env, seed=1, n_steps=n_steps, batch_size=n_envs * n_steps // minibatches, n_epochs=10,
-                    ent_coef=0.01, mlp_impl=mlp_impl)
+                    ent_coef=0.01, mlp_impl=mlp_impl, fused_update=fused_update)
     dev = model.device
 
     def sync():
@@ -388,7 +398,9 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
         "config": {"task": task, "envs_per_gpu": n_envs, "n_steps": n_steps, "epochs": 10, "minibatches_per_epoch": minibatches,
                    "minibatch_rows_per_gpu": n_envs * n_steps // minibatches, "mlp": "6-256-256-{5,1} tanh, separate towers",
                    "mlp_impl": ("bf16 tcgen05/TMEM hidden-layer GEMMs, fp32 accumulate (csrc/mlp_tc.cu)" if mlp_impl == "bf16"
-                                else "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)")},
+                                else "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)"),
+                   "update": ("fused forward+loss+backward kernel per tower + MN-major wgrad (csrc/mlp_train.cu)"
+                              if model.fused_update else "unfused (forward, loss, backward kernels)")},
         "update_tflops": flop_update / (train_ms * 1e-3) / 1e12,
         "ep_rew_mean": row["rollout/ep_rew_mean"], "approx_kl": row["train/approx_kl"],
     }
