@@ -5,32 +5,37 @@
 //     evaluate_actions (tower forward) -> advantage normalisation -> clipped surrogate / value MSE / entropy
 //     -> autograd backward through head, layer 2 and layer 1
 // that the unfused path runs as 9 kernels with every [rows,256] activation making a round trip through HBM
-// (10 KB per sample).  Here one persistent CTA per SM walks 128-row tiles and keeps everything on chip:
+// (10 KB per sample).  Here one persistent CTA per SM walks 128-row tiles and keeps everything on chip.
+// CUDA cores do only the element-wise work, one thread = (row, 64-column quarter); every reduction over the
+// rows of a tile is a tcgen05.mma whose accumulator lives in TMEM for the whole kernel:
 //
-//   P1  gather obs rows, layer 1 on CUDA cores            -> H1 (bf16) in the shared-memory operand tile
-//   P2  tcgen05.mma  Z2 = H1 . W2^T  (W2 resident, K-major)   -> TMEM;  H1 rows leave for HBM meanwhile
-//   P3  TMEM -> bias + tanh -> head dot products           -> H2 (bf16) overwrites the tile (MMA done)
-//   P4  loss per row (softmax / ratio / clip / entropy, or value MSE), analytic d(loss)/d(head output)
-//   P5  dZ2 = (dout . Wh) * (1 - H2^2) in place; dWh, db2 accumulated in registers
-//   P6  tcgen05.mma  dH1 = dZ2 . W2  — the SAME resident W2 bytes read through an MN-major descriptor
-//       (no transposed copy);  dZ2 rows leave for HBM meanwhile
-//   P7  TMEM -> dH1 (bf16) -> tile;  dZ1 = dH1 * (1 - H1^2);  dW1, db1 accumulated in registers
+//   P1  layer 1 (K = obs_dim) on CUDA cores -> H1 (bf16): shared-memory tile (K-major) + a TMEM stash for P7
+//   M1  Z2 = H1 . W2^T            16 x (M128 N256 K16), W2 resident in shared memory          -> ACC (TMEM)
+//   P3  ACC -> bias + tanh -> H2 (bf16) overwrites the tile; head dot products; P4 loss per row, d(loss)/d(head)
+//       written as a [128][16] bf16 hi/lo tile DOUT
+//   M2  dH2 = DOUT . Wh (one K=16 MMA) -> ACC;   dWh += H2^T . DOUT (H2 tile read MN-major)  -> GWH (TMEM)
+//   P5  dZ2 = ACC * (1 - H2^2) -> tile
+//   M3  dH1 = dZ2 . W2 — the SAME resident W2 bytes through an MN-major descriptor              -> ACC
+//       db2 += dZ2^T . 1 (ones column of the XB tile)                                           -> GB2 (TMEM)
+//       meanwhile the CUDA cores compute layer 1 of the NEXT tile into registers
+//   P7  dZ1 = ACC * (1 - H1^2) (H1 from the TMEM stash) -> tile
+//   M4  dW1|db1 += dZ1^T . [x_hi | x_lo | 1]  (XB tile, bf16 hi/lo split of the fp32 observations)  -> GW1 (TMEM)
 //
 // Only H1 and dZ2 (2 x 512 B per sample) are written out, for the split-K weight-gradient GEMM
-// dW2 = dZ2^T . H1 whose 256x256 fp32 accumulator needs all 512 TMEM columns (tc_wgrad_mn_kernel below: both
-// operands are read through MN-major descriptors straight from row-major staging, no transposes).
+// dW2 = dZ2^T . H1 whose 256x256 fp32 accumulator needs all 512 TMEM columns (tc_wgrad_mn_kernel below).
 //
-// MN-major trick: a [rows][256] bf16 tile staged in the canonical K-major SWIZZLE_NONE layout
-// (chunk (r, cb) of 16 bytes at (r/8)*G + cb*C + (r%8)*16) is, byte for byte, also the canonical MN-major
-// layout of its transpose with SBO = C (stride between 8-element groups along MN) and LBO = G (stride between
-// 8-row groups along K) — cute::UMMA "((1,n),(8,k)):((X,SBO),(1,LBO))" in uint128 units.
+// MN-major trick: a [rows][C] bf16 tile staged in the canonical K-major SWIZZLE_NONE layout
+// (16-byte chunk (r, cb) at (r/8)*G + cb*S + (r%8)*16) is, byte for byte, also the canonical MN-major layout of
+// its transpose with SBO = S (stride between 8-element groups along MN) and LBO = G (stride between 8-row groups
+// along K) — cute::UMMA "((1,n),(8,k)):((X,SBO),(1,LBO))" in uint128 units.  So one staged tile serves as the
+// K-major A operand of one GEMM and the MN-major A/B operand of the next, and W2 needs no transposed copy.
 #include <algorithm>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_common.cuh"
 
-static constexpr int kTrainThreads = 512;                  // 16 warps
+static constexpr int kTrainThreads = 512;                  // 16 warps: row = (warp%4)*32 + lane, column quarter = warp/4
 
 __host__ __device__ constexpr uint32_t make_idesc_major(int M, int N, int a_mn, int b_mn) {
     return make_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -41,6 +46,30 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// 32 lanes x 16 consecutive columns, issue only (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// pins 16 registers behind the preceding (volatile) wait: their consumers cannot be scheduled above it
+__device__ __forceinline__ void launder16(uint32_t *r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 struct TowerTrainArgs {
     // tower parameters (fp32 views into the flat vector; W2 from the bf16 pack)
@@ -64,19 +93,23 @@ struct TowerTrainArgs {
     float *stats;                        // float[8] (tmla_ppo_loss layout), accumulated
 };
 
+// small [rows][16] bf16 operand tiles: chunk (r, cb) at (r/8)*256 + cb*128 + (r%8)*16
+static constexpr uint32_t ksS = 128, ksG = 256;
+
 template <int D, int NOUT>
 struct TrainSmem {
-    static constexpr uint32_t w = 0;                                   // W2 bf16, K-major (kLBO/kSBO)
-    static constexpr uint32_t a = kWBytes;                             // the tile: H1 -> H2 -> dZ2 -> dH1 (kaLBO/kaSBO)
-    static constexpr uint32_t w1 = a + kABytes;                        // float [256][D]
-    static constexpr uint32_t b1 = w1 + H * D * 4;                     // float [256]
+    static constexpr bool kWhSmem = NOUT == 1;                         // the fp32 head weights fit only for the value tower
+    static constexpr uint32_t w = 0;                                   // W2 bf16 [256][256], K-major (kLBO/kSBO)
+    static constexpr uint32_t tile = kWBytes;                          // [128][256] bf16, same layout: H1 -> H2 -> dZ2 -> dZ1
+    static constexpr uint32_t wht = tile + 128 * 512;                  // [256 j][16] bf16: Wh^T hi | hi | lo   (B of dH2 = DOUT . Wh)
+    static constexpr uint32_t dout = wht + 256 * 32;                   // [128 r][16] bf16: dout hi | lo | hi
+    static constexpr uint32_t xb = dout + 128 * 32;                    // [128 r][16] bf16: x hi | x lo | 1
+    static constexpr uint32_t w1t = xb + 128 * 32;                     // float [D][256]  (W1 transposed)
+    static constexpr uint32_t b1 = w1t + D * H * 4;                    // float [256]
     static constexpr uint32_t b2 = b1 + H * 4;                         // float [256]
-    static constexpr uint32_t wh = b2 + H * 4;                         // float [NOUT][256]
-    static constexpr uint32_t xs = wh + NOUT * H * 4;                  // float [128][D]
-    static constexpr uint32_t part = xs + 128 * D * 4;                 // float [3][128][NOUT]
-    static constexpr uint32_t dout = part + 3 * 128 * NOUT * 4;        // float [128][NOUT]
-    static constexpr uint32_t scal = dout + 128 * NOUT * 4;            // float [16]: stats[0..5), dbh[NOUT]
-    static constexpr uint32_t bar = (scal + 64 + 15) & ~15u;
+    static constexpr uint32_t part = b2 + H * 4;                       // float [3][128][NOUT] head partial sums of column quarters 1..3
+    static constexpr uint32_t wh = part + 3 * 128 * NOUT * 4;          // float [NOUT][256] (kWhSmem only)
+    static constexpr uint32_t bar = wh + (kWhSmem ? NOUT * H * 4 : 0);
     static constexpr uint32_t total = bar + 64;
 };
 
@@ -84,68 +117,68 @@ template <int D, int NOUT>
 __global__ void __launch_bounds__(kTrainThreads, 1)
 tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     using L = TrainSmem<D, NOUT>;
-    constexpr int NT = kTrainThreads;
     constexpr bool PI = NOUT > 1;
-    constexpr int XPT = (128 * D + NT - 1) / NT;
-    constexpr int NV = NOUT + 1 + D + 1;                   // per-column gradient values: dWh[NOUT], db2, dW1[D], db1
+    static_assert(3 * NOUT <= 16 && 2 * D + 1 <= 16, "operand tiles are 16 columns wide");
+    // TMEM columns: ACC (Z2 / dH2 / dH1), H1 stash (bf16 pairs), persistent gradient accumulators
+    constexpr uint32_t C_ACC = 0, C_H1 = 256, C_GWH = 384, C_GB2 = 416, C_GW1 = 448;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *Ws = smem + L::w, *As = smem + L::a;
-    float *w1s = reinterpret_cast<float *>(smem + L::w1), *b1s = reinterpret_cast<float *>(smem + L::b1);
-    float *b2s = reinterpret_cast<float *>(smem + L::b2), *whs = reinterpret_cast<float *>(smem + L::wh);
-    float *xs = reinterpret_cast<float *>(smem + L::xs), *part = reinterpret_cast<float *>(smem + L::part);
-    float *douts = reinterpret_cast<float *>(smem + L::dout), *scal = reinterpret_cast<float *>(smem + L::scal);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::bar);
+    uint8_t *Ws = smem + L::w, *Ts = smem + L::tile;
+    float *w1t = reinterpret_cast<float *>(smem + L::w1t), *b1s = reinterpret_cast<float *>(smem + L::b1);
+    float *b2s = reinterpret_cast<float *>(smem + L::b2), *part = reinterpret_cast<float *>(smem + L::part);
+    float *whs = reinterpret_cast<float *>(smem + L::wh);
+    uint64_t *bar0 = reinterpret_cast<uint64_t *>(smem + L::bar), *bar1 = bar0 + 1;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t M = p.M;
     const int64_t ntiles = (M + 127) / 128;
     if ((int64_t)blockIdx.x >= ntiles) return;
 
-    // column-owner role (P1, P5, P7b): 4 hidden units c0..c0+3, rows rgrp + 8*i
-    const int half = warp & 1, rgrp = warp >> 1;
-    const int c0 = half * 128 + lane * 4;
-    const uint32_t slot0 = (uint32_t)(c0 >> 3) * kaLBO + (uint32_t)rgrp * 16 + (uint32_t)(lane & 1) * 8;   // + i*kaSBO
-    // row-owner role (P3, P7a): row rt of the tile, 64-column quarter cq
-    const int rt = (warp & 3) * 32 + lane, cq = warp >> 2;
+    const int rt = (warp & 3) * 32 + lane, cq = warp >> 2;  // this thread's row of the tile and 64-column quarter
+    uint8_t *trow = Ts + (rt >> 3) * kSBO + (rt & 7) * 16;  // + kb * kLBO: 16-byte chunk kb of row rt
 
-    float xpre[XPT];
+    float xrow[D];
     int32_t a_pre = 0;
     float f0_pre = 0.0f, f1_pre = 0.0f;                    // policy: advantage, old log-prob;  value: return
     auto prefetch = [&](int64_t tile) {
-        const int64_t row0 = tile * 128;
+        const int64_t row = tile * 128 + rt;
 #pragma unroll
-        for (int i = 0; i < XPT; ++i) {
-            const int e = tid + NT * i, r = e / D, k = e - r * D;
-            float v = 0.0f;
-            if (e < 128 * D && row0 + r < M) {
-                const int64_t src = p.index ? (int64_t)__ldg(p.index + row0 + r) : row0 + r;
-                v = __ldg(p.x + src * D + k);
+        for (int k = 0; k < D; ++k) xrow[k] = 0.0f;
+        if (row < M) {
+            const int64_t src = p.index ? (int64_t)__ldg(p.index + row) : row;
+#pragma unroll
+            for (int k = 0; k < D; ++k) xrow[k] = __ldg(p.x + src * D + k);
+            if (cq == 0) {
+                if (PI) { a_pre = __ldg(p.actions + src); f0_pre = __ldg(p.adv + src); f1_pre = __ldg(p.old_logp + src); }
+                else f0_pre = __ldg(p.returns + src);
             }
-            xpre[i] = v;
-        }
-        if (tid < 128 && row0 + tid < M) {
-            const int64_t src = p.index ? (int64_t)__ldg(p.index + row0 + tid) : row0 + tid;
-            if (PI) { a_pre = __ldg(p.actions + src); f0_pre = __ldg(p.adv + src); f1_pre = __ldg(p.old_logp + src); }
-            else f0_pre = __ldg(p.returns + src);
         }
     };
     prefetch(blockIdx.x);
 
-    if (warp == 0) tmem_alloc<256>(tmem_holder);
-    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_holder);
+    if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_barrier_init(); }
     stage_rows<H>(Ws, p.W2, 0, H);
-    for (int e = tid; e < H * D; e += NT) w1s[e] = p.W1[e];
-    for (int e = tid; e < NOUT * H; e += NT) whs[e] = p.Wh[e];
+    for (int e = tid; e < H * D; e += kTrainThreads) { const int j = e / D, k = e - j * D; w1t[k * H + j] = p.W1[e]; }
+    if (L::kWhSmem) for (int e = tid; e < NOUT * H; e += kTrainThreads) whs[e] = p.Wh[e];
     if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
-    if (tid < 16) scal[tid] = 0.0f;
+    for (int e = tid; e < H * 16; e += kTrainThreads) {    // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
+        const int j = e >> 4, c = e & 15;
+        float v = 0.0f;
+        if (c < 3 * NOUT) {
+            const float w = p.Wh[(c % NOUT) * H + j];
+            v = c < 2 * NOUT ? w : w - bf16_round(w);
+        }
+        *reinterpret_cast<__nv_bfloat16 *>(smem + L::wht + (j >> 3) * ksG + (c >> 3) * ksS + (j & 7) * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t idesc_fwd = make_idesc_major(128, 256, 0, 0);   // A K-major, B K-major
-    const uint32_t idesc_dgr = make_idesc_major(128, 256, 0, 1);   // A K-major, B MN-major (W2 read transposed)
-    const uint32_t a_addr = smem_u32(As), w_addr = smem_u32(Ws);
-    uint32_t phase = 0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
+    const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
+    uint32_t ph0 = 0, ph1 = 0;
 
     // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased)
     float adv_mean = 0.0f, adv_inv_std = 1.0f;
@@ -157,312 +190,335 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         adv_inv_std = 1.0f / ((float)sqrt(var) + 1e-8f);
         if (blockIdx.x == 0 && tid == 0) { p.stats[6] = adv_mean; p.stats[7] = (float)sqrt(var); }
     }
+    float st_acc[4] = {0.f, 0.f, 0.f, 0.f}, dbh_acc[NOUT];   // per-thread running sums (threads of column quarter 0)
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) dbh_acc[a] = 0.0f;
 
-    // per-column gradient accumulators, persistent across the CTA's tiles (pairs for the packed fp32 pipe)
-    float2 gWh01[NOUT], gWh23[NOUT], gW101[D], gW123[D];
-    float2 gb2_01 = make_float2(0.f, 0.f), gb2_23 = gb2_01, gb1_01 = gb2_01, gb1_23 = gb2_01;
+    // layer 1 of this thread's (row, 64 columns): H1 = tanh(x W1^T + b1), packed bf16 pairs
+    uint32_t h1p[32];
+    auto layer1 = [&]() {
 #pragma unroll
-    for (int a = 0; a < NOUT; ++a) gWh01[a] = gWh23[a] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < D; ++k) gW101[k] = gW123[k] = make_float2(0.f, 0.f);
-
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row0 = tile * 128;
-        const int32_t a_cur = a_pre;
-        const float f0_cur = f0_pre, f1_cur = f1_pre;
-#pragma unroll
-        for (int i = 0; i < XPT; ++i) { const int e = tid + NT * i; if (e < 128 * D) xs[e] = xpre[i]; }
-        __syncthreads();
-        // ---- P1: layer 1, H1 = tanh(x W1^T + b1) -> K-major tile
-        {
-            float2 w01[D], w23[D];
+        for (int g = 0; g < 16; ++g) {
+            const int col = cq * 64 + g * 4;
+            const float4 bb = *reinterpret_cast<const float4 *>(b1s + col);
+            float2 v01 = make_float2(bb.x, bb.y), v23 = make_float2(bb.z, bb.w);
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                w01[k] = make_float2(w1s[(c0 + 0) * D + k], w1s[(c0 + 1) * D + k]);
-                w23[k] = make_float2(w1s[(c0 + 2) * D + k], w1s[(c0 + 3) * D + k]);
+                const float4 ww = *reinterpret_cast<const float4 *>(w1t + k * H + col);
+                const float2 xx = make_float2(xrow[k], xrow[k]);
+                v01 = __ffma2_rn(xx, make_float2(ww.x, ww.y), v01);
+                v23 = __ffma2_rn(xx, make_float2(ww.z, ww.w), v23);
             }
-            const float4 bb = *reinterpret_cast<const float4 *>(b1s + c0);
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const float *xr = xs + (rgrp + 8 * i) * D;
-                float2 v01 = make_float2(bb.x, bb.y), v23 = make_float2(bb.z, bb.w);
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    const float2 xx = make_float2(xr[k], xr[k]);
-                    v01 = __ffma2_rn(xx, w01[k], v01);
-                    v23 = __ffma2_rn(xx, w23[k], v23);
-                }
-                *reinterpret_cast<uint2 *>(As + i * kaSBO + slot0) =
-                    make_uint2(pack_bf16(tanh_fast(v01.x), tanh_fast(v01.y)), pack_bf16(tanh_fast(v23.x), tanh_fast(v23.y)));
-            }
+            h1p[2 * g] = pack_bf16(tanh_fast(v01.x), tanh_fast(v01.y));
+            h1p[2 * g + 1] = pack_bf16(tanh_fast(v23.x), tanh_fast(v23.y));
         }
+    };
+    // coalesced copy of the tile to global rows: warp = 8-row group, a quarter-warp reads 128 contiguous bytes
+    auto copy_out = [&](__nv_bfloat16 *dst, int64_t row0) {
+        const int r = warp * 8 + (lane & 7);
+        const uint8_t *src = Ts + warp * kSBO + (lane & 7) * 16;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4 *>(src + (4 * i + (lane >> 3)) * kLBO);
+        if (row0 + r < M) {
+            uint4 *g = reinterpret_cast<uint4 *>(dst + (row0 + r) * H) + (lane >> 3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[4 * i] = v[i];
+        }
+    };
+    layer1();
+
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int64_t row0 = tile * 128;
+        const bool has_next = tile + gridDim.x < ntiles;
+        const int32_t a_cur = a_pre;
+        const float f0_cur = f0_pre, f1_cur = f1_pre;
+        // ---- P1: H1 (computed during the previous tile's M3) -> tile + TMEM stash; XB = [x_hi | x_lo | 1]
+        if (it > 0) { mbar_wait(bar1, ph1); ph1 ^= 1u; tc_fence_after(); }   // M4 of the previous tile has read the tile and XB
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4 *>(trow + (cq * 8 + c) * kLBO) = make_uint4(h1p[4 * c], h1p[4 * c + 1], h1p[4 * c + 2], h1p[4 * c + 3]);
+        tmem_st16(lane_base + C_H1 + cq * 32, h1p);
+        tmem_st16(lane_base + C_H1 + cq * 32 + 16, h1p + 16);
+        if (cq == 0) {
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { v[k] = xrow[k]; v[D + k] = xrow[k] - bf16_round(xrow[k]); }
+            v[2 * D] = 1.0f;
+            uint8_t *xr = smem + L::xb + (rt >> 3) * ksG + (rt & 7) * 16;
+            *reinterpret_cast<uint4 *>(xr) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4 *>(xr + ksS) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        }
+        tmem_wait_st();
         fence_proxy_async();
+        tc_fence_before();
         __syncthreads();
-        // ---- P2: Z2 = H1 . W2^T on the tensor core; H1 rows -> HBM and next-tile prefetch meanwhile
+        // ---- M1: Z2 = H1 . W2^T -> ACC;  H1 rows -> HBM and next-tile prefetch meanwhile
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)
-                umma_bf16(tmem_base, make_desc_raw(a_addr + kk * 2 * kaLBO, kaLBO, kaSBO),
-                          make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO), idesc_fwd, kk > 0 ? 1u : 0u);
-            umma_commit(bar);
+                umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
+                          make_idesc_major(128, 256, 0, 0), kk > 0 ? 1u : 0u);
+            umma_commit(bar0);
         }
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp + 16 * i;
-            const uint4 v = *reinterpret_cast<const uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16);
-            if (row0 + r < M) reinterpret_cast<uint4 *>(p.h1_out + (row0 + r) * H)[lane] = v;
-        }
-        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        copy_out(p.h1_out, row0);
+        if (has_next) prefetch(tile + gridDim.x);
+        mbar_wait(bar0, ph0);
+        ph0 ^= 1u;
         tc_fence_after();
         __syncthreads();                                   // every warp has copied its H1 rows out: the tile may be overwritten
-        // ---- P3: H2 = tanh(Z2 + b2) -> tile (K-major), head partial dot products
+        // ---- P3: H2 = tanh(Z2 + b2) -> tile (and registers, for P5); head partial dot products
+        uint32_t h2p[32];
+        float z[NOUT];
         {
             float2 hs[NOUT];
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) hs[a] = make_float2(0.f, 0.f);
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cq * 64);
-            uint8_t *trow = As + (rt >> 3) * kaSBO + (rt & 7) * 16;
-#pragma unroll 1
+            const uint32_t taddr = lane_base + C_ACC + cq * 64;
+            uint32_t acc[2][16];
+            tmem_ld16_nowait(taddr, acc[0]);
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t acc[16];
-                tmem_ld16(taddr + c * 16, acc);
+                tmem_wait_ld();
+                launder16(acc[c & 1]);
+                if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
                 const int col = cq * 64 + c * 16;
                 float hv[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 bb = *reinterpret_cast<const float4 *>(b2s + col + 4 * q);
-                    hv[4 * q + 0] = tanh_fast(__uint_as_float(acc[4 * q + 0]) + bb.x);
-                    hv[4 * q + 1] = tanh_fast(__uint_as_float(acc[4 * q + 1]) + bb.y);
-                    hv[4 * q + 2] = tanh_fast(__uint_as_float(acc[4 * q + 2]) + bb.z);
-                    hv[4 * q + 3] = tanh_fast(__uint_as_float(acc[4 * q + 3]) + bb.w);
+                    hv[4 * q + 0] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 0]) + bb.x);
+                    hv[4 * q + 1] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 1]) + bb.y);
+                    hv[4 * q + 2] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 2]) + bb.z);
+                    hv[4 * q + 3] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 3]) + bb.w);
                 }
 #pragma unroll
                 for (int a = 0; a < NOUT; ++a)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 ww = *reinterpret_cast<const float4 *>(whs + a * H + col + 4 * q);
+                        const float4 ww = L::kWhSmem ? *reinterpret_cast<const float4 *>(whs + a * H + col + 4 * q)
+                                                     : __ldg(reinterpret_cast<const float4 *>(p.Wh + a * H + col + 4 * q));
                         hs[a] = __ffma2_rn(make_float2(hv[4 * q + 0], hv[4 * q + 1]), make_float2(ww.x, ww.y), hs[a]);
                         hs[a] = __ffma2_rn(make_float2(hv[4 * q + 2], hv[4 * q + 3]), make_float2(ww.z, ww.w), hs[a]);
                     }
-                uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = pack_bf16(hv[2 * j], hv[2 * j + 1]);
+                for (int j = 0; j < 8; ++j) h2p[8 * c + j] = pack_bf16(hv[2 * j], hv[2 * j + 1]);
                 const int kb = col >> 3;
-                *reinterpret_cast<uint4 *>(trow + kb * kaLBO) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kaLBO) = make_uint4(o[4], o[5], o[6], o[7]);
+                *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(h2p[8 * c], h2p[8 * c + 1], h2p[8 * c + 2], h2p[8 * c + 3]);
+                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(h2p[8 * c + 4], h2p[8 * c + 5], h2p[8 * c + 6], h2p[8 * c + 7]);
             }
             if (cq > 0) {
 #pragma unroll
                 for (int a = 0; a < NOUT; ++a) part[((cq - 1) * 128 + rt) * NOUT + a] = hs[a].x + hs[a].y;
-            }
-            tc_fence_before();
-            __syncthreads();                               // TMEM drained, H2 tile and partial sums complete
-            // ---- P4: loss of row rt (threads of column quarter 0 = tid 0..127), d(loss)/d(head output)
-            if (cq == 0) {
-                const bool valid = row0 + rt < M;
-                float z[NOUT], dz[NOUT];
+            } else {
 #pragma unroll
-                for (int a = 0; a < NOUT; ++a)
-                    z[a] = (((hs[a].x + hs[a].y) + part[rt * NOUT + a]) + (part[(128 + rt) * NOUT + a] + part[(256 + rt) * NOUT + a])) + __ldg(p.Bh + a);
-                if (p.out && valid) {
-#pragma unroll
-                    for (int a = 0; a < NOUT; ++a) p.out[(row0 + rt) * NOUT + a] = z[a];
-                }
-                float st[4] = {0.f, 0.f, 0.f, 0.f};        // policy: pg, entropy-loss, kl, clipfrac;  value: st[0] = squared error
-                if (PI) {
-                    float m = z[0];
-#pragma unroll
-                    for (int j = 1; j < NOUT; ++j) m = fmaxf(m, z[j]);
-                    float pr[NOUT], lp[NOUT], S = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < NOUT; ++j) { pr[j] = expf(z[j] - m); S += pr[j]; }
-                    const float logS = logf(S), invS = 1.0f / S;
-                    float ent = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < NOUT; ++j) { lp[j] = (z[j] - m) - logS; pr[j] *= invS; ent -= pr[j] * lp[j]; }
-                    float logp = lp[0];
-#pragma unroll
-                    for (int j = 1; j < NOUT; ++j) logp = (a_cur == j) ? lp[j] : logp;
-                    float adv = f0_cur;
-                    if (p.normalize) adv = (adv - adv_mean) * adv_inv_std;
-                    const float lr = logp - f1_cur;
-                    const float ratio = expf(lr);
-                    const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
-                    const float s1 = adv * ratio, s2 = adv * fminf(fmaxf(ratio, lo), hi);
-                    const bool inside = (ratio >= lo) && (ratio <= hi);
-                    const bool active = inside || (s1 < s2);
-                    const float dlogp = active ? (-adv * ratio * p.inv_rows) : 0.0f;
-#pragma unroll
-                    for (int j = 0; j < NOUT; ++j)
-                        dz[j] = valid ? dlogp * ((a_cur == j ? 1.0f : 0.0f) - pr[j]) + p.ent_coef * p.inv_rows * pr[j] * (lp[j] + ent) : 0.0f;
-                    if (valid) {
-                        st[0] = -fminf(s1, s2); st[1] = -ent; st[2] = (ratio - 1.0f) - lr;
-                        st[3] = (fabsf(ratio - 1.0f) > p.clip) ? 1.0f : 0.0f;
-                    }
-                } else {
-                    const float dv = z[0] - f0_cur;
-                    dz[0] = valid ? p.vf_coef * 2.0f * dv * p.inv_rows : 0.0f;
-                    if (valid) st[0] = dv * dv;
-                }
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a) douts[rt * NOUT + a] = dz[a];
-                // per-tile scalar reductions: stats and the head-bias gradient
-#pragma unroll
-                for (int q = 0; q < (PI ? 4 : 1); ++q) {
-                    const float s = warp_sum_f(st[q]);
-                    if (lane == 0) atomicAdd(scal + q, s);
-                }
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a) {
-                    const float s = warp_sum_f(dz[a]);
-                    if (lane == 0) atomicAdd(scal + 8 + a, s);
-                }
+                for (int a = 0; a < NOUT; ++a) z[a] = hs[a].x + hs[a].y;
             }
         }
-        __syncthreads();
-        // ---- P5: dZ2 = (dout . Wh) * (1 - H2^2) in place;  dWh += dout^T H2,  db2 += sum dZ2
-        {
-            float2 wh01[NOUT], wh23[NOUT];
+        tc_fence_before();
+        __syncthreads();                                   // ACC drained, H2 tile and partial sums complete
+        // ---- P4: loss of row rt (threads of column quarter 0), d(loss)/d(head output) -> DOUT tile (bf16 hi | lo | hi)
+        if (cq == 0) {
+            const bool valid = row0 + rt < M;
+            float dz[NOUT];
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a)
+                z[a] = ((z[a] + part[rt * NOUT + a]) + (part[(128 + rt) * NOUT + a] + part[(256 + rt) * NOUT + a])) + __ldg(p.Bh + a);
+            if (p.out && valid) {
+#pragma unroll
+                for (int a = 0; a < NOUT; ++a) p.out[(row0 + rt) * NOUT + a] = z[a];
+            }
+            if (PI) {
+                float m = z[0];
+#pragma unroll
+                for (int j = 1; j < NOUT; ++j) m = fmaxf(m, z[j]);
+                float pr[NOUT], lp[NOUT], S = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j) { pr[j] = __expf(z[j] - m); S += pr[j]; }
+                const float logS = __logf(S), invS = __fdividef(1.0f, S);
+                float ent = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j) { lp[j] = (z[j] - m) - logS; pr[j] *= invS; ent -= pr[j] * lp[j]; }
+                float logp = lp[0];
+#pragma unroll
+                for (int j = 1; j < NOUT; ++j) logp = (a_cur == j) ? lp[j] : logp;
+                float adv = f0_cur;
+                if (p.normalize) adv = (adv - adv_mean) * adv_inv_std;
+                const float lr = logp - f1_cur;
+                const float ratio = __expf(lr);
+                const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+                const float s1 = adv * ratio, s2 = adv * fminf(fmaxf(ratio, lo), hi);
+                const bool inside = (ratio >= lo) && (ratio <= hi);
+                const bool active = inside || (s1 < s2);
+                const float dlogp = active ? (-adv * ratio * p.inv_rows) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j)
+                    dz[j] = valid ? dlogp * ((a_cur == j ? 1.0f : 0.0f) - pr[j]) + p.ent_coef * p.inv_rows * pr[j] * (lp[j] + ent) : 0.0f;
+                if (valid) {
+                    st_acc[0] += -fminf(s1, s2); st_acc[1] += -ent; st_acc[2] += (ratio - 1.0f) - lr;
+                    st_acc[3] += (fabsf(ratio - 1.0f) > p.clip) ? 1.0f : 0.0f;
+                }
+            } else {
+                const float dv = z[0] - f0_cur;
+                dz[0] = valid ? p.vf_coef * 2.0f * dv * p.inv_rows : 0.0f;
+                if (valid) st_acc[0] += dv * dv;
+            }
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = 0.0f;
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) {
-                const float4 ww = *reinterpret_cast<const float4 *>(whs + a * H + c0);
-                wh01[a] = make_float2(ww.x, ww.y); wh23[a] = make_float2(ww.z, ww.w);
+                dbh_acc[a] += dz[a];
+                v[a] = dz[a]; v[NOUT + a] = dz[a] - bf16_round(dz[a]); v[2 * NOUT + a] = dz[a];
             }
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = rgrp + 8 * i;
-                uint2 *slot = reinterpret_cast<uint2 *>(As + i * kaSBO + slot0);
-                const uint2 hr = *slot;
-                const float2 h01 = make_float2(bf16_lo(hr.x), bf16_hi(hr.x)), h23 = make_float2(bf16_lo(hr.y), bf16_hi(hr.y));
-                float2 d01 = make_float2(0.f, 0.f), d23 = d01;
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a) {
-                    const float da = douts[r * NOUT + a];
-                    const float2 dd = make_float2(da, da);
-                    d01 = __ffma2_rn(dd, wh01[a], d01);
-                    d23 = __ffma2_rn(dd, wh23[a], d23);
-                    gWh01[a] = __ffma2_rn(dd, h01, gWh01[a]);
-                    gWh23[a] = __ffma2_rn(dd, h23, gWh23[a]);
-                }
-                const float2 one = make_float2(1.f, 1.f);
-                const float2 s01 = __ffma2_rn(make_float2(-h01.x, -h01.y), h01, one), s23 = __ffma2_rn(make_float2(-h23.x, -h23.y), h23, one);
-                d01 = __fmul2_rn(d01, s01); d23 = __fmul2_rn(d23, s23);
-                gb2_01 = __fadd2_rn(gb2_01, d01); gb2_23 = __fadd2_rn(gb2_23, d23);
-                *slot = make_uint2(pack_bf16(d01.x, d01.y), pack_bf16(d23.x, d23.y));
-            }
+            uint8_t *dr = smem + L::dout + (rt >> 3) * ksG + (rt & 7) * 16;
+            *reinterpret_cast<uint4 *>(dr) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4 *>(dr + ksS) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
         }
         fence_proxy_async();
         __syncthreads();
-        // ---- P6: dH1 = dZ2 . W2 on the tensor core (W2 tile read MN-major); dZ2 rows -> HBM, H1 rows come back
+        // ---- M2: dH2 = DOUT . Wh -> ACC (one K=16 MMA);  dWh += H2^T . DOUT -> GWH (H2 tile and DOUT read MN-major)
+        if (tid == 0) {
+            tc_fence_after();
+            umma_bf16(tmem_base + C_ACC, make_desc_raw(dout_addr, ksS, ksG), make_desc_raw(wht_addr, ksS, ksG), make_idesc_major(128, 256, 0, 0), 0u);
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)                 // hidden units 0..127 / 128..255 = accumulator lanes
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)             // K = 16 rows of the tile per step
+                    umma_bf16(tmem_base + C_GWH + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                              make_desc_raw(dout_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar1);
+        }
+        mbar_wait(bar1, ph1);
+        ph1 ^= 1u;
+        tc_fence_after();
+        // ---- P5: dZ2 = dH2 * (1 - H2^2) -> tile (this thread overwrites its own H2 chunks; M2 has finished reading them)
+        {
+            const uint32_t taddr = lane_base + C_ACC + cq * 64;
+            uint32_t acc[2][16];
+            tmem_ld16_nowait(taddr, acc[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_wait_ld();
+                launder16(acc[c & 1]);
+                if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h0 = bf16_lo(h2p[8 * c + j]), h1 = bf16_hi(h2p[8 * c + j]);
+                    o[j] = pack_bf16(__uint_as_float(acc[c & 1][2 * j]) * (1.0f - h0 * h0), __uint_as_float(acc[c & 1][2 * j + 1]) * (1.0f - h1 * h1));
+                }
+                const int kb = (cq * 64 + c * 16) >> 3;
+                *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- M3: dH1 = dZ2 . W2 -> ACC (W2 tile read MN-major);  db2 += dZ2^T . XB -> GB2 (its ones column is db2)
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)            // K = layer-2 output index j: 16 rows of the W2 tile per step
-                umma_bf16(tmem_base, make_desc_raw(a_addr + kk * 2 * kaLBO, kaLBO, kaSBO),
-                          make_desc_raw(w_addr + kk * 2 * kSBO, /*LBO (K groups)*/ kSBO, /*SBO (N groups)*/ kLBO), idesc_dgr, kk > 0 ? 1u : 0u);
-            umma_commit(bar);
-        }
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp + 16 * i;
-            const uint4 v = *reinterpret_cast<const uint4 *>(As + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16);
-            if (row0 + r < M) reinterpret_cast<uint4 *>(p.dz2_out + (row0 + r) * H)[lane] = v;
-        }
-        uint2 h1pre[16];                                   // this thread's H1 values (written in P2, L2-resident)
+                umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO),
+                          make_desc_raw(w_addr + kk * 2 * kSBO, /*LBO: K groups*/ kSBO, /*SBO: N groups*/ kLBO), make_idesc_major(128, 256, 0, 1), kk > 0 ? 1u : 0u);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int64_t r = row0 + rgrp + 8 * i;
-            h1pre[i] = (r < M) ? *reinterpret_cast<const uint2 *>(p.h1_out + r * H + c0) : make_uint2(0u, 0u);
+            for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(tmem_base + C_GB2 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                              make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar0);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        copy_out(p.dz2_out, row0);
+        if (has_next) layer1();                            // next tile's layer 1 on the CUDA cores while the tensor core runs M3
+        mbar_wait(bar0, ph0);
+        ph0 ^= 1u;
         tc_fence_after();
         __syncthreads();                                   // dZ2 rows copied out by every warp
-        // ---- P7a: dH1 (fp32, TMEM) -> bf16 -> tile
+        // ---- P7: dZ1 = dH1 * (1 - H1^2) -> tile (H1 from the TMEM stash)
         {
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cq * 64);
-            uint8_t *trow = As + (rt >> 3) * kaSBO + (rt & 7) * 16;
-#pragma unroll 2
+            const uint32_t taddr = lane_base + C_ACC + cq * 64;
+            uint32_t hst[32], acc[2][16];
+            tmem_ld16_nowait(lane_base + C_H1 + cq * 32, hst);
+            tmem_ld16_nowait(lane_base + C_H1 + cq * 32 + 16, hst + 16);
+            tmem_ld16_nowait(taddr, acc[0]);
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t acc[16];
-                tmem_ld16(taddr + c * 16, acc);
+                tmem_wait_ld();
+                launder16(acc[c & 1]);
+                if (c == 0) { launder16(hst); launder16(hst + 16); }
+                if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
                 uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                for (int j = 0; j < 8; ++j) {
+                    const float h0 = bf16_lo(hst[8 * c + j]), h1 = bf16_hi(hst[8 * c + j]);
+                    o[j] = pack_bf16(__uint_as_float(acc[c & 1][2 * j]) * (1.0f - h0 * h0), __uint_as_float(acc[c & 1][2 * j + 1]) * (1.0f - h1 * h1));
+                }
                 const int kb = (cq * 64 + c * 16) >> 3;
-                *reinterpret_cast<uint4 *>(trow + kb * kaLBO) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kaLBO) = make_uint4(o[4], o[5], o[6], o[7]);
+                *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
+        fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        // ---- P7b: dZ1 = dH1 * (1 - H1^2);  dW1 += dZ1^T x,  db1 += sum dZ1  (fully unrolled: h1pre stays in registers)
+        // ---- M4: dW1 | db1 += dZ1^T . [x_hi | x_lo | 1] -> GW1
+        if (tid == 0) {
+            tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint2 dr = *reinterpret_cast<const uint2 *>(As + i * kaSBO + slot0);
-            const uint2 hr = h1pre[i];
-            const float2 h01 = make_float2(bf16_lo(hr.x), bf16_hi(hr.x)), h23 = make_float2(bf16_lo(hr.y), bf16_hi(hr.y));
-            const float2 one = make_float2(1.f, 1.f);
-            const float2 s01 = __ffma2_rn(make_float2(-h01.x, -h01.y), h01, one), s23 = __ffma2_rn(make_float2(-h23.x, -h23.y), h23, one);
-            const float2 d01 = __fmul2_rn(make_float2(bf16_lo(dr.x), bf16_hi(dr.x)), s01);
-            const float2 d23 = __fmul2_rn(make_float2(bf16_lo(dr.y), bf16_hi(dr.y)), s23);
-            gb1_01 = __fadd2_rn(gb1_01, d01); gb1_23 = __fadd2_rn(gb1_23, d23);
-            const float *xr = xs + (rgrp + 8 * i) * D;
+            for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float2 xx = make_float2(xr[k], xr[k]);
-                gW101[k] = __ffma2_rn(d01, xx, gW101[k]);
-                gW123[k] = __ffma2_rn(d23, xx, gW123[k]);
-            }
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(tmem_base + C_GW1 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                              make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar1);
         }
-        __syncthreads();                                   // tile and xs are free for the next iteration
     }
+    mbar_wait(bar1, ph1);                                  // the last M4
+    tc_fence_after();
 
-    // ---- flush: reduce the 8 row-group partials per column through shared memory, then one atomic per value
-    float *red = reinterpret_cast<float *>(smem);          // [8 rgrp][NV][256] floats <= 128 KB (the W2 region; all MMAs are done)
-    {
-        auto put = [&](int v, float2 lo, float2 hi) {
-            *reinterpret_cast<float4 *>(red + ((rgrp * NV + v) * H + c0)) = make_float4(lo.x, lo.y, hi.x, hi.y);
-        };
+    // ---- flush: TMEM gradient accumulators (lane = hidden unit) -> one atomic per value; scalar sums
+    if (warp < 4) {
 #pragma unroll
-        for (int a = 0; a < NOUT; ++a) put(a, gWh01[a], gWh23[a]);
-        put(NOUT, gb2_01, gb2_23);
+        for (int mh = 0; mh < 2; ++mh) {
+            const int j = mh * 128 + rt;
+            uint32_t g[16];
+            tmem_ld16(lane_base + C_GWH + mh * 16, g);
 #pragma unroll
-        for (int k = 0; k < D; ++k) put(NOUT + 1 + k, gW101[k], gW123[k]);
-        put(NOUT + 1 + D, gb1_01, gb1_23);
-    }
-    __syncthreads();
-    for (int e = tid; e < NV * H; e += NT) {
-        const int v = e / H, col = e - v * H;
-        float s = 0.0f;
+            for (int a = 0; a < NOUT; ++a) atomicAdd(p.gWh + a * H + j, __uint_as_float(g[a]) + __uint_as_float(g[NOUT + a]));
+            tmem_ld16(lane_base + C_GB2 + mh * 16, g);
+            atomicAdd(p.gB2 + j, __uint_as_float(g[2 * D]));
+            tmem_ld16(lane_base + C_GW1 + mh * 16, g);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) s += red[(g * NV + v) * H + col];
-        float *dst;
-        if (v < NOUT) dst = p.gWh + v * H + col;
-        else if (v == NOUT) dst = p.gB2 + col;
-        else if (v <= NOUT + D) dst = p.gW1 + col * D + (v - NOUT - 1);
-        else dst = p.gB1 + col;
-        atomicAdd(dst, s);
-    }
-    if (tid < 16) {
-        const float s = scal[tid];
-        if (tid >= 8) { if (tid - 8 < NOUT) atomicAdd(p.gBh + (tid - 8), s); }
-        else if (PI) {
-            // stats: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss
-            if (tid == 0) { atomicAdd(p.stats + 0, s * p.inv_rows); atomicAdd(p.stats + 5, s * p.inv_rows); }
-            if (tid == 1) { atomicAdd(p.stats + 2, s * p.inv_rows); atomicAdd(p.stats + 5, p.ent_coef * s * p.inv_rows); }
-            if (tid == 2) atomicAdd(p.stats + 3, s * p.inv_rows);
-            if (tid == 3) atomicAdd(p.stats + 4, s * p.inv_rows);
-        } else if (tid == 0) {
-            atomicAdd(p.stats + 1, s * p.inv_rows); atomicAdd(p.stats + 5, p.vf_coef * s * p.inv_rows);
+            for (int k = 0; k < D; ++k) atomicAdd(p.gW1 + j * D + k, __uint_as_float(g[k]) + __uint_as_float(g[D + k]));
+            atomicAdd(p.gB1 + j, __uint_as_float(g[2 * D]));
+        }
+        // stats: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss
+#pragma unroll
+        for (int q = 0; q < (PI ? 4 : 1); ++q) st_acc[q] = warp_sum_f(st_acc[q]) * p.inv_rows;
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) dbh_acc[a] = warp_sum_f(dbh_acc[a]);
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < NOUT; ++a) atomicAdd(p.gBh + a, dbh_acc[a]);
+            if (PI) {
+                atomicAdd(p.stats + 0, st_acc[0]); atomicAdd(p.stats + 2, st_acc[1]);
+                atomicAdd(p.stats + 3, st_acc[2]); atomicAdd(p.stats + 4, st_acc[3]);
+                atomicAdd(p.stats + 5, st_acc[0] + p.ent_coef * st_acc[1]);
+            } else {
+                atomicAdd(p.stats + 1, st_acc[0]); atomicAdd(p.stats + 5, p.vf_coef * st_acc[0]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem_base);
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 // --------------------------------------------------------- G[256,256] += X[rows,256]^T . Y[rows,256]
@@ -672,7 +728,6 @@ static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
     static int attr_done = 0;
     constexpr uint32_t smem = TrainSmem<D, NOUT>::total;
     static_assert(smem <= 232448, "fused tower training kernel exceeds the 227 KB shared-memory limit");
-    static_assert((NOUT + 1 + D + 1) * 8 * H * 4 <= (int)kWBytes, "gradient flush stage must fit in the W2 region");
     if (!attr_done) {
         TMLA_CUDA(cudaFuncSetAttribute(tc_tower_train_kernel<D, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = 1;
