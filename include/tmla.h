@@ -232,7 +232,7 @@ int tmla_tc_debug(int swap_lbo_sbo);
  *   obs float[total,D], index int32[rows] (NULL = identity) selects the minibatch rows of obs AND of the
  *   [T*N] buffers actions/advantages/old_logp/returns;  adv_sums from tmla_adv_stats (all-reduced by the caller
  *   when world_size>1), global_rows = rows summed over ranks;
- *   grads float[num_params] OVERWRITTEN;  scratch bf16[tmla_ppo_minibatch_scratch(hidden, rows)];
+ *   grads float[num_params] OVERWRITTEN;  scratch bf16[tmla_ppo_minibatch_scratch(hidden, rows)] (tile images);
  *   stats_out float[8] as tmla_ppo_loss;  logits_out float[rows,A] / values_out float[rows]: optional (NULL).
  * tmla_ppo_minibatch_supported: 1 when the fused path covers (obs_dim, hidden, n_actions) — ball3d, gridworld,
  * push; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
@@ -245,13 +245,13 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
                             void *scratch, float *stats_out, float *logits_out, float *values_out, void *stream);
 
 /* test hooks of csrc/mlp_train.cu:
- *   tmla_tc_wgrad_mn: same contract as tmla_tc_wgrad, operands read through MN-major UMMA descriptors (no
- *                     transposing stage), cp.async ring;  tmla_tc_wgrad_select(impl): which of the two the fused
- *                     minibatch uses (1 = MN-major, default; 0 = transposing);
+ *   tmla_tc_wgrad_tiled: G[256,256] (fp32, accumulated) += X^T . Y where X and Y are given as TILE IMAGES — per 128
+ *                     rows one 64 KB block in the shared-memory operand layout, 16-byte chunk (r, cb) of a tile at
+ *                     byte (r/8)*4096 + cb*128 + (r%8)*16 — exactly what the fused training kernel writes with one
+ *                     bulk-TMA store per tile; operands are read through MN-major UMMA descriptors;
  *   tmla_tc_probe   : one-CTA descriptor check, A bf16[128,256], B bf16[256,256]:
  *                     mode 0 out[128,256] = A.B^T | mode 1 out[128,256] = A.B | mode 2 out[256,256] = A^T.B[0:128] */
-int tmla_tc_wgrad_mn(const void *X, const void *Y, float *G, int64_t rows, void *stream);
-int tmla_tc_wgrad_select(int impl);
+int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_padded, void *stream);
 int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream);
 
 #ifdef __cplusplus

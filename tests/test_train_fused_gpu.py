@@ -3,7 +3,8 @@ descriptors) against the unfused bf16 path (same arithmetic, different kernels) 
 
 Stated tolerances:
   * descriptor probe / wgrad: fp32 accumulation of exact bf16 products -> |d| <= 2e-3 * max(1, |ref|)
-  * head outputs (logits, values) fused vs unfused bf16: 2e-3 abs (same bf16 pipeline, other summation order)
+  * head outputs (logits, values) fused vs unfused bf16: 5e-3 abs (the fused head GEMM reads H2 rounded to bf16,
+    2^-9 relative per element over 256 terms; the unfused head reads the fp32 tanh outputs)
   * gradients fused vs unfused bf16: cosine > 0.9999, relative L2 error < 1e-2 (one extra bf16 rounding of dH1)
   * gradients fused vs fp32: cosine > 0.999, relative L2 error < 5e-2 (the bf16-path tolerance of test_trainer_gpu)
   * loss statistics: 1e-4 abs/rel
@@ -41,21 +42,28 @@ def test_mn_major_descriptor_probe(mode):
     assert bool((err <= tol).all()), f"mode {mode}: max err {float(err.max())}, nan {int(torch.isnan(out).sum())}"
 
 
-@pytest.mark.parametrize("rows", [64, 100, 1000, 64 * 148 * 3 + 17, 64 * 148 * 4 + 64])
-def test_wgrad_mn_matches_torch(rows):
+def _tile_image(x):
+    """[rows,256] bf16 (rows % 128 == 0) -> tile images: per 128 rows, 16-byte chunk (r, cb) at (r/8)*4096 + cb*128 + (r%8)*16."""
+    tiles = x.shape[0] // 128
+    return x.view(tiles, 16, 8, 32, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+@pytest.mark.parametrize("rows", [128, 1024, 128 * 148 + 128, 128 * 148 * 3 + 384])
+def test_wgrad_tiled_matches_torch(rows):
     nat = _nat()
     g = torch.Generator(device="cuda").manual_seed(rows)
     X = _bf16(torch.randn((rows, 256), device="cuda", generator=g) * 0.1)
     Y = _bf16(torch.randn((rows, 256), device="cuda", generator=g))
+    Xt, Yt = _tile_image(X), _tile_image(Y)
     G = torch.zeros((256, 256), device="cuda")
-    nat.check(nat.lib.tmla_tc_wgrad_mn(nat.ptr(X), nat.ptr(Y), nat.ptr(G), rows, nat.current_stream()))
+    nat.check(nat.lib.tmla_tc_wgrad_tiled(nat.ptr(Xt), nat.ptr(Yt), nat.ptr(G), rows, nat.current_stream()))
     torch.cuda.synchronize()
     ref = X.float().t() @ Y.float()
     err = (G - ref).abs()
     scale = float(ref.abs().max())
     assert float(err.max()) <= 2e-3 * max(1.0, scale), f"rows {rows}: max err {float(err.max())} (scale {scale})"
     # accumulates (+=) like tmla_tc_wgrad
-    nat.check(nat.lib.tmla_tc_wgrad_mn(nat.ptr(X), nat.ptr(Y), nat.ptr(G), rows, nat.current_stream()))
+    nat.check(nat.lib.tmla_tc_wgrad_tiled(nat.ptr(Xt), nat.ptr(Yt), nat.ptr(G), rows, nat.current_stream()))
     torch.cuda.synchronize()
     assert float((G - 2 * ref).abs().max()) <= 4e-3 * max(1.0, scale)
 
@@ -74,17 +82,16 @@ def _setup(task, n, T, seed=5):
     return env, m
 
 
-@pytest.mark.parametrize("task,n,T,rows,wgrad_impl", [
-    ("ball3d", 64, 8, 100, 1),                # one partial tile
-    ("ball3d", 512, 32, 4096, 1),
-    ("gridworld", 300, 40, 1000, 1),
-    ("push", 512, 90, 128 * 148 * 2 + 77, 1),  # several tiles per CTA + ragged tail
-    ("ball3d", 512, 32, 4096, 0),             # transposing wgrad kernel under the fused tower kernel
+@pytest.mark.parametrize("task,n,T,rows", [
+    ("ball3d", 64, 8, 100),                   # one partial tile
+    ("ball3d", 512, 32, 4096),
+    ("gridworld", 300, 40, 1000),
+    ("push", 512, 90, 128 * 148 * 2 + 77),    # several tiles per CTA + ragged tail
+    ("ball3d", 1024, 64, 128 * 148 * 3),      # exactly three full rounds
 ])
-def test_fused_minibatch_matches_unfused(task, n, T, rows, wgrad_impl):
+def test_fused_minibatch_matches_unfused(task, n, T, rows):
     from three_mlagents_b200 import ops
 
-    nat = _nat()
     env, m = _setup(task, n, T)
     d, a = env.obs_dim, env.n_actions
     assert ops.ppo_minibatch_supported(d, a)
@@ -100,16 +107,14 @@ def test_fused_minibatch_matches_unfused(task, n, T, rows, wgrad_impl):
     dl32, dv32, _ = ops.ppo_loss(l32, v32, m.act, m.adv, m.logp, m.ret, index=idx, adv_sums=sums)
     g32 = ops.mlp_backward(m.params, obs_flat, d, a, c32, dl32, dv32, index=idx)
     # fused
-    nat.check(nat.lib.tmla_tc_wgrad_select(wgrad_impl))
-    try:
-        logits = torch.full((rows, a), float("nan"), device="cuda")
-        values = torch.full((rows,), float("nan"), device="cuda")
-        g_f, st_f = ops.ppo_minibatch(m.params, m.wpack, obs_flat, d, a, m.act, m.adv, m.logp, m.ret, index=idx, rows=rows,
-                                      adv_sums=sums, logits=logits, values=values)
-        torch.cuda.synchronize()
-    finally:
-        nat.check(nat.lib.tmla_tc_wgrad_select(1))
-    assert float((logits - l16).abs().max()) < 2e-3 and float((values - v16).abs().max()) < 2e-3
+    logits = torch.full((rows, a), float("nan"), device="cuda")
+    values = torch.full((rows,), float("nan"), device="cuda")
+    g_f, st_f = ops.ppo_minibatch(m.params, m.wpack, obs_flat, d, a, m.act, m.adv, m.logp, m.ret, index=idx, rows=rows,
+                                  adv_sums=sums, logits=logits, values=values)
+    torch.cuda.synchronize()
+    dl_max, dv_max = float((logits - l16).abs().max()), float((values - v16).abs().max())
+    print(f"{task} rows={rows}: head outputs fused vs unfused-bf16: logits {dl_max:.2e} values {dv_max:.2e}")
+    assert dl_max < 5e-3 and dv_max < 5e-3
     assert torch.allclose(st_f[:6], st_ref[:6], rtol=1e-4, atol=1e-4), (st_f, st_ref)
     assert torch.allclose(st_f[6:], st_ref[6:], rtol=1e-6, atol=1e-7)
     off = 0

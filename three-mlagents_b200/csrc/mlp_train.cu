@@ -11,8 +11,9 @@
 //
 //   P1  layer 1 (K = obs_dim) on CUDA cores -> H1 (bf16): shared-memory tile (K-major) + a TMEM stash for P7
 //   M1  Z2 = H1 . W2^T            16 x (M128 N256 K16), W2 resident in shared memory          -> ACC (TMEM)
-//   P3  ACC -> bias + tanh -> H2 (bf16) overwrites the tile; head dot products; P4 loss per row, d(loss)/d(head)
-//       written as a [128][16] bf16 hi/lo tile DOUT
+//   P3  ACC -> bias + tanh -> H2 (bf16) overwrites the tile
+//   MH  head outputs = H2 . [Wh_hi | Wh_lo]^T  (N = 16)                                       -> HEAD (TMEM)
+//   P4  loss per row, d(loss)/d(head) written as a [128][16] bf16 hi/lo tile DOUT
 //   M2  dH2 = DOUT . Wh (one K=16 MMA) -> ACC;   dWh += H2^T . DOUT (H2 tile read MN-major)  -> GWH (TMEM)
 //   P5  dZ2 = ACC * (1 - H2^2) -> tile
 //   M3  dH1 = dZ2 . W2 — the SAME resident W2 bytes through an MN-major descriptor              -> ACC
@@ -22,7 +23,10 @@
 //   M4  dW1|db1 += dZ1^T . [x_hi | x_lo | 1]  (XB tile, bf16 hi/lo split of the fp32 observations)  -> GW1 (TMEM)
 //
 // Only H1 and dZ2 (2 x 512 B per sample) are written out, for the split-K weight-gradient GEMM
-// dW2 = dZ2^T . H1 whose 256x256 fp32 accumulator needs all 512 TMEM columns (tc_wgrad_mn_kernel below).
+// dW2 = dZ2^T . H1 whose 256x256 fp32 accumulator needs all 512 TMEM columns (tc_wgrad_tiled_kernel below).
+// They leave as whole 64 KB tile IMAGES (the shared-memory operand layout, byte for byte) through one bulk-TMA
+// store per tile (cp.async.bulk.global.shared::cta) and come back the same way, so neither kernel spends a
+// single LSU instruction on them.
 //
 // MN-major trick: a [rows][C] bf16 tile staged in the canonical K-major SWIZZLE_NONE layout
 // (16-byte chunk (r, cb) at (r/8)*G + cb*S + (r%8)*16) is, byte for byte, also the canonical MN-major layout of
@@ -68,6 +72,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// bulk TMA (1-D, no tensor map): shared -> global store tracked by bulk async-groups, global -> shared load
+// tracked by an mbarrier transaction count
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -87,7 +106,7 @@ struct TowerTrainArgs {
     int normalize;
     float clip, ent_coef, vf_coef, inv_rows;
     // outputs
-    __nv_bfloat16 *h1_out, *dz2_out;    // [M][256] each, for the dW2 GEMM
+    __nv_bfloat16 *h1_out, *dz2_out;    // ceil(M/128) tile images of 64 KB each (shared-memory operand layout), for the dW2 GEMM
     float *out;                          // optional [M][NOUT] head outputs (logits / values)
     float *gW1, *gB1, *gB2, *gWh, *gBh;  // gradient slices (accumulated with atomics; caller zeroes)
     float *stats;                        // float[8] (tmla_ppo_loss layout), accumulated
@@ -98,7 +117,6 @@ static constexpr uint32_t ksS = 128, ksG = 256;
 
 template <int D, int NOUT>
 struct TrainSmem {
-    static constexpr bool kWhSmem = NOUT == 1;                         // the fp32 head weights fit only for the value tower
     static constexpr uint32_t w = 0;                                   // W2 bf16 [256][256], K-major (kLBO/kSBO)
     static constexpr uint32_t tile = kWBytes;                          // [128][256] bf16, same layout: H1 -> H2 -> dZ2 -> dZ1
     static constexpr uint32_t wht = tile + 128 * 512;                  // [256 j][16] bf16: Wh^T hi | hi | lo   (B of dH2 = DOUT . Wh)
@@ -107,9 +125,8 @@ struct TrainSmem {
     static constexpr uint32_t w1t = xb + 128 * 32;                     // float [D][256]  (W1 transposed)
     static constexpr uint32_t b1 = w1t + D * H * 4;                    // float [256]
     static constexpr uint32_t b2 = b1 + H * 4;                         // float [256]
-    static constexpr uint32_t part = b2 + H * 4;                       // float [3][128][NOUT] head partial sums of column quarters 1..3
-    static constexpr uint32_t wh = part + 3 * 128 * NOUT * 4;          // float [NOUT][256] (kWhSmem only)
-    static constexpr uint32_t bar = wh + (kWhSmem ? NOUT * H * 4 : 0);
+    static constexpr uint32_t whb = b2 + H * 4;                        // [16][256] bf16 K-major: Wh hi rows | Wh lo rows (B of the head GEMM)
+    static constexpr uint32_t bar = whb + 16 * 512;
     static constexpr uint32_t total = bar + 64;
 };
 
@@ -120,12 +137,11 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     constexpr bool PI = NOUT > 1;
     static_assert(3 * NOUT <= 16 && 2 * D + 1 <= 16, "operand tiles are 16 columns wide");
     // TMEM columns: ACC (Z2 / dH2 / dH1), H1 stash (bf16 pairs), persistent gradient accumulators
-    constexpr uint32_t C_ACC = 0, C_H1 = 256, C_GWH = 384, C_GB2 = 416, C_GW1 = 448;
+    constexpr uint32_t C_ACC = 0, C_H1 = 256, C_GWH = 384, C_GB2 = 416, C_GW1 = 448, C_HEAD = 480;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *Ws = smem + L::w, *Ts = smem + L::tile;
     float *w1t = reinterpret_cast<float *>(smem + L::w1t), *b1s = reinterpret_cast<float *>(smem + L::b1);
-    float *b2s = reinterpret_cast<float *>(smem + L::b2), *part = reinterpret_cast<float *>(smem + L::part);
-    float *whs = reinterpret_cast<float *>(smem + L::wh);
+    float *b2s = reinterpret_cast<float *>(smem + L::b2);
     uint64_t *bar0 = reinterpret_cast<uint64_t *>(smem + L::bar), *bar1 = bar0 + 1;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,12 +155,16 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     float xrow[D];
     int32_t a_pre = 0;
     float f0_pre = 0.0f, f1_pre = 0.0f;                    // policy: advantage, old log-prob;  value: return
-    auto prefetch = [&](int64_t tile) {
+    int64_t src_next;                                      // buffer row of this thread's row in the tile after the prefetched one
+    auto load_index = [&](int64_t tile) {                  // -1: past the end
         const int64_t row = tile * 128 + rt;
+        src_next = (tile < ntiles && row < M) ? (p.index ? (int64_t)__ldg(p.index + row) : row) : -1;
+    };
+    auto prefetch = [&](int64_t tile_after) {              // loads the rows selected by src_next, then the index for `tile_after`
+        const int64_t src = src_next;
 #pragma unroll
         for (int k = 0; k < D; ++k) xrow[k] = 0.0f;
-        if (row < M) {
-            const int64_t src = p.index ? (int64_t)__ldg(p.index + row) : row;
+        if (src >= 0) {
 #pragma unroll
             for (int k = 0; k < D; ++k) xrow[k] = __ldg(p.x + src * D + k);
             if (cq == 0) {
@@ -152,14 +172,21 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 else f0_pre = __ldg(p.returns + src);
             }
         }
+        load_index(tile_after);
     };
-    prefetch(blockIdx.x);
+    load_index(blockIdx.x);
+    prefetch((int64_t)blockIdx.x + gridDim.x);
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
     if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_barrier_init(); }
     stage_rows<H>(Ws, p.W2, 0, H);
     for (int e = tid; e < H * D; e += kTrainThreads) { const int j = e / D, k = e - j * D; w1t[k * H + j] = p.W1[e]; }
-    if (L::kWhSmem) for (int e = tid; e < NOUT * H; e += kTrainThreads) whs[e] = p.Wh[e];
+    for (int e = tid; e < 16 * H; e += kTrainThreads) {    // WHB[n][j]: n in [0,NOUT) hi, [NOUT,2NOUT) lo
+        const int n = e >> 8, j = e & (H - 1);
+        float v = 0.0f;
+        if (n < 2 * NOUT) { const float w = p.Wh[(n % NOUT) * H + j]; v = n < NOUT ? w : w - bf16_round(w); }
+        *reinterpret_cast<__nv_bfloat16 *>(smem + L::whb + (n >> 3) * kSBO + (j >> 3) * kLBO + (n & 7) * 16 + (j & 7) * 2) = __float2bfloat16_rn(v);
+    }
     if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
     for (int e = tid; e < H * 16; e += kTrainThreads) {    // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
         const int j = e >> 4, c = e & 15;
@@ -178,6 +205,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
     const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
+    const uint32_t whb_addr = smem_u32(smem + L::whb);
     uint32_t ph0 = 0, ph1 = 0;
 
     // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased)
@@ -211,19 +239,6 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
             h1p[2 * g] = pack_bf16(tanh_fast(v01.x), tanh_fast(v01.y));
             h1p[2 * g + 1] = pack_bf16(tanh_fast(v23.x), tanh_fast(v23.y));
-        }
-    };
-    // coalesced copy of the tile to global rows: warp = 8-row group, a quarter-warp reads 128 contiguous bytes
-    auto copy_out = [&](__nv_bfloat16 *dst, int64_t row0) {
-        const int r = warp * 8 + (lane & 7);
-        const uint8_t *src = Ts + warp * kSBO + (lane & 7) * 16;
-        uint4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4 *>(src + (4 * i + (lane >> 3)) * kLBO);
-        if (row0 + r < M) {
-            uint4 *g = reinterpret_cast<uint4 *>(dst + (row0 + r) * H) + (lane >> 3);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[4 * i] = v[i];
         }
     };
     layer1();
@@ -264,20 +279,18 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
                           make_idesc_major(128, 256, 0, 0), kk > 0 ? 1u : 0u);
             umma_commit(bar0);
+            bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2);   // the H1 tile image -> HBM, asynchronously
+            bulk_commit();
         }
-        copy_out(p.h1_out, row0);
-        if (has_next) prefetch(tile + gridDim.x);
+        if (has_next) prefetch(tile + 2 * (int64_t)gridDim.x);
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
         tc_fence_after();
-        __syncthreads();                                   // every warp has copied its H1 rows out: the tile may be overwritten
-        // ---- P3: H2 = tanh(Z2 + b2) -> tile (and registers, for P5); head partial dot products
+        if (tid == 0) bulk_wait_read_all();                // the bulk store has read the tile: it may be overwritten
+        __syncthreads();
+        // ---- P3: H2 = tanh(Z2 + b2) -> tile (and registers, for P5)
         uint32_t h2p[32];
-        float z[NOUT];
         {
-            float2 hs[NOUT];
-#pragma unroll
-            for (int a = 0; a < NOUT; ++a) hs[a] = make_float2(0.f, 0.f);
             const uint32_t taddr = lane_base + C_ACC + cq * 64;
             uint32_t acc[2][16];
             tmem_ld16_nowait(taddr, acc[0]);
@@ -287,47 +300,42 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 launder16(acc[c & 1]);
                 if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
                 const int col = cq * 64 + c * 16;
-                float hv[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 bb = *reinterpret_cast<const float4 *>(b2s + col + 4 * q);
-                    hv[4 * q + 0] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 0]) + bb.x);
-                    hv[4 * q + 1] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 1]) + bb.y);
-                    hv[4 * q + 2] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 2]) + bb.z);
-                    hv[4 * q + 3] = tanh_fast(__uint_as_float(acc[c & 1][4 * q + 3]) + bb.w);
+                    h2p[8 * c + 2 * q] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 0]) + bb.x), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 1]) + bb.y));
+                    h2p[8 * c + 2 * q + 1] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 2]) + bb.z), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 3]) + bb.w));
                 }
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 ww = L::kWhSmem ? *reinterpret_cast<const float4 *>(whs + a * H + col + 4 * q)
-                                                     : __ldg(reinterpret_cast<const float4 *>(p.Wh + a * H + col + 4 * q));
-                        hs[a] = __ffma2_rn(make_float2(hv[4 * q + 0], hv[4 * q + 1]), make_float2(ww.x, ww.y), hs[a]);
-                        hs[a] = __ffma2_rn(make_float2(hv[4 * q + 2], hv[4 * q + 3]), make_float2(ww.z, ww.w), hs[a]);
-                    }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) h2p[8 * c + j] = pack_bf16(hv[2 * j], hv[2 * j + 1]);
                 const int kb = col >> 3;
                 *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(h2p[8 * c], h2p[8 * c + 1], h2p[8 * c + 2], h2p[8 * c + 3]);
                 *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(h2p[8 * c + 4], h2p[8 * c + 5], h2p[8 * c + 6], h2p[8 * c + 7]);
             }
-            if (cq > 0) {
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a) part[((cq - 1) * 128 + rt) * NOUT + a] = hs[a].x + hs[a].y;
-            } else {
-#pragma unroll
-                for (int a = 0; a < NOUT; ++a) z[a] = hs[a].x + hs[a].y;
-            }
         }
+        fence_proxy_async();
         tc_fence_before();
-        __syncthreads();                                   // ACC drained, H2 tile and partial sums complete
+        __syncthreads();                                   // ACC drained, H2 tile complete
+        // ---- MH: head outputs = H2 . [Wh_hi | Wh_lo]^T -> HEAD (16 columns)
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < H / 16; ++kk)
+                umma_bf16(tmem_base + C_HEAD, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(whb_addr + kk * 2 * kLBO, kLBO, kSBO),
+                          make_idesc_major(128, 16, 0, 0), kk > 0 ? 1u : 0u);
+            umma_commit(bar1);
+        }
+        mbar_wait(bar1, ph1);
+        ph1 ^= 1u;
+        tc_fence_after();
         // ---- P4: loss of row rt (threads of column quarter 0), d(loss)/d(head output) -> DOUT tile (bf16 hi | lo | hi)
         if (cq == 0) {
             const bool valid = row0 + rt < M;
-            float dz[NOUT];
+            float z[NOUT], dz[NOUT];
+            {
+                uint32_t hd[16];
+                tmem_ld16(lane_base + C_HEAD, hd);
 #pragma unroll
-            for (int a = 0; a < NOUT; ++a)
-                z[a] = ((z[a] + part[rt * NOUT + a]) + (part[(128 + rt) * NOUT + a] + part[(256 + rt) * NOUT + a])) + __ldg(p.Bh + a);
+                for (int a = 0; a < NOUT; ++a) z[a] = (__uint_as_float(hd[a]) + __uint_as_float(hd[NOUT + a])) + __ldg(p.Bh + a);
+            }
             if (p.out && valid) {
 #pragma unroll
                 for (int a = 0; a < NOUT; ++a) p.out[(row0 + rt) * NOUT + a] = z[a];
@@ -380,6 +388,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             *reinterpret_cast<uint4 *>(dr + ksS) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
         }
         fence_proxy_async();
+        tc_fence_before();
         __syncthreads();
         // ---- M2: dH2 = DOUT . Wh -> ACC (one K=16 MMA);  dWh += H2^T . DOUT -> GWH (H2 tile and DOUT read MN-major)
         if (tid == 0) {
@@ -434,13 +443,15 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                     umma_bf16(tmem_base + C_GB2 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
                               make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
             umma_commit(bar0);
+            bulk_store(p.dz2_out + tile * (128 * H), t_addr, 128 * H * 2);  // the dZ2 tile image -> HBM
+            bulk_commit();
         }
-        copy_out(p.dz2_out, row0);
         if (has_next) layer1();                            // next tile's layer 1 on the CUDA cores while the tensor core runs M3
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
         tc_fence_after();
-        __syncthreads();                                   // dZ2 rows copied out by every warp
+        if (tid == 0) bulk_wait_read_all();
+        __syncthreads();
         // ---- P7: dZ1 = dH1 * (1 - H1^2) -> tile (H1 from the TMEM stash)
         {
             const uint32_t taddr = lane_base + C_ACC + cq * 64;
@@ -516,95 +527,78 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
         }
     }
+    if (tid == 0) bulk_wait_all();                         // the last tile images have reached global memory
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-// --------------------------------------------------------- G[256,256] += X[rows,256]^T . Y[rows,256]
-// MN-major operands: 64-row chunks of X and Y are copied row-major -> padded K-major-by-row tiles with cp.async
-// (16 bytes per thread, no registers, no transposes) through a 3-stage ring; the tensor core reads both tiles
-// through MN-major descriptors.  256x256 fp32 accumulators in all 512 TMEM columns; split-K over CTAs finished
-// with red.global.add.v4.f32.
-static constexpr int kmRows = 64;
-static constexpr uint32_t kmTile = (kmRows / 8) * kaSBO;       // 36864 B: 64 rows x 256 columns (padded)
-static constexpr uint32_t kmStage = 2 * kmTile;                // X and Y
-static constexpr int kmStages = 3;
-static constexpr uint32_t kWgradMnSmem = kmStages * kmStage + 128;   // 221312 (>= the 128 KB epilogue stage)
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// --------------------------------------------------------- G[256,256] += X^T . Y  over tile images
+// X (dZ2) and Y (H1) arrive as the 64 KB tile images the training kernel wrote: 128 rows x 256 columns bf16 in the
+// shared-memory operand layout (16-byte chunk (r, cb) at (r/8)*4096 + cb*128 + (r%8)*16).  A 64-row half image is
+// 32 KB of contiguous global memory, so one chunk = two bulk-TMA loads (cp.async.bulk, mbarrier complete_tx) into
+// a 3-stage ring — no per-thread loads, no transposes: the tensor core reads both operands through MN-major
+// descriptors.  Warp-specialised: one producer thread, one MMA-issuing thread, full/empty mbarriers per stage;
+// 256x256 fp32 accumulators in all 512 TMEM columns; split-K over CTAs finished with red.global.add.v4.f32.
+static constexpr uint32_t kwChunk = 64 * H * 2;               // 32768 B: 64 rows of one operand
+static constexpr uint32_t kwStage = 2 * kwChunk;              // X and Y
+static constexpr int kwStages = 3;
+static constexpr uint32_t kWgradTiledSmem = kwStages * kwStage + 128;   // 196736 (>= the 128 KB epilogue stage)
 
 __global__ void __launch_bounds__(256, 1)
-tc_wgrad_mn_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ Y, float *__restrict__ G, int64_t rows) {
+tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 *__restrict__ Yt, float *__restrict__ G, int64_t nchunks) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kmStages * kmStage);      // bar[0..2]
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kmStages * kmStage + 64);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kwStages * kwStage);   // full[3], empty[3], done
+    uint64_t *empty = full + kwStages, *done = empty + kwStages;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kwStages * kwStage + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t nchunks = (rows + kmRows - 1) / kmRows;
     if ((int64_t)blockIdx.x >= nchunks) return;
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
-    if (tid == 32) { for (int s = 0; s < kmStages; ++s) mbar_init(bar + s, 1); fence_barrier_init(); }
+    if (tid == 32) {
+        for (int s = 0; s < kwStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t idesc = make_idesc_major(128, 256, 1, 1);
     const uint32_t s_addr = smem_u32(smem);
     const int64_t stride = gridDim.x;
     const int64_t my_chunks = (nchunks - blockIdx.x + stride - 1) / stride;
 
-    auto issue = [&](int64_t j) {                          // async copy of this CTA's j-th chunk into stage j % 3
-        const int64_t row0 = (blockIdx.x + j * stride) * kmRows;
-        const uint32_t st = s_addr + (uint32_t)(j % kmStages) * kmStage;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp + 8 * i;
-            const bool ok = row0 + r < rows;
-            const int64_t g = (ok ? row0 + r : 0) * H + lane * 8;
-            const uint32_t d = st + (r >> 3) * kaSBO + lane * kaLBO + (r & 7) * 16;
-            cp_async16(d, X + g, ok ? 16u : 0u);
-            cp_async16(d + kmTile, Y + g, ok ? 16u : 0u);
+    if (tid == 0) {                                        // producer: bulk-TMA loads, one stage ahead of the ring's tail
+        uint32_t pe[kwStages] = {0u, 0u, 0u};
+        for (int64_t j = 0; j < my_chunks; ++j) {
+            const int s = (int)(j % kwStages);
+            if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }   // the MMAs of chunk j-3 have read this stage
+            const int64_t c = blockIdx.x + j * stride;
+            mbar_expect_tx(full + s, kwStage);
+            bulk_load(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s);
+            bulk_load(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s);
         }
-    };
-    uint32_t ph[kmStages] = {0u, 0u, 0u};
-    issue(0);
-    cp_async_commit();
-    if (my_chunks > 1) issue(1);
-    cp_async_commit();
-    for (int64_t j = 0; j < my_chunks; ++j) {
-        const int s = (int)(j % kmStages);
-        cp_async_wait<1>();                                // this thread's copies of chunk j have landed
-        fence_proxy_async();
-        __syncthreads();                                   // ... and everybody else's
-        if (tid == 0) {
+    } else if (tid == 32) {                                // MMA issuer
+        uint32_t pf[kwStages] = {0u, 0u, 0u};
+        const uint32_t idesc = make_idesc_major(128, 256, 1, 1);
+        for (int64_t j = 0; j < my_chunks; ++j) {
+            const int s = (int)(j % kwStages);
+            mbar_wait(full + s, pf[s]);
+            pf[s] ^= 1u;
             tc_fence_after();
-            const uint32_t x_addr = s_addr + s * kmStage, y_addr = x_addr + kmTile;
+            const uint32_t x_addr = s_addr + s * kwStage, y_addr = x_addr + kwChunk;
 #pragma unroll
-            for (int mh = 0; mh < 2; ++mh)                 // output rows (X columns) 0..127 / 128..255 -> TMEM columns 0..255 / 256..511
+            for (int mh = 0; mh < 2; ++mh)                 // X columns 0..127 / 128..255 -> TMEM columns 0..255 / 256..511
 #pragma unroll
-                for (int kk = 0; kk < kmRows / 16; ++kk)   // K = 16 rows of the chunk = two 8-row groups
-                    umma_bf16(tmem_base + mh * 256, make_desc_raw(x_addr + mh * 16 * kaLBO + kk * 2 * kaSBO, kaSBO, kaLBO),
-                              make_desc_raw(y_addr + kk * 2 * kaSBO, kaSBO, kaLBO), idesc, (j == 0 && kk == 0) ? 0u : 1u);
-            umma_commit(bar + s);
+                for (int kk = 0; kk < 4; ++kk)             // K = 16 rows = two 8-row groups
+                    umma_bf16(tmem_base + mh * 256, make_desc_raw(x_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                              make_desc_raw(y_addr + kk * 2 * kSBO, kSBO, kLBO), idesc, (j == 0 && kk == 0) ? 0u : 1u);
+            umma_commit(empty + s);
         }
-        // refill the stage that chunk j-1 used (its MMAs were issued one iteration ago) with chunk j+2
-        if (j + 2 < my_chunks) {
-            if (j >= 1) { const int sp = (int)((j + 2) % kmStages); mbar_wait(bar + sp, ph[sp]); ph[sp] ^= 1u; }
-            issue(j + 2);
-        }
-        cp_async_commit();
+        umma_commit(done);
     }
-    // drain: wait for the last commit of every stage that still has one pending
-    for (int64_t j = (my_chunks > 3 ? my_chunks - 3 : 0); j < my_chunks; ++j) {
-        const bool waited = (j + 3 < my_chunks);           // already consumed by a refill wait
-        if (!waited) { const int s = (int)(j % kmStages); mbar_wait(bar + s, ph[s]); ph[s] ^= 1u; }
-    }
+    __syncwarp();
+    mbar_wait(done, 0);
     tc_fence_after();
     // epilogue: TMEM -> registers -> smem stage (fp32 [128][256], 16-byte chunks XOR-swizzled by row) ->
     // coalesced red.global.add.v4.f32
@@ -701,24 +695,22 @@ tc_probe_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__rest
 }
 
 // ------------------------------------------------------------------------------------ host side
-int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st);   // mlp_tc.cu (PRMT-transposing variant)
-
 static int sm_count_train() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
     return n;
 }
 
-static int g_wgrad_impl = 1;                               // 1 = MN-major cp.async kernel, 0 = PRMT-transposing kernel (mlp_tc.cu)
-
-int tc_wgrad_mn_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st) {
+// Xt, Yt: tile images covering `rows_padded` rows (a multiple of 128)
+static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64_t rows_padded, cudaStream_t st) {
     static int attr_done = 0;
     if (!attr_done) {
-        TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradMnSmem));
+        TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradTiledSmem));
         attr_done = 1;
     }
-    const unsigned grid = (unsigned)std::min<int64_t>((rows + kmRows - 1) / kmRows, sm_count_train());
-    tc_wgrad_mn_kernel<<<grid, 256, kWgradMnSmem, st>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)Y, G, rows);
+    const int64_t nchunks = rows_padded / 64;
+    const unsigned grid = (unsigned)std::min<int64_t>(nchunks, sm_count_train());
+    tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G, nchunks);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -744,7 +736,7 @@ int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions) {
     return (hidden == H && (obs_dim == 4 || obs_dim == 6) && n_actions == 5) ? 1 : 0;
 }
 
-int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 2 * rows * (int64_t)hidden; }
+int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 2 * ((rows + 127) / 128 * 128) * (int64_t)hidden; }
 
 int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *obs,
                             const int32_t *index, int64_t rows, int64_t global_rows, const int32_t *actions,
@@ -762,7 +754,8 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
     TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
     TMLA_CUDA(cudaMemsetAsync(stats_out, 0, 8 * sizeof(float), st));
-    __nv_bfloat16 *h1 = reinterpret_cast<__nv_bfloat16 *>(scratch), *dz2 = h1 + rows * H;
+    const int64_t rows_padded = (rows + 127) / 128 * 128;  // whole tile images; rows past `rows` contribute exact zeros (dZ2 = 0)
+    __nv_bfloat16 *h1 = reinterpret_cast<__nv_bfloat16 *>(scratch), *dz2 = h1 + rows_padded * H;
     for (int t = 0; t < 2; ++t) {
         TowerTrainArgs a;
         a.W1 = params + o.w1[t]; a.B1 = params + o.b1[t];
@@ -779,20 +772,15 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         if (obs_dim == 6) rc = t == 0 ? tower_train_launch_t<6, 5>(a, st) : tower_train_launch_t<6, 1>(a, st);
         else rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
         if (rc) return rc;
-        rc = g_wgrad_impl ? tc_wgrad_mn_launch(dz2, h1, grads + o.w2[t], rows, st) : tc_wgrad_launch(dz2, h1, grads + o.w2[t], rows, st);
+        rc = tc_wgrad_tiled_launch(dz2, h1, grads + o.w2[t], rows_padded, st);
         if (rc) return rc;
     }
     return TMLA_OK;
 }
 
-int tmla_tc_wgrad_mn(const void *X, const void *Y, float *G, int64_t rows, void *stream) {
-    TMLA_REQUIRE(X && Y && G && rows > 0, "bad arguments");
-    return tc_wgrad_mn_launch(X, Y, G, rows, (cudaStream_t)stream);
-}
-
-int tmla_tc_wgrad_select(int impl) {
-    g_wgrad_impl = impl ? 1 : 0;
-    return TMLA_OK;
+int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_padded, void *stream) {
+    TMLA_REQUIRE(Xt && Yt && G && rows_padded > 0 && rows_padded % 128 == 0, "bad arguments (rows_padded must be a positive multiple of 128)");
+    return tc_wgrad_tiled_launch(Xt, Yt, G, rows_padded, (cudaStream_t)stream);
 }
 
 int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream) {

@@ -82,8 +82,7 @@ SIGNATURES = {
     "tmla_ppo_minibatch_scratch": (i64, [_i, i64]),
     "tmla_ppo_minibatch_bf16": (_i, [vp, vp, _i, _i, _i, vp, vp, i64, i64, vp, vp, vp, vp, vp, _i, f32, f32, f32, vp, vp, vp,
                                      vp, vp, vp]),
-    "tmla_tc_wgrad_mn": (_i, [vp, vp, vp, i64, vp]),
-    "tmla_tc_wgrad_select": (_i, [_i]),
+    "tmla_tc_wgrad_tiled": (_i, [vp, vp, vp, i64, vp]),
     "tmla_tc_probe": (_i, [vp, vp, vp, _i, vp]),
 }
 

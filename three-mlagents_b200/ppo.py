@@ -137,7 +137,7 @@ class CudaPPO:
             self.dlogits = torch.empty((B, A), **f32)
             self.dvalues = torch.empty(B, **f32)
             self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
-        self.scratch_mb = torch.empty(2 * B * HIDDEN, dtype=self._act_dtype, device=dev)
+        self.scratch_mb = torch.empty(2 * ((B + 127) // 128 * 128) * HIDDEN, dtype=self._act_dtype, device=dev)
         self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
