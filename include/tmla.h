@@ -176,9 +176,11 @@ int tmla_mlp_backward(const float *params, int obs_dim, int hidden, int n_action
 
 /* bf16 / tensor-core variant of the same network (csrc/mlp_tc.cu): identical semantics, the 256x256 hidden
  * layers run on tcgen05 with bf16 operands and fp32 accumulation, activations (act_cache, scratch) are bf16.
- *   wpack: bf16[4][256][256] = {pi.W2, pi.W2^T, vf.W2, vf.W2^T}, refreshed by tmla_mlp_pack_bf16 after every
+ *   wpack: bf16[TMLA_WPACK_MATRICES][256][256] = {pi.W2, pi.W2^T, vf.W2, vf.W2^T, pi.W2 image, vf.W2 image} (image = the
+ *   shared-memory operand layout the fused minibatch kernel loads with one bulk-TMA copy), refreshed by tmla_mlp_pack_bf16 after every
  *   optimizer step.  act_cache: bf16[4,rows,256] (forward: may be NULL when obs_dim <= 6 = inference only, the
  *   fused tower kernel then keeps no activations); scratch: bf16[2,rows,256]. */
+#define TMLA_WPACK_MATRICES 6
 int tmla_mlp_pack_bf16(const float *params, int obs_dim, int hidden, int n_actions, void *wpack, void *stream);
 int tmla_mlp_forward_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *x,
                           const int32_t *index, int64_t rows, const int32_t *rows_dev, float *logits, float *values,

@@ -24,7 +24,7 @@ __device__ __forceinline__ void act_store(__nv_bfloat16 *p, int64_t i, float v) 
 int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, const void *aux, void *out, int64_t M,
                      const int32_t *rows_dev, cudaStream_t st);
 int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st);
-int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st);
+int tc_pack_w2_launch(const float *w2, void *w, void *wt, void *img, cudaStream_t st);
 int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
                             const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
                             void *h1, void *h2, cudaStream_t st);
@@ -803,7 +803,8 @@ int tmla_mlp_backward_bf16(const float *params, const void *wpack, int obs_dim, 
                                             dlogits, dvalues, grads, (__nv_bfloat16 *)scratch, (cudaStream_t)stream);
 }
 
-// bf16 copies of the two hidden-layer weights per tower: wpack = [pi.W2, pi.W2^T, vf.W2, vf.W2^T], each [256][256] bf16
+// bf16 copies of the two hidden-layer weights per tower: wpack = [pi.W2, pi.W2^T, vf.W2, vf.W2^T, pi.W2 image, vf.W2 image],
+// each 256*256 bf16 (the images are the shared-memory operand layout of csrc/mlp_train.cu)
 int tmla_mlp_pack_bf16(const float *params, int obs_dim, int hidden, int n_actions, void *wpack, void *stream) {
     TMLA_REQUIRE(params && wpack, "NULL buffer");
     int rc = check_shape(obs_dim, hidden, n_actions);
@@ -811,7 +812,7 @@ int tmla_mlp_pack_bf16(const float *params, int obs_dim, int hidden, int n_actio
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
     for (int t = 0; t < 2; ++t) {
         __nv_bfloat16 *w = reinterpret_cast<__nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
-        rc = tc_pack_w2_launch(params + o.w2[t], w, w + H * H, (cudaStream_t)stream);
+        rc = tc_pack_w2_launch(params + o.w2[t], w, w + H * H, reinterpret_cast<__nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return TMLA_OK;

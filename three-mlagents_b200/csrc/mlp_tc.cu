@@ -491,14 +491,19 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
-// W2 [out][in] fp32 -> bf16 copy and bf16 transpose ([in][out]) for the dgrad GEMM
-__global__ void pack_w2_kernel(const float *__restrict__ w2, __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__restrict__ wt) {
+// W2 [out][in] fp32 -> bf16 copy, bf16 transpose ([in][out]) for the unfused dgrad GEMM, and the 128 KB shared-memory
+// operand IMAGE (16-byte chunk (j, kb) at (j/8)*4096 + kb*128 + (j%8)*16) that the fused training kernel pulls in with
+// one bulk-TMA load
+__global__ void pack_w2_kernel(const float *__restrict__ w2, __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__restrict__ wt,
+                               __nv_bfloat16 *__restrict__ img) {
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const float v = w2[(by + j) * H + bx + threadIdx.x];
         tile[j][threadIdx.x] = v;
         w[(by + j) * H + bx + threadIdx.x] = __float2bfloat16_rn(v);
+        const int r = by + j, k = bx + threadIdx.x;
+        img[(r >> 3) * 2048 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7)] = __float2bfloat16_rn(v);
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) wt[(bx + j) * H + by + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][j]);
@@ -569,8 +574,8 @@ int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, c
     return TMLA_EINVAL;
 }
 
-int tc_pack_w2_launch(const float *w2, void *w, void *wt, cudaStream_t st) {
-    pack_w2_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(w2, (__nv_bfloat16 *)w, (__nv_bfloat16 *)wt);
+int tc_pack_w2_launch(const float *w2, void *w, void *wt, void *img, cudaStream_t st) {
+    pack_w2_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(w2, (__nv_bfloat16 *)w, (__nv_bfloat16 *)wt, (__nv_bfloat16 *)img);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }

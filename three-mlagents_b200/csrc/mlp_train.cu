@@ -58,6 +58,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void launder8(uint32_t *r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // pins 16 registers behind the preceding (volatile) wait: their consumers cannot be scheduled above it
 __device__ __forceinline__ void launder16(uint32_t *r) {
@@ -87,13 +95,27 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc),
                  "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// per-thread asynchronous global -> shared copies (LDGSTS): the prefetched rows never occupy registers
+template <int BYTES>
+__device__ __forceinline__ void cp_async_ca(uint32_t dst, const void *src, uint32_t src_bytes) {   // src_bytes 0 = zero-fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// one elected lane of a converged warp (warp-uniform control flow keeps the tcgen05 operands in uniform registers;
+// a `tid == 0` branch makes the compiler wrap every MMA in a lane-serialising loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 struct TowerTrainArgs {
     // tower parameters (fp32 views into the flat vector; W2 from the bf16 pack)
     const float *W1, *B1;
-    const __nv_bfloat16 *W2;
+    const __nv_bfloat16 *W2;       // the 128 KB operand image written by tmla_mlp_pack_bf16
     const float *B2, *Wh, *Bh;
     // minibatch
     const float *x;                 // obs [total][D]
@@ -119,14 +141,17 @@ template <int D, int NOUT>
 struct TrainSmem {
     static constexpr uint32_t w = 0;                                   // W2 bf16 [256][256], K-major (kLBO/kSBO)
     static constexpr uint32_t tile = kWBytes;                          // [128][256] bf16, same layout: H1 -> H2 -> dZ2 -> dZ1
-    static constexpr uint32_t wht = tile + 128 * 512;                  // [256 j][16] bf16: Wh^T hi | hi | lo   (B of dH2 = DOUT . Wh)
+    static constexpr uint32_t wht = tile + 128 * 512;                  // [256 j][16] bf16: Wh^T hi | hi | lo  (K-major B of dH2 = DOUT . Wh; MN-major B of the head GEMM)
     static constexpr uint32_t dout = wht + 256 * 32;                   // [128 r][16] bf16: dout hi | lo | hi
     static constexpr uint32_t xb = dout + 128 * 32;                    // [128 r][16] bf16: x hi | x lo | 1
     static constexpr uint32_t w1t = xb + 128 * 32;                     // float [D][256]  (W1 transposed)
     static constexpr uint32_t b1 = w1t + D * H * 4;                    // float [256]
     static constexpr uint32_t b2 = b1 + H * 4;                         // float [256]
-    static constexpr uint32_t whb = b2 + H * 4;                        // [16][256] bf16 K-major: Wh hi rows | Wh lo rows (B of the head GEMM)
-    static constexpr uint32_t bar = whb + 16 * 512;
+    static constexpr uint32_t xs = b2 + H * 4;                         // float [128][D]: next tile's observation rows (cp.async staging)
+    static constexpr uint32_t ls = xs + 128 * D * 4;                   // [128][3] words: next tile's loss inputs (action|adv|old_logp or return)
+    static constexpr uint32_t idx = ls + 128 * 12;                     // int32 [2][128]: buffer rows of the next two tiles (-1 = past the end)
+    static constexpr uint32_t racc = idx + 2 * 128 * 4;                // float [128][9]: per-row running sums (4 loss statistics, NOUT head-bias gradients)
+    static constexpr uint32_t bar = racc + 128 * 9 * 4 + 16;           // + adv_mean, adv_inv_std
     static constexpr uint32_t total = bar + 64;
 };
 
@@ -145,6 +170,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     uint64_t *bar0 = reinterpret_cast<uint64_t *>(smem + L::bar), *bar1 = bar0 + 1;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // the same value, provably warp-uniform
     const int64_t M = p.M;
     const int64_t ntiles = (M + 127) / 128;
     if ((int64_t)blockIdx.x >= ntiles) return;
@@ -152,41 +178,55 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     const int rt = (warp & 3) * 32 + lane, cq = warp >> 2;  // this thread's row of the tile and 64-column quarter
     uint8_t *trow = Ts + (rt >> 3) * kSBO + (rt & 7) * 16;  // + kb * kLBO: 16-byte chunk kb of row rt
 
-    float xrow[D];
-    int32_t a_pre = 0;
-    float f0_pre = 0.0f, f1_pre = 0.0f;                    // policy: advantage, old log-prob;  value: return
-    int64_t src_next;                                      // buffer row of this thread's row in the tile after the prefetched one
-    auto load_index = [&](int64_t tile) {                  // -1: past the end
-        const int64_t row = tile * 128 + rt;
-        src_next = (tile < ntiles && row < M) ? (p.index ? (int64_t)__ldg(p.index + row) : row) : -1;
-    };
-    auto prefetch = [&](int64_t tile_after) {              // loads the rows selected by src_next, then the index for `tile_after`
-        const int64_t src = src_next;
-#pragma unroll
-        for (int k = 0; k < D; ++k) xrow[k] = 0.0f;
-        if (src >= 0) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) xrow[k] = __ldg(p.x + src * D + k);
-            if (cq == 0) {
-                if (PI) { a_pre = __ldg(p.actions + src); f0_pre = __ldg(p.adv + src); f1_pre = __ldg(p.old_logp + src); }
-                else f0_pre = __ldg(p.returns + src);
-            }
+    // Prefetch = cp.async straight into shared memory (no registers, nothing blocks; a prefetched value held in a
+    // register gets spilled by ptxas, and the spill store waits for the load).  Per 128-row tile: the minibatch index,
+    // then the observation rows it selects, then the loss inputs — thread (rt, cq) copies piece cq of row rt.
+    float *xs = reinterpret_cast<float *>(smem + L::xs);
+    uint32_t *lsb = reinterpret_cast<uint32_t *>(smem + L::ls);
+    int32_t *idxs = reinterpret_cast<int32_t *>(smem + L::idx);
+    auto fetch_index = [&](uint32_t parity, int64_t tile) {          // index of `tile` -> idxs[parity]
+        if (cq == 3) {
+            const int64_t row = tile * 128 + rt;
+            if (tile < ntiles && row < M && p.index) cp_async_ca<4>(smem_u32(idxs + parity * 128 + rt), p.index + row, 4u);
+            else idxs[parity * 128 + rt] = (tile < ntiles && row < M) ? (int32_t)row : -1;
         }
-        load_index(tile_after);
     };
-    load_index(blockIdx.x);
-    prefetch((int64_t)blockIdx.x + gridDim.x);
+    auto fetch_rows = [&](uint32_t parity) {                         // observation rows selected by idxs[parity] -> xs
+        const int32_t sn = idxs[parity * 128 + rt];
+        const bool ok = sn >= 0;
+        const int64_t src = ok ? (int64_t)sn : 0;
+        constexpr int XP = D == 6 ? 3 : 1;
+        if (cq < XP) {
+            if (D == 6) cp_async_ca<8>(smem_u32(xs + rt * D + cq * 2), p.x + src * D + cq * 2, ok ? 8u : 0u);
+            else cp_async_ca<16>(smem_u32(xs + rt * D), p.x + src * D, ok ? 16u : 0u);
+        }
+    };
+    auto fetch_loss_inputs = [&](uint32_t parity) {                  // loss inputs of the rows selected by idxs[parity] -> ls
+        if (cq == 3) {
+            const int32_t sn = idxs[parity * 128 + rt];
+            const bool ok = sn >= 0;
+            const int64_t src = ok ? (int64_t)sn : 0;
+            const uint32_t dst = smem_u32(lsb + rt * 3);
+            if (PI) {
+                cp_async_ca<4>(dst, p.actions + src, ok ? 4u : 0u);
+                cp_async_ca<4>(dst + 4, p.adv + src, ok ? 4u : 0u);
+                cp_async_ca<4>(dst + 8, p.old_logp + src, ok ? 4u : 0u);
+            } else cp_async_ca<4>(dst, p.returns + src, ok ? 4u : 0u);
+        }
+    };
+    fetch_index(0u, blockIdx.x);
+    fetch_index(1u, (int64_t)blockIdx.x + gridDim.x);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    fetch_rows(0u);
+    fetch_loss_inputs(0u);
+    cp_async_commit();
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
     if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_barrier_init(); }
-    stage_rows<H>(Ws, p.W2, 0, H);
-    for (int e = tid; e < H * D; e += kTrainThreads) { const int j = e / D, k = e - j * D; w1t[k * H + j] = p.W1[e]; }
-    for (int e = tid; e < 16 * H; e += kTrainThreads) {    // WHB[n][j]: n in [0,NOUT) hi, [NOUT,2NOUT) lo
-        const int n = e >> 8, j = e & (H - 1);
-        float v = 0.0f;
-        if (n < 2 * NOUT) { const float w = p.Wh[(n % NOUT) * H + j]; v = n < NOUT ? w : w - bf16_round(w); }
-        *reinterpret_cast<__nv_bfloat16 *>(smem + L::whb + (n >> 3) * kSBO + (j >> 3) * kLBO + (n & 7) * 16 + (j & 7) * 2) = __float2bfloat16_rn(v);
-    }
+    if (tid == 32) { mbar_expect_tx(bar0, kWBytes); bulk_load(smem_u32(Ws), p.W2, kWBytes, bar0); }   // W2 image: one bulk-TMA load
+    for (int e = tid; e < H * D; e += kTrainThreads) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
     if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
     for (int e = tid; e < H * 16; e += kTrainThreads) {    // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
         const int j = e >> 4, c = e & 15;
@@ -197,48 +237,62 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         *reinterpret_cast<__nv_bfloat16 *>(smem + L::wht + (j >> 3) * ksG + (c >> 3) * ksS + (j & 7) * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
     }
+    cp_async_wait_all();                                   // the first tile's rows
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
     const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
-    const uint32_t whb_addr = smem_u32(smem + L::whb);
     uint32_t ph0 = 0, ph1 = 0;
+    mbar_wait(bar0, ph0);                                  // the W2 image has landed
+    ph0 ^= 1u;
 
-    // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased)
-    float adv_mean = 0.0f, adv_inv_std = 1.0f;
-    if (PI && p.normalize) {
-        const double cnt = p.adv_sums[2], mu = p.adv_sums[0] / cnt;
-        double var = (p.adv_sums[1] - p.adv_sums[0] * mu) / (cnt - 1.0);
-        var = var > 0.0 ? var : 0.0;
-        adv_mean = (float)mu;
-        adv_inv_std = 1.0f / ((float)sqrt(var) + 1e-8f);
-        if (blockIdx.x == 0 && tid == 0) { p.stats[6] = adv_mean; p.stats[7] = (float)sqrt(var); }
+    // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased) and the per-row running
+    // sums live in shared memory: registers are the scarce resource of this kernel
+    float *racc = reinterpret_cast<float *>(smem + L::racc), *advc = racc + 128 * 9;
+    if (tid == 0) {
+        float adv_mean = 0.0f, adv_inv_std = 1.0f;
+        if (PI && p.normalize) {
+            const double cnt = p.adv_sums[2], mu = p.adv_sums[0] / cnt;
+            double var = (p.adv_sums[1] - p.adv_sums[0] * mu) / (cnt - 1.0);
+            var = var > 0.0 ? var : 0.0;
+            adv_mean = (float)mu;
+            adv_inv_std = 1.0f / ((float)sqrt(var) + 1e-8f);
+            if (blockIdx.x == 0) { p.stats[6] = adv_mean; p.stats[7] = (float)sqrt(var); }
+        }
+        advc[0] = adv_mean; advc[1] = adv_inv_std;
     }
-    float st_acc[4] = {0.f, 0.f, 0.f, 0.f}, dbh_acc[NOUT];   // per-thread running sums (threads of column quarter 0)
-#pragma unroll
-    for (int a = 0; a < NOUT; ++a) dbh_acc[a] = 0.0f;
+    for (int e = tid; e < 128 * 9; e += kTrainThreads) racc[e] = 0.0f;
+    __syncthreads();
 
-    // layer 1 of this thread's (row, 64 columns): H1 = tanh(x W1^T + b1), packed bf16 pairs
-    uint32_t h1p[32];
+    // layer 1, H1 = tanh(x W1^T + b1): this thread computes rows l1row + 8*i (i < 4) x 16 columns from l1col — every
+    // weight load then serves four rows (broadcast LDS.128 costs four shared-memory cycles each, and one
+    // row x 64 columns per thread needed 112 of them); observation rows come from the cp.async staging tile.
+    const int l1row = (warp & 3) * 32 + (lane & 7), l1col = cq * 64 + (lane >> 3) * 16;
+    uint32_t h1p[32];                                      // [4 rows][8 packed pairs]
     auto layer1 = [&]() {
+        float xr[4][D];
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-            const int col = cq * 64 + g * 4;
-            const float4 bb = *reinterpret_cast<const float4 *>(b1s + col);
-            float2 v01 = make_float2(bb.x, bb.y), v23 = make_float2(bb.z, bb.w);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float4 ww = *reinterpret_cast<const float4 *>(w1t + k * H + col);
-                const float2 xx = make_float2(xrow[k], xrow[k]);
-                v01 = __ffma2_rn(xx, make_float2(ww.x, ww.y), v01);
-                v23 = __ffma2_rn(xx, make_float2(ww.z, ww.w), v23);
+            for (int k = 0; k < D; ++k) xr[i][k] = xs[(l1row + 8 * i) * D + k];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {                      // two hidden units per step (keeps the live weight registers at 14)
+            const int col = l1col + g * 2;
+            const float2 bb = *reinterpret_cast<const float2 *>(b1s + col);
+            float2 ww[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) ww[k] = *reinterpret_cast<const float2 *>(w1t + k * H + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 v = bb;
+#pragma unroll
+                for (int k = 0; k < D; ++k) v = __ffma2_rn(make_float2(xr[i][k], xr[i][k]), ww[k], v);
+                h1p[i * 8 + g] = pack_bf16(tanh_fast(v.x), tanh_fast(v.y));
             }
-            h1p[2 * g] = pack_bf16(tanh_fast(v01.x), tanh_fast(v01.y));
-            h1p[2 * g + 1] = pack_bf16(tanh_fast(v23.x), tanh_fast(v23.y));
         }
     };
     layer1();
@@ -247,49 +301,60 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int64_t row0 = tile * 128;
         const bool has_next = tile + gridDim.x < ntiles;
-        const int32_t a_cur = a_pre;
-        const float f0_cur = f0_pre, f1_cur = f1_pre;
         // ---- P1: H1 (computed during the previous tile's M3) -> tile + TMEM stash; XB = [x_hi | x_lo | 1]
         if (it > 0) { mbar_wait(bar1, ph1); ph1 ^= 1u; tc_fence_after(); }   // M4 of the previous tile has read the tile and XB
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4 *>(trow + (cq * 8 + c) * kLBO) = make_uint4(h1p[4 * c], h1p[4 * c + 1], h1p[4 * c + 2], h1p[4 * c + 3]);
-        tmem_st16(lane_base + C_H1 + cq * 32, h1p);
-        tmem_st16(lane_base + C_H1 + cq * 32 + 16, h1p + 16);
+        for (int i = 0; i < 4; ++i) {                      // a quarter-warp writes 8 different rows of one chunk column: conflict-free
+            uint8_t *dst = Ts + ((l1row + 8 * i) >> 3) * kSBO + (l1col >> 3) * kLBO + (lane & 7) * 16;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(h1p[i * 8], h1p[i * 8 + 1], h1p[i * 8 + 2], h1p[i * 8 + 3]);
+            *reinterpret_cast<uint4 *>(dst + kLBO) = make_uint4(h1p[i * 8 + 4], h1p[i * 8 + 5], h1p[i * 8 + 6], h1p[i * 8 + 7]);
+        }
         if (cq == 0) {
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < D; ++k) { v[k] = xrow[k]; v[D + k] = xrow[k] - bf16_round(xrow[k]); }
+            for (int k = 0; k < D; ++k) { const float xv = xs[rt * D + k]; v[k] = xv; v[D + k] = xv - bf16_round(xv); }
             v[2 * D] = 1.0f;
             uint8_t *xr = smem + L::xb + (rt >> 3) * ksG + (rt & 7) * 16;
             *reinterpret_cast<uint4 *>(xr) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4 *>(xr + ksS) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
         }
-        tmem_wait_st();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        // ---- M1: Z2 = H1 . W2^T -> ACC;  H1 rows -> HBM and next-tile prefetch meanwhile
-        if (tid == 0) {
+        // ---- M1: Z2 = H1 . W2^T -> ACC;  meanwhile the H1 image -> HBM, H1 rows -> TMEM stash, next-tile prefetch
+        if (warp_u == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)
                 umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
                           make_idesc_major(128, 256, 0, 0), kk > 0 ? 1u : 0u);
             umma_commit(bar0);
-            bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2);   // the H1 tile image -> HBM, asynchronously
-            bulk_commit();
         }
-        if (has_next) prefetch(tile + 2 * (int64_t)gridDim.x);
+        if (tid == 32) { bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2); bulk_commit(); }   // the H1 tile image -> HBM, asynchronously
+        if (has_next) {                                    // xs is free (layer 1 and XB of this tile are done), so is this tile's index slot
+            fetch_rows((it + 1) & 1u);
+            fetch_index(it & 1u, tile + 2 * (int64_t)gridDim.x);
+            cp_async_commit();
+        }
+        {                                                  // this thread's (row, 64 columns) of H1 -> TMEM stash for P7
+            uint32_t hrow[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(trow + (cq * 8 + c) * kLBO);
+                hrow[4 * c] = v.x; hrow[4 * c + 1] = v.y; hrow[4 * c + 2] = v.z; hrow[4 * c + 3] = v.w;
+            }
+            tmem_st16(lane_base + C_H1 + cq * 32, hrow);
+            tmem_st16(lane_base + C_H1 + cq * 32 + 16, hrow + 16);
+            tmem_wait_st();
+        }
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
         tc_fence_after();
-        if (tid == 0) bulk_wait_read_all();                // the bulk store has read the tile: it may be overwritten
+        if (tid == 32) bulk_wait_read_all();                // the bulk store has read the tile: it may be overwritten
         __syncthreads();
-        // ---- P3: H2 = tanh(Z2 + b2) -> tile (and registers, for P5)
-        uint32_t h2p[32];
+        // ---- P3: H2 = tanh(Z2 + b2) -> tile
         {
             const uint32_t taddr = lane_base + C_ACC + cq * 64;
             uint32_t acc[2][16];
@@ -300,27 +365,28 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 launder16(acc[c & 1]);
                 if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
                 const int col = cq * 64 + c * 16;
+                uint32_t o[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 bb = *reinterpret_cast<const float4 *>(b2s + col + 4 * q);
-                    h2p[8 * c + 2 * q] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 0]) + bb.x), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 1]) + bb.y));
-                    h2p[8 * c + 2 * q + 1] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 2]) + bb.z), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 3]) + bb.w));
+                    o[2 * q] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 0]) + bb.x), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 1]) + bb.y));
+                    o[2 * q + 1] = pack_bf16(tanh_fast(__uint_as_float(acc[c & 1][4 * q + 2]) + bb.z), tanh_fast(__uint_as_float(acc[c & 1][4 * q + 3]) + bb.w));
                 }
                 const int kb = col >> 3;
-                *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(h2p[8 * c], h2p[8 * c + 1], h2p[8 * c + 2], h2p[8 * c + 3]);
-                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(h2p[8 * c + 4], h2p[8 * c + 5], h2p[8 * c + 6], h2p[8 * c + 7]);
+                *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();                                   // ACC drained, H2 tile complete
-        // ---- MH: head outputs = H2 . [Wh_hi | Wh_lo]^T -> HEAD (16 columns)
-        if (tid == 0) {
+        // ---- MH: head outputs = H2 . WHT -> HEAD (16 columns: hi | hi | lo parts of Wh; WHT read MN-major)
+        if (warp_u == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)
-                umma_bf16(tmem_base + C_HEAD, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(whb_addr + kk * 2 * kLBO, kLBO, kSBO),
-                          make_idesc_major(128, 16, 0, 0), kk > 0 ? 1u : 0u);
+                umma_bf16(tmem_base + C_HEAD, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(wht_addr + kk * 2 * ksG, ksG, ksS),
+                          make_idesc_major(128, 16, 0, 1), kk > 0 ? 1u : 0u);
             umma_commit(bar1);
         }
         mbar_wait(bar1, ph1);
@@ -330,11 +396,14 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         if (cq == 0) {
             const bool valid = row0 + rt < M;
             float z[NOUT], dz[NOUT];
+            const uint32_t *lin = lsb + rt * 3;             // action | adv | old_logp  or  return
+            const int32_t a_cur = (int32_t)lin[0];
+            const float f0_cur = __uint_as_float(PI ? lin[1] : lin[0]), f1_cur = __uint_as_float(lin[2]);
             {
                 uint32_t hd[16];
                 tmem_ld16(lane_base + C_HEAD, hd);
 #pragma unroll
-                for (int a = 0; a < NOUT; ++a) z[a] = (__uint_as_float(hd[a]) + __uint_as_float(hd[NOUT + a])) + __ldg(p.Bh + a);
+                for (int a = 0; a < NOUT; ++a) z[a] = (__uint_as_float(hd[a]) + __uint_as_float(hd[2 * NOUT + a])) + __ldg(p.Bh + a);
             }
             if (p.out && valid) {
 #pragma unroll
@@ -355,7 +424,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
 #pragma unroll
                 for (int j = 1; j < NOUT; ++j) logp = (a_cur == j) ? lp[j] : logp;
                 float adv = f0_cur;
-                if (p.normalize) adv = (adv - adv_mean) * adv_inv_std;
+                if (p.normalize) adv = (adv - advc[0]) * advc[1];
                 const float lr = logp - f1_cur;
                 const float ratio = __expf(lr);
                 const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
@@ -367,20 +436,21 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 for (int j = 0; j < NOUT; ++j)
                     dz[j] = valid ? dlogp * ((a_cur == j ? 1.0f : 0.0f) - pr[j]) + p.ent_coef * p.inv_rows * pr[j] * (lp[j] + ent) : 0.0f;
                 if (valid) {
-                    st_acc[0] += -fminf(s1, s2); st_acc[1] += -ent; st_acc[2] += (ratio - 1.0f) - lr;
-                    st_acc[3] += (fabsf(ratio - 1.0f) > p.clip) ? 1.0f : 0.0f;
+                    float *ra = racc + rt * 9;
+                    ra[0] += -fminf(s1, s2); ra[1] += -ent; ra[2] += (ratio - 1.0f) - lr;
+                    ra[3] += (fabsf(ratio - 1.0f) > p.clip) ? 1.0f : 0.0f;
                 }
             } else {
                 const float dv = z[0] - f0_cur;
                 dz[0] = valid ? p.vf_coef * 2.0f * dv * p.inv_rows : 0.0f;
-                if (valid) st_acc[0] += dv * dv;
+                if (valid) racc[rt * 9] += dv * dv;
             }
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0.0f;
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) {
-                dbh_acc[a] += dz[a];
+                racc[rt * 9 + 4 + a] += dz[a];
                 v[a] = dz[a]; v[NOUT + a] = dz[a] - bf16_round(dz[a]); v[2 * NOUT + a] = dz[a];
             }
             uint8_t *dr = smem + L::dout + (rt >> 3) * ksG + (rt & 7) * 16;
@@ -391,7 +461,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         tc_fence_before();
         __syncthreads();
         // ---- M2: dH2 = DOUT . Wh -> ACC (one K=16 MMA);  dWh += H2^T . DOUT -> GWH (H2 tile and DOUT read MN-major)
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {
             tc_fence_after();
             umma_bf16(tmem_base + C_ACC, make_desc_raw(dout_addr, ksS, ksG), make_desc_raw(wht_addr, ksS, ksG), make_idesc_major(128, 256, 0, 0), 0u);
 #pragma unroll
@@ -412,25 +482,28 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             tmem_ld16_nowait(taddr, acc[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                const int kb = (cq * 64 + c * 16) >> 3;
+                const uint4 ha = *reinterpret_cast<const uint4 *>(trow + kb * kLBO), hb = *reinterpret_cast<const uint4 *>(trow + (kb + 1) * kLBO);
+                const uint32_t h2[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
                 tmem_wait_ld();
                 launder16(acc[c & 1]);
                 if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
                 uint32_t o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float h0 = bf16_lo(h2p[8 * c + j]), h1 = bf16_hi(h2p[8 * c + j]);
+                    const float h0 = bf16_lo(h2[j]), h1 = bf16_hi(h2[j]);
                     o[j] = pack_bf16(__uint_as_float(acc[c & 1][2 * j]) * (1.0f - h0 * h0), __uint_as_float(acc[c & 1][2 * j + 1]) * (1.0f - h1 * h1));
                 }
-                const int kb = (cq * 64 + c * 16) >> 3;
                 *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
+        cp_async_wait_all();                               // this thread's pieces of the next tile's rows have landed
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         // ---- M3: dH1 = dZ2 . W2 -> ACC (W2 tile read MN-major);  db2 += dZ2^T . XB -> GB2 (its ones column is db2)
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)            // K = layer-2 output index j: 16 rows of the W2 tile per step
@@ -443,44 +516,47 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                     umma_bf16(tmem_base + C_GB2 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
                               make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
             umma_commit(bar0);
-            bulk_store(p.dz2_out + tile * (128 * H), t_addr, 128 * H * 2);  // the dZ2 tile image -> HBM
-            bulk_commit();
         }
-        if (has_next) layer1();                            // next tile's layer 1 on the CUDA cores while the tensor core runs M3
+        if (tid == 32) { bulk_store(p.dz2_out + tile * (128 * H), t_addr, 128 * H * 2); bulk_commit(); }  // the dZ2 tile image -> HBM
+        if (has_next) {
+            fetch_loss_inputs((it + 1) & 1u);              // ls is free: P4 of this tile is done
+            cp_async_commit();
+            layer1();                                      // next tile's layer 1 on the CUDA cores while the tensor core runs M3
+        }
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
         tc_fence_after();
-        if (tid == 0) bulk_wait_read_all();
+        if (tid == 32) bulk_wait_read_all();
         __syncthreads();
-        // ---- P7: dZ1 = dH1 * (1 - H1^2) -> tile (H1 from the TMEM stash)
+        // ---- P7: dZ1 = dH1 * (1 - H1^2) -> tile (H1 from the TMEM stash, 8 packed pairs per 16 accumulator columns).
+        // Not software-pipelined: the next tile's H1 (32 registers) is live here and this is the register-pressure peak.
         {
-            const uint32_t taddr = lane_base + C_ACC + cq * 64;
-            uint32_t hst[32], acc[2][16];
-            tmem_ld16_nowait(lane_base + C_H1 + cq * 32, hst);
-            tmem_ld16_nowait(lane_base + C_H1 + cq * 32 + 16, hst + 16);
-            tmem_ld16_nowait(taddr, acc[0]);
+            const uint32_t taddr = lane_base + C_ACC + cq * 64, saddr = lane_base + C_H1 + cq * 32;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                uint32_t hst[8], acc[16];
+                tmem_ld8_nowait(saddr + c * 8, hst);
+                tmem_ld16_nowait(taddr + c * 16, acc);
                 tmem_wait_ld();
-                launder16(acc[c & 1]);
-                if (c == 0) { launder16(hst); launder16(hst + 16); }
-                if (c < 3) tmem_ld16_nowait(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+                launder16(acc);
+                launder8(hst);
                 uint32_t o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float h0 = bf16_lo(hst[8 * c + j]), h1 = bf16_hi(hst[8 * c + j]);
-                    o[j] = pack_bf16(__uint_as_float(acc[c & 1][2 * j]) * (1.0f - h0 * h0), __uint_as_float(acc[c & 1][2 * j + 1]) * (1.0f - h1 * h1));
+                    const float h0 = bf16_lo(hst[j]), h1 = bf16_hi(hst[j]);
+                    o[j] = pack_bf16(__uint_as_float(acc[2 * j]) * (1.0f - h0 * h0), __uint_as_float(acc[2 * j + 1]) * (1.0f - h1 * h1));
                 }
                 const int kb = (cq * 64 + c * 16) >> 3;
                 *reinterpret_cast<uint4 *>(trow + kb * kLBO) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4 *>(trow + (kb + 1) * kLBO) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
+        cp_async_wait_all();                               // next tile's loss inputs and the index after it have landed
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         // ---- M4: dW1 | db1 += dZ1^T . [x_hi | x_lo | 1] -> GW1
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int mh = 0; mh < 2; ++mh)
@@ -511,10 +587,11 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             atomicAdd(p.gB1 + j, __uint_as_float(g[2 * D]));
         }
         // stats: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss
+        float st_acc[4], dbh_acc[NOUT];
 #pragma unroll
-        for (int q = 0; q < (PI ? 4 : 1); ++q) st_acc[q] = warp_sum_f(st_acc[q]) * p.inv_rows;
+        for (int q = 0; q < 4; ++q) st_acc[q] = warp_sum_f(racc[rt * 9 + q]) * p.inv_rows;
 #pragma unroll
-        for (int a = 0; a < NOUT; ++a) dbh_acc[a] = warp_sum_f(dbh_acc[a]);
+        for (int a = 0; a < NOUT; ++a) dbh_acc[a] = warp_sum_f(racc[rt * 9 + 4 + a]);
         if (lane == 0) {
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) atomicAdd(p.gBh + a, dbh_acc[a]);
@@ -527,7 +604,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
         }
     }
-    if (tid == 0) bulk_wait_all();                         // the last tile images have reached global memory
+    if (tid == 32) bulk_wait_all();                        // the last tile images have reached global memory
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
@@ -552,6 +629,7 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 
     uint64_t *empty = full + kwStages, *done = empty + kwStages;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kwStages * kwStage + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     if ((int64_t)blockIdx.x >= nchunks) return;
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
@@ -563,7 +641,7 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     const uint32_t s_addr = smem_u32(smem);
     const int64_t stride = gridDim.x;
     const int64_t my_chunks = (nchunks - blockIdx.x + stride - 1) / stride;
@@ -578,7 +656,7 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 
             bulk_load(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s);
             bulk_load(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s);
         }
-    } else if (tid == 32) {                                // MMA issuer
+    } else if (warp_u == 1 && elect_one()) {               // MMA issuer
         uint32_t pf[kwStages] = {0u, 0u, 0u};
         const uint32_t idesc = make_idesc_major(128, 256, 1, 1);
         for (int64_t j = 0; j < my_chunks; ++j) {
@@ -759,7 +837,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     for (int t = 0; t < 2; ++t) {
         TowerTrainArgs a;
         a.W1 = params + o.w1[t]; a.B1 = params + o.b1[t];
-        a.W2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
+        a.W2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H;
         a.B2 = params + o.b2[t]; a.Wh = params + o.wh[t]; a.Bh = params + o.bh[t];
         a.x = obs; a.index = index; a.M = rows;
         a.actions = actions; a.adv = advantages; a.old_logp = old_logp; a.returns = returns;

@@ -59,9 +59,10 @@ def permutation(seed: int, epoch: int, T: int, n: int, out=None, device="cuda"):
 
 
 def mlp_pack(params, obs_dim, n_actions, wpack=None):
-    """bf16 copies {pi.W2, pi.W2^T, vf.W2, vf.W2^T} for the tensor-core path (refresh after every optimizer step)."""
+    """bf16 copies {pi.W2, pi.W2^T, vf.W2, vf.W2^T, pi.W2 image, vf.W2 image} for the tensor-core path (refresh after
+    every optimizer step)."""
     if wpack is None:
-        wpack = torch.empty((4, HIDDEN, HIDDEN), dtype=torch.bfloat16, device=params.device)
+        wpack = torch.empty((6, HIDDEN, HIDDEN), dtype=torch.bfloat16, device=params.device)
     _chk(wpack, torch.bfloat16, "wpack")
     check(lib.tmla_mlp_pack_bf16(ptr(params), obs_dim, HIDDEN, n_actions, ptr(wpack), _s()))
     return wpack
