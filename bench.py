@@ -46,7 +46,10 @@ def _ncu_traffic():
         vals = {}
         with open(path) as f:
             for line in f:
-                k, unit, v = line.strip().split(",")[:3]
+                parts = line.strip().split(",")
+                if len(parts) < 3:
+                    continue
+                k, unit, v = parts[:3]
                 if k.startswith("dram__bytes_"):
                     vals[k] = float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
         return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]

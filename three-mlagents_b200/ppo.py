@@ -460,6 +460,23 @@ def bench_kernels(device: int = 0, n_envs: int = 65536, n_steps: int = 128) -> d
     res["tc_linear_dgrad"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1536.0 * B / us / 1e3}
     us = timed(lambda: nat.check(nat.lib.tmla_tc_wgrad(nat.ptr(Abf), nat.ptr(Hbf), nat.ptr(G), B, s)))
     res["tc_wgrad"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1024.0 * B / us / 1e3}
+    # fused minibatch path (csrc/mlp_train.cu): the TMA-fed split-K wgrad over tile images, and one whole minibatch
+    # (tower kernels for pi and vf + two wgrads) at 807 936 FLOP per sample
+    us = timed(lambda: nat.check(nat.lib.tmla_tc_wgrad_tiled(nat.ptr(Abf), nat.ptr(Hbf), nat.ptr(G), B, s)))
+    res["tc_wgrad_tiled"] = {"us": us, "TFLOP/s": flop / us / 1e6, "GB/s": 1024.0 * B / us / 1e3,
+                             "note": "bulk-TMA loads of 64 KB tile images, MN-major UMMA operands, 3-stage mbarrier ring"}
+    D = 6
+    obs = torch.randn((T * N, D), device=dev, generator=g)
+    params = orthogonal_init(D, A, 1).to(dev)
+    wpack = ops.mlp_pack(params, D, A)
+    grads = torch.empty_like(params)
+    scratch = torch.empty(nat.lib.tmla_ppo_minibatch_scratch(HIDDEN, B), dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(8, device=dev)
+    adv_sums = ops.adv_stats(adv, idx, B, sums)
+    us = timed(lambda: ops.ppo_minibatch(params, wpack, obs, D, A, act, adv, logp, ret, index=idx, rows=B, adv_sums=adv_sums,
+                                         grads=grads, scratch=scratch, stats=stats))
+    res["ppo_minibatch_fused"] = {"us": us, "TFLOP/s": 807936.0 * B / us / 1e6, "rows": B,
+                                  "note": "forward + loss + backward of both towers: 2 fused tower kernels + 2 tiled wgrads"}
     return res
 
 
