@@ -196,6 +196,10 @@ int tmla_mlp_backward_bf16(const float *params, const void *wpack, int obs_dim, 
  *   with world_size>1 the caller all-reduces adv_sums between the two calls (global-minibatch
  *   normalisation) and passes the global row count to tmla_ppo_loss. */
 int tmla_adv_stats(const float *advantages, const int32_t *index, int64_t rows, double *adv_sums, void *stream);
+/* the same statistics for every minibatch of an epoch in one launch: minibatch m covers index[m*mb_rows, min(total,
+ * (m+1)*mb_rows)); adv_sums double[ceil(total/mb_rows)][3].  One all-reduce per epoch then replaces one per minibatch. */
+int tmla_adv_stats_batched(const float *advantages, const int32_t *index, int64_t total, int64_t mb_rows, double *adv_sums,
+                           void *stream);
 int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actions, const float *advantages,
                   const float *old_logp, const float *returns, const int32_t *index, int64_t rows,
                   int64_t global_rows, int n_actions, const double *adv_sums, int normalize_advantage,

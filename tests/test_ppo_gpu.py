@@ -212,3 +212,23 @@ def test_step_policy_sampling_and_bootstrap_records():
     want[tindex[:n_trunc].cpu().numpy()] = np.float32(0.99) * np.arange(n_trunc, dtype=np.float32)
     assert np.array_equal(buf.cpu().numpy(), want)
     env.close()
+
+
+def test_adv_stats_batched_matches_per_minibatch():
+    """One launch for all minibatches of an epoch == tmla_adv_stats per minibatch (double accumulation: 1e-9 relative)."""
+    from three_mlagents_b200 import ops
+
+    T, n, B = 37, 300, 1000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    adv = torch.randn((T, n), device="cuda", generator=g) * 3 + 0.7
+    perm = ops.permutation(5, 2, T, n)
+    total = T * n
+    sums = ops.adv_stats_batched(adv, perm, total, B)
+    torch.cuda.synchronize()
+    assert sums.shape == ((total + B - 1) // B, 3)
+    for mb, start in enumerate(range(0, total, B)):
+        rows = min(B, total - start)
+        one = ops.adv_stats(adv, perm[start:start + rows], rows)
+        assert torch.allclose(sums[mb], one, rtol=1e-9, atol=1e-9), (mb, sums[mb], one)
+        ref = adv.reshape(-1)[perm[start:start + rows].long()].double()
+        assert abs(float(sums[mb, 0]) - float(ref.sum())) < 1e-6 and int(sums[mb, 2]) == rows

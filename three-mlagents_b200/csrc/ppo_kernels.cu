@@ -124,6 +124,31 @@ adv_stats_kernel(const float *__restrict__ adv, const int32_t *__restrict__ inde
     }
 }
 
+// all minibatches of an epoch in one launch: blockIdx.y = minibatch, rows [mb*mb_rows, min(total, (mb+1)*mb_rows))
+__global__ void __launch_bounds__(256)
+adv_stats_batched_kernel(const float *__restrict__ adv, const int32_t *__restrict__ index, int64_t total, int64_t mb_rows, double *sums) {
+    __shared__ double sh[2][8];
+    const int64_t lo = (int64_t)blockIdx.y * mb_rows, hi = min(total, lo + mb_rows);
+    double s = 0.0, ss = 0.0;
+    for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += (int64_t)gridDim.x * blockDim.x) {
+        const double a = (double)adv[index ? index[r] : r];
+        s += a; ss += a * a;
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = s; sh[1][w] = ss; }
+    __syncthreads();
+    if (w == 0) {
+        s = l < 8 ? sh[0][l] : 0.0; ss = l < 8 ? sh[1][l] : 0.0;
+        s = warp_sum(s); ss = warp_sum(ss);
+        if (l == 0) {
+            double *o = sums + 3 * blockIdx.y;
+            atomicAdd(o + 0, s); atomicAdd(o + 1, ss);
+            if (blockIdx.x == 0) atomicAdd(o + 2, (double)(hi - lo));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ PPO loss
 // One thread per sample of the minibatch.  Everything SB3's PPO.train does between evaluate_actions
 // and loss.backward() for Categorical policies, with the analytic gradient of
@@ -292,6 +317,18 @@ int tmla_adv_stats(const float *advantages, const int32_t *index, int64_t rows, 
     TMLA_CUDA(cudaMemsetAsync(adv_sums, 0, 3 * sizeof(double), (cudaStream_t)stream));
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(rows, 256 * 8), 148 * 8);
     adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(advantages, index, rows, adv_sums);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
+int tmla_adv_stats_batched(const float *advantages, const int32_t *index, int64_t total, int64_t mb_rows, double *adv_sums,
+                           void *stream) {
+    TMLA_REQUIRE(advantages && adv_sums && total > 0 && mb_rows > 0, "bad arguments");
+    const int64_t n_mb = ceil_div64(total, mb_rows);
+    TMLA_REQUIRE(n_mb <= 65535, "too many minibatches");
+    TMLA_CUDA(cudaMemsetAsync(adv_sums, 0, 3 * sizeof(double) * n_mb, (cudaStream_t)stream));
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div64(mb_rows, 256 * 8), 148 * 2);
+    adv_stats_batched_kernel<<<dim3(gx, (unsigned)n_mb), 256, 0, (cudaStream_t)stream>>>(advantages, index, total, mb_rows, adv_sums);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }

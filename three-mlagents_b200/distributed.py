@@ -1,7 +1,7 @@
 """Multi-GPU protocol of the hot path: one process per GPU, environments sharded by global
-env id, ONE data-path collective — a sum all-reduce of the flat fp32 gradient per minibatch — plus a 24-byte
-all-reduce of the advantage statistics so that normalisation and the loss mean keep global-minibatch
-semantics.  The reference is single-process (no torch.distributed anywhere); this module is
+env id, ONE data-path collective — a sum all-reduce of the flat fp32 gradient per minibatch — plus one tiny
+all-reduce per epoch of the advantage statistics of all its minibatches ([n_minibatches, 3] doubles) so that
+normalisation and the loss mean keep global-minibatch semantics.  The reference is single-process (no torch.distributed anywhere); this module is
 new surface, kept tiny so the same functions run under gloo on CPU (tests) and NCCL on GPUs.
 """
 from __future__ import annotations

@@ -72,6 +72,7 @@ SIGNATURES = {
     "tmla_mlp_forward_bf16": (_i, [vp, vp, _i, _i, _i, vp, vp, i64, vp, vp, vp, vp, vp]),
     "tmla_mlp_backward_bf16": (_i, [vp, vp, _i, _i, _i, vp, vp, i64, vp, vp, vp, vp, vp, vp]),
     "tmla_adv_stats": (_i, [vp, vp, i64, vp, vp]),
+    "tmla_adv_stats_batched": (_i, [vp, vp, i64, i64, vp, vp]),
     "tmla_ppo_loss": (_i, [vp, vp, vp, vp, vp, vp, vp, i64, i64, _i, vp, _i, f32, f32, f32, vp, vp, vp, vp]),
     "tmla_tc_linear": (_i, [_i, vp, vp, vp, vp, vp, i64, vp, vp]),
     "tmla_tc_wgrad": (_i, [vp, vp, vp, i64, vp]),

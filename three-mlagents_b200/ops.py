@@ -124,6 +124,16 @@ def adv_stats(advantages, index, rows, sums=None):
     return sums
 
 
+def adv_stats_batched(advantages, index, total, mb_rows, sums=None):
+    """(sum, sum of squares, count) of the advantages of every minibatch of an epoch: double[n_mb, 3]."""
+    n_mb = (total + mb_rows - 1) // mb_rows
+    if sums is None:
+        sums = torch.empty((n_mb, 3), dtype=torch.float64, device=advantages.device)
+    _chk(sums, torch.float64, "sums")
+    check(lib.tmla_adv_stats_batched(ptr(advantages), ptr(index), int(total), int(mb_rows), ptr(sums), _s()))
+    return sums
+
+
 def ppo_loss(logits, values, actions, advantages, old_logp, returns, *, index=None, rows=None, global_rows=None,
              adv_sums=None, normalize=True, clip_range=0.2, ent_coef=0.01, vf_coef=0.5, dlogits=None, dvalues=None,
              stats=None):

@@ -138,7 +138,7 @@ class CudaPPO:
             self.dvalues = torch.empty(B, **f32)
             self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
         self.scratch_mb = torch.empty(2 * ((B + 127) // 128 * 128) * HIDDEN, dtype=self._act_dtype, device=dev)
-        self.adv_sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.adv_sums = torch.zeros(((total + B - 1) // B, 3), dtype=torch.float64, device=dev)   # one row per minibatch of an epoch
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
         self.norm_out = torch.zeros(129, **f32)
@@ -184,13 +184,13 @@ class CudaPPO:
         for _ in range(self.n_epochs):
             ops.permutation(self.seed + 7919 * self.rank, self._epoch_counter, T, N, out=self.perm)
             self._epoch_counter += 1
-            for start in range(0, total, B):
+            if self.normalize_advantage:                  # advantage statistics of all minibatches: one launch, one all-reduce
+                ops.adv_stats_batched(self.adv, self.perm, total, B, self.adv_sums)
+                allreduce_sum_(self.adv_sums)
+            for mb, start in enumerate(range(0, total, B)):
                 rows = min(B, total - start)
                 idx = self.perm[start:start + rows]
-                sums = None
-                if self.normalize_advantage and rows * self.world > 1:
-                    sums = ops.adv_stats(self.adv, idx, rows, self.adv_sums)
-                    allreduce_sum_(sums)
+                sums = self.adv_sums[mb] if self.normalize_advantage and rows * self.world > 1 else None
                 if self.fused_update:
                     ops.ppo_minibatch(self.params, self.wpack, obs_flat, D, A, self.act, self.adv, self.logp, self.ret,
                                       index=idx, rows=rows, global_rows=rows * self.world, adv_sums=sums,
