@@ -280,8 +280,10 @@ def run_cuda(args):
         try:
             from three_mlagents_b200.ppo import bench_ppo
 
-            out["ppo"] = bench_ppo(local_rank, rank, world, iters=args.ppo_iters)
-            if world == 1:
+            # BASELINE configs[2] (ball3d, 64K envs/GPU) by default; --ppo-task gridworld|push = configs[3]/[4] (32K envs/GPU)
+            ppo_envs = args.ppo_envs or (N_ENVS if args.ppo_task == "ball3d" else 32768)
+            out["ppo"] = bench_ppo(local_rank, rank, world, iters=args.ppo_iters, task=args.ppo_task, n_envs=ppo_envs)
+            if world == 1 and args.ppo_task == "ball3d":
                 from three_mlagents_b200.ppo import bench_kernels
 
                 out["ppo"]["kernels"] = bench_kernels(local_rank)
@@ -307,6 +309,8 @@ def main():
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ppo-iters", type=int, default=3)
+    ap.add_argument("--ppo-task", default="ball3d", choices=["ball3d", "gridworld", "push"])
+    ap.add_argument("--ppo-envs", type=int, default=0, help="envs per GPU for the PPO section (default: 65536 ball3d, 32768 otherwise)")
     ap.add_argument("--quick", action="store_true", help="fused rollout only (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -389,14 +389,16 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     tot_ms, roll_ms, train_ms = (float(x) for x in tot)
     samples = world * n_envs * n_steps * iters
-    flop_update = 807936.0 * n_envs * n_steps * 10 * iters          # SURVEY.md §8(d), ball3d fwd+bwd per sample
+    flop_sample = 807936.0 if env.obs_dim == 6 else 803840.0      # fwd+bwd per sample (ball3d | gridworld, push)
+    flop_update = flop_sample * n_envs * n_steps * 10 * iters
     row = model._log_row(10 * minibatches, roll_ms / 1e3 / iters, train_ms / 1e3 / iters, time.time())
     env.close()
     return {
         "value": samples / (tot_ms * 1e-3), "unit": "samples/s (env-steps consumed per second, rollout+GAE+update)",
         "iters": iters, "ms_per_iter": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": train_ms / iters,
         "config": {"task": task, "envs_per_gpu": n_envs, "n_steps": n_steps, "epochs": 10, "minibatches_per_epoch": minibatches,
-                   "minibatch_rows_per_gpu": n_envs * n_steps // minibatches, "mlp": "6-256-256-{5,1} tanh, separate towers",
+                   "minibatch_rows_per_gpu": n_envs * n_steps // minibatches,
+                   "mlp": f"{env.obs_dim}-256-256-{{{env.n_actions},1}} tanh, separate towers",
                    "mlp_impl": ("bf16 tcgen05/TMEM hidden-layer GEMMs, fp32 accumulate (csrc/mlp_tc.cu)" if mlp_impl == "bf16"
                                 else "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)"),
                    "update": ("fused forward+loss+backward kernel per tower + MN-major wgrad (csrc/mlp_train.cu)"
