@@ -40,7 +40,8 @@ extern "C" {
 #define TMLA_ENOMEM       -3
 #define TMLA_EACTION      -4      /* an out-of-range action was seen by a step kernel */
 
-typedef enum { TMLA_BASIC = 0, TMLA_BALL3D = 1, TMLA_GRIDWORLD = 2, TMLA_PUSH = 3 } tmla_task;
+typedef enum { TMLA_BASIC = 0, TMLA_BALL3D = 1, TMLA_GRIDWORLD = 2, TMLA_PUSH = 3, TMLA_WALLJUMP = 4 } tmla_task;
+#define TMLA_NUM_TASKS 5
 
 typedef struct tmla_env tmla_env;     /* opaque handle: packed SoA state of n envs on one GPU */
 
@@ -50,15 +51,16 @@ typedef struct { int32_t pos, steps; float ep_return; } tmla_basic_state;       
 typedef struct { double rot[2]; float pos[2]; float vel[2]; int32_t steps; float ep_return; int32_t episode, pad_; } tmla_ball3d_state; /* ball3d.py:49-58; episode = auto-reset stream index */
 typedef struct { int32_t agent[2], green[2], red[2], goal_type, steps; float ep_return; } tmla_gridworld_state;  /* gridworld.py:46-51 */
 typedef struct { int32_t agent[2], box[2], goal_x, steps; float ep_return; } tmla_push_state;                    /* push.py:42-49 */
+typedef struct { int32_t agent_x, in_air, wall, steps; float ep_return; } tmla_walljump_state;                   /* walljump.py:39-45 */
 
 int         tmla_version(void);
 const char *tmla_last_error(void);
 
 /* task metadata — replaces the space declarations in make_*_env (envs.py:38-44,169-199) */
-int tmla_task_from_name(const char *name);            /* "basic"|"ball3d"|"gridworld"|"push" -> tmla_task or TMLA_EINVAL */
-int tmla_task_obs_dim(int task);                      /* 21 / 6 / 4 / 4 */
-int tmla_task_num_actions(int task);                  /* 3 / 5 / 5 / 5 */
-int tmla_task_max_steps(int task);                    /* 50 / 200 / 100 / 120 */
+int tmla_task_from_name(const char *name);            /* "basic"|"ball3d"|"gridworld"|"push"|"walljump" -> tmla_task or TMLA_EINVAL */
+int tmla_task_obs_dim(int task);                      /* 21 / 6 / 4 / 4 / 4 */
+int tmla_task_num_actions(int task);                  /* 3 / 5 / 5 / 5 / 4 */
+int tmla_task_max_steps(int task);                    /* 50 / 200 / 100 / 120 / 150 */
 int tmla_task_state_size(int task);                   /* sizeof(tmla_<task>_state) */
 
 /* make_vector_env (training.py:71-89): n_envs envs whose global ids are
@@ -241,7 +243,7 @@ int tmla_tc_debug(int swap_lbo_sbo);
  *   grads float[num_params] OVERWRITTEN;  scratch bf16[tmla_ppo_minibatch_scratch(hidden, rows)] (tile images);
  *   stats_out float[8] as tmla_ppo_loss;  logits_out float[rows,A] / values_out float[rows]: optional (NULL).
  * tmla_ppo_minibatch_supported: 1 when the fused path covers (obs_dim, hidden, n_actions) — ball3d, gridworld,
- * push; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
+ * push, walljump; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
 int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions);
 int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows);
 int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *obs,

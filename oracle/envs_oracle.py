@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement (vectorised NumPy) of the four
-reference tasks on the hot path, plus the adapter / DummyVecEnv / Monitor
+reference tasks on the hot path (plus walljump), plus the adapter / DummyVecEnv / Monitor
 semantics around them.  The product path never imports this module; only
 tests/, `__graft_entry__.smoke()` and bench.py's `cpu_baseline` leg do.
 
@@ -13,6 +13,7 @@ Reference anchors (relative to /root/reference/backend):
   ball3d     examples/ball3d.py:10-113
   gridworld  examples/gridworld.py:14-95
   push       examples/push.py:10-125
+  walljump   examples/walljump.py:14-98
   adapter    mlagents/envs.py:87-159  (time-limit truncation, terminated/truncated split)
   vec/auto-reset + Monitor: SB3 DummyVecEnv/Monitor semantics, SURVEY.md §8(a) A7
 Reset draws use this repo's Philox streams (oracle/philox.py), not MT19937.
@@ -43,6 +44,7 @@ TASKS = {
     "ball3d":    (6, 5, 200),     # ball3d.py:12,24,38 ; envs.py:169-175
     "gridworld": (4, 5, 100),     # gridworld.py:14-30 ; envs.py:181-187
     "push":      (4, 5, 120),     # push.py:10-24 ; envs.py:193-199
+    "walljump":  (4, 4, 150),     # walljump.py:14-21 ; envs.py:202-213
 }
 
 STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
@@ -53,6 +55,7 @@ STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format o
                            ("goal_type", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
                       ("steps", "<i4"), ("ep_return", "<f4")]),
+    "walljump": np.dtype([("agent_x", "<i4"), ("in_air", "<i4"), ("wall", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
 }
 
 f32 = np.float32
@@ -85,7 +88,20 @@ def basic_reward_lut():
     return np.array([a, b, c], dtype=np.float32)
 
 
+def walljump_reward_lut():
+    """walljump.py:58,77,81,91: -0.01, (-0.01)-0.02, (-0.01)-0.03 in doubles -> f32; index 3 = goal."""
+    a = -0.01
+    b = -0.01
+    b -= 0.02
+    c = -0.01
+    c -= 0.03
+    return np.array([a, b, c, 1.0], dtype=np.float32)
+
+
 PUSH_LUT = push_reward_lut()
+WALLJUMP_LUT = walljump_reward_lut()
+WJ_WIDTH, WJ_WALL_X, WJ_JUMP = 20, 10, 3          # walljump.py:14,34-35
+WJ_DELTAS = np.array([0, 1, -1, 1], dtype=np.int32)   # walljump.py:18 (jump also moves forward)
 BASIC_LUT = basic_reward_lut()
 
 
@@ -108,6 +124,10 @@ def observe(task, st):
         ab = (st["box"] - st["agent"]).astype(np.float64) / 5.0
         bg = (goal - st["box"]).astype(np.float64) / 5.0
         return np.concatenate([ab, bg], axis=1).astype(np.float32)
+    if task == "walljump":       # walljump.py:48-53 (Python double division, then f32)
+        x = st["agent_x"].astype(np.float64)
+        return np.stack([(WJ_WIDTH - 1 - x) / (WJ_WIDTH - 1), (WJ_WALL_X - x) / (WJ_WIDTH - 1), st["wall"].astype(np.float64),
+                         (st["in_air"] == 0).astype(np.float64)], axis=1).astype(np.float32)
     raise KeyError(task)
 
 
@@ -186,6 +206,25 @@ def transition(task, st, actions):
         done = top | (st["steps"] >= 120)                           # push.py:122-123
         hit = st["steps"] >= max_steps
         terminated, truncated = done & ~hit, hit
+    elif task == "walljump":
+        x0, air = st["agent_x"].copy(), st["in_air"].copy()
+        just_jumped = (a == 3) & (air == 0)                          # walljump.py:62-65
+        air = np.where(just_jumped, WJ_JUMP, air)
+        px_ = np.clip(x0 + WJ_DELTAS[a], 0, WJ_WIDTH - 1)            # walljump.py:68-69
+        crossing = ((x0 < WJ_WALL_X) & (WJ_WALL_X <= px_)) | ((px_ < WJ_WALL_X) & (WJ_WALL_X <= x0))   # :72-74
+        blocked = crossing & (st["wall"] == 1) & (air == 0)          # walljump.py:75-77
+        px_ = np.where(blocked, x0, px_)
+        ridx = np.where(blocked, 1, 0)
+        ridx = np.where(just_jumped & ~crossing & (np.abs(WJ_WALL_X - x0) > 1), 2, ridx)   # walljump.py:80-81 (never both)
+        air = np.where(air > 0, air - 1, air)                        # walljump.py:86-87
+        goal = px_ == WJ_WIDTH - 1                                   # walljump.py:90-92
+        ridx = np.where(goal, 3, ridx)
+        st["agent_x"], st["in_air"] = px_, air
+        st["steps"] += 1
+        reward = WALLJUMP_LUT[ridx]
+        done = goal | (st["steps"] >= 150)                           # walljump.py:94-96
+        hit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit, hit
     else:
         raise KeyError(task)
     return observe(task, st), reward, terminated, truncated
@@ -237,6 +276,10 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET, episode=None):
         st["agent"] = np.stack([a // 6, a % 6], 1)
         st["box"] = np.stack([bx // 6, bx % 6], 1)
         st["goal_x"] = px.bounded(b[2], 6)
+    elif task == "walljump":                                        # walljump.py:39-45: int(np.random.rand() < 0.7)
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        u24 = (b[0] >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        st["wall"] = (u24 < np.float32(0.7)).astype(np.int32)
     return st
 
 

@@ -67,6 +67,8 @@ def _state_of(task, env):
             "box": np.asarray(inner.box_pos, dtype=np.int32),
             "goal_x": np.int32(inner.goal_pos[0]),
         }
+    if task == "walljump":
+        return {"agent_x": np.int32(inner.agent_x), "in_air": np.int32(inner.in_air), "wall": np.int32(inner.wall_height)}
     raise KeyError(task)
 
 
@@ -84,6 +86,10 @@ def _actions(task, n_actions, rng):
         acts[:, 0] = 1   # stay put for 50 steps -> pure truncation episodes
     if task == "ball3d":
         acts[:, 4] = 4   # no-op forever
+    if task == "walljump":
+        acts[:, 8] = np.where(np.arange(T) % 4 == 0, 3, 1)      # jump every 4th step, walk otherwise: clears the wall
+        acts[:, 9] = np.where(np.arange(T) % 7 < 5, 1, 2)       # mostly forward with retreats: bumps into the wall repeatedly
+        acts[:, 10] = np.where(np.arange(T) % 9 == 8, 3, 0)     # jumps in place far from the wall: unneeded-jump penalty
     return acts.astype(np.int32)
 
 
@@ -155,14 +161,19 @@ def reset_samples(task, make_env, n=4096):
 def main():
     make_env = _import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
-    for task in ("basic", "ball3d", "gridworld", "push"):
+    only = set(sys.argv[1:])                 # e.g. `python oracle/make_golden.py walljump` regenerates one task
+    for task in ("basic", "ball3d", "gridworld", "push", "walljump"):
+        if only and task not in only:
+            continue
         g = record(task, make_env)
         path = os.path.join(OUT_DIR, f"{task}.npz")
         np.savez_compressed(path, **g)
         n_ep = int((g["terminated"] | g["truncated"]).sum())
         print(f"{task}: {path}  episodes={n_ep} terminated={int(g['terminated'].sum())} "
               f"truncated={int(g['truncated'].sum())}  size={os.path.getsize(path)/1024:.0f} KiB")
-    for task in ("ball3d", "gridworld", "push"):
+    for task in ("ball3d", "gridworld", "push", "walljump"):
+        if only and task not in only:
+            continue
         s = reset_samples(task, make_env)
         path = os.path.join(OUT_DIR, f"{task}_resets.npz")
         np.savez_compressed(path, **s)

@@ -17,6 +17,7 @@ STATE_KEYS = {
     "ball3d": ("rot", "pos", "vel"),
     "gridworld": ("agent", "green", "red", "goal_type"),
     "push": ("agent", "box", "goal_x"),
+    "walljump": ("agent_x", "in_air", "wall"),
 }
 
 

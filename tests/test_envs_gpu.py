@@ -15,7 +15,7 @@ from oracle import envs_oracle as eo
 
 pytestmark = pytest.mark.gpu
 
-TASKS = ("basic", "ball3d", "gridworld", "push")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump")
 # north_star: "ball3d trajectories must stay within a stated float tolerance over 1,000 steps".
 # The only non-bit-exact operation on the device is sin(double) (own polynomial vs libm, <= 1 ulp of
 # f64); everything else follows NumPy's rounding sequence exactly, so 1e-5 absolute is generous.
@@ -182,7 +182,7 @@ def test_reference_known_answer_through_single_env_api():
         env.close()
 
 
-@pytest.mark.parametrize("task,n", [("ball3d", 65536), ("gridworld", 32768), ("push", 32768)])
+@pytest.mark.parametrize("task,n", [("ball3d", 65536), ("gridworld", 32768), ("push", 32768), ("walljump", 32768)])
 def test_full_size_properties(task, n):
     """BASELINE.json sizes: size-independent invariants of a 128-step fused rollout."""
     T, d = 128, eo.TASKS[task][0]
@@ -211,6 +211,10 @@ def test_full_size_properties(task, n):
         live = ~dn[:-1]
         pos_next = (o[:-1, :, 2:4] + o[1:, :, 4:6] * np.float32(0.02)).astype(np.float32)
         assert np.array_equal(pos_next[live], o[1:, :, 2:4][live])
+    elif task == "walljump":
+        assert set(np.unique(o[..., :2])).issubset(set((np.arange(-9, 20) / 19.0).astype(np.float32)))
+        assert set(np.unique(o[..., 2:])).issubset({np.float32(0), np.float32(1)})
+        assert abs(float(o[0, :, 2].mean()) - 0.7) < 0.02            # wall present in 70 % of the fresh episodes
     else:
         assert set(np.unique(o[..., :2])).issubset(set((np.arange(-5, 6) / (4.0 if task == "gridworld" else 5.0)).astype(np.float32)))
     # Monitor accumulator == sum of rewards since last done (f32 sequential sum)

@@ -7,7 +7,7 @@ from oracle import envs_oracle as eo
 from oracle import philox as px
 import replay_util as _replay
 
-TASKS = ("basic", "ball3d", "gridworld", "push")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump")
 
 
 def test_philox_known_answers():
@@ -50,6 +50,12 @@ def test_reward_luts_are_f32_of_double():
     assert np.array_equal(g["reward"], g["reward64"].astype(np.float32))
     assert set(np.unique(g["reward"])).issubset(set(eo.PUSH_LUT.tolist()) | {np.float32(1.0)})
     assert eo.BASIC_LUT.view(np.uint32).tolist() == [0xBC23D70A, 0x3DB851EC, 0x3F7D70A4]
+    w = _replay.load("walljump")
+    assert np.array_equal(w["reward"], w["reward64"].astype(np.float32))
+    assert set(np.unique(w["reward"]).tolist()) == set(eo.WALLJUMP_LUT.tolist())          # all four values occur in the trace
+    assert eo.WALLJUMP_LUT.view(np.uint32).tolist() == [0xBC23D70A, 0xBCF5C28F, 0xBD23D70A, 0x3F800000]   # csrc/envs.cuh
+    # the device divides in f32: f32(k/19.0) == f32(k)/f32(19) for every reachable numerator
+    assert all(np.float32(k / 19.0) == np.float32(k) / np.float32(19) for k in range(-9, 20))
 
 
 def test_reference_known_answer_basic():
@@ -59,6 +65,16 @@ def test_reference_known_answer_basic():
     obs, rew, term, trunc = eo.transition("basic", st, np.array([2]))
     assert int(st["pos"][0]) == 11 and not term[0] and not trunc[0]
     assert obs.shape == (1, 21) and obs[0, 11] == 1.0 and obs.sum() == 1.0
+
+
+def test_walljump_reset_distribution_matches_reference():
+    """walljump.py:39-45: agent at 0, grounded, wall present with probability 0.7."""
+    ref = np.load(_replay.GOLDEN + "/walljump_resets.npz")
+    n = 200_000
+    st = eo.draw_reset("walljump", 7, np.arange(n), 3)
+    assert (st["agent_x"] == 0).all() and (st["in_air"] == 0).all() and (ref["agent_x"] == 0).all() and (ref["in_air"] == 0).all()
+    assert set(np.unique(st["wall"]).tolist()) == {0, 1} and set(np.unique(ref["wall"]).tolist()) == {0, 1}
+    assert abs(st["wall"].mean() - 0.7) < 4 * np.sqrt(0.21 / n) and abs(ref["wall"].mean() - 0.7) < 4 * np.sqrt(0.21 / len(ref["wall"]))
 
 
 @pytest.mark.parametrize("task", ("ball3d", "gridworld", "push"))

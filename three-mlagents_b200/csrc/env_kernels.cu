@@ -1,4 +1,4 @@
-// env_kernels.cu — batched environment stepping for basic / ball3d / gridworld / push (sm_100a).
+// env_kernels.cu — batched environment stepping for basic / ball3d / gridworld / push / walljump (sm_100a).
 //
 // Replaces SB3 `DummyVecEnv.step_wait` (a serial Python loop over envs) + `Monitor` + the reference's
 // `LegacySingleAgentGymAdapter.step/reset` (backend/mlagents/envs.py:110-152) and the task dynamics
@@ -420,6 +420,7 @@ __global__ void selftest_arith_kernel(unsigned long long *out) {
         case TMLA_BALL3D: { using TaskT = Ball3DTask; CALL; } break;      \
         case TMLA_GRIDWORLD: { using TaskT = GridWorldTask; CALL; } break; \
         case TMLA_PUSH: { using TaskT = PushTask; CALL; } break;          \
+        case TMLA_WALLJUMP: { using TaskT = WallJumpTask; CALL; } break;  \
         default: tmla_set_error("unknown task %d", task); return TMLA_EINVAL; \
     }
 
@@ -430,11 +431,12 @@ static EnvPtrs ptrs_of(const tmla_env *h) {
 }
 static inline unsigned grid_for(int64_t n) { return (unsigned)ceil_div64(n, kBlock); }
 
-static const int kObsDim[4] = {BasicTask::D, Ball3DTask::D, GridWorldTask::D, PushTask::D};
-static const int kNumActions[4] = {BasicTask::A, Ball3DTask::A, GridWorldTask::A, PushTask::A};
-static const int kMaxSteps[4] = {BasicTask::MAX_STEPS, Ball3DTask::MAX_STEPS, GridWorldTask::MAX_STEPS, PushTask::MAX_STEPS};
-static const int kStateSize[4] = {(int)sizeof(tmla_basic_state), (int)sizeof(tmla_ball3d_state),
-                                  (int)sizeof(tmla_gridworld_state), (int)sizeof(tmla_push_state)};
+static const int kObsDim[TMLA_NUM_TASKS] = {BasicTask::D, Ball3DTask::D, GridWorldTask::D, PushTask::D, WallJumpTask::D};
+static const int kNumActions[TMLA_NUM_TASKS] = {BasicTask::A, Ball3DTask::A, GridWorldTask::A, PushTask::A, WallJumpTask::A};
+static const int kMaxSteps[TMLA_NUM_TASKS] = {BasicTask::MAX_STEPS, Ball3DTask::MAX_STEPS, GridWorldTask::MAX_STEPS, PushTask::MAX_STEPS,
+                                              WallJumpTask::MAX_STEPS};
+static const int kStateSize[TMLA_NUM_TASKS] = {(int)sizeof(tmla_basic_state), (int)sizeof(tmla_ball3d_state), (int)sizeof(tmla_gridworld_state),
+                                               (int)sizeof(tmla_push_state), (int)sizeof(tmla_walljump_state)};
 
 // staging layout shared by the device block and its pinned host mirror (16-byte aligned sections):
 //   actions i32[n] | obs f32[n,D] | reward f32[n] | done u8[n] | truncated u8[n] | flags i32[4] {n_done, bad_action}
@@ -466,12 +468,13 @@ int tmla_task_from_name(const char *name) {
     if (!strcmp(name, "ball3d")) return TMLA_BALL3D;
     if (!strcmp(name, "gridworld")) return TMLA_GRIDWORLD;
     if (!strcmp(name, "push")) return TMLA_PUSH;
-    tmla_set_error("no CUDA backend for task '%s' (have: basic, ball3d, gridworld, push)", name);
+    if (!strcmp(name, "walljump")) return TMLA_WALLJUMP;
+    tmla_set_error("no CUDA backend for task '%s' (have: basic, ball3d, gridworld, push, walljump)", name);
     return TMLA_EINVAL;
 }
 #define TASK_META(fn, table)                                                                   \
     int fn(int task) {                                                                         \
-        if (task < 0 || task > 3) { tmla_set_error(#fn ": unknown task %d", task); return TMLA_EINVAL; } \
+        if (task < 0 || task >= TMLA_NUM_TASKS) { tmla_set_error(#fn ": unknown task %d", task); return TMLA_EINVAL; } \
         return table[task];                                                                    \
     }
 TASK_META(tmla_task_obs_dim, kObsDim)
@@ -481,7 +484,7 @@ TASK_META(tmla_task_state_size, kStateSize)
 
 int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int device, tmla_env **out) {
     TMLA_REQUIRE(out != nullptr, "out is NULL");
-    TMLA_REQUIRE(task >= 0 && task <= 3, "unknown task");
+    TMLA_REQUIRE(task >= 0 && task < TMLA_NUM_TASKS, "unknown task");
     TMLA_REQUIRE(n_envs > 0 && n_envs < (int64_t)1 << 31, "n_envs must be in (0, 2^31)");
     int ndev = 0;
     TMLA_CUDA(cudaGetDeviceCount(&ndev));

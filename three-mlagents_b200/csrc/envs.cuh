@@ -14,6 +14,7 @@
 // CPU side by oracle/envs_oracle.py against reference-made golden traces:
 //     basic      mlagents/envs.py:17-84        ball3d     examples/ball3d.py:10-113
 //     gridworld  examples/gridworld.py:14-95   push       examples/push.py:10-125
+//     walljump   examples/walljump.py:14-98
 //     adapter    mlagents/envs.py:125-152 (steps>=limit -> truncated; terminated = done && !truncated)
 #pragma once
 #include "common.cuh"
@@ -407,6 +408,73 @@ struct PushTask {
         int bx = tmla_bounded(b.y, 35); bx += (bx >= a);
         s.ax = a / 6; s.ay = a % 6; s.bx = bx / 6; s.by = bx % 6;
         s.goal_x = tmla_bounded(b.z, 6);
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};
+
+// ------------------------------------------------------------ walljump (examples/walljump.py:14-98)
+// 1-D track of 20 cells, a wall at x = 10 present with probability 0.7, a jump lasts 3 steps.  Integer state;
+// the rewards are the Python doubles -0.01, -0.01-0.02, -0.01-0.03 and 1.0 rounded once to f32
+// (0xbc23d70a, 0xbcf5c28f, 0xbd23d70a; the golden traces hold exactly these four values).
+struct WallJumpTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
+    static constexpr int D = 4, A = 4, MAX_STEPS = 150, NBUF = 1, WIDTH = 20, WALL_X = 10, JUMP = 3;
+    typedef tmla_walljump_state Wire;
+    struct State { int x, in_air, wall, steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int) { return sizeof(uint2); }
+
+    // packed word: x bits 0..4 | in_air bits 5..6 | wall bit 7 | steps bits 19..26
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const uint2 w = reinterpret_cast<const uint2 *>(buf[0])[i];
+        return State{(int)(w.x & 31u), (int)((w.x >> 5) & 3u), (int)((w.x >> 7) & 1u), (int)((w.x >> 19) & 255u), __uint_as_float(w.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        const uint32_t w = (uint32_t)s.x | ((uint32_t)s.in_air << 5) | ((uint32_t)s.wall << 7) | ((uint32_t)s.steps << 19);
+        reinterpret_cast<uint2 *>(buf[0])[i] = make_uint2(w, __float_as_uint(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        return State{iclamp(w.agent_x, 0, WIDTH - 1), iclamp(w.in_air, 0, JUMP), w.wall & 1, w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) { return Wire{s.x, s.in_air, s.wall, s.steps, s.ep_ret}; }
+
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // walljump.py:48-53
+        // f32(k/19.0) == f32(k)/f32(19) for every reachable k in [-9,19] (tests/test_oracle_cpu.py); IEEE f32 division
+        o[0] = __fdiv_rn((float)(WIDTH - 1 - s.x), 19.0f);
+        o[1] = __fdiv_rn((float)(WALL_X - s.x), 19.0f);
+        o[2] = (float)s.wall;
+        o[3] = s.in_air == 0 ? 1.0f : 0.0f;
+    }
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
+        bool just_jumped = false;
+        if (a == 3 && s.in_air == 0) { s.in_air = JUMP; just_jumped = true; }       // walljump.py:62-65
+        const int dx = (a == 1 || a == 3) ? 1 : (a == 2 ? -1 : 0);                  // ACTION_DELTAS, walljump.py:18
+        int px = iclamp(s.x + dx, 0, WIDTH - 1);                                    // walljump.py:68-69
+        const bool crossing = (s.x < WALL_X && WALL_X <= px) || (px < WALL_X && WALL_X <= s.x);   // walljump.py:72-74
+        uint32_t rbits = 0xBC23D70Au;                                               // f32(-0.01)
+        if (crossing && s.wall == 1 && s.in_air == 0) { px = s.x; rbits = 0xBCF5C28Fu; }          // walljump.py:75-77: -0.01 - 0.02
+        if (just_jumped && !crossing && abs(WALL_X - s.x) > 1) rbits = 0xBD23D70Au;                // walljump.py:80-81: -0.01 - 0.03
+        s.x = px;
+        if (s.in_air > 0) s.in_air -= 1;                                            // walljump.py:86-87
+        bool done = false;
+        if (s.x == WIDTH - 1) { rbits = 0x3F800000u; done = true; }                 // walljump.py:90-92
+        s.steps += 1;
+        done = done || (s.steps >= 150);                                            // walljump.py:94-96
+        reward = __uint_as_float(rbits);
+        trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
+        term = done && !trunc;
+    }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                 // walljump.py:39-45
+        s.x = 0; s.in_air = 0;
+        s.wall = tmla_u24(b.x) < 0.7f ? 1 : 0;                                      // int(np.random.rand() < 0.7)
         s.steps = 0; s.ep_ret = 0.0f;
     }
 };

@@ -610,8 +610,10 @@ static int ensure_pipe_attrs() {
     static int done = 0;
     if (done) return TMLA_OK;
 #define PIPE_ATTR(K) TMLA_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem))
-    PIPE_ATTR(head_forward_bf16_kernel<1>); PIPE_ATTR(head_forward_bf16_kernel<3>); PIPE_ATTR(head_forward_bf16_kernel<5>);
-    PIPE_ATTR(head_backward_bf16_kernel<1>); PIPE_ATTR(head_backward_bf16_kernel<3>); PIPE_ATTR(head_backward_bf16_kernel<5>);
+    PIPE_ATTR(head_forward_bf16_kernel<1>); PIPE_ATTR(head_forward_bf16_kernel<3>); PIPE_ATTR(head_forward_bf16_kernel<4>);
+    PIPE_ATTR(head_forward_bf16_kernel<5>);
+    PIPE_ATTR(head_backward_bf16_kernel<1>); PIPE_ATTR(head_backward_bf16_kernel<3>); PIPE_ATTR(head_backward_bf16_kernel<4>);
+    PIPE_ATTR(head_backward_bf16_kernel<5>);
     PIPE_ATTR(l1_backward_bf16_kernel<4>); PIPE_ATTR(l1_backward_bf16_kernel<6>);
 #undef PIPE_ATTR
     done = 1;
@@ -666,11 +668,13 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
             const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8 * kPipeDepth), 148 * 4);
             if (t == 1) head_forward_bf16_kernel<1><<<gh, 256, kPipeSmem, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
             else if (n_actions == 3) head_forward_bf16_kernel<3><<<gh, 256, kPipeSmem, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+            else if (n_actions == 4) head_forward_bf16_kernel<4><<<gh, 256, kPipeSmem, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
             else head_forward_bf16_kernel<5><<<gh, 256, kPipeSmem, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
         } else {
             const unsigned gh = (unsigned)std::min<int64_t>(ceil_div64(rows, 8), 148 * 8);
             if (t == 1) head_forward_kernel<1, AT><<<gh, 256, 0, st>>>(params + o.wh[1], params + o.bh[1], h2, rows, rows_dev, out);
             else if (n_actions == 3) head_forward_kernel<3, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
+            else if (n_actions == 4) head_forward_kernel<4, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
             else head_forward_kernel<5, AT><<<gh, 256, 0, st>>>(params + o.wh[0], params + o.bh[0], h2, rows, rows_dev, out);
         }
         TMLA_LAUNCH_CHECK();
@@ -696,10 +700,12 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
         if constexpr (BF) {
             if (t == 1) head_backward_bf16_kernel<1><<<gr, 256, kPipeSmem, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
             else if (n_actions == 3) head_backward_bf16_kernel<3><<<gr, 256, kPipeSmem, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            else if (n_actions == 4) head_backward_bf16_kernel<4><<<gr, 256, kPipeSmem, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
             else head_backward_bf16_kernel<5><<<gr, 256, kPipeSmem, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
         } else {
             if (t == 1) head_backward_kernel<1, AT><<<gr, H, 0, st>>>(params + o.wh[1], h2, dout, rows, rpb, dz2, grads + o.wh[1], grads + o.bh[1], grads + o.b2[1]);
             else if (n_actions == 3) head_backward_kernel<3, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
+            else if (n_actions == 4) head_backward_kernel<4, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
             else head_backward_kernel<5, AT><<<gr, H, 0, st>>>(params + o.wh[0], h2, dout, rows, rpb, dz2, grads + o.wh[0], grads + o.bh[0], grads + o.b2[0]);
         }
         TMLA_LAUNCH_CHECK();
@@ -749,7 +755,7 @@ int64_t tmla_mlp_num_params(int obs_dim, int hidden, int n_actions) {
 static int check_shape(int D, int hidden, int A) {
     if (hidden != H) { tmla_set_error("hidden must be 256 (net_arch of training.py:363-365), got %d", hidden); return TMLA_EINVAL; }
     if (!(D == 4 || D == 6 || D == 21)) { tmla_set_error("obs_dim must be 4, 6 or 21, got %d", D); return TMLA_EINVAL; }
-    if (!(A == 3 || A == 5)) { tmla_set_error("n_actions must be 3 or 5, got %d", A); return TMLA_EINVAL; }
+    if (!(A >= 3 && A <= 5)) { tmla_set_error("n_actions must be 3, 4 or 5, got %d", A); return TMLA_EINVAL; }
     return TMLA_OK;
 }
 

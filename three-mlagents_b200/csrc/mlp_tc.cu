@@ -569,7 +569,7 @@ int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, c
                             const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
                             void *h1, void *h2, cudaStream_t st) {
 #define TF(DD, NN) if (D == DD && nout == NN) return tower_forward_launch_t<DD, NN>(W1, B1, W2, B2, Wh, Bh, x, index, M, rows_dev, out, h1, h2, st)
-    TF(6, 5); TF(6, 1); TF(4, 5); TF(4, 1);
+    TF(6, 5); TF(6, 1); TF(4, 5); TF(4, 4); TF(4, 1);
 #undef TF
     return TMLA_EINVAL;
 }

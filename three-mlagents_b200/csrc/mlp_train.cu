@@ -811,7 +811,7 @@ static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
 extern "C" {
 
 int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions) {
-    return (hidden == H && (obs_dim == 4 || obs_dim == 6) && n_actions == 5) ? 1 : 0;
+    return (hidden == H && ((obs_dim == 6 && n_actions == 5) || (obs_dim == 4 && (n_actions == 4 || n_actions == 5)))) ? 1 : 0;
 }
 
 int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 2 * ((rows + 127) / 128 * 128) * (int64_t)hidden; }
@@ -825,7 +825,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     TMLA_REQUIRE(rows > 0 && global_rows >= rows, "bad row counts");
     TMLA_REQUIRE(!normalize_advantage || adv_sums, "adv_sums required when normalising");
     if (!tmla_ppo_minibatch_supported(obs_dim, hidden, n_actions)) {
-        tmla_set_error("tmla_ppo_minibatch_bf16: fused path covers hidden=256, obs_dim 4 or 6, 5 actions (got %d/%d/%d)", obs_dim, hidden, n_actions);
+        tmla_set_error("tmla_ppo_minibatch_bf16: fused path covers hidden=256 with (obs_dim, actions) = (6,5), (4,5), (4,4) (got %d/%d/%d)", obs_dim, hidden, n_actions);
         return TMLA_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -848,7 +848,8 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         a.stats = stats_out;
         int rc;
         if (obs_dim == 6) rc = t == 0 ? tower_train_launch_t<6, 5>(a, st) : tower_train_launch_t<6, 1>(a, st);
-        else rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
+        else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
+        else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st) : tower_train_launch_t<4, 1>(a, st);
         if (rc) return rc;
         rc = tc_wgrad_tiled_launch(dz2, h1, grads + o.w2[t], rows_padded, st);
         if (rc) return rc;

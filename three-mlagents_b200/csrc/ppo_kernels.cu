@@ -348,8 +348,9 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
     ppo_loss_kernel<AA><<<grid, 256, 0, st>>>(logits, values, actions, advantages, old_logp, returns, index, rows, inv, \
                                               adv_sums, normalize_advantage, clip_range, ent_coef, vf_coef, dlogits, dvalues, stats_out)
     if (n_actions == 3) LOSS_LAUNCH(3);
+    else if (n_actions == 4) LOSS_LAUNCH(4);
     else if (n_actions == 5) LOSS_LAUNCH(5);
-    else { tmla_set_error("tmla_ppo_loss: n_actions must be 3 or 5 (got %d)", n_actions); return TMLA_EINVAL; }
+    else { tmla_set_error("tmla_ppo_loss: n_actions must be 3, 4 or 5 (got %d)", n_actions); return TMLA_EINVAL; }
 #undef LOSS_LAUNCH
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;

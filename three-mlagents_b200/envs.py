@@ -93,3 +93,7 @@ def make_gridworld_env() -> CudaTaskEnv:    # envs.py:178-187
 
 def make_push_env() -> CudaTaskEnv:         # envs.py:190-199
     return CudaTaskEnv("push")
+
+
+def make_walljump_env() -> CudaTaskEnv:     # envs.py:202-213
+    return CudaTaskEnv("walljump")

@@ -60,4 +60,6 @@ def spaces_for(task_id: str):
         return Box(-np.inf, np.inf, (6,), np.float32), Discrete(5)
     if task_id in ("gridworld", "push"):   # envs.py:181-199
         return Box(-1.0, 1.0, (4,), np.float32), Discrete(5)
+    if task_id == "walljump":              # envs.py:202-213
+        return Box(-1.0, 1.0, (4,), np.float32), Discrete(4)
     raise KeyError(task_id)

@@ -29,6 +29,7 @@ STATE_DTYPES = {   # wire structs of include/tmla.h
                            ("goal_type", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
                       ("steps", "<i4"), ("ep_return", "<f4")]),
+    "walljump": np.dtype([("agent_x", "<i4"), ("in_air", "<i4"), ("wall", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
 }
 
 
