@@ -1,0 +1,48 @@
+"""Cycle budget of one tile of tc_tower_train_kernel, measured with clock64 marks (not sampling):
+    TMLA_EXTRA_NVCC_FLAGS=-DTMLA_PHASE_CLOCKS python three-mlagents_b200/build.py --force && python profiles/phase_clocks.py
+Thread 0 of CTA 0 accumulates the cycles between consecutive marks of the tile loop over one BASELINE config-3
+minibatch per tower (262 144 rows, 14 tiles for CTA 0).  Rebuild without the flag afterwards."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from three_mlagents_b200 import native, ops
+from three_mlagents_b200.ppo import HIDDEN, orthogonal_init
+
+NAMES = ["wait M4(prev)", "P1 store + XB -> barrier", "M1 window (prefetch, H1 stash) -> MMA1 done", "H1 image read + barrier",
+         "P3 (bias, tanh, H2) -> barrier", "MH round trip", "P4 loss -> barrier", "M2 round trip", "P5 dZ2 -> barrier",
+         "M3 window (layer 1 of the next tile) -> dgrad done", "dZ2 image read + barrier", "P7 dZ1 -> barrier"]
+lib = native.lib
+lib.tmla_debug_phase_cycles.restype = C.c_int
+lib.tmla_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int]
+dev = torch.device("cuda", 0)
+T, N, D, A = 128, 65536, 6, 5
+B = T * N // 32
+g = torch.Generator(device=dev).manual_seed(0)
+obs = torch.randn((T * N, D), device=dev, generator=g)
+act = torch.randint(0, A, (T, N), device=dev, dtype=torch.int32)
+adv = torch.randn((T, N), device=dev, generator=g)
+logp = -torch.rand((T, N), device=dev, generator=g)
+ret = torch.randn((T, N), device=dev, generator=g)
+idx = ops.permutation(1, 0, T, N)[:B].contiguous()
+params = orthogonal_init(D, A, 1).to(dev)
+wpack = ops.mlp_pack(params, D, A)
+sums = ops.adv_stats(adv, idx, B)
+for _ in range(3):
+    ops.ppo_minibatch(params, wpack, obs, D, A, act, adv, logp, ret, index=idx, rows=B, adv_sums=sums)
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * 32)()
+lib.tmla_debug_phase_cycles(None, 1)
+reps = 5
+for _ in range(reps):
+    ops.ppo_minibatch(params, wpack, obs, D, A, act, adv, logp, ret, index=idx, rows=B, adv_sums=sums)
+torch.cuda.synchronize()
+lib.tmla_debug_phase_cycles(buf, 0)
+tiles = 14 * 2 * reps            # CTA 0: 14 tiles per tower kernel, 2 towers
+tot = sum(buf[i] for i in range(12))
+print(f"cycles per tile (CTA 0, both towers averaged): {tot / tiles:.0f}")
+for i, nm in enumerate(NAMES):
+    print(f"  {buf[i] / tiles:8.0f}  {100.0 * buf[i] / tot:5.1f} %  {nm}")

@@ -21,7 +21,7 @@ SOURCES = ["error.cu", "env_kernels.cu", "ppo_kernels.cu", "mlp_kernels.cu", "ml
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("TMLA_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DTMLA_PHASE_CLOCKS for profiles/phase_clocks.py
 
 
 def _nvcc() -> str:

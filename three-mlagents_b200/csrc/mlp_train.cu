@@ -39,7 +39,7 @@
 #include "tc_common.cuh"
 #include "mlp_common.cuh"
 
-static constexpr int kTrainThreads = 512;                  // 16 warps: row = (warp%4)*32 + lane, column quarter = warp/4
+static constexpr int kTrainThreads = 512;                  // 16 worker warps: row = (warp%4)*32 + lane, column quarter = warp/4 (+ 1 driver warp)
 
 __host__ __device__ constexpr uint32_t make_idesc_major(int M, int N, int a_mn, int b_mn) {
     return make_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -102,6 +102,9 @@ __device__ __forceinline__ void cp_async_ca(uint32_t dst, const void *src, uint3
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // one elected lane of a converged warp (warp-uniform control flow keeps the tcgen05 operands in uniform registers;
 // a `tid == 0` branch makes the compiler wrap every MMA in a lane-serialising loop)
 __device__ __forceinline__ bool elect_one() {
@@ -111,6 +114,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// optional phase clocks (compile with -DTMLA_PHASE_CLOCKS): thread 0 of every CTA accumulates the cycles between
+// consecutive marks of the worker tile loop in shared memory; CTA 0 publishes them (profiles/phase_clocks.py)
+#ifdef TMLA_PHASE_CLOCKS
+__device__ unsigned long long g_phase_cycles[32];
+#define TMLA_PH(i) do { if (tid == 0) { const long long c__ = clock64(); ph_acc[i] += (unsigned long long)(c__ - ph_clock); ph_clock = c__; } } while (0)
+#else
+#define TMLA_PH(i) do { } while (0)
+#endif
 
 struct TowerTrainArgs {
     // tower parameters (fp32 views into the flat vector; W2 from the bf16 pack)
@@ -152,11 +164,15 @@ struct TrainSmem {
     static constexpr uint32_t idx = ls + 128 * 12;                     // int32 [2][128]: buffer rows of the next two tiles (-1 = past the end)
     static constexpr uint32_t racc = idx + 2 * 128 * 4;                // float [128][9]: per-row running sums (4 loss statistics, NOUT head-bias gradients)
     static constexpr uint32_t bar = racc + 128 * 9 * 4 + 16;           // + adv_mean, adv_inv_std
+#ifdef TMLA_PHASE_CLOCKS
+    static constexpr uint32_t total = bar + 64 + 256;
+#else
     static constexpr uint32_t total = bar + 64;
+#endif
 };
 
 template <int D, int NOUT>
-__global__ void __launch_bounds__(kTrainThreads, 1)
+__global__ void __launch_bounds__(kTrainThreads + 32, 1)
 tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     using L = TrainSmem<D, NOUT>;
     constexpr bool PI = NOUT > 1;
@@ -167,10 +183,16 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     uint8_t *Ws = smem + L::w, *Ts = smem + L::tile;
     float *w1t = reinterpret_cast<float *>(smem + L::w1t), *b1s = reinterpret_cast<float *>(smem + L::b1);
     float *b2s = reinterpret_cast<float *>(smem + L::b2);
-    uint64_t *bar0 = reinterpret_cast<uint64_t *>(smem + L::bar), *bar1 = bar0 + 1;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 16);
+    uint64_t *bar0 = reinterpret_cast<uint64_t *>(smem + L::bar), *bar1 = bar0 + 1;   // MMA groups done: M1/M3 and MH/M2/M4
+    uint64_t *rdy = bar0 + 2, *bar_st = bar0 + 3;         // workers -> driver "operands staged"; driver -> workers "tile image read"
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bar + 32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // the same value, provably warp-uniform
+    // Warps 0..15 are the workers (CUDA-core phases); warp 16 is the DRIVER: one elected lane issues every tcgen05.mma
+    // and bulk-TMA store.  tcgen05.mma issue blocks while the tensor core's queue is full (measured: ~2400 cycles for
+    // the 16 MMAs of M1), so a worker warp that also issues stalls the whole CTA at the next barrier.
+    const bool is_driver = warp_u == kTrainThreads / 32;
+    auto worker_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kTrainThreads) : "memory"); };
     const int64_t M = p.M;
     const int64_t ntiles = (M + 127) / 128;
     if ((int64_t)blockIdx.x >= ntiles) return;
@@ -224,11 +246,11 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     cp_async_commit();
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
-    if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_barrier_init(); }
+    if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(rdy, 1); mbar_init(bar_st, 1); fence_barrier_init(); }
     if (tid == 32) { mbar_expect_tx(bar0, kWBytes); bulk_load(smem_u32(Ws), p.W2, kWBytes, bar0); }   // W2 image: one bulk-TMA load
-    for (int e = tid; e < H * D; e += kTrainThreads) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
+    for (int e = tid; e < H * D; e += blockDim.x) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
     if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
-    for (int e = tid; e < H * 16; e += kTrainThreads) {    // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
+    for (int e = tid; e < H * 16; e += blockDim.x) {       // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
         const int j = e >> 4, c = e & 15;
         float v = 0.0f;
         if (c < 3 * NOUT) {
@@ -246,7 +268,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
     const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
-    uint32_t ph0 = 0, ph1 = 0;
+    uint32_t ph0 = 0, ph1 = 0, phs = 0;                     // phs: parity of bar_st (workers) / rdy (driver)
     mbar_wait(bar0, ph0);                                  // the W2 image has landed
     ph0 ^= 1u;
 
@@ -265,7 +287,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         advc[0] = adv_mean; advc[1] = adv_inv_std;
     }
-    for (int e = tid; e < 128 * 9; e += kTrainThreads) racc[e] = 0.0f;
+    for (int e = tid; e < 128 * 9; e += blockDim.x) racc[e] = 0.0f;
     __syncthreads();
 
     // layer 1, H1 = tanh(x W1^T + b1): this thread computes rows l1row + 8*i (i < 4) x 16 columns from l1col — every
@@ -295,14 +317,87 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
         }
     };
-    layer1();
+    if (!is_driver) layer1();
 
     uint32_t it = 0;
+#ifdef TMLA_PHASE_CLOCKS
+    unsigned long long *ph_acc = reinterpret_cast<unsigned long long *>(smem + L::bar + 64);
+    if (tid == 0) for (int i = 0; i < 32; ++i) ph_acc[i] = 0;
+    long long ph_clock = clock64();
+#endif
+    if (is_driver) {
+        // ================================ driver warp: tensor core + bulk TMA ================================
+        if (elect_one()) {
+            auto wait_ready = [&] { mbar_wait(rdy, phs); phs ^= 1u; tc_fence_after(); };
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                // M1: Z2 = H1 . W2^T -> ACC, and the H1 tile image -> HBM.  The store is issued FIRST: tcgen05.mma issue
+                // blocks while the tensor core's queue is full, the bulk copy then runs beside the MMAs
+                wait_ready();
+                bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2);
+                bulk_commit();
+#pragma unroll
+                for (int kk = 0; kk < H / 16; ++kk)
+                    umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
+                              make_idesc_major(128, 256, 0, 0), kk > 0 ? 1u : 0u);
+                umma_commit(bar0);
+                bulk_wait_read_all();                      // the store has read the tile: the workers may overwrite it with H2
+                mbar_arrive(bar_st);
+                // MH: head outputs = H2 . WHT -> HEAD (16 columns: hi | hi | lo parts of Wh; WHT read MN-major)
+                wait_ready();
+#pragma unroll
+                for (int kk = 0; kk < H / 16; ++kk)
+                    umma_bf16(tmem_base + C_HEAD, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(wht_addr + kk * 2 * ksG, ksG, ksS),
+                              make_idesc_major(128, 16, 0, 1), kk > 0 ? 1u : 0u);
+                umma_commit(bar1);
+                // M2: dH2 = DOUT . Wh -> ACC (one K=16 MMA);  dWh += H2^T . DOUT -> GWH (H2 tile and DOUT read MN-major)
+                wait_ready();
+                umma_bf16(tmem_base + C_ACC, make_desc_raw(dout_addr, ksS, ksG), make_desc_raw(wht_addr, ksS, ksG), make_idesc_major(128, 256, 0, 0), 0u);
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh)             // hidden units 0..127 / 128..255 = accumulator lanes
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)         // K = 16 rows of the tile per step
+                        umma_bf16(tmem_base + C_GWH + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                                  make_desc_raw(dout_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(bar1);
+                // M3: dH1 = dZ2 . W2 -> ACC (W2 tile read MN-major);  db2 += dZ2^T . XB -> GB2 (its ones column is db2);
+                //     then the dZ2 tile image -> HBM
+                wait_ready();
+                bulk_store(p.dz2_out + tile * (128 * H), t_addr, 128 * H * 2);
+                bulk_commit();
+#pragma unroll
+                for (int kk = 0; kk < H / 16; ++kk)        // K = layer-2 output index j: 16 rows of the W2 tile per step
+                    umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO),
+                              make_desc_raw(w_addr + kk * 2 * kSBO, /*LBO: K groups*/ kSBO, /*SBO: N groups*/ kLBO), make_idesc_major(128, 256, 0, 1), kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16(tmem_base + C_GB2 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                                  make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(bar0);
+                bulk_wait_read_all();
+                mbar_arrive(bar_st);
+                // M4: dW1 | db1 += dZ1^T . [x_hi | x_lo | 1] -> GW1
+                wait_ready();
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16(tmem_base + C_GW1 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                                  make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(bar1);
+            }
+            bulk_wait_all();                               // the last tile images have reached global memory
+        }
+        __syncwarp();
+    } else
+    // ======================================== worker warps: CUDA-core phases ========================================
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int64_t row0 = tile * 128;
         const bool has_next = tile + gridDim.x < ntiles;
         // ---- P1: H1 (computed during the previous tile's M3) -> tile + TMEM stash; XB = [x_hi | x_lo | 1]
         if (it > 0) { mbar_wait(bar1, ph1); ph1 ^= 1u; tc_fence_after(); }   // M4 of the previous tile has read the tile and XB
+        TMLA_PH(0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                      // a quarter-warp writes 8 different rows of one chunk column: conflict-free
             uint8_t *dst = Ts + ((l1row + 8 * i) >> 3) * kSBO + (l1col >> 3) * kLBO + (lane & 7) * 16;
@@ -322,17 +417,10 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        worker_sync();
+        TMLA_PH(1);
         // ---- M1: Z2 = H1 . W2^T -> ACC;  meanwhile the H1 image -> HBM, H1 rows -> TMEM stash, next-tile prefetch
-        if (warp_u == 0 && elect_one()) {
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < H / 16; ++kk)
-                umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
-                          make_idesc_major(128, 256, 0, 0), kk > 0 ? 1u : 0u);
-            umma_commit(bar0);
-        }
-        if (tid == 32) { bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2); bulk_commit(); }   // the H1 tile image -> HBM, asynchronously
+        if (tid == 0) mbar_arrive(rdy);                    // -> driver: M1 (+ H1 image store)
         if (has_next) {                                    // xs is free (layer 1 and XB of this tile are done), so is this tile's index slot
             fetch_rows((it + 1) & 1u);
             fetch_index(it & 1u, tile + 2 * (int64_t)gridDim.x);
@@ -351,9 +439,12 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
+        TMLA_PH(2);
         tc_fence_after();
-        if (tid == 32) bulk_wait_read_all();                // the bulk store has read the tile: it may be overwritten
-        __syncthreads();
+        mbar_wait(bar_st, phs);                            // the H1 image store has read the tile: it may be overwritten
+        phs ^= 1u;
+        worker_sync();
+        TMLA_PH(3);
         // ---- P3: H2 = tanh(Z2 + b2) -> tile
         {
             const uint32_t taddr = lane_base + C_ACC + cq * 64;
@@ -379,18 +470,13 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();                                   // ACC drained, H2 tile complete
+        worker_sync();                                   // ACC drained, H2 tile complete
+        TMLA_PH(4);
         // ---- MH: head outputs = H2 . WHT -> HEAD (16 columns: hi | hi | lo parts of Wh; WHT read MN-major)
-        if (warp_u == 0 && elect_one()) {
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < H / 16; ++kk)
-                umma_bf16(tmem_base + C_HEAD, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(wht_addr + kk * 2 * ksG, ksG, ksS),
-                          make_idesc_major(128, 16, 0, 1), kk > 0 ? 1u : 0u);
-            umma_commit(bar1);
-        }
+        if (tid == 0) mbar_arrive(rdy);                    // -> driver: MH
         mbar_wait(bar1, ph1);
         ph1 ^= 1u;
+        TMLA_PH(5);
         tc_fence_after();
         // ---- P4: loss of row rt (threads of column quarter 0), d(loss)/d(head output) -> DOUT tile (bf16 hi | lo | hi)
         if (cq == 0) {
@@ -459,21 +545,13 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        worker_sync();
+        TMLA_PH(6);
         // ---- M2: dH2 = DOUT . Wh -> ACC (one K=16 MMA);  dWh += H2^T . DOUT -> GWH (H2 tile and DOUT read MN-major)
-        if (warp_u == 0 && elect_one()) {
-            tc_fence_after();
-            umma_bf16(tmem_base + C_ACC, make_desc_raw(dout_addr, ksS, ksG), make_desc_raw(wht_addr, ksS, ksG), make_idesc_major(128, 256, 0, 0), 0u);
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh)                 // hidden units 0..127 / 128..255 = accumulator lanes
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)             // K = 16 rows of the tile per step
-                    umma_bf16(tmem_base + C_GWH + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
-                              make_desc_raw(dout_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bar1);
-        }
+        if (tid == 0) mbar_arrive(rdy);                    // -> driver: M2
         mbar_wait(bar1, ph1);
         ph1 ^= 1u;
+        TMLA_PH(7);
         tc_fence_after();
         // ---- P5: dZ2 = dH2 * (1 - H2^2) -> tile (this thread overwrites its own H2 chunks; M2 has finished reading them)
         {
@@ -501,23 +579,10 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         cp_async_wait_all();                               // this thread's pieces of the next tile's rows have landed
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        worker_sync();
+        TMLA_PH(8);
         // ---- M3: dH1 = dZ2 . W2 -> ACC (W2 tile read MN-major);  db2 += dZ2^T . XB -> GB2 (its ones column is db2)
-        if (warp_u == 0 && elect_one()) {
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < H / 16; ++kk)            // K = layer-2 output index j: 16 rows of the W2 tile per step
-                umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO),
-                          make_desc_raw(w_addr + kk * 2 * kSBO, /*LBO: K groups*/ kSBO, /*SBO: N groups*/ kLBO), make_idesc_major(128, 256, 0, 1), kk > 0 ? 1u : 0u);
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh)
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    umma_bf16(tmem_base + C_GB2 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
-                              make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bar0);
-        }
-        if (tid == 32) { bulk_store(p.dz2_out + tile * (128 * H), t_addr, 128 * H * 2); bulk_commit(); }  // the dZ2 tile image -> HBM
+        if (tid == 0) mbar_arrive(rdy);                    // -> driver: M3 (+ dZ2 image store)
         if (has_next) {
             fetch_loss_inputs((it + 1) & 1u);              // ls is free: P4 of this tile is done
             cp_async_commit();
@@ -525,9 +590,12 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         mbar_wait(bar0, ph0);
         ph0 ^= 1u;
+        TMLA_PH(9);
         tc_fence_after();
-        if (tid == 32) bulk_wait_read_all();
-        __syncthreads();
+        mbar_wait(bar_st, phs);                            // the dZ2 image store has read the tile
+        phs ^= 1u;
+        worker_sync();
+        TMLA_PH(10);
         // ---- P7: dZ1 = dH1 * (1 - H1^2) -> tile (H1 from the TMEM stash, 8 packed pairs per 16 accumulator columns).
         // Not software-pipelined: the next tile's H1 (32 registers) is live here and this is the register-pressure peak.
         {
@@ -554,21 +622,15 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         cp_async_wait_all();                               // next tile's loss inputs and the index after it have landed
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        worker_sync();
+        TMLA_PH(11);
         // ---- M4: dW1 | db1 += dZ1^T . [x_hi | x_lo | 1] -> GW1
-        if (warp_u == 0 && elect_one()) {
-            tc_fence_after();
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh)
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    umma_bf16(tmem_base + C_GW1 + mh * 16, make_desc_raw(t_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
-                              make_desc_raw(xb_addr + kk * 2 * ksG, ksG, ksS), make_idesc_major(128, 16, 1, 1), (it > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bar1);
-        }
+        if (tid == 0) mbar_arrive(rdy);                    // -> driver: M4
     }
-    mbar_wait(bar1, ph1);                                  // the last M4
-    tc_fence_after();
+    if (!is_driver) { mbar_wait(bar1, ph1); tc_fence_after(); }   // the last M4
+#ifdef TMLA_PHASE_CLOCKS
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 32; ++i) g_phase_cycles[i] += ph_acc[i];
+#endif
 
     // ---- flush: TMEM gradient accumulators (lane = hidden unit) -> one atomic per value; scalar sums
     if (warp < 4) {
@@ -604,7 +666,6 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
         }
     }
-    if (tid == 32) bulk_wait_all();                        // the last tile images have reached global memory
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
@@ -803,7 +864,7 @@ static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
         attr_done = 1;
     }
     const unsigned grid = (unsigned)std::min<int64_t>((a.M + 127) / 128, sm_count_train());
-    tc_tower_train_kernel<D, NOUT><<<grid, kTrainThreads, smem, st>>>(a);
+    tc_tower_train_kernel<D, NOUT><<<grid, kTrainThreads + 32, smem, st>>>(a);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -861,6 +922,14 @@ int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_p
     TMLA_REQUIRE(Xt && Yt && G && rows_padded > 0 && rows_padded % 128 == 0, "bad arguments (rows_padded must be a positive multiple of 128)");
     return tc_wgrad_tiled_launch(Xt, Yt, G, rows_padded, (cudaStream_t)stream);
 }
+
+#ifdef TMLA_PHASE_CLOCKS
+int tmla_debug_phase_cycles(unsigned long long *out32, int reset) {      // debug builds only; not part of include/tmla.h
+    if (out32) TMLA_CUDA(cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof(g_phase_cycles)));
+    if (reset) { unsigned long long z[32] = {0}; TMLA_CUDA(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z))); }
+    return TMLA_OK;
+}
+#endif
 
 int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream) {
     TMLA_REQUIRE(A && B && out && mode >= 0 && mode <= 2, "bad arguments");
