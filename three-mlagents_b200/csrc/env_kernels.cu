@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(kBlock)
 step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t step_index,
             const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
-            float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag) {
+            float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag,
+            float *__restrict__ compact) {
+    // compact != NULL (host-facing step): finished envs append one record {env index, ep_return, ep_length, terminal_obs[D]}
+    // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays
     constexpr int D = Task::D;
     __shared__ __align__(16) float s_obs[kBlock * D];
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
@@ -116,7 +119,14 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             if (terminal_obs) thread_store_obs<D>(o, terminal_obs + i * D);
             if (ep_return) ep_return[i] = s.ep_ret;
             if (ep_length) ep_length[i] = s.steps;
-            if (n_done) atomicAdd(n_done, 1);
+            int slot = 0;
+            if (n_done) slot = atomicAdd(n_done, 1);
+            if (compact) {
+                float *rec = compact + (int64_t)slot * (3 + D);
+                rec[0] = __int_as_float((int)i); rec[1] = s.ep_ret; rec[2] = __int_as_float(s.steps);
+#pragma unroll
+                for (int j = 0; j < D; ++j) rec[3 + j] = o[j];
+            }
             Task::reset(s, seed, env_base + (uint64_t)i, step_index + 1, TMLA_TAG_RESET);
             Task::observe(s, o);
         }
@@ -440,10 +450,11 @@ static const int kStateSize[TMLA_NUM_TASKS] = {(int)sizeof(tmla_basic_state), (i
 
 // staging layout shared by the device block and its pinned host mirror (16-byte aligned sections):
 //   actions i32[n] | obs f32[n,D] | reward f32[n] | done u8[n] | truncated u8[n] | flags i32[4] {n_done, bad_action}
-//   | terminal_obs f32[n,D] | ep_return f32[n] | ep_length i32[n]
-// obs..flags is one contiguous span -> ONE device-to-host copy per step; the episode-end payload behind it
-// is fetched only when n_done > 0.
-struct StageLayout { size_t act, obs, rew, done, trunc, flags, tobs, ret, len, end; };
+//   | terminal_obs f32[n,D] | ep_return f32[n] | ep_length i32[n] | compact records f32[n,3+D]
+// obs..flags is one contiguous span -> ONE device-to-host copy per step; the episode-end payload is fetched as
+// n_done compact records (36 B each for ball3d) and scattered into the dense host arrays: only the entries of envs
+// whose `done` flag is set are meaningful after a step.
+struct StageLayout { size_t act, obs, rew, done, trunc, flags, tobs, ret, len, crec, end; };
 static StageLayout stage_layout(int64_t n, int D) {
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
     StageLayout L;
@@ -456,7 +467,8 @@ static StageLayout stage_layout(int64_t n, int D) {
     L.tobs = L.flags + 16;
     L.ret = L.tobs + 4 * n * D;
     L.len = L.ret + 4 * n;
-    L.end = L.len + 4 * n;
+    L.crec = L.len + 4 * n;                     // compact episode-end records {idx, ret, len, tobs[D]}, at most n of them
+    L.end = L.crec + 4 * n * (3 + D);
     return L;
 }
 
@@ -554,7 +566,7 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
     cudaStream_t st = (cudaStream_t)stream;
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
-                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag)));
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     return TMLA_OK;
@@ -576,15 +588,25 @@ int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                              ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
                              (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
-                             (float *)(d + L.tobs), (float *)(d + L.ret), (int32_t *)(d + L.len), dflags, dflags + 1)));
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec))));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     TMLA_CUDA(cudaMemcpyAsync(p + L.obs, d + L.obs, L.tobs - L.obs, cudaMemcpyDeviceToHost, st));
     TMLA_CUDA(cudaStreamSynchronize(st));
     const int32_t nd = hflags[0];
-    if (nd > 0) {   // episode-end payload (terminal obs, Monitor r/l) only when something finished
-        TMLA_CUDA(cudaMemcpyAsync(p + L.tobs, d + L.tobs, L.end - L.tobs, cudaMemcpyDeviceToHost, st));
+    if (nd > 0) {   // episode-end payload: nd compact records, scattered into the dense host arrays
+        const size_t rec = (size_t)4 * (3 + D);
+        TMLA_CUDA(cudaMemcpyAsync(p + L.crec, d + L.crec, rec * nd, cudaMemcpyDeviceToHost, st));
         TMLA_CUDA(cudaStreamSynchronize(st));
+        float *tobs = (float *)(p + L.tobs), *ret = (float *)(p + L.ret);
+        int32_t *len = (int32_t *)(p + L.len);
+        for (int32_t s = 0; s < nd; ++s) {
+            const float *r = (const float *)(p + L.crec + rec * s);
+            int32_t i, l;
+            memcpy(&i, r, 4); memcpy(&l, r + 2, 4);
+            ret[i] = r[1]; len[i] = l;
+            memcpy(tobs + (size_t)i * D, r + 3, (size_t)4 * D);
+        }
     }
     if (n_done) *n_done = nd;
     if (hflags[1]) {
@@ -626,10 +648,15 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
     memcpy(reward, p + L.rew, 4 * n);
     memcpy(done, p + L.done, n);
     memcpy(truncated, p + L.trunc, n);
-    if (nd > 0) {
-        if (terminal_obs) memcpy(terminal_obs, p + L.tobs, 4 * n * D);
-        if (ep_return) memcpy(ep_return, p + L.ret, 4 * n);
-        if (ep_length) memcpy(ep_length, p + L.len, 4 * n);
+    if (nd > 0) {   // "written only where done": copy the rows of the finished envs, not three dense arrays
+        const float *tobs = (const float *)(p + L.tobs), *ret = (const float *)(p + L.ret);
+        const int32_t *len = (const int32_t *)(p + L.len);
+        for (int64_t i = 0; i < n; ++i) {
+            if (!done[i]) continue;
+            if (terminal_obs) memcpy(terminal_obs + i * D, tobs + i * D, (size_t)4 * D);
+            if (ep_return) ep_return[i] = ret[i];
+            if (ep_length) ep_length[i] = len[i];
+        }
     }
     if (n_done) *n_done = nd;
     return rc;

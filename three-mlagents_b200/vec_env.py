@@ -35,11 +35,12 @@ STATE_DTYPES = {   # wire structs of include/tmla.h
 
 class LazyInfos(Sequence):
     """`infos` of one vec-step, materialised per index on demand (64K dicts per step would
-    dominate the step time; SB3 only reads the entries of finished episodes)."""
+    dominate the step time; SB3 only reads the entries of finished episodes).  Holds a snapshot of the
+    finished envs' payload only (`finished` sorted env indices -> compact rows)."""
 
-    def __init__(self, n, done, truncated, terminal_obs, ep_return, ep_length, t_elapsed):
+    def __init__(self, n, done, truncated, finished, terminal_obs, ep_return, ep_length, t_elapsed):
         self._n, self._done, self._trunc = n, done, truncated
-        self._tobs, self._ret, self._len, self._t = terminal_obs, ep_return, ep_length, t_elapsed
+        self._idx, self._tobs, self._ret, self._len, self._t = finished, terminal_obs, ep_return, ep_length, t_elapsed
 
     def __len__(self):
         return self._n
@@ -53,14 +54,15 @@ class LazyInfos(Sequence):
             raise IndexError(i)
         info: dict[str, Any] = {"TimeLimit.truncated": bool(self._trunc[i])}
         if self._done[i]:
-            info["terminal_observation"] = self._tobs[i]
-            info["episode"] = {"r": round(float(self._ret[i]), 6), "l": int(self._len[i]), "t": round(self._t, 6)}
-            info["steps"] = int(self._len[i])
+            k = int(np.searchsorted(self._idx, i))
+            info["terminal_observation"] = self._tobs[k]
+            info["episode"] = {"r": round(float(self._ret[k]), 6), "l": int(self._len[k]), "t": round(self._t, 6)}
+            info["steps"] = int(self._len[k])
         return info
 
     def finished(self):
         """Indices of envs whose episode ended on this step."""
-        return np.nonzero(self._done)[0]
+        return self._idx if self._idx is not None else np.nonzero(self._done)[0]
 
 
 class CudaVecEnv:
@@ -129,14 +131,15 @@ class CudaVecEnv:
         trunc = self._trunc.astype(bool)
         obs, rew = self._obs.copy(), self._rew.copy()
         if nd.value:
-            infos = LazyInfos(self.num_envs, done, trunc, self._tobs.copy(), self._ret.copy(), self._len.copy(),
-                              time.time() - self._t0)
+            fin = np.nonzero(done)[0]                       # the pinned arrays are valid exactly at these indices
+            ret, length = self._ret[fin], self._len[fin]
+            infos = LazyInfos(self.num_envs, done, trunc, fin, self._tobs[fin], ret, length, time.time() - self._t0)
             if self._monitor is not None:
                 t = round(time.time() - self._t0, 6)
-                for i in np.nonzero(done)[0]:
-                    self._monitor.write(f"{round(float(self._ret[i]), 6)},{int(self._len[i])},{t}\n")
+                for r, l in zip(ret, length):
+                    self._monitor.write(f"{round(float(r), 6)},{int(l)},{t}\n")
         else:
-            infos = LazyInfos(self.num_envs, done, trunc, None, None, None, 0.0)
+            infos = LazyInfos(self.num_envs, done, trunc, None, None, None, None, 0.0)
         return obs, rew, done, infos
 
     def step(self, actions):
