@@ -104,6 +104,10 @@ int tmla_reset_host(tmla_env *h, float *obs);
 int tmla_host_views(tmla_env *h, int32_t **actions, float **obs, float **reward, uint8_t **done,
                     uint8_t **truncated, float **terminal_obs, float **ep_return, int32_t **ep_length);
 int tmla_step_pinned(tmla_env *h, int64_t *n_done);
+/* The same episode-end payload as *n_done compact records in the pinned block, in no particular order:
+ * {int32 env index, float ep_return, int32 ep_length, float terminal_obs[D]} = (3 + D) 32-bit words each — what a
+ * binding should read instead of scanning `done` (Monitor / infos of the finished envs only). */
+int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_record);
 
 /* state injection / extraction (parity tests): `aos` is n structs of the task's wire type. */
 int tmla_get_state(tmla_env *h, void *aos, void *stream);

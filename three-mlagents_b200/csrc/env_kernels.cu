@@ -632,6 +632,14 @@ int tmla_host_views(tmla_env *h, int32_t **actions, float **obs, float **reward,
     return TMLA_OK;
 }
 
+int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_record) {
+    TMLA_REQUIRE(h && records && floats_per_record, "NULL argument");
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    *records = (const float *)((char *)h->h_stage + L.crec);
+    *floats_per_record = 3 + kObsDim[h->task];
+    return TMLA_OK;
+}
+
 int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
                    float *terminal_obs, float *ep_return, int32_t *ep_length, int64_t *n_done) {
     TMLA_REQUIRE(h, "handle is NULL");

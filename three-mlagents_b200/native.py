@@ -53,6 +53,7 @@ SIGNATURES = {
     "tmla_reset_host": (_i, [vp, vp]),
     "tmla_host_views": (_i, [vp] + [C.POINTER(vp)] * 8),
     "tmla_step_pinned": (_i, [vp, C.POINTER(i64)]),
+    "tmla_host_records": (_i, [vp, C.POINTER(vp), C.POINTER(i32)]),
     "tmla_get_state": (_i, [vp, vp, vp]),
     "tmla_set_state": (_i, [vp, vp, vp]),
     "tmla_check_actions": (_i, [vp, vp]),

@@ -98,6 +98,10 @@ class CudaVecEnv:
         self._tobs = view(ptrs[5], C.c_float, (n, d))
         self._ret = view(ptrs[6], C.c_float, (n,))
         self._len = view(ptrs[7], C.c_int32, (n,))
+        recp, recw = native.vp(), native.i32(0)
+        check(lib.tmla_host_records(self._h, C.byref(recp), C.byref(recw)))
+        rec = view(recp, C.c_float, (n, recw.value))          # compact episode-end records {idx, ret, len, tobs[d]}
+        self._rec_f, self._rec_i = rec, rec.view(np.int32)
         self._actions = None
         self._t0 = time.time()
         self._dev = None      # device-side buffers for step_tensor, allocated lazily
@@ -131,9 +135,11 @@ class CudaVecEnv:
         trunc = self._trunc.astype(bool)
         obs, rew = self._obs.copy(), self._rew.copy()
         if nd.value:
-            fin = np.nonzero(done)[0]                       # the pinned arrays are valid exactly at these indices
-            ret, length = self._ret[fin], self._len[fin]
-            infos = LazyInfos(self.num_envs, done, trunc, fin, self._tobs[fin], ret, length, time.time() - self._t0)
+            k = int(nd.value)                               # compact records of the finished envs, sorted by env index
+            order = np.argsort(self._rec_i[:k, 0], kind="stable")
+            rec_f, rec_i = self._rec_f[:k][order], self._rec_i[:k][order]
+            fin, ret, length = rec_i[:, 0].astype(np.int64), rec_f[:, 1], rec_i[:, 2]
+            infos = LazyInfos(self.num_envs, done, trunc, fin, rec_f[:, 3:], ret, length, time.time() - self._t0)
             if self._monitor is not None:
                 t = round(time.time() - self._t0, 6)
                 for r, l in zip(ret, length):
