@@ -7,12 +7,15 @@
 // that the unfused path runs as 9 kernels with every [rows,256] activation making a round trip through HBM
 // (10 KB per sample).  Here one persistent CTA per SM walks 128-row tiles and keeps everything on chip.
 // CUDA cores do only the element-wise work, one thread = (row, 64-column quarter); every reduction over the
-// rows of a tile is a tcgen05.mma whose accumulator lives in TMEM for the whole kernel:
+// rows of a tile is a tcgen05.mma whose accumulator lives in TMEM for the whole kernel.  17 warps: 16 workers run the
+// P phases, one DRIVER warp issues every MMA group (M*) and bulk-TMA store — tcgen05.mma issue blocks while the tensor
+// core's queue is full, which would otherwise stall a worker warp (and with it every CTA barrier) for the length of
+// the group.  Workers signal "operands staged" on one mbarrier, the driver commits each group to a "done" mbarrier:
 //
 //   P1  layer 1 (K = obs_dim) on CUDA cores -> H1 (bf16): shared-memory tile (K-major) + a TMEM stash for P7
 //   M1  Z2 = H1 . W2^T            16 x (M128 N256 K16), W2 resident in shared memory          -> ACC (TMEM)
 //   P3  ACC -> bias + tanh -> H2 (bf16) overwrites the tile
-//   MH  head outputs = H2 . [Wh_hi | Wh_lo]^T  (N = 16)                                       -> HEAD (TMEM)
+//   MH  head outputs = H2 . WHT  (N = 16: hi | hi | lo parts of Wh, WHT read MN-major)        -> HEAD (TMEM)
 //   P4  loss per row, d(loss)/d(head) written as a [128][16] bf16 hi/lo tile DOUT
 //   M2  dH2 = DOUT . Wh (one K=16 MMA) -> ACC;   dWh += H2^T . DOUT (H2 tile read MN-major)  -> GWH (TMEM)
 //   P5  dZ2 = ACC * (1 - H2^2) -> tile
