@@ -52,15 +52,17 @@ def test_train_task_ball3d_defaults_small(tmp_path, monkeypatch):
     assert res.algorithm == "ppo" and res.total_timesteps == 16384 and np.isfinite(res.mean_reward)
 
 
-@pytest.mark.parametrize("task,steps", [("ball3d", 40_000_000), ("gridworld", 40_000_000), ("push", 60_000_000), ("walljump", 40_000_000)])
-def test_ppo_reaches_registry_reward_threshold(task, steps, tmp_path, monkeypatch):
+@pytest.mark.parametrize("task,steps,episodes", [("ball3d", 40_000_000, 256), ("gridworld", 80_000_000, 8192),
+                                                 ("push", 120_000_000, 2048), ("walljump", 40_000_000, 256)])
+def test_ppo_reaches_registry_reward_threshold(task, steps, episodes, tmp_path, monkeypatch):
     """The whole device-resident pipeline learns: evaluation return above the reference registry's reward_threshold
     (registry.py:74-132: ball3d 150.0, gridworld 0.75, push 0.65, walljump 0.7) with the reference's PPO hyper-parameters
-    and a rollout geometry scaled to 4096 envs (profiles/r1_learn_check.txt)."""
+    and a rollout geometry scaled to 4096 envs (profiles/r1_learn_check.txt).  gridworld saturates near 0.78 (three seeds:
+    0.777 / 0.777 / 0.781), so it is evaluated on 8192 episodes (standard error 0.007) to keep the 0.03 margin meaningful."""
     from three_mlagents_b200.registry import get_task
     from three_mlagents_b200.training import TrainConfig, train_task
 
     monkeypatch.chdir(tmp_path)
-    res = train_task(TrainConfig(task, total_timesteps=steps, algorithm="ppo", n_envs=4096, eval_episodes=256, eval_freq=10**12,
+    res = train_task(TrainConfig(task, total_timesteps=steps, algorithm="ppo", n_envs=4096, eval_episodes=episodes, eval_freq=10**12,
                                  verbose=0, run_name="thr"), model_kwargs={"n_steps": 128, "batch_size": 32768})
     assert res.mean_reward >= get_task(task).reward_threshold, (task, res.mean_reward)
