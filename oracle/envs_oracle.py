@@ -14,6 +14,7 @@ Reference anchors (relative to /root/reference/backend):
   gridworld  examples/gridworld.py:14-95
   push       examples/push.py:10-125
   walljump   examples/walljump.py:14-98
+  brickbreak examples/brick_break.py:11-133
   adapter    mlagents/envs.py:87-159  (time-limit truncation, terminated/truncated split)
   vec/auto-reset + Monitor: SB3 DummyVecEnv/Monitor semantics, SURVEY.md §8(a) A7
 Reset draws use this repo's Philox streams (oracle/philox.py), not MT19937.
@@ -45,6 +46,7 @@ TASKS = {
     "gridworld": (4, 5, 100),     # gridworld.py:14-30 ; envs.py:181-187
     "push":      (4, 5, 120),     # push.py:10-24 ; envs.py:193-199
     "walljump":  (4, 4, 150),     # walljump.py:14-21 ; envs.py:202-213
+    "brickbreak": (45, 3, 2000),  # brick_break.py:14-38 (2 + 2 + 1 + 5*8 obs) ; envs.py:216-227
 }
 
 STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
@@ -56,6 +58,8 @@ STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format o
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
                       ("steps", "<i4"), ("ep_return", "<f4")]),
     "walljump": np.dtype([("agent_x", "<i4"), ("in_air", "<i4"), ("wall", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "brickbreak": np.dtype([("pos", "<f8", (2,)), ("vel", "<f8", (2,)), ("paddle", "<f8"), ("bricks", "u1", (40,)),
+                            ("steps", "<i4"), ("ep_return", "<f4")]),
 }
 
 f32 = np.float32
@@ -128,7 +132,28 @@ def observe(task, st):
         x = st["agent_x"].astype(np.float64)
         return np.stack([(WJ_WIDTH - 1 - x) / (WJ_WIDTH - 1), (WJ_WALL_X - x) / (WJ_WIDTH - 1), st["wall"].astype(np.float64),
                          (st["in_air"] == 0).astype(np.float64)], axis=1).astype(np.float32)
+    if task == "brickbreak":     # brick_break.py:118-126: f64 concatenate, the adapter casts to f32 (envs.py:150)
+        return np.concatenate([st["pos"] / np.array([40.0, 40.0]), st["vel"], (st["paddle"] / 40.0)[:, None],
+                               st["bricks"].astype(np.float64)], axis=1).astype(np.float32)
     raise KeyError(task)
+
+
+# ---- deterministic sin/cos on [-pi/4, pi/4] for the brickbreak serve angle: Horner in plain f64 mul/add (no fma), the
+# ---- same operation order as csrc/envs.cuh so that oracle and device resets agree bit for bit
+_SIN_C = (-1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800, -1.0 / 1307674368000)
+_COS_C = (-1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600, -1.0 / 87178291200, 1.0 / 20922789888000)
+
+
+def sin_cos_quarter(y):
+    y = np.asarray(y, dtype=np.float64)
+    z = y * y
+    ps = np.full_like(z, _SIN_C[-1])
+    for c in _SIN_C[-2::-1]:
+        ps = ps * z + c
+    pc = np.full_like(z, _COS_C[-1])
+    for c in _COS_C[-2::-1]:
+        pc = pc * z + c
+    return y + (y * z) * ps, 1.0 + z * pc
 
 
 # ---- transitions (no reset) -------------------------------------------------------------
@@ -225,6 +250,41 @@ def transition(task, st, actions):
         done = goal | (st["steps"] >= 150)                           # walljump.py:94-96
         hit = st["steps"] >= max_steps
         terminated, truncated = done & ~hit, hit
+    elif task == "brickbreak":
+        paddle = st["paddle"] + np.where(a == 0, -3.0, np.where(a == 2, 3.0, 0.0))       # brick_break.py:51-54
+        paddle = np.minimum(np.maximum(paddle, 4.0), 36.0)                                # :56-58
+        pos = st["pos"] + st["vel"]                                                        # :61
+        vel = st["vel"].copy()
+        wall_x = (pos[:, 0] <= 1.0) | (pos[:, 0] >= 39.0)                                  # :67-73
+        vel[:, 0] = np.where(wall_x, -vel[:, 0], vel[:, 0])
+        vel[:, 1] = np.where(pos[:, 1] >= 39.0, -vel[:, 1], vel[:, 1])
+        reward = np.zeros(n, np.float64)
+        hit = (vel[:, 1] < 0) & (pos[:, 1] - 1.0 <= 2.0) & (pos[:, 0] >= paddle - 4.0) & (pos[:, 0] <= paddle + 4.0)   # :76-81
+        vel[:, 1] = np.where(hit, -vel[:, 1], vel[:, 1])
+        offset = (pos[:, 0] - paddle) / 4.0                                                # :83
+        vel[:, 0] = np.where(hit, vel[:, 0] + offset * 0.5, vel[:, 0])
+        reward = np.where(hit, 0.1, reward)
+        bricks = st["bricks"].copy()
+        found = np.zeros(n, bool)
+        for r in range(5):                                                                  # :88-105, first live brick in row-major order
+            for c in range(8):
+                bx, by = c * 5.0, 20.0 + r * 2.0
+                cond = (~found & (bricks[:, r * 8 + c] == 1) & (pos[:, 0] >= bx) & (pos[:, 0] <= bx + 5.0)
+                        & (pos[:, 1] >= by) & (pos[:, 1] <= by + 2.0))
+                bricks[:, r * 8 + c] = np.where(cond, 0, bricks[:, r * 8 + c])
+                vel[:, 1] = np.where(cond, -vel[:, 1], vel[:, 1])
+                found |= cond
+        reward = np.where(found, 1.0, reward)
+        lost = pos[:, 1] < 1.0                                                              # :109-111
+        reward = np.where(lost, -1.0, reward)
+        cleared = bricks.sum(1) == 0                                                        # :113-115
+        reward = np.where(cleared, 10.0, reward)
+        st["pos"], st["vel"], st["paddle"], st["bricks"] = pos, vel, paddle, bricks
+        st["steps"] += 1
+        done = lost | cleared | (st["steps"] > 2000)                                        # :117-118
+        reward = reward.astype(np.float32)
+        hit_limit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit_limit, hit_limit
     else:
         raise KeyError(task)
     return observe(task, st), reward, terminated, truncated
@@ -276,6 +336,14 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET, episode=None):
         st["agent"] = np.stack([a // 6, a % 6], 1)
         st["box"] = np.stack([bx // 6, bx % 6], 1)
         st["goal_x"] = px.bounded(b[2], 6)
+    elif task == "brickbreak":                                      # brick_break.py:39-46
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        angle = np.pi / 4 + (np.pi / 2) * px.u32_unit(b[0])         # np.random.uniform(pi/4, 3pi/4) = lo + (hi - lo) * u
+        s_, c_ = sin_cos_quarter(angle - np.pi / 2)                 # cos(angle) = -sin(angle - pi/2), sin(angle) = cos(angle - pi/2)
+        st["pos"] = np.array([20.0, 10.0])
+        st["vel"] = np.stack([-s_ * 1.5, c_ * 1.5], 1)
+        st["paddle"] = 20.0
+        st["bricks"] = 1
     elif task == "walljump":                                        # walljump.py:39-45: int(np.random.rand() < 0.7)
         b = px.stream_block(seed, env_ids, k, tag, 0)
         u24 = (b[0] >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)

@@ -18,6 +18,7 @@ STATE_KEYS = {
     "gridworld": ("agent", "green", "red", "goal_type"),
     "push": ("agent", "box", "goal_x"),
     "walljump": ("agent_x", "in_air", "wall"),
+    "brickbreak": ("pos", "vel", "paddle", "bricks"),
 }
 
 

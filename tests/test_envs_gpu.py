@@ -15,7 +15,7 @@ from oracle import envs_oracle as eo
 
 pytestmark = pytest.mark.gpu
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak")
 # north_star: "ball3d trajectories must stay within a stated float tolerance over 1,000 steps".
 # The only non-bit-exact operation on the device is sin(double) (own polynomial vs libm, <= 1 ulp of
 # f64); everything else follows NumPy's rounding sequence exactly, so 1e-5 absolute is generous.
@@ -238,3 +238,39 @@ def test_fast_arithmetic_is_exact():
     assert bad5 == 0
     print("sin_small vs libdevice sin: max distance", sin_ulp, "ulp (double)")
     assert sin_ulp <= 2
+
+
+def test_brickbreak_time_limit_and_clear_bonus_against_oracle():
+    """Paths the 1000-step golden trace cannot reach (brick_break.py:113-118, envs.py:141-145): the adapter's 2000-step
+    truncation and the +10 bonus for the last brick, by state injection, CUDA kernel vs the pinned oracle."""
+    task = "brickbreak"
+    st = np.zeros(4, eo.STATE_DTYPES[task])
+    st["pos"] = [[20.0, 12.0], [20.0, 12.0], [12.3, 19.2], [7.0, 19.5]]
+    st["vel"] = [[0.3, 1.1], [0.3, 1.1], [0.1, 1.4], [0.2, 1.2]]
+    st["paddle"] = 20.0
+    st["bricks"] = 1
+    st["steps"] = [1997, 10, 5, 1998]
+    st["bricks"][2] = 0
+    st["bricks"][2][2] = 1                      # one brick left at column 2, row 0: x in [10, 15], y in [20, 22]
+    env = _vec(task, 4, seed=9)
+    env.set_state(st.copy())
+    ora = st.copy()
+    acts = torch.ones(4, dtype=torch.int32, device="cuda")
+    seen = {"trunc": 0, "clear": 0}
+    for t in range(3):
+        b = env.step_tensor(acts)
+        obs, rew, term, trunc = eo.transition(task, ora, np.ones(4, np.int64))
+        done = term | trunc
+        assert np.array_equal(b["done"].cpu().numpy().astype(bool), done), t
+        assert np.array_equal(b["trunc"].cpu().numpy().astype(bool), trunc & ~term), t
+        assert np.array_equal(b["rew"].cpu().numpy().view(np.uint32), rew.view(np.uint32)), t
+        if done.any():
+            tobs = b["tobs"].cpu().numpy()
+            assert np.array_equal(tobs[done].view(np.uint32), obs[done].view(np.uint32))
+            seen["trunc"] += int((trunc & ~term).sum())
+            seen["clear"] += int((rew[done] == 10.0).sum())
+            got = env.get_state()                # continue the oracle from the device's Philox reset
+            for k in ("pos", "vel", "paddle", "bricks", "steps"):
+                ora[k][done] = got[k][done]
+    assert seen["trunc"] >= 2 and seen["clear"] == 1, seen
+    env.close()

@@ -7,7 +7,7 @@ from oracle import envs_oracle as eo
 from oracle import philox as px
 import replay_util as _replay
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak")
 
 
 def test_philox_known_answers():
@@ -75,6 +75,25 @@ def test_walljump_reset_distribution_matches_reference():
     assert (st["agent_x"] == 0).all() and (st["in_air"] == 0).all() and (ref["agent_x"] == 0).all() and (ref["in_air"] == 0).all()
     assert set(np.unique(st["wall"]).tolist()) == {0, 1} and set(np.unique(ref["wall"]).tolist()) == {0, 1}
     assert abs(st["wall"].mean() - 0.7) < 4 * np.sqrt(0.21 / n) and abs(ref["wall"].mean() - 0.7) < 4 * np.sqrt(0.21 / len(ref["wall"]))
+
+
+def test_brickbreak_reset_distribution_matches_reference():
+    """brick_break.py:39-46: ball at (20, 10), paddle at 20, all 40 bricks, serve angle ~ U(pi/4, 3pi/4) at speed 1.5."""
+    ref = np.load(_replay.GOLDEN + "/brickbreak_resets.npz")
+    n = 200_000
+    st = eo.draw_reset("brickbreak", 7, np.arange(n), 3)
+    for s in (st, ref):
+        assert (s["pos"] == np.array([20.0, 10.0])).all() and (s["paddle"] == 20.0).all() and (s["bricks"] == 1).all()
+        speed = np.linalg.norm(s["vel"], axis=1)
+        assert np.abs(speed - 1.5).max() < 1e-14
+        ang = np.arctan2(s["vel"][:, 1], s["vel"][:, 0])
+        assert ang.min() >= np.pi / 4 - 1e-12 and ang.max() <= 3 * np.pi / 4 + 1e-12
+    ang = np.arctan2(st["vel"][:, 1], st["vel"][:, 0])
+    assert abs(ang.mean() - np.pi / 2) < 4 * (np.pi / 2) / np.sqrt(12 * n) and abs(ang.std() - (np.pi / 2) / np.sqrt(12)) < 0.005
+    # the deterministic polynomial agrees with libm to the last bits
+    y = np.linspace(-np.pi / 4, np.pi / 4, 100001)
+    s_, c_ = eo.sin_cos_quarter(y)
+    assert np.abs(s_ - np.sin(y)).max() < 3e-16 and np.abs(c_ - np.cos(y)).max() < 3e-16
 
 
 @pytest.mark.parametrize("task", ("ball3d", "gridworld", "push"))

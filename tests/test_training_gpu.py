@@ -52,6 +52,16 @@ def test_train_task_ball3d_defaults_small(tmp_path, monkeypatch):
     assert res.algorithm == "ppo" and res.total_timesteps == 16384 and np.isfinite(res.mean_reward)
 
 
+def test_train_task_brickbreak_runs_on_the_unfused_path(tmp_path, monkeypatch):
+    """brickbreak (45 inputs, 3 actions) trains through the three-call bf16 path (the fused kernel covers obs_dim <= 6)."""
+    from three_mlagents_b200.training import TrainConfig, train_task
+
+    monkeypatch.chdir(tmp_path)
+    res = train_task(TrainConfig("brickbreak", total_timesteps=2 * 256 * 128, n_envs=256, eval_episodes=16, eval_freq=10**12, verbose=0,
+                                 run_name="bb"), model_kwargs={"n_steps": 128, "batch_size": 8192})
+    assert res.algorithm == "ppo" and np.isfinite(res.mean_reward) and res.eval_episodes == 16
+
+
 @pytest.mark.parametrize("task,steps,episodes", [("ball3d", 40_000_000, 256), ("gridworld", 80_000_000, 8192),
                                                  ("push", 120_000_000, 2048), ("walljump", 40_000_000, 256)])
 def test_ppo_reaches_registry_reward_threshold(task, steps, episodes, tmp_path, monkeypatch):

@@ -14,7 +14,7 @@
 // CPU side by oracle/envs_oracle.py against reference-made golden traces:
 //     basic      mlagents/envs.py:17-84        ball3d     examples/ball3d.py:10-113
 //     gridworld  examples/gridworld.py:14-95   push       examples/push.py:10-125
-//     walljump   examples/walljump.py:14-98
+//     walljump   examples/walljump.py:14-98    brickbreak examples/brick_break.py:11-133
 //     adapter    mlagents/envs.py:125-152 (steps>=limit -> truncated; terminated = done && !truncated)
 #pragma once
 #include "common.cuh"
@@ -475,6 +475,121 @@ struct WallJumpTask {
         const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                 // walljump.py:39-45
         s.x = 0; s.in_air = 0;
         s.wall = tmla_u24(b.x) < 0.7f ? 1 : 0;                                      // int(np.random.rand() < 0.7)
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};
+
+// ------------------------------------------------------- brickbreak (examples/brick_break.py:11-133)
+// 40x40 court, 8-wide paddle, 5x8 bricks of 5x2 at y = 20..30; the whole state is float64 in the reference (NumPy arrays and
+// Python floats), so every operation below is an explicit f64 add/mul/div in the reference's order (no FMA contraction).
+// The serve angle uses a fixed Horner polynomial for sin/cos (plain mul/add), the same sequence as
+// oracle/envs_oracle.py:sin_cos_quarter, so that oracle and device resets agree bit for bit.
+struct BrickBreakTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
+    static constexpr int D = 45, A = 3, MAX_STEPS = 2000, NBUF = 4;
+    typedef tmla_brickbreak_state Wire;
+    struct State { double px, py, vx, vy, paddle; unsigned long long bricks; int steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int b) { return b < 3 ? 16 : sizeof(int2); }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const double2 p = reinterpret_cast<const double2 *>(buf[0])[i], v = reinterpret_cast<const double2 *>(buf[1])[i];
+        const double2 pb = reinterpret_cast<const double2 *>(buf[2])[i];      // paddle | bricks bit mask
+        const int2 m = reinterpret_cast<const int2 *>(buf[3])[i];
+        return State{p.x, p.y, v.x, v.y, pb.x, (unsigned long long)__double_as_longlong(pb.y), m.x, __int_as_float(m.y)};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        reinterpret_cast<double2 *>(buf[0])[i] = make_double2(s.px, s.py);
+        reinterpret_cast<double2 *>(buf[1])[i] = make_double2(s.vx, s.vy);
+        reinterpret_cast<double2 *>(buf[2])[i] = make_double2(s.paddle, __longlong_as_double((long long)s.bricks));
+        reinterpret_cast<int2 *>(buf[3])[i] = make_int2(s.steps, __float_as_int(s.ep_ret));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        unsigned long long m = 0;
+        for (int b = 0; b < 40; ++b) m |= (unsigned long long)(w.bricks[b] ? 1 : 0) << b;
+        return State{w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.paddle, m, w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w; w.pos[0] = s.px; w.pos[1] = s.py; w.vel[0] = s.vx; w.vel[1] = s.vy; w.paddle = s.paddle;
+        for (int b = 0; b < 40; ++b) w.bricks[b] = (uint8_t)((s.bricks >> b) & 1ull);
+        w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+    }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // brick_break.py:118-126, cast envs.py:150
+        o[0] = __double2float_rn(__ddiv_rn(s.px, 40.0));
+        o[1] = __double2float_rn(__ddiv_rn(s.py, 40.0));
+        o[2] = __double2float_rn(s.vx);
+        o[3] = __double2float_rn(s.vy);
+        o[4] = __double2float_rn(__ddiv_rn(s.paddle, 40.0));
+#pragma unroll
+        for (int b = 0; b < 40; ++b) o[5 + b] = (float)((s.bricks >> b) & 1ull);
+    }
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
+        double paddle = __dadd_rn(s.paddle, a == 0 ? -3.0 : (a == 2 ? 3.0 : 0.0));        // brick_break.py:51-54
+        paddle = fmin(fmax(paddle, 4.0), 36.0);                                            // :56-58
+        const double px = __dadd_rn(s.px, s.vx), py = __dadd_rn(s.py, s.vy);               // :61
+        double vx = s.vx, vy = s.vy;
+        if (px <= 1.0 || px >= 39.0) vx = -vx;                                             // :67-73
+        if (py >= 39.0) vy = -vy;
+        double r = 0.0;
+        if (vy < 0.0 && __dsub_rn(py, 1.0) <= 2.0 && px >= __dsub_rn(paddle, 4.0) && px <= __dadd_rn(paddle, 4.0)) {   // :76-86
+            vy = -vy;
+            const double offset = __ddiv_rn(__dsub_rn(px, paddle), 4.0);
+            vx = __dadd_rn(vx, __dmul_rn(offset, 0.5));
+            r = 0.1;
+        }
+        unsigned long long bricks = s.bricks;
+        if (py >= 20.0 && py <= 30.0) {                                                    // :88-105 (rows span y = 20 .. 30)
+            bool found = false;
+#pragma unroll 1
+            for (int row = 0; row < 5 && !found; ++row) {
+                const double by = 20.0 + 2.0 * row;
+                if (!(py >= by && py <= by + 2.0)) continue;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    const double bx = 5.0 * c;
+                    if (((bricks >> (row * 8 + c)) & 1ull) && px >= bx && px <= bx + 5.0) {
+                        bricks &= ~(1ull << (row * 8 + c));
+                        vy = -vy;
+                        r = 1.0;
+                        found = true;
+                        break;
+                    }
+                }
+            }
+        }
+        bool done = false;
+        if (py < 1.0) { r = -1.0; done = true; }                                           // :109-111
+        if (bricks == 0ull) { r = 10.0; done = true; }                                     // :113-115
+        s.px = px; s.py = py; s.vx = vx; s.vy = vy; s.paddle = paddle; s.bricks = bricks;
+        s.steps += 1;
+        if (s.steps > 2000) done = true;                                                   // :117-118
+        reward = __double2float_rn(r);
+        trunc = s.steps >= MAX_STEPS;                                                      // envs.py:141-145
+        term = done && !trunc;
+    }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                        // brick_break.py:39-46
+        const double angle = __dadd_rn(0.78539816339744830962, __dmul_rn(1.57079632679489661923, u32_to_unit(b.x)));
+        const double y = __dsub_rn(angle, 1.57079632679489661923), z = __dmul_rn(y, y);
+        double ps = -1.0 / 1307674368000.0, pc = 1.0 / 20922789888000.0;
+        const double sc[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
+        const double cc[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -1.0 / 2.0};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ps = __dadd_rn(__dmul_rn(ps, z), sc[j]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) pc = __dadd_rn(__dmul_rn(pc, z), cc[j]);
+        const double sn = __dadd_rn(y, __dmul_rn(__dmul_rn(y, z), ps)), cs = __dadd_rn(1.0, __dmul_rn(z, pc));
+        s.px = 20.0; s.py = 10.0;
+        s.vx = __dmul_rn(-sn, 1.5); s.vy = __dmul_rn(cs, 1.5);                             // cos(angle) = -sin(y), sin(angle) = cos(y)
+        s.paddle = 20.0;
+        s.bricks = (1ull << 40) - 1ull;
         s.steps = 0; s.ep_ret = 0.0f;
     }
 };

@@ -97,3 +97,7 @@ def make_push_env() -> CudaTaskEnv:         # envs.py:190-199
 
 def make_walljump_env() -> CudaTaskEnv:     # envs.py:202-213
     return CudaTaskEnv("walljump")
+
+
+def make_brick_break_env() -> CudaTaskEnv:  # envs.py:216-227
+    return CudaTaskEnv("brickbreak")

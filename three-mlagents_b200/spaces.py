@@ -62,4 +62,6 @@ def spaces_for(task_id: str):
         return Box(-1.0, 1.0, (4,), np.float32), Discrete(5)
     if task_id == "walljump":              # envs.py:202-213
         return Box(-1.0, 1.0, (4,), np.float32), Discrete(4)
+    if task_id == "brickbreak":            # envs.py:216-227 (shape probed from BrickBreakEnv().reset(): 2 + 2 + 1 + 40)
+        return Box(-np.inf, np.inf, (45,), np.float32), Discrete(3)
     raise KeyError(task_id)

@@ -30,6 +30,8 @@ STATE_DTYPES = {   # wire structs of include/tmla.h
     "push": np.dtype([("agent", "<i4", (2,)), ("box", "<i4", (2,)), ("goal_x", "<i4"),
                       ("steps", "<i4"), ("ep_return", "<f4")]),
     "walljump": np.dtype([("agent_x", "<i4"), ("in_air", "<i4"), ("wall", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "brickbreak": np.dtype([("pos", "<f8", (2,)), ("vel", "<f8", (2,)), ("paddle", "<f8"), ("bricks", "u1", (40,)),
+                            ("steps", "<i4"), ("ep_return", "<f4")]),
 }
 
 
