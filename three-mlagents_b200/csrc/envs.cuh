@@ -146,14 +146,24 @@ struct Ball3DTask {
         const double ab = fma(b, z2, a), cd = fma(c.s15, z2, cc);
         return fma(x * z, fma(cd, z4, ab), x);
     }
-    struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; uint32_t episode; };
+    // rx/rz change only when an action tilts THAT axis (at most one per step), so G*sin(rot)*DT and the f32 observation of
+    // each axis are cached in the state and only the tilted axis is re-evaluated: one sin polynomial per step instead of two.
+    // Bit-identical by construction (the cached value is what the reference recomputes from an unchanged rot).
+    struct State { double rx, rz; float px, pz, vx, vz; int steps; float ep_ret; uint32_t episode; double axdt, azdt; float orx, orz; };
+    static __device__ __forceinline__ void refresh(State &s) {              // caches from rx/rz (load, state injection, reset)
+        s.axdt = __dmul_rn(__dmul_rn(kB3.g, sin_small(s.rx)), kB3.dt);       // ball3d.py:81-84: (G*sin(rot))*DT
+        s.azdt = __dmul_rn(__dmul_rn(kB3.g, sin_small(s.rz)), kB3.dt);
+        s.orx = __double2float_rn(s.rx); s.orz = __double2float_rn(s.rz);
+    }
     static __host__ __device__ size_t plane_bytes(int b) { return b == 0 ? sizeof(double2) : (b == 1 ? sizeof(float4) : sizeof(int2)); }
 
     static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
         const double2 r = reinterpret_cast<const double2 *>(buf[0])[i];     // 128-bit
         const float4 pv = reinterpret_cast<const float4 *>(buf[1])[i];      // 128-bit
         const int2 m = reinterpret_cast<const int2 *>(buf[2])[i];
-        return State{r.x, r.y, pv.x, pv.y, pv.z, pv.w, m.x & 255, __int_as_float(m.y), (uint32_t)m.x >> 8};   // steps | episode<<8
+        State s{r.x, r.y, pv.x, pv.y, pv.z, pv.w, m.x & 255, __int_as_float(m.y), (uint32_t)m.x >> 8, 0.0, 0.0, 0.0f, 0.0f};   // steps | episode<<8
+        refresh(s);
+        return s;
     }
     static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
         reinterpret_cast<double2 *>(buf[0])[i] = make_double2(s.rx, s.rz);
@@ -161,14 +171,15 @@ struct Ball3DTask {
         reinterpret_cast<int2 *>(buf[2])[i] = make_int2((int)((uint32_t)s.steps | (s.episode << 8)), __float_as_int(s.ep_ret));
     }
     static __device__ State from_wire(const Wire &w) {
-        return State{w.rot[0], w.rot[1], w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.steps, w.ep_return, (uint32_t)w.episode & 0xFFFFFFu};
+        return State{w.rot[0], w.rot[1], w.pos[0], w.pos[1], w.vel[0], w.vel[1], w.steps, w.ep_return, (uint32_t)w.episode & 0xFFFFFFu,
+                     0.0, 0.0, 0.0f, 0.0f};                                    // caches are rebuilt by load()
     }
     static __device__ Wire to_wire(const State &s) {
         Wire w; w.rot[0] = s.rx; w.rot[1] = s.rz; w.pos[0] = s.px; w.pos[1] = s.pz;
         w.vel[0] = s.vx; w.vel[1] = s.vz; w.steps = s.steps; w.ep_return = s.ep_ret; w.episode = (int32_t)s.episode; w.pad_ = 0; return w;
     }
     static __device__ __forceinline__ void observe(const State &s, float *o) {   // ball3d.py:61-72
-        o[0] = __double2float_rn(s.rx); o[1] = __double2float_rn(s.rz);
+        o[0] = s.orx; o[1] = s.orz;
         o[2] = s.px; o[3] = s.pz; o[4] = s.vx; o[5] = s.vz;
     }
     // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
@@ -179,25 +190,25 @@ struct Ball3DTask {
         // XOR-ed into the high word; adding the 0.0 entries is the identity (rot is never -0.0) and is skipped.
         const int td_hi = __double2hiint(c.tilt_delta), td_lo = __double2loint(c.tilt_delta);
         const double sd = __hiloint2double(td_hi ^ (int)((unsigned)a << 31), td_lo);   // a odd -> -delta
-        double rx = s.rx, rz = s.rz;
-        if (a < 2) rx = __dadd_rn(rx, sd);                                          // ball3d.py:77
-        else if (a < 4) rz = __dadd_rn(rz, sd);
-        if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back
-            asm volatile("");     // keep this a branch: 4 conversions on the XU pipe for <1 % of the lanes
-            rx = (double)__double2float_rn(rx);
-            rz = (double)__double2float_rn(rz);
+        if (a < 4) {                                                                // action 4 adds (0, 0): nothing changes
+            const bool tilt_x = a < 2;
+            double rot = __dadd_rn(tilt_x ? s.rx : s.rz, sd);                        // ball3d.py:77
+            if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back (the untouched
+                asm volatile("");     // axis is already an f32 value); kept a branch: conversions for <1 % of the lanes
+                rot = (double)__double2float_rn(rot);
+            }
+            rot = clip_sym(rot, c.max_tilt);                                         // ball3d.py:78 (float64 from here)
+            const double adt = __dmul_rn(__dmul_rn(c.g, sin_small_c(c, rot)), c.dt); // ball3d.py:81-84
+            const float orot = __double2float_rn(rot);
+            if (tilt_x) { s.rx = rot; s.axdt = adt; s.orx = orot; } else { s.rz = rot; s.azdt = adt; s.orz = orot; }
         }
-        rx = clip_sym(rx, c.max_tilt);                                              // ball3d.py:78 (float64 from here)
-        rz = clip_sym(rz, c.max_tilt);
-        const double ax = __dmul_rn(c.g, sin_small_c(c, rx));                       // ball3d.py:81-82
-        const double az = __dmul_rn(c.g, sin_small_c(c, rz));
-        float vx = __double2float_rn(__dadd_rn((double)s.vx, __dmul_rn(ax, c.dt))); // ball3d.py:83-84
-        float vz = __double2float_rn(__dadd_rn((double)s.vz, __dmul_rn(az, c.dt)));
+        float vx = __double2float_rn(__dadd_rn((double)s.vx, s.axdt));              // ball3d.py:83-84
+        float vz = __double2float_rn(__dadd_rn((double)s.vz, s.azdt));
         vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
         vz = __fmul_rn(vz, 0.98f);
         const float px = __fadd_rn(s.px, __fmul_rn(vx, 0.02f));                     // ball3d.py:90
         const float pz = __fadd_rn(s.pz, __fmul_rn(vz, 0.02f));
-        s.rx = rx; s.rz = rz; s.vx = vx; s.vz = vz; s.px = px; s.pz = pz;
+        s.vx = vx; s.vz = vz; s.px = px; s.pz = pz;
         s.steps += 1;
         const bool off = (fabsf(px) > 3.0f) || (fabsf(pz) > 3.0f);                  // ball3d.py:96-98
         const bool timeout = s.steps >= 200;                                        // ball3d.py:99
@@ -243,6 +254,7 @@ struct Ball3DTask {
     static __device__ __forceinline__ void begin_episode(State &s, const Spare &sp, uint32_t episode) {
         s.rx = (double)sp.rx; s.rz = (double)sp.rz; s.px = sp.px; s.pz = sp.pz; s.vx = sp.vx; s.vz = sp.vz;
         s.steps = 0; s.ep_ret = 0.0f; s.episode = episode;
+        refresh(s);
     }
     static __device__ __forceinline__ uint32_t next_episode(const State &s) { return (s.episode + 1u) & 0xFFFFFFu; }
     static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
