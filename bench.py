@@ -268,8 +268,8 @@ def run_cuda(args):
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N_ENVS,
                 "d2h_bytes_per_step": N_ENVS * (4 * OBS_DIM + 4 + 1 + 1),
-                "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_pinned (H2D actions, kernel, one D2H, sync; "
-                       "results copied out of the pinned block into fresh NumPy arrays)", "steps": n_e2e},
+                "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_block (H2D actions, kernel, one D2H straight into a pooled pinned "
+                       "result block, sync); the returned NumPy arrays are slices of that block, reused only when dropped", "steps": n_e2e},
         "step_api": {"value": step_api, "unit": "env-steps/s", "us_per_launch": 1e3 * api_ms / n_api,
                      "frac_hbm": (89.0 * N_ENVS / (api_ms / n_api * 1e-3) / 1e9) / peak,
                      "note": "one tmla_step launch per env step on device tensors; 5.8 MB working set, launch-bound"},

@@ -109,6 +109,17 @@ int tmla_step_pinned(tmla_env *h, int64_t *n_done);
  * {int32 env index, float ep_return, int32 ep_length, float terminal_obs[D]} = (3 + D) 32-bit words each — what a
  * binding should read instead of scanning `done` (Monitor / infos of the finished envs only). */
 int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_record);
+/* Result blocks: pinned host memory a binding hands out to ITS caller, so that the copy engine writes a step's results
+ * straight into the arrays the caller receives (no copy out of a staging block).  Layout, as byte offsets from the block:
+ * offsets[0..5] = obs f32[n,D], reward f32[n], done u8[n], truncated u8[n], flags i32[4] {n_done, bad_action, -, -},
+ * records (3 + D words each, as tmla_host_records); *bytes = size of a block.  tmla_step_block is tmla_step_pinned with the
+ * results (and the n_done compact records) landing in `block`; the actions still come from the pinned action view.
+ * The reference's DummyVecEnv returns fresh copies each step (SB3 dummy_vec_env.py step_wait): a binding keeps a small
+ * pool of blocks and reuses one only when its caller has dropped every array over it (vec_env.py does this by refcount). */
+int tmla_result_block_layout(tmla_env *h, int64_t offsets[6], int64_t *bytes);
+int tmla_result_block_alloc(tmla_env *h, void **block);
+int tmla_result_block_free(void *block);
+int tmla_step_block(tmla_env *h, void *block, int64_t *n_done);
 
 /* state injection / extraction (parity tests): `aos` is n structs of the task's wire type. */
 int tmla_get_state(tmla_env *h, void *aos, void *stream);

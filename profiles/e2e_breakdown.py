@@ -14,10 +14,7 @@ def t(fn, n=300):
     return (time.perf_counter() - t0) / n * 1e6
 print("full step            us", round(t(lambda i: env.step(acts[i % 64])), 1))
 nd = native.i64(0)
-print("step_pinned only     us", round(t(lambda i: check(lib.tmla_step_pinned(env._h, C.byref(nd)))), 1))
+blk = env._blocks
+print("step_block only      us", round(t(lambda i: check(lib.tmla_step_block(env._h, blk._ptr[blk.scratch], C.byref(nd)))), 1))
 print("copyto actions       us", round(t(lambda i: np.copyto(env._pin_act, acts[i % 64], casting="unsafe")), 1))
-print("obs.copy             us", round(t(lambda i: env._obs.copy()), 1))
-print("rew.copy             us", round(t(lambda i: env._rew.copy()), 1))
-print("done astype x2       us", round(t(lambda i: (env._done.astype(bool), env._trunc.astype(bool))), 1))
-d = env._done.astype(bool)
-print("nonzero+gather       us", round(t(lambda i: (lambda f: (env._tobs[f], env._ret[f], env._len[f]))(np.nonzero(d)[0])), 1))
+print("acquire + views      us", round(t(lambda i: blk.views(blk.acquire(), 500)), 1))

@@ -161,6 +161,44 @@ def test_host_step_contract(task):
     env.close(); dev.close()
 
 
+def test_host_step_results_stay_valid_while_referenced():
+    """DummyVecEnv returns fresh arrays every step (SB3 dummy_vec_env.py step_wait); CudaVecEnv returns slices of pooled
+    pinned result blocks and reuses a block only once nothing references it.  Keep 40 steps' results alive and check each
+    one — observations, rewards, dones and the episode-end payload — against the device path afterwards.  basic ends
+    episodes fast (3.5 % of the envs per step): the first steps with finished episodes exceed the 256-record head of the
+    copy-engine path's D2H (TMLA_HOST_STEP=copy), which then fetches the remainder with a second copy."""
+    n = 16384
+    env, dev = _vec("basic", n, seed=3), _vec("basic", n, seed=3)
+    env.reset(); dev.reset_tensor()
+    rng = np.random.default_rng(5)
+    kept = []
+    most = 0
+    for t in range(40):
+        a = rng.integers(0, env.n_actions, n)
+        out = env.step(a)
+        b = dev.step_tensor(torch.from_numpy(a.astype(np.int32)).cuda())
+        kept.append((out, {k: v.cpu().numpy().copy() for k, v in b.items()}))
+    for (obs, rew, dones, infos), ref in kept:
+        assert np.array_equal(obs, ref["obs"]) and np.array_equal(rew, ref["rew"])
+        assert np.array_equal(dones, ref["done"].astype(bool))
+        fin = infos.finished()
+        assert np.array_equal(fin, np.nonzero(ref["done"])[0])
+        most = max(most, len(fin))
+        ret, length = infos.episode_stats()
+        assert np.array_equal(ret, ref["ret"][fin]) and np.array_equal(length, ref["len"][fin])
+        for i in fin[:8]:
+            info = infos[int(i)]
+            assert np.array_equal(info["terminal_observation"], ref["tobs"][i])
+            assert info["TimeLimit.truncated"] == bool(ref["trunc"][i])
+    assert most > 256
+    pooled = sum(1 for (obs, *_), _ in kept if not obs.flags.owndata)
+    assert 1 <= pooled <= 8 and all(obs.flags.owndata for (obs, *_), _ in kept[8:])      # beyond the pool: ordinary copies
+    del kept, out, obs, rew, dones, infos, info
+    obs, *_ = env.step(np.zeros(n, np.int64))
+    assert not obs.flags.owndata                                                           # blocks came back to the pool
+    env.close(); dev.close()
+
+
 def test_reference_known_answer_through_single_env_api():
     # backend/tests/test_mlagents.py:32-45
     from three_mlagents_b200 import make_env

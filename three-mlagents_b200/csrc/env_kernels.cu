@@ -9,6 +9,7 @@
 //
 // These kernels are HBM-bound integer/byte/float32 work: no tensor cores, no GEMM reshaping.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "envs.cuh"
@@ -26,6 +27,7 @@ struct tmla_env {
     size_t stage_bytes;
     cudaStream_t own_stream;
     int32_t *d_ndone;         // device counter of finished episodes in the last step
+    int64_t rec_hint;         // records fetched with the first D2H of a host step (1.5x the last count + 256)
 };
 
 struct EnvPtrs { void *buf[4]; };
@@ -95,9 +97,11 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
             float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag,
-            float *__restrict__ compact) {
+            float *__restrict__ compact, int32_t *__restrict__ host_flags) {
     // compact != NULL (host-facing step): finished envs append one record {env index, ep_return, ep_length, terminal_obs[D]}
-    // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays
+    // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays.
+    // host_flags != NULL (zero-copy host step): the last CTA to finish publishes {n_done, bad_action} to mapped host memory
+    // and re-arms the device counters n_done[0..2] (count, bad action, ticket), so the step needs no memset and no flag copy.
     constexpr int D = Task::D;
     __shared__ __align__(16) float s_obs[kBlock * D];
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
@@ -136,6 +140,15 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     }
     __syncthreads();
     block_store_obs<D, kBlock, false>(s_obs, obs + i0 * D, (int)min((int64_t)kBlock, n - i0));
+    if (host_flags && threadIdx.x == 0) {        // (the __syncthreads above orders this CTA's atomics before the ticket)
+        __threadfence();
+        if (atomicAdd(n_done + 2, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            host_flags[0] = *(volatile int32_t *)n_done;
+            host_flags[1] = *(volatile int32_t *)(n_done + 1);
+            n_done[0] = 0; n_done[1] = 0; n_done[2] = 0;
+        }
+    }
 }
 
 // --------------------------------------------------------------- fused T-step random-policy rollout
@@ -451,11 +464,13 @@ static const int kStateSize[TMLA_NUM_TASKS] = {(int)sizeof(tmla_basic_state), (i
 
 // staging layout shared by the device block and its pinned host mirror (16-byte aligned sections):
 //   actions i32[n] | obs f32[n,D] | reward f32[n] | done u8[n] | truncated u8[n] | flags i32[4] {n_done, bad_action}
-//   | terminal_obs f32[n,D] | ep_return f32[n] | ep_length i32[n] | compact records f32[n,3+D]
-// obs..flags is one contiguous span -> ONE device-to-host copy per step; the episode-end payload is fetched as
-// n_done compact records (36 B each for ball3d) and scattered into the dense host arrays: only the entries of envs
-// whose `done` flag is set are meaningful after a step.
-struct StageLayout { size_t act, obs, rew, done, trunc, flags, tobs, ret, len, crec, end; };
+//   | compact records f32[n,3+D] | terminal_obs f32[n,D] | ep_return f32[n] | ep_length i32[n]   (the last three host-only)
+// obs..flags plus the head of the record area is one contiguous span -> ONE device-to-host copy per step.  The same span,
+// re-based at `obs`, is the layout of a RESULT BLOCK (tmla_result_block_*): pinned memory a binding hands out to its caller,
+// so that the copy engine writes a step's results straight into the arrays the caller receives.  The episode-end payload
+// travels as n_done compact records (36 B each for ball3d); the dense terminal_obs/ep_return/ep_length views of
+// tmla_step_pinned are filled from them on the host: only the entries of envs whose `done` flag is set are meaningful.
+struct StageLayout { size_t act, obs, rew, done, trunc, flags, crec, tobs, ret, len, end; };
 static StageLayout stage_layout(int64_t n, int D) {
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
     StageLayout L;
@@ -465,11 +480,11 @@ static StageLayout stage_layout(int64_t n, int D) {
     L.done = L.rew + 4 * n;
     L.trunc = L.done + n;
     L.flags = up(L.trunc + n);
-    L.tobs = L.flags + 16;
+    L.crec = L.flags + 16;                      // compact episode-end records {idx, ret, len, tobs[D]}, at most n of them
+    L.tobs = up(L.crec + 4 * n * (3 + D));
     L.ret = L.tobs + 4 * n * D;
     L.len = L.ret + 4 * n;
-    L.crec = L.len + 4 * n;                     // compact episode-end records {idx, ret, len, tobs[D]}, at most n of them
-    L.end = L.crec + 4 * n * (3 + D);
+    L.end = L.len + 4 * n;
     return L;
 }
 
@@ -508,6 +523,7 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
     if (!h) { tmla_set_error("out of host memory"); return TMLA_ENOMEM; }
     memset(h, 0, sizeof(*h));
     h->task = task; h->n = n_envs; h->seed = seed; h->env_id_base = env_id_base; h->device = device;
+    h->rec_hint = 256;
     int nbuf = 0;
     size_t pb[4] = {0, 0, 0, 0};
     TASK_SWITCH(task, nbuf = TaskT::NBUF; for (int b = 0; b < nbuf; ++b) pb[b] = TaskT::plane_bytes(b));
@@ -526,6 +542,7 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
         return TMLA_ENOMEM;
     }
     TMLA_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+    TMLA_CUDA(cudaMemset((char *)h->d_stage + stage_layout(n_envs, D).flags, 0, 16));
     TMLA_CUDA(cudaMemset(h->d_ndone, 0, sizeof(int32_t)));
     *out = h;
     int rc = tmla_reset(h, nullptr, nullptr);
@@ -568,41 +585,91 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
     cudaStream_t st = (cudaStream_t)stream;
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
-                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr)));
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     return TMLA_OK;
 }
 
-// VecEnv.step with the actions already in the pinned stage and the results left there (zero-copy host API:
-// tmla_host_views hands out the pinned pointers).  H2D actions -> kernel -> one D2H, then a synchronise.
-int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
-    TMLA_REQUIRE(h, "handle is NULL");
+// VecEnv.step with the actions already in the pinned stage: H2D actions -> kernel -> ONE D2H of obs..flags and the head of
+// the record area straight into `block` (pinned, result-block layout), then a synchronise.  The head is sized from the
+// previous step's count; only a step that finishes more episodes than that pays a second copy.
+static bool host_step_mapped() {      // TMLA_HOST_STEP=copy selects the copy-engine path (default: zero-copy mapped writes)
+    static const bool mapped = [] { const char *e = getenv("TMLA_HOST_STEP"); return !(e && !strcmp(e, "copy")); }();
+    return mapped;
+}
+static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
     TMLA_CUDA(cudaSetDevice(h->device));
     const int64_t n = h->n;
     const int D = kObsDim[h->task];
     const StageLayout L = stage_layout(n, D);
     char *d = (char *)h->d_stage, *p = (char *)h->h_stage;
     cudaStream_t st = h->own_stream;
-    int32_t *dflags = (int32_t *)(d + L.flags), *hflags = (int32_t *)(p + L.flags);
+    int32_t *dflags = (int32_t *)(d + L.flags);
+    const int32_t *bflags = (const int32_t *)(block + (L.flags - L.obs));
+    if (host_step_mapped()) {
+        // zero-copy: pinned memory is device-addressable under UVA.  The kernel reads the actions and writes obs / reward /
+        // done / truncated / records over PCIe itself (coalesced 128-byte lines), overlapping the transfer with the step
+        // arithmetic and saving the two copy-engine hand-offs; only the 16-byte flag word is copied afterwards.
+        char *b = block - L.obs;      // block-relative addressing with stage offsets
+        TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
+                                 ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(p + L.act),
+                                 (float *)(b + L.obs), (float *)(b + L.rew), (uint8_t *)(b + L.done), (uint8_t *)(b + L.trunc),
+                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags))));
+        TMLA_LAUNCH_CHECK();
+        h->step_count += 1;
+        TMLA_CUDA(cudaStreamSynchronize(st));      // ONE launch + one synchronise per step (the flag word of d_stage is zeroed at create)
+        if (n_done) *n_done = bflags[0];
+        if (bflags[1]) {
+            tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+            return TMLA_EACTION;
+        }
+        return TMLA_OK;
+    }
     TMLA_CUDA(cudaMemcpyAsync(d + L.act, p + L.act, 4 * n, cudaMemcpyHostToDevice, st));
     TMLA_CUDA(cudaMemsetAsync(dflags, 0, 16, st));
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                              ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
                              (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
-                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec))));
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
-    TMLA_CUDA(cudaMemcpyAsync(p + L.obs, d + L.obs, L.tobs - L.obs, cudaMemcpyDeviceToHost, st));
+    const size_t rec = (size_t)4 * (3 + D);
+    const int64_t head = h->rec_hint < n ? h->rec_hint : n;
+    TMLA_CUDA(cudaMemcpyAsync(block, d + L.obs, (L.crec - L.obs) + rec * head, cudaMemcpyDeviceToHost, st));
     TMLA_CUDA(cudaStreamSynchronize(st));
-    const int32_t nd = hflags[0];
+    const int32_t nd = bflags[0];
+    if (nd > head) {
+        TMLA_CUDA(cudaMemcpyAsync(block + (L.crec - L.obs) + rec * head, d + L.crec + rec * head, rec * (nd - head), cudaMemcpyDeviceToHost, st));
+        TMLA_CUDA(cudaStreamSynchronize(st));
+    }
+    h->rec_hint = 256 + nd + nd / 2;
+    if (n_done) *n_done = nd;
+    if (bflags[1]) {
+        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+        return TMLA_EACTION;
+    }
+    return TMLA_OK;
+}
+
+int tmla_step_block(tmla_env *h, void *block, int64_t *n_done) {
+    TMLA_REQUIRE(h && block, "handle/block is NULL");
+    return step_into_block(h, (char *)block, n_done);
+}
+
+int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    const int D = kObsDim[h->task];
+    const StageLayout L = stage_layout(h->n, D);
+    char *p = (char *)h->h_stage;
+    int64_t nd = 0;
+    const int rc = step_into_block(h, p + L.obs, &nd);
+    if (rc != TMLA_OK && rc != TMLA_EACTION) return rc;
     if (nd > 0) {   // episode-end payload: nd compact records, scattered into the dense host arrays
         const size_t rec = (size_t)4 * (3 + D);
-        TMLA_CUDA(cudaMemcpyAsync(p + L.crec, d + L.crec, rec * nd, cudaMemcpyDeviceToHost, st));
-        TMLA_CUDA(cudaStreamSynchronize(st));
         float *tobs = (float *)(p + L.tobs), *ret = (float *)(p + L.ret);
         int32_t *len = (int32_t *)(p + L.len);
-        for (int32_t s = 0; s < nd; ++s) {
+        for (int64_t s = 0; s < nd; ++s) {
             const float *r = (const float *)(p + L.crec + rec * s);
             int32_t i, l;
             memcpy(&i, r, 4); memcpy(&l, r + 2, 4);
@@ -611,10 +678,29 @@ int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
         }
     }
     if (n_done) *n_done = nd;
-    if (hflags[1]) {
-        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
-        return TMLA_EACTION;
+    return rc;
+}
+
+int tmla_result_block_layout(tmla_env *h, int64_t offsets[6], int64_t *bytes) {
+    TMLA_REQUIRE(h && offsets && bytes, "NULL argument");
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    const size_t o[6] = {L.obs, L.rew, L.done, L.trunc, L.flags, L.crec};
+    for (int i = 0; i < 6; ++i) offsets[i] = (int64_t)(o[i] - L.obs);
+    *bytes = (int64_t)(L.tobs - L.obs);
+    return TMLA_OK;
+}
+int tmla_result_block_alloc(tmla_env *h, void **block) {
+    TMLA_REQUIRE(h && block, "NULL argument");
+    TMLA_CUDA(cudaSetDevice(h->device));
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    if (cudaMallocHost(block, L.tobs - L.obs) != cudaSuccess) {
+        tmla_set_error("cudaMallocHost(result block, %zu bytes): %s", L.tobs - L.obs, cudaGetErrorString(cudaGetLastError()));
+        return TMLA_ENOMEM;
     }
+    return TMLA_OK;
+}
+int tmla_result_block_free(void *block) {
+    if (block) TMLA_CUDA(cudaFreeHost(block));
     return TMLA_OK;
 }
 
@@ -652,21 +738,20 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
     char *p = (char *)h->h_stage;
     memcpy(p + L.act, actions, 4 * n);
     int64_t nd = 0;
-    const int rc = tmla_step_pinned(h, &nd);
+    const int rc = step_into_block(h, p + L.obs, &nd);
     if (rc != TMLA_OK && rc != TMLA_EACTION) return rc;
     memcpy(obs, p + L.obs, 4 * n * D);
     memcpy(reward, p + L.rew, 4 * n);
     memcpy(done, p + L.done, n);
     memcpy(truncated, p + L.trunc, n);
-    if (nd > 0) {   // "written only where done": copy the rows of the finished envs, not three dense arrays
-        const float *tobs = (const float *)(p + L.tobs), *ret = (const float *)(p + L.ret);
-        const int32_t *len = (const int32_t *)(p + L.len);
-        for (int64_t i = 0; i < n; ++i) {
-            if (!done[i]) continue;
-            if (terminal_obs) memcpy(terminal_obs + i * D, tobs + i * D, (size_t)4 * D);
-            if (ep_return) ep_return[i] = ret[i];
-            if (ep_length) ep_length[i] = len[i];
-        }
+    const size_t rec = (size_t)4 * (3 + D);
+    for (int64_t s = 0; s < nd; ++s) {   // "written only where done": the records of the finished envs, not three dense arrays
+        const float *r = (const float *)(p + L.crec + rec * s);
+        int32_t i, l;
+        memcpy(&i, r, 4); memcpy(&l, r + 2, 4);
+        if (terminal_obs) memcpy(terminal_obs + (size_t)i * D, r + 3, (size_t)4 * D);
+        if (ep_return) ep_return[i] = r[1];
+        if (ep_length) ep_length[i] = l;
     }
     if (n_done) *n_done = nd;
     return rc;

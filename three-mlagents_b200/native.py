@@ -54,6 +54,10 @@ SIGNATURES = {
     "tmla_host_views": (_i, [vp] + [C.POINTER(vp)] * 8),
     "tmla_step_pinned": (_i, [vp, C.POINTER(i64)]),
     "tmla_host_records": (_i, [vp, C.POINTER(vp), C.POINTER(i32)]),
+    "tmla_result_block_layout": (_i, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "tmla_result_block_alloc": (_i, [vp, C.POINTER(vp)]),
+    "tmla_result_block_free": (_i, [vp]),
+    "tmla_step_block": (_i, [vp, vp, C.POINTER(i64)]),
     "tmla_get_state": (_i, [vp, vp, vp]),
     "tmla_set_state": (_i, [vp, vp, vp]),
     "tmla_check_actions": (_i, [vp, vp]),

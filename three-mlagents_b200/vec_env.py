@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 from typing import Any, Sequence
 
@@ -37,12 +38,26 @@ STATE_DTYPES = {   # wire structs of include/tmla.h
 
 class LazyInfos(Sequence):
     """`infos` of one vec-step, materialised per index on demand (64K dicts per step would
-    dominate the step time; SB3 only reads the entries of finished episodes).  Holds a snapshot of the
-    finished envs' payload only (`finished` sorted env indices -> compact rows)."""
+    dominate the step time; SB3 only reads the entries of finished episodes).  Holds the finished envs' payload as the
+    compact records the step kernel wrote ({env index, ep_return, ep_length, terminal_obs[D]}, unordered); they are
+    sorted by env index on first access."""
 
-    def __init__(self, n, done, truncated, finished, terminal_obs, ep_return, ep_length, t_elapsed):
-        self._n, self._done, self._trunc = n, done, truncated
-        self._idx, self._tobs, self._ret, self._len, self._t = finished, terminal_obs, ep_return, ep_length, t_elapsed
+    def __init__(self, n, done, truncated, records, t_elapsed):
+        self._n, self._done, self._trunc, self._rec, self._t = n, done, truncated, records, t_elapsed
+        self._idx = None
+
+    def _sort(self):
+        if self._idx is None:
+            if self._rec is None or len(self._rec) == 0:
+                self._idx = np.zeros(0, np.int64)
+                self._tobs, self._ret, self._len = np.zeros((0, 0), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32)
+            else:
+                rec_i = self._rec.view(np.int32)
+                order = np.argsort(rec_i[:, 0], kind="stable")
+                rec = self._rec[order]                       # a copy: the pinned block can go back to the pool
+                rec_i = rec.view(np.int32)
+                self._idx, self._ret, self._len, self._tobs = rec_i[:, 0].astype(np.int64), rec[:, 1], rec_i[:, 2], rec[:, 3:]
+            self._rec = None
 
     def __len__(self):
         return self._n
@@ -56,6 +71,7 @@ class LazyInfos(Sequence):
             raise IndexError(i)
         info: dict[str, Any] = {"TimeLimit.truncated": bool(self._trunc[i])}
         if self._done[i]:
+            self._sort()
             k = int(np.searchsorted(self._idx, i))
             info["terminal_observation"] = self._tobs[k]
             info["episode"] = {"r": round(float(self._ret[k]), 6), "l": int(self._len[k]), "t": round(self._t, 6)}
@@ -63,8 +79,67 @@ class LazyInfos(Sequence):
         return info
 
     def finished(self):
-        """Indices of envs whose episode ended on this step."""
-        return self._idx if self._idx is not None else np.nonzero(self._done)[0]
+        """Indices of envs whose episode ended on this step (ascending)."""
+        self._sort()
+        return self._idx
+
+    def episode_stats(self):
+        """(returns, lengths) of the episodes that ended on this step, ordered like `finished()`."""
+        self._sort()
+        return self._ret, self._len
+
+
+class _ResultBlocks:
+    """Pool of pinned result blocks (include/tmla.h `tmla_result_block_*`).  A step's D2H copy lands directly in the block
+    whose slices are returned to the caller as obs / rewards / dones / infos.  DummyVecEnv returns fresh copies every step
+    (SB3 dummy_vec_env.py `step_wait`), so a block is handed out again only when no array over it is alive — every view of
+    a block holds a reference to its `raw` array, and `sys.getrefcount(raw)` says when they are all gone.  A caller that
+    keeps more than `cap` steps' results alive gets ordinary NumPy copies from then on."""
+
+    def __init__(self, handle, n, d, cap=8):
+        self._h, self._cap = handle, cap
+        off = (native.i64 * 6)()
+        nbytes = native.i64(0)
+        check(lib.tmla_result_block_layout(handle, off, C.byref(nbytes)))
+        self.off, self.nbytes = [int(x) for x in off], int(nbytes.value)
+        self._raw, self._ptr = [], []
+        self.n, self.d = n, d
+        self.scratch = self._alloc()      # never handed out: the fallback copies out of it
+        self._alloc(); self._alloc()      # the usual case — the caller holds one step's results while asking for the next
+
+    def _alloc(self):
+        q = native.vp()
+        check(lib.tmla_result_block_alloc(self._h, C.byref(q)))
+        raw = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(q.value))
+        self._raw.append(raw)
+        self._ptr.append(q)
+        return len(self._raw) - 1
+
+    def acquire(self):
+        """Index of a block nobody references, or None when `cap` blocks are all still in use."""
+        raws = self._raw
+        for k in range(1, len(raws)):
+            if sys.getrefcount(raws[k]) == 2:          # the list + getrefcount's argument
+                return k
+        return self._alloc() if len(raws) <= self._cap else None
+
+    def views(self, k, n_done):
+        raw, (o_obs, o_rew, o_done, o_trunc, _, o_rec) = self._raw[k], self.off[:6]
+        n, d = self.n, self.d
+        obs = raw[o_obs:o_obs + 4 * n * d].view(np.float32).reshape(n, d)
+        rew = raw[o_rew:o_rew + 4 * n].view(np.float32)
+        done = raw[o_done:o_done + n].view(np.bool_)
+        trunc = raw[o_trunc:o_trunc + n].view(np.bool_)
+        rec = raw[o_rec:o_rec + 4 * (3 + d) * n_done].view(np.float32).reshape(n_done, 3 + d) if n_done else None
+        return obs, rew, done, trunc, rec
+
+    def close(self):
+        raws, self._raw = self._raw, []
+        for k in range(len(raws)):
+            if sys.getrefcount(raws[k]) == 2:          # `raws` + getrefcount's argument
+                lib.tmla_result_block_free(self._ptr[k])
+            # else: a caller still holds arrays over this block; leave the pinned memory to process teardown
+        self._ptr = []
 
 
 class CudaVecEnv:
@@ -83,27 +158,11 @@ class CudaVecEnv:
         check(lib.tmla_create(native.TASK_IDS[task_id], self.num_envs, int(seed) & (2**64 - 1), int(env_id_base),
                               self.device_index, C.byref(self._h)))
         n, d = self.num_envs, self.obs_dim
-        # NumPy views straight onto the handle's pinned host block (tmla_host_views): the D2H copy of a
-        # step lands in these arrays, no intermediate memcpy.
-        ptrs = [native.vp() for _ in range(8)]
-        check(lib.tmla_host_views(self._h, *[C.byref(q) for q in ptrs]))
-
-        def view(q, ctype, shape):
-            count = int(np.prod(shape))
-            return np.ctypeslib.as_array((ctype * count).from_address(q.value)).reshape(shape)
-
-        self._pin_act = view(ptrs[0], C.c_int32, (n,))
-        self._obs = view(ptrs[1], C.c_float, (n, d))
-        self._rew = view(ptrs[2], C.c_float, (n,))
-        self._done = view(ptrs[3], C.c_uint8, (n,))
-        self._trunc = view(ptrs[4], C.c_uint8, (n,))
-        self._tobs = view(ptrs[5], C.c_float, (n, d))
-        self._ret = view(ptrs[6], C.c_float, (n,))
-        self._len = view(ptrs[7], C.c_int32, (n,))
-        recp, recw = native.vp(), native.i32(0)
-        check(lib.tmla_host_records(self._h, C.byref(recp), C.byref(recw)))
-        rec = view(recp, C.c_float, (n, recw.value))          # compact episode-end records {idx, ret, len, tobs[d]}
-        self._rec_f, self._rec_i = rec, rec.view(np.int32)
+        # NumPy view of the handle's pinned action buffer (tmla_host_views); results land in pooled pinned result blocks
+        q = native.vp()
+        check(lib.tmla_host_views(self._h, C.byref(q), None, None, None, None, None, None, None))
+        self._pin_act = np.ctypeslib.as_array((C.c_int32 * n).from_address(q.value))
+        self._blocks = _ResultBlocks(self._h, n, d)
         self._actions = None
         self._t0 = time.time()
         self._dev = None      # device-side buffers for step_tensor, allocated lazily
@@ -120,8 +179,9 @@ class CudaVecEnv:
         return [None if seed is None else seed + i for i in range(min(self.num_envs, 1))]
 
     def reset(self) -> np.ndarray:
-        check(lib.tmla_reset_host(self._h, ptr(self._obs)))
-        return self._obs.copy()
+        obs = np.empty((self.num_envs, self.obs_dim), np.float32)
+        check(lib.tmla_reset_host(self._h, ptr(obs)))
+        return obs
 
     def step_async(self, actions) -> None:
         a = np.asarray(actions).reshape(-1)
@@ -131,23 +191,22 @@ class CudaVecEnv:
         self._actions = self._pin_act
 
     def step_wait(self):
+        blocks = self._blocks
+        k = blocks.acquire()
         nd = native.i64(0)
-        check(lib.tmla_step_pinned(self._h, C.byref(nd)))
-        done = self._done.astype(bool)                      # fresh arrays: the pinned block is reused next step
-        trunc = self._trunc.astype(bool)
-        obs, rew = self._obs.copy(), self._rew.copy()
-        if nd.value:
-            k = int(nd.value)                               # compact records of the finished envs, sorted by env index
-            order = np.argsort(self._rec_i[:k, 0], kind="stable")
-            rec_f, rec_i = self._rec_f[:k][order], self._rec_i[:k][order]
-            fin, ret, length = rec_i[:, 0].astype(np.int64), rec_f[:, 1], rec_i[:, 2]
-            infos = LazyInfos(self.num_envs, done, trunc, fin, rec_f[:, 3:], ret, length, time.time() - self._t0)
+        check(lib.tmla_step_block(self._h, blocks._ptr[blocks.scratch if k is None else k], C.byref(nd)))
+        if k is None:     # the caller holds every pooled block: ordinary copies out of the scratch block
+            obs, rew, done, trunc, rec = (None if v is None else v.copy() for v in blocks.views(blocks.scratch, int(nd.value)))
+        else:
+            obs, rew, done, trunc, rec = blocks.views(k, int(nd.value))
+        if rec is not None:
+            infos = LazyInfos(self.num_envs, done, trunc, rec, time.time() - self._t0)
             if self._monitor is not None:
                 t = round(time.time() - self._t0, 6)
-                for r, l in zip(ret, length):
+                for r, l in zip(*infos.episode_stats()):
                     self._monitor.write(f"{round(float(r), 6)},{int(l)},{t}\n")
         else:
-            infos = LazyInfos(self.num_envs, done, trunc, None, None, None, None, 0.0)
+            infos = LazyInfos(self.num_envs, done, trunc, None, 0.0)
         return obs, rew, done, infos
 
     def step(self, actions):
@@ -156,6 +215,7 @@ class CudaVecEnv:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
+            self._blocks.close()
             lib.tmla_destroy(self._h)
             self._h = native.vp()
         if getattr(self, "_monitor", None) is not None:
