@@ -189,19 +189,19 @@ struct Ball3DTask {
         // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0).  The sign is
         // XOR-ed into the high word; adding the 0.0 entries is the identity (rot is never -0.0) and is skipped.
         const int td_hi = __double2hiint(c.tilt_delta), td_lo = __double2loint(c.tilt_delta);
-        const double sd = __hiloint2double(td_hi ^ (int)((unsigned)a << 31), td_lo);   // a odd -> -delta
-        if (a < 4) {                                                                // action 4 adds (0, 0): nothing changes
-            const bool tilt_x = a < 2;
-            double rot = __dadd_rn(tilt_x ? s.rx : s.rz, sd);                        // ball3d.py:77
-            if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back (the untouched
-                asm volatile("");     // axis is already an f32 value); kept a branch: conversions for <1 % of the lanes
-                rot = (double)__double2float_rn(rot);
-            }
-            rot = clip_sym(rot, c.max_tilt);                                         // ball3d.py:78 (float64 from here)
-            const double adt = __dmul_rn(__dmul_rn(c.g, sin_small_c(c, rot)), c.dt); // ball3d.py:81-84
-            const float orot = __double2float_rn(rot);
-            if (tilt_x) { s.rx = rot; s.axdt = adt; s.orx = orot; } else { s.rz = rot; s.azdt = adt; s.orz = orot; }
+        // a odd -> -delta; action 4 adds (0, 0): it runs through the z axis with a zero delta (rot + 0, the clip and the f32
+        // round trip of an f32 value are identities, the cached products are recomputed to the same bits) — no divergent branch
+        const double sd = __hiloint2double(a < 4 ? td_hi ^ (int)((unsigned)a << 31) : 0, a < 4 ? td_lo : 0);
+        const bool tilt_x = a < 2;
+        double rot = __dadd_rn(tilt_x ? s.rx : s.rz, sd);                            // ball3d.py:77
+        if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back (the untouched
+            asm volatile("");     // axis is already an f32 value); kept a branch: conversions for <1 % of the lanes
+            rot = (double)__double2float_rn(rot);
         }
+        rot = clip_sym(rot, c.max_tilt);                                             // ball3d.py:78 (float64 from here)
+        const double adt = __dmul_rn(__dmul_rn(c.g, sin_small_c(c, rot)), c.dt);     // ball3d.py:81-84
+        const float orot = __double2float_rn(rot);
+        if (tilt_x) { s.rx = rot; s.axdt = adt; s.orx = orot; } else { s.rz = rot; s.azdt = adt; s.orz = orot; }
         float vx = __double2float_rn(__dadd_rn((double)s.vx, s.axdt));              // ball3d.py:83-84
         float vz = __double2float_rn(__dadd_rn((double)s.vz, s.azdt));
         vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
