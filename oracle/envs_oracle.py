@@ -15,6 +15,7 @@ Reference anchors (relative to /root/reference/backend):
   push       examples/push.py:10-125
   walljump   examples/walljump.py:14-98
   brickbreak examples/brick_break.py:11-133
+  bicycle    examples/bicycle.py:11-146
   adapter    mlagents/envs.py:87-159  (time-limit truncation, terminated/truncated split)
   vec/auto-reset + Monitor: SB3 DummyVecEnv/Monitor semantics, SURVEY.md §8(a) A7
 Reset draws use this repo's Philox streams (oracle/philox.py), not MT19937.
@@ -47,6 +48,7 @@ TASKS = {
     "push":      (4, 5, 120),     # push.py:10-24 ; envs.py:193-199
     "walljump":  (4, 4, 150),     # walljump.py:14-21 ; envs.py:202-213
     "brickbreak": (45, 3, 2000),  # brick_break.py:14-38 (2 + 2 + 1 + 5*8 obs) ; envs.py:216-227
+    "bicycle":   (7, 3, 2000),    # bicycle.py:130-145 ; envs.py:230-241
 }
 
 STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
@@ -60,9 +62,25 @@ STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format o
     "walljump": np.dtype([("agent_x", "<i4"), ("in_air", "<i4"), ("wall", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
     "brickbreak": np.dtype([("pos", "<f8", (2,)), ("vel", "<f8", (2,)), ("paddle", "<f8"), ("bricks", "u1", (40,)),
                             ("steps", "<i4"), ("ep_return", "<f4")]),
+    "bicycle": np.dtype([("x", "<f8"), ("z", "<f8"), ("theta", "<f8"), ("phi", "<f8"), ("phi_dot", "<f8"), ("delta", "<f8"),
+                         ("goal", "<f8", (2,)), ("dist", "<f8"), ("steps", "<i4"), ("ep_return", "<f4")]),
 }
 
 f32 = np.float32
+
+# bicycle.py:15-31 — the constants as the reference's Python expressions evaluate them
+BIKE_DT = 0.02
+BIKE_GH = 9.8 / 0.8                  # self.g / self.h
+BIKE_VLH = 5.0 ** 2 / (1.0 * 0.8)    # self.v**2 / (self.L * self.h)
+BIKE_VL = 5.0 / 1.0                  # self.v / self.L
+BIKE_MAX_PHI = np.pi / 4
+BIKE_MAX_DELTA = np.pi / 6
+
+
+def dot2(a, b):
+    """Row-wise np.dot of [n,2] arrays THROUGH np.dot (the reference's np.linalg.norm / np.dot on 2-vectors go to BLAS ddot,
+    which on FMA hosts rounds as fma(a1, b1, a0*b0) — measured; csrc/envs.cuh:BicycleTask uses exactly that)."""
+    return np.array([np.dot(a[i], b[i]) for i in range(a.shape[0])], dtype=np.float64).reshape(a.shape[0])
 
 
 def push_reward_lut():
@@ -132,6 +150,12 @@ def observe(task, st):
         x = st["agent_x"].astype(np.float64)
         return np.stack([(WJ_WIDTH - 1 - x) / (WJ_WIDTH - 1), (WJ_WALL_X - x) / (WJ_WIDTH - 1), st["wall"].astype(np.float64),
                          (st["in_air"] == 0).astype(np.float64)], axis=1).astype(np.float32)
+    if task == "bicycle":        # bicycle.py:128-145: the goal direction is re-derived from the state; the adapter casts to f32
+        vec = st["goal"] - np.stack([st["x"], st["z"]], 1)
+        dist = np.sqrt(dot2(vec, vec))
+        nv = np.where(dist[:, None] > 0, vec / np.where(dist > 0, dist, 1.0)[:, None], 0.0)
+        return np.stack([st["phi"], st["phi_dot"], st["delta"], np.cos(st["theta"]), np.sin(st["theta"]), nv[:, 0], nv[:, 1]],
+                        axis=1).astype(np.float32)
     if task == "brickbreak":     # brick_break.py:118-126: f64 concatenate, the adapter casts to f32 (envs.py:150)
         return np.concatenate([st["pos"] / np.array([40.0, 40.0]), st["vel"], (st["paddle"] / 40.0)[:, None],
                                st["bricks"].astype(np.float64)], axis=1).astype(np.float32)
@@ -285,6 +309,37 @@ def transition(task, st, actions):
         reward = reward.astype(np.float32)
         hit_limit = st["steps"] >= max_steps
         terminated, truncated = done & ~hit_limit, hit_limit
+    elif task == "bicycle":
+        # bicycle.py:59-126 in the reference's operation order (Python doubles).  np.sin/np.cos are libm; np.tan and `** 0.5`
+        # (libm pow, not sqrt) are whatever this host's NumPy dispatches to — the CUDA side is compared within a tolerance.
+        delta = st["delta"] + np.where(a == 0, -0.05, np.where(a == 2, 0.05, 0.0))                # :63-69
+        delta = np.minimum(np.maximum(delta, -BIKE_MAX_DELTA), BIKE_MAX_DELTA)                     # :70
+        phi_ddot = BIKE_GH * np.sin(st["phi"]) - (BIKE_VLH * np.tan(delta)) * np.cos(st["phi"])   # :74-76
+        phi_dot = st["phi_dot"] + phi_ddot * BIKE_DT                                               # :77
+        phi = st["phi"] + phi_dot * BIKE_DT                                                        # :78
+        delta = delta * 0.95                                                                       # :81
+        theta = st["theta"] + (BIKE_VL * np.tan(delta)) * BIKE_DT                                  # :84
+        x = st["x"] + (5.0 * np.cos(theta)) * BIKE_DT                                              # :85
+        z = st["z"] + (5.0 * np.sin(theta)) * BIKE_DT                                              # :86
+        gv = st["goal"] - np.stack([x, z], 1)
+        new_dist = np.sqrt(dot2(gv, gv))                                                           # :91 np.linalg.norm
+        progress = (st["dist"] - new_dist) * 10.0                                                  # :94
+        upright = (1.0 - np.power(np.abs(phi) / BIKE_MAX_PHI, 0.5)) * 0.2                          # :98
+        hv = np.stack([np.cos(theta), np.sin(theta)], 1)                                           # :101
+        ngv = gv / np.where(new_dist > 0, new_dist, 1.0)[:, None]                                  # :103-105
+        heading = dot2(hv, ngv) * 0.3                                                              # :106
+        steering = -(np.abs(delta) / BIKE_MAX_DELTA) * 0.1                                         # :109
+        reward = progress + upright + heading + steering                                           # :111
+        st["x"], st["z"], st["theta"], st["phi"], st["phi_dot"], st["delta"], st["dist"] = x, z, theta, phi, phi_dot, delta, new_dist
+        st["steps"] += 1
+        fell = np.abs(phi) > BIKE_MAX_PHI                                                          # :113-115
+        reward = np.where(fell, -10.0, reward)
+        reached = new_dist < 2.0                                                                   # :120-122
+        reward = np.where(reached, 50.0, reward)
+        done = fell | reached | (st["steps"] > 2000)                                               # :117-118
+        reward = reward.astype(np.float32)
+        hit_limit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit_limit, hit_limit
     else:
         raise KeyError(task)
     return observe(task, st), reward, terminated, truncated
@@ -344,6 +399,14 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET, episode=None):
         st["vel"] = np.stack([-s_ * 1.5, c_ * 1.5], 1)
         st["paddle"] = 20.0
         st["bricks"] = 1
+    elif task == "bicycle":                                         # bicycle.py:40-58
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        st["phi"] = -0.1 + 0.2 * px.u32_unit(b[0])                  # np.random.uniform(lo, hi) = lo + (hi - lo) * u
+        st["phi_dot"] = -0.1 + 0.2 * px.u32_unit(b[1])
+        radius = 15.0 + 10.0 * px.u32_unit(b[2])
+        s_, c_ = sin_cos_quarter(-np.pi / 4 + (np.pi / 2) * px.u32_unit(b[3]))
+        st["goal"] = np.stack([radius * c_, radius * s_], 1)
+        st["dist"] = np.sqrt(dot2(st["goal"], st["goal"]))          # np.linalg.norm(goal - [0, 0])
     elif task == "walljump":                                        # walljump.py:39-45: int(np.random.rand() < 0.7)
         b = px.stream_block(seed, env_ids, k, tag, 0)
         u24 = (b[0] >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)

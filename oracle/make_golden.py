@@ -70,6 +70,10 @@ def _state_of(task, env):
     if task == "brickbreak":
         return {"pos": np.asarray(inner.ball_pos, dtype=np.float64).copy(), "vel": np.asarray(inner.ball_vel, dtype=np.float64).copy(),
                 "paddle": np.float64(inner.paddle_x), "bricks": np.asarray(inner.bricks, dtype=np.uint8).reshape(-1).copy()}
+    if task == "bicycle":
+        return {"x": np.float64(inner.x), "z": np.float64(inner.z), "theta": np.float64(inner.theta), "phi": np.float64(inner.phi),
+                "phi_dot": np.float64(inner.phi_dot), "delta": np.float64(inner.delta),
+                "goal": np.asarray(inner.goal_pos, dtype=np.float64).copy(), "dist": np.float64(inner.dist_to_goal)}
     if task == "walljump":
         return {"agent_x": np.int32(inner.agent_x), "in_air": np.int32(inner.in_air), "wall": np.int32(inner.wall_height)}
     raise KeyError(task)
@@ -92,6 +96,10 @@ def _actions(task, n_actions, rng):
     if task == "brickbreak":
         acts[:, 6] = np.where(np.arange(T) % 5 < 3, 0, 2)       # drifts left, keeps the paddle near the wall clip
         acts[:, 7] = np.where(np.arange(T) % 11 < 6, 2, 0)
+    if task == "bicycle":
+        acts[:, 1] = 1                                           # never steers: falls over from the initial lean
+        acts[:, 6] = np.where(np.arange(T) % 6 < 3, 0, 2)       # slow weave
+        acts[:, 7] = np.where(np.arange(T) % 10 < 5, 2, 0)
     if task == "walljump":
         acts[:, 8] = np.where(np.arange(T) % 4 == 0, 3, 1)      # jump every 4th step, walk otherwise: clears the wall
         acts[:, 9] = np.where(np.arange(T) % 7 < 5, 1, 2)       # mostly forward with retreats: bumps into the wall repeatedly
@@ -168,7 +176,7 @@ def main():
     make_env = _import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
     only = set(sys.argv[1:])                 # e.g. `python oracle/make_golden.py walljump` regenerates one task
-    for task in ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak"):
+    for task in ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle"):
         if only and task not in only:
             continue
         g = record(task, make_env)
@@ -177,7 +185,7 @@ def main():
         n_ep = int((g["terminated"] | g["truncated"]).sum())
         print(f"{task}: {path}  episodes={n_ep} terminated={int(g['terminated'].sum())} "
               f"truncated={int(g['truncated'].sum())}  size={os.path.getsize(path)/1024:.0f} KiB")
-    for task in ("ball3d", "gridworld", "push", "walljump", "brickbreak"):
+    for task in ("ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle"):
         if only and task not in only:
             continue
         s = reset_samples(task, make_env)

@@ -33,7 +33,7 @@ def test_metadata_calls_match_reference_spaces():
     lib = native.lib
     assert lib.tmla_version() == 100
     want = {"basic": (21, 3, 50, 12), "ball3d": (6, 5, 200, 48), "gridworld": (4, 5, 100, 36), "push": (4, 5, 120, 28),
-            "walljump": (4, 4, 150, 20), "brickbreak": (45, 3, 2000, 88)}
+            "walljump": (4, 4, 150, 20), "brickbreak": (45, 3, 2000, 88), "bicycle": (7, 3, 2000, 80)}
     for name, (d, a, m, sz) in want.items():
         t = lib.tmla_task_from_name(name.encode())
         assert t == native.TASK_IDS[name]
@@ -48,6 +48,7 @@ def test_metadata_calls_match_reference_spaces():
     assert lib.tmla_mlp_num_params(4, 256, 4) == 135429          # walljump: 135686 - (256 + 1)
     assert lib.tmla_mlp_num_params(45, 256, 3) == 143876 + 2 * 256 * 24   # brickbreak: 45 instead of 21 inputs per tower
     assert lib.tmla_ppo_minibatch_supported(4, 256, 4) == 1 and lib.tmla_ppo_minibatch_supported(21, 256, 3) == 0
+    assert lib.tmla_ppo_minibatch_supported(7, 256, 3) == 1 and lib.tmla_mlp_num_params(7, 256, 3) == 143876 - 2 * 256 * 14   # bicycle
 
 
 def test_wire_structs_match_numpy_dtypes():
@@ -77,7 +78,7 @@ def test_registry_surface():
     from three_mlagents_b200 import registry
 
     assert len(registry.TASKS) == 19
-    assert registry.CUDA_TASKS == ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak")
+    assert registry.CUDA_TASKS == ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
     assert m.get_task("brick-break").id == "brickbreak"            # tests/test_mlagents.py:47-49
     assert m.get_task("self_driving_car").id == "self-driving-car"
     with pytest.raises(KeyError):
@@ -86,7 +87,7 @@ def test_registry_surface():
         m.make_env("fish")
     card = m.get_task("basic").card()
     assert card["trainable"] is True and "env_factory" not in card
-    assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["brickbreak", "ball3d", "basic", "gridworld", "push", "walljump"]
+    assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["brickbreak", "ball3d", "bicycle", "basic", "gridworld", "push", "walljump"]
     fams = [(t.family, t.id) for t in m.list_tasks()]
     assert fams == sorted(fams)
 

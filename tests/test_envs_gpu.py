@@ -15,7 +15,7 @@ from oracle import envs_oracle as eo
 
 pytestmark = pytest.mark.gpu
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
 # north_star: "ball3d trajectories must stay within a stated float tolerance over 1,000 steps".
 # The only non-bit-exact operation on the device is sin(double) (own polynomial vs libm, <= 1 ulp of
 # f64); everything else follows NumPy's rounding sequence exactly, so 1e-5 absolute is generous.
@@ -31,6 +31,9 @@ def _vec(task, n, **kw):
 def _close(task, got, want, what):
     if task == "ball3d":
         np.testing.assert_allclose(got, want, rtol=0, atol=BALL3D_TOL, err_msg=what)
+    elif task in _replay.LIBM_TASKS:      # bicycle: the reference's own bits depend on its host's libm / SVML / BLAS (replay_util.py)
+        tol = _replay.LIBM_TASKS[task]
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol["reward_atol" if "reward" in what else "obs_atol"], err_msg=what)
     else:
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), what
 
@@ -64,8 +67,8 @@ def test_golden_replay_matches_reference(task):
             st = _replay.inject_resets(task, g, t, env.get_state(), done)
             env.set_state(st)
     env.check_actions()
-    if task == "ball3d":
-        print(f"ball3d: {exact}/{total} observation words bit-identical to the reference")
+    if task == "ball3d" or task in _replay.LIBM_TASKS:
+        print(f"{task}: {exact}/{total} observation words bit-identical to the reference")
         assert exact / total > 0.999
     env.close()
 
@@ -93,7 +96,13 @@ def test_lockstep_with_oracle_and_philox_resets(task):
             np.testing.assert_allclose(b["ret"].cpu().numpy()[done], info["episode_return"][done], rtol=1e-6, atol=1e-6)
     assert n_done > 0
     st = env.get_state()
-    if task != "ball3d":
+    if task in _replay.LIBM_TASKS:
+        for k in st.dtype.names:
+            if k == "steps":
+                assert np.array_equal(st[k], ora.state[k]), k
+            elif k != "ep_return":
+                np.testing.assert_allclose(st[k], ora.state[k], rtol=0, atol=1e-9, err_msg=k)
+    elif task != "ball3d":
         for k in st.dtype.names:
             if k != "ep_return":
                 assert np.array_equal(st[k], ora.state[k]), k
@@ -311,4 +320,38 @@ def test_brickbreak_time_limit_and_clear_bonus_against_oracle():
             for k in ("pos", "vel", "paddle", "bricks", "steps"):
                 ora[k][done] = got[k][done]
     assert seen["trunc"] >= 2 and seen["clear"] == 1, seen
+    env.close()
+
+
+def test_bicycle_goal_fall_and_time_limit_against_oracle():
+    """Paths the golden trace (scripted and random steering, 863 falls) does not reach: the +50 goal reward
+    (bicycle.py:120-122, which also overrides a fall on the same step), the adapter's 2000-step truncation
+    (envs.py:141-145) and the steering clip (bicycle.py:70) — by state injection, CUDA kernel vs the pinned oracle."""
+    task = "bicycle"
+    tol = _replay.LIBM_TASKS[task]
+    st = np.zeros(6, eo.STATE_DTYPES[task])
+    st["goal"] = [[20.0, 0.0]] * 6
+    st["x"] = [17.95, 3.0, 3.0, 17.95, 1.0, 17.7]
+    st["phi"] = [0.0, 0.0, 0.78, 0.78, 0.01, 0.0]
+    st["phi_dot"] = [0.0, 0.0, 1.0, 1.0, 0.0, 0.0]
+    st["delta"] = [0.0, 0.0, 0.0, 0.0, np.pi / 6, 0.0]
+    st["steps"] = [7, 1999, 30, 30, 5, 1999]
+    st["dist"] = 20.0 - st["x"]
+    env = _vec(task, 6, seed=9)
+    env.set_state(st.copy())
+    ora = st.copy()
+    a = np.array([1, 1, 1, 1, 2, 1])
+    b = env.step_tensor(torch.from_numpy(a.astype(np.int32)).cuda())
+    obs, rew, term, trunc = eo.transition(task, ora, a)
+    assert list(rew) == [50.0, rew[1], -10.0, 50.0, rew[4], rew[5]] and 0.0 < rew[1] < 2.0
+    assert list(term) == [True, False, True, True, False, False] and list(trunc) == [False, True, False, False, False, True]
+    assert np.array_equal(b["done"].cpu().numpy().astype(bool), term | trunc)
+    assert np.array_equal(b["trunc"].cpu().numpy().astype(bool), trunc & ~term)
+    np.testing.assert_allclose(b["rew"].cpu().numpy(), rew, rtol=0, atol=tol["reward_atol"])
+    np.testing.assert_allclose(b["tobs"].cpu().numpy()[term | trunc], obs[term | trunc], rtol=0, atol=tol["obs_atol"])
+    np.testing.assert_allclose(b["obs"].cpu().numpy()[4], obs[4], rtol=0, atol=tol["obs_atol"])
+    assert abs(float(ora["delta"][4]) - 0.95 * np.pi / 6) < 1e-15          # clipped at max_delta, then decayed
+    got = env.get_state()
+    np.testing.assert_allclose(got["delta"][4], ora["delta"][4], rtol=0, atol=1e-15)
+    assert (got["steps"][[0, 1, 2, 3, 5]] == 0).all() and got["steps"][4] == 6  # finished envs were re-drawn on the device
     env.close()

@@ -7,7 +7,7 @@ from oracle import envs_oracle as eo
 from oracle import philox as px
 import replay_util as _replay
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
 
 
 def test_philox_known_answers():
@@ -30,19 +30,28 @@ def test_oracle_matches_reference_golden(task):
     T, E = acts.shape
     st = _replay.initial_state(task, g, eo.STATE_DTYPES[task])
     np.testing.assert_array_equal(eo.observe(task, st), g["init_obs"])
+    inexact = 0
     for t in range(T):
         obs, rew, term, trunc = eo.transition(task, st, acts[t])
         assert np.array_equal(term, g["terminated"][t]), (task, t)
         assert np.array_equal(trunc, g["truncated"][t]), (task, t)
         # bit-exact: integer tasks by construction, ball3d because the restatement
         # reproduces NumPy's promotion/rounding order
-        assert np.array_equal(obs.view(np.uint32), g["obs"][t].view(np.uint32)), (task, t)
-        assert np.array_equal(rew.view(np.uint32), g["reward"][t].view(np.uint32)), (task, t)
+        if task in _replay.LIBM_TASKS:   # bit-exact on the host that made the fixture; elsewhere libm/SVML/BLAS may differ by an ulp
+            tol = _replay.LIBM_TASKS[task]
+            inexact += int((obs.view(np.uint32) != g["obs"][t].view(np.uint32)).sum()) + int((rew.view(np.uint32) != g["reward"][t].view(np.uint32)).sum())
+            np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=tol["obs_atol"])
+            np.testing.assert_allclose(rew, g["reward"][t], rtol=0, atol=tol["reward_atol"])
+        else:
+            assert np.array_equal(obs.view(np.uint32), g["obs"][t].view(np.uint32)), (task, t)
+            assert np.array_equal(rew.view(np.uint32), g["reward"][t].view(np.uint32)), (task, t)
         done = term | trunc
         st = _replay.inject_resets(task, g, t, st, done)
         if done.any():
             idx = np.nonzero(done)[0]
             np.testing.assert_array_equal(eo.observe(task, st)[idx], g["reset_obs"][t][idx])
+    print(f"{task}: {inexact} values differ in the last bits from the fixture")
+    assert inexact <= 1e-3 * T * E * (obs.shape[1] + 1)
 
 
 def test_reward_luts_are_f32_of_double():
@@ -94,6 +103,25 @@ def test_brickbreak_reset_distribution_matches_reference():
     y = np.linspace(-np.pi / 4, np.pi / 4, 100001)
     s_, c_ = eo.sin_cos_quarter(y)
     assert np.abs(s_ - np.sin(y)).max() < 3e-16 and np.abs(c_ - np.cos(y)).max() < 3e-16
+
+
+def test_bicycle_reset_distribution_matches_reference():
+    """bicycle.py:40-58: origin, zero heading/steer, lean and lean rate ~ U(-0.1, 0.1), goal at radius U(15, 25) and bearing
+    U(-pi/4, pi/4), dist_to_goal = |goal|.  20 000 Philox draws (dot2 goes through np.dot per env) vs 4096 reference resets."""
+    ref = np.load(_replay.GOLDEN + "/bicycle_resets.npz")
+    n = 20_000
+    st = eo.draw_reset("bicycle", 7, np.arange(n), 3)
+    for s in (st, ref):
+        for k in ("x", "z", "theta", "delta"):
+            assert (s[k] == 0.0).all()
+        assert np.abs(s["phi"]).max() <= 0.1 and np.abs(s["phi_dot"]).max() <= 0.1
+        rad, ang = np.linalg.norm(s["goal"], axis=1), np.arctan2(s["goal"][:, 1], s["goal"][:, 0])
+        assert rad.min() >= 15.0 - 1e-12 and rad.max() <= 25.0 + 1e-12 and np.abs(ang).max() <= np.pi / 4 + 1e-12
+        assert np.abs(s["dist"] - rad).max() < 1e-13
+        m = len(rad)
+        assert abs(rad.mean() - 20.0) < 4 * 10.0 / np.sqrt(12 * m) and abs(ang.mean()) < 4 * (np.pi / 2) / np.sqrt(12 * m)
+        assert abs(s["phi"].mean()) < 4 * 0.2 / np.sqrt(12 * m) and abs(s["phi"].std() - 0.2 / np.sqrt(12)) < 0.002
+        assert abs(np.corrcoef(s["phi"], s["phi_dot"])[0, 1]) < 5 / np.sqrt(m)
 
 
 @pytest.mark.parametrize("task", ("ball3d", "gridworld", "push"))

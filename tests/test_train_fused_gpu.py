@@ -89,6 +89,7 @@ def _setup(task, n, T, seed=5):
     ("push", 512, 90, 128 * 148 * 2 + 77),    # several tiles per CTA + ragged tail
     ("ball3d", 1024, 64, 128 * 148 * 3),      # exactly three full rounds
     ("walljump", 400, 60, 5000),              # 4 actions (NOUT = 4)
+    ("bicycle", 400, 60, 128 * 148 + 333),    # 7 inputs (28-byte rows, 4-byte cp.async pieces), 3 actions
 ])
 def test_fused_minibatch_matches_unfused(task, n, T, rows):
     from three_mlagents_b200 import ops

@@ -62,6 +62,20 @@ def test_train_task_brickbreak_runs_on_the_unfused_path(tmp_path, monkeypatch):
     assert res.algorithm == "ppo" and np.isfinite(res.mean_reward) and res.eval_episodes == 16
 
 
+def test_train_task_bicycle_learns_to_stay_up(tmp_path, monkeypatch):
+    """bicycle (7 inputs, 3 actions; no registry threshold) through the fused update: a random policy falls after ~37 steps
+    (tests/golden/bicycle.npz: 863 episodes in 32 000 steps, about -10 + 36 * 0.3 per episode); 20 M steps of PPO must keep the
+    bike up for much longer, i.e. collect a clearly positive return."""
+    from three_mlagents_b200.ppo import CudaPPO
+    from three_mlagents_b200.training import TrainConfig, train_task
+
+    monkeypatch.chdir(tmp_path)
+    res = train_task(TrainConfig("bicycle", total_timesteps=20_000_000, algorithm="ppo", n_envs=4096, eval_episodes=256, eval_freq=10**12,
+                                 verbose=0, run_name="bk"), model_kwargs={"n_steps": 128, "batch_size": 32768})
+    print("bicycle eval mean reward", res.mean_reward)
+    assert res.mean_reward > 20.0, res.mean_reward
+
+
 @pytest.mark.parametrize("task,steps,episodes", [("ball3d", 40_000_000, 256), ("gridworld", 80_000_000, 8192),
                                                  ("push", 120_000_000, 2048), ("walljump", 40_000_000, 256)])
 def test_ppo_reaches_registry_reward_threshold(task, steps, episodes, tmp_path, monkeypatch):

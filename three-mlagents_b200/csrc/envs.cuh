@@ -496,6 +496,21 @@ struct WallJumpTask {
 // Python floats), so every operation below is an explicit f64 add/mul/div in the reference's order (no FMA contraction).
 // The serve angle uses a fixed Horner polynomial for sin/cos (plain mul/add), the same sequence as
 // oracle/envs_oracle.py:sin_cos_quarter, so that oracle and device resets agree bit for bit.
+// sin/cos on [-pi/4, pi/4] as fixed Horner polynomials in plain f64 mul/add (no fma, no libm): reset draws that need an
+// angle use this on the device and in the oracle (oracle/envs_oracle.py:sin_cos_quarter), so the two agree bit for bit.
+static __device__ __forceinline__ void sin_cos_quarter(double y, double &sn, double &cs) {
+    const double z = __dmul_rn(y, y);
+    double ps = -1.0 / 1307674368000.0, pc = 1.0 / 20922789888000.0;
+    const double sc[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
+    const double cc[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -1.0 / 2.0};
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ps = __dadd_rn(__dmul_rn(ps, z), sc[j]);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pc = __dadd_rn(__dmul_rn(pc, z), cc[j]);
+    sn = __dadd_rn(y, __dmul_rn(__dmul_rn(y, z), ps));
+    cs = __dadd_rn(1.0, __dmul_rn(z, pc));
+}
+
 struct BrickBreakTask {
     static constexpr bool HAS_SPARE = false;
     typedef NoSpare Spare;
@@ -589,19 +604,114 @@ struct BrickBreakTask {
     static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
         const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                        // brick_break.py:39-46
         const double angle = __dadd_rn(0.78539816339744830962, __dmul_rn(1.57079632679489661923, u32_to_unit(b.x)));
-        const double y = __dsub_rn(angle, 1.57079632679489661923), z = __dmul_rn(y, y);
-        double ps = -1.0 / 1307674368000.0, pc = 1.0 / 20922789888000.0;
-        const double sc[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
-        const double cc[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -1.0 / 2.0};
-#pragma unroll
-        for (int j = 0; j < 6; ++j) ps = __dadd_rn(__dmul_rn(ps, z), sc[j]);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) pc = __dadd_rn(__dmul_rn(pc, z), cc[j]);
-        const double sn = __dadd_rn(y, __dmul_rn(__dmul_rn(y, z), ps)), cs = __dadd_rn(1.0, __dmul_rn(z, pc));
+        double sn, cs;
+        sin_cos_quarter(__dsub_rn(angle, 1.57079632679489661923), sn, cs);
         s.px = 20.0; s.py = 10.0;
         s.vx = __dmul_rn(-sn, 1.5); s.vy = __dmul_rn(cs, 1.5);                             // cos(angle) = -sin(y), sin(angle) = cos(y)
         s.paddle = 20.0;
         s.bricks = (1ull << 40) - 1ull;
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};
+
+// ---------------------------------------------------------------------------------------- bicycle
+// examples/bicycle.py:11-146 behind the legacy adapter (envs.py:230-241): float64 lean/steer dynamics with sin, cos, tan and a
+// square root per step, in the reference's operation order.  The reference's own results depend on its host's libm / SVML /
+// BLAS builds (np.tan, `** 0.5` = pow, ddot; see oracle/envs_oracle.py), so this task is held to a stated tolerance, not to
+// bit equality: CUDA's f64 sin/cos/tan are within 2 ulp, `** 0.5` is __dsqrt_rn, the 2-vector dots round like the FMA ddot.
+struct BicycleTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
+    static constexpr int D = 7, A = 3, MAX_STEPS = 2000, NBUF = 4;
+    typedef tmla_bicycle_state Wire;
+    struct State { double x, z, theta, phi, phi_dot, delta, gx, gz, dist; int steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int b) { return b < 3 ? 16 : 32; }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        const double2 p = reinterpret_cast<const double2 *>(buf[0])[i], q = reinterpret_cast<const double2 *>(buf[1])[i];
+        const double2 r = reinterpret_cast<const double2 *>(buf[2])[i];
+        const double2 g = reinterpret_cast<const double2 *>(buf[3])[2 * i], m = reinterpret_cast<const double2 *>(buf[3])[2 * i + 1];
+        const long long meta = __double_as_longlong(m.y);                       // steps | ep_return bits << 32
+        return State{p.x, p.y, q.x, q.y, r.x, r.y, g.x, g.y, m.x, (int)(meta & 0xFFFFFFFFll), __int_as_float((int)(meta >> 32))};
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        reinterpret_cast<double2 *>(buf[0])[i] = make_double2(s.x, s.z);
+        reinterpret_cast<double2 *>(buf[1])[i] = make_double2(s.theta, s.phi);
+        reinterpret_cast<double2 *>(buf[2])[i] = make_double2(s.phi_dot, s.delta);
+        const long long meta = (long long)(unsigned)s.steps | ((long long)__float_as_int(s.ep_ret) << 32);
+        reinterpret_cast<double2 *>(buf[3])[2 * i] = make_double2(s.gx, s.gz);
+        reinterpret_cast<double2 *>(buf[3])[2 * i + 1] = make_double2(s.dist, __longlong_as_double(meta));
+    }
+    static __device__ State from_wire(const Wire &w) {
+        return State{w.x, w.z, w.theta, w.phi, w.phi_dot, w.delta, w.goal[0], w.goal[1], w.dist, w.steps, w.ep_return};
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w; w.x = s.x; w.z = s.z; w.theta = s.theta; w.phi = s.phi; w.phi_dot = s.phi_dot; w.delta = s.delta;
+        w.goal[0] = s.gx; w.goal[1] = s.gz; w.dist = s.dist; w.steps = s.steps; w.ep_return = s.ep_ret; return w;
+    }
+    // np.linalg.norm / np.dot on 2-vectors = BLAS ddot, which rounds as fma(a1, b1, a0*b0) on FMA hosts (oracle: dot2)
+    static __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) { return __fma_rn(a1, b1, __dmul_rn(a0, b0)); }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // bicycle.py:128-145, cast envs.py:150
+        const double v0 = __dsub_rn(s.gx, s.x), v1 = __dsub_rn(s.gz, s.z);
+        const double dist = __dsqrt_rn(dot2(v0, v1, v0, v1));
+        double st, ct;
+        sincos(s.theta, &st, &ct);
+        o[0] = __double2float_rn(s.phi); o[1] = __double2float_rn(s.phi_dot); o[2] = __double2float_rn(s.delta);
+        o[3] = __double2float_rn(ct); o[4] = __double2float_rn(st);
+        o[5] = dist > 0.0 ? __double2float_rn(__ddiv_rn(v0, dist)) : 0.0f;
+        o[6] = dist > 0.0 ? __double2float_rn(__ddiv_rn(v1, dist)) : 0.0f;
+    }
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
+        constexpr double DT = 0.02, GH = 9.8 / 0.8, VLH = 25.0 / (1.0 * 0.8), VL = 5.0 / 1.0;        // bicycle.py:15-20 as evaluated
+        constexpr double MAX_PHI = 3.141592653589793 / 4, MAX_DELTA = 3.141592653589793 / 6;       // :29-30
+        double delta = __dadd_rn(s.delta, a == 0 ? -0.05 : (a == 2 ? 0.05 : 0.0));                 // :63-69
+        delta = fmin(fmax(delta, -MAX_DELTA), MAX_DELTA);                                          // :70
+        double sp, cp;
+        sincos(s.phi, &sp, &cp);
+        const double phi_ddot = __dsub_rn(__dmul_rn(GH, sp), __dmul_rn(__dmul_rn(VLH, tan(delta)), cp));   // :74-76
+        const double phi_dot = __dadd_rn(s.phi_dot, __dmul_rn(phi_ddot, DT));                      // :77
+        const double phi = __dadd_rn(s.phi, __dmul_rn(phi_dot, DT));                               // :78
+        delta = __dmul_rn(delta, 0.95);                                                            // :81
+        const double theta = __dadd_rn(s.theta, __dmul_rn(__dmul_rn(VL, tan(delta)), DT));         // :84
+        double st, ct;
+        sincos(theta, &st, &ct);
+        const double x = __dadd_rn(s.x, __dmul_rn(__dmul_rn(5.0, ct), DT));                        // :85
+        const double z = __dadd_rn(s.z, __dmul_rn(__dmul_rn(5.0, st), DT));                        // :86
+        const double g0 = __dsub_rn(s.gx, x), g1 = __dsub_rn(s.gz, z);
+        const double nd = __dsqrt_rn(dot2(g0, g1, g0, g1));                                        // :91
+        const double progress = __dmul_rn(__dsub_rn(s.dist, nd), 10.0);                            // :94
+        const double upright = __dmul_rn(__dsub_rn(1.0, __dsqrt_rn(__ddiv_rn(fabs(phi), MAX_PHI))), 0.2);   // :98
+        const double den = nd > 0.0 ? nd : 1.0;                                                    // :103-105
+        const double heading = __dmul_rn(dot2(ct, st, __ddiv_rn(g0, den), __ddiv_rn(g1, den)), 0.3);   // :101-106
+        const double steering = __dmul_rn(-__ddiv_rn(fabs(delta), MAX_DELTA), 0.1);                // :109
+        double r = __dadd_rn(__dadd_rn(__dadd_rn(progress, upright), heading), steering);          // :111
+        s.x = x; s.z = z; s.theta = theta; s.phi = phi; s.phi_dot = phi_dot; s.delta = delta; s.dist = nd;
+        s.steps += 1;
+        bool done = false;
+        if (fabs(phi) > MAX_PHI) { r = -10.0; done = true; }                                       // :113-115
+        if (s.steps > 2000) done = true;                                                           // :117-118
+        if (nd < 2.0) { r = 50.0; done = true; }                                                   // :120-122
+        reward = __double2float_rn(r);
+        trunc = s.steps >= MAX_STEPS;                                                              // envs.py:141-145
+        term = done && !trunc;
+    }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                                // bicycle.py:40-58
+        s.x = 0.0; s.z = 0.0; s.theta = 0.0; s.delta = 0.0;
+        s.phi = __dadd_rn(-0.1, __dmul_rn(0.2, u32_to_unit(b.x)));                                 // uniform(lo, hi) = lo + (hi - lo) * u
+        s.phi_dot = __dadd_rn(-0.1, __dmul_rn(0.2, u32_to_unit(b.y)));
+        const double radius = __dadd_rn(15.0, __dmul_rn(10.0, u32_to_unit(b.z)));
+        double sn, cs;
+        sin_cos_quarter(__dadd_rn(-0.78539816339744830962, __dmul_rn(1.57079632679489661923, u32_to_unit(b.w))), sn, cs);
+        s.gx = __dmul_rn(radius, cs); s.gz = __dmul_rn(radius, sn);
+        s.dist = __dsqrt_rn(dot2(s.gx, s.gz, s.gx, s.gz));
         s.steps = 0; s.ep_ret = 0.0f;
     }
 };

@@ -165,8 +165,9 @@ struct TrainSmem {
     static constexpr uint32_t xs = b2 + H * 4;                         // float [128][D]: next tile's observation rows (cp.async staging)
     static constexpr uint32_t ls = xs + 128 * D * 4;                   // [128][3] words: next tile's loss inputs (action|adv|old_logp or return)
     static constexpr uint32_t idx = ls + 128 * 12;                     // int32 [2][128]: buffer rows of the next two tiles (-1 = past the end)
-    static constexpr uint32_t racc = idx + 2 * 128 * 4;                // float [128][9]: per-row running sums (4 loss statistics, NOUT head-bias gradients)
-    static constexpr uint32_t bar = racc + 128 * 9 * 4 + 16;           // + adv_mean, adv_inv_std
+    static constexpr uint32_t RS = (4 + NOUT) | 1;                     // odd row stride (bank-conflict free)
+    static constexpr uint32_t racc = idx + 2 * 128 * 4;                // float [128][RS]: per-row running sums (4 loss statistics, NOUT head-bias gradients)
+    static constexpr uint32_t bar = racc + 128 * RS * 4 + 16;          // + adv_mean, adv_inv_std
 #ifdef TMLA_PHASE_CLOCKS
     static constexpr uint32_t total = bar + 64 + 256;
 #else
@@ -220,11 +221,12 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         const int32_t sn = idxs[parity * 128 + rt];
         const bool ok = sn >= 0;
         const int64_t src = ok ? (int64_t)sn : 0;
-        constexpr int XP = D == 6 ? 3 : 1;
-        if (cq < XP) {
-            if (D == 6) cp_async_ca<8>(smem_u32(xs + rt * D + cq * 2), p.x + src * D + cq * 2, ok ? 8u : 0u);
-            else cp_async_ca<16>(smem_u32(xs + rt * D), p.x + src * D, ok ? 16u : 0u);
-        }
+        if (D == 7) {                                                // 28-byte rows: 4-byte pieces cq and cq + 4
+            cp_async_ca<4>(smem_u32(xs + rt * D + cq), p.x + src * D + cq, ok ? 4u : 0u);
+            if (cq + 4 < D) cp_async_ca<4>(smem_u32(xs + rt * D + cq + 4), p.x + src * D + cq + 4, ok ? 4u : 0u);
+        } else if (D == 6) {
+            if (cq < 3) cp_async_ca<8>(smem_u32(xs + rt * D + cq * 2), p.x + src * D + cq * 2, ok ? 8u : 0u);
+        } else if (cq < 1) cp_async_ca<16>(smem_u32(xs + rt * D), p.x + src * D, ok ? 16u : 0u);
     };
     auto fetch_loss_inputs = [&](uint32_t parity) {                  // loss inputs of the rows selected by idxs[parity] -> ls
         if (cq == 3) {
@@ -277,7 +279,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
 
     // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased) and the per-row running
     // sums live in shared memory: registers are the scarce resource of this kernel
-    float *racc = reinterpret_cast<float *>(smem + L::racc), *advc = racc + 128 * 9;
+    float *racc = reinterpret_cast<float *>(smem + L::racc), *advc = racc + 128 * L::RS;
     if (tid == 0) {
         float adv_mean = 0.0f, adv_inv_std = 1.0f;
         if (PI && p.normalize) {
@@ -290,7 +292,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
         advc[0] = adv_mean; advc[1] = adv_inv_std;
     }
-    for (int e = tid; e < 128 * 9; e += blockDim.x) racc[e] = 0.0f;
+    for (int e = tid; e < 128 * (int)L::RS; e += blockDim.x) racc[e] = 0.0f;
     __syncthreads();
 
     // layer 1, H1 = tanh(x W1^T + b1): this thread computes rows l1row + 8*i (i < 4) x 16 columns from l1col — every
@@ -525,21 +527,21 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 for (int j = 0; j < NOUT; ++j)
                     dz[j] = valid ? dlogp * ((a_cur == j ? 1.0f : 0.0f) - pr[j]) + p.ent_coef * p.inv_rows * pr[j] * (lp[j] + ent) : 0.0f;
                 if (valid) {
-                    float *ra = racc + rt * 9;
+                    float *ra = racc + rt * L::RS;
                     ra[0] += -fminf(s1, s2); ra[1] += -ent; ra[2] += (ratio - 1.0f) - lr;
                     ra[3] += (fabsf(ratio - 1.0f) > p.clip) ? 1.0f : 0.0f;
                 }
             } else {
                 const float dv = z[0] - f0_cur;
                 dz[0] = valid ? p.vf_coef * 2.0f * dv * p.inv_rows : 0.0f;
-                if (valid) racc[rt * 9] += dv * dv;
+                if (valid) racc[rt * L::RS] += dv * dv;
             }
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0.0f;
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) {
-                racc[rt * 9 + 4 + a] += dz[a];
+                racc[rt * L::RS + 4 + a] += dz[a];
                 v[a] = dz[a]; v[NOUT + a] = dz[a] - bf16_round(dz[a]); v[2 * NOUT + a] = dz[a];
             }
             uint8_t *dr = smem + L::dout + (rt >> 3) * ksG + (rt & 7) * 16;
@@ -654,9 +656,9 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         // stats: pg_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss
         float st_acc[4], dbh_acc[NOUT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) st_acc[q] = warp_sum_f(racc[rt * 9 + q]) * p.inv_rows;
+        for (int q = 0; q < 4; ++q) st_acc[q] = warp_sum_f(racc[rt * L::RS + q]) * p.inv_rows;
 #pragma unroll
-        for (int a = 0; a < NOUT; ++a) dbh_acc[a] = warp_sum_f(racc[rt * 9 + 4 + a]);
+        for (int a = 0; a < NOUT; ++a) dbh_acc[a] = warp_sum_f(racc[rt * L::RS + 4 + a]);
         if (lane == 0) {
 #pragma unroll
             for (int a = 0; a < NOUT; ++a) atomicAdd(p.gBh + a, dbh_acc[a]);
@@ -875,7 +877,8 @@ static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
 extern "C" {
 
 int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions) {
-    return (hidden == H && ((obs_dim == 6 && n_actions == 5) || (obs_dim == 4 && (n_actions == 4 || n_actions == 5)))) ? 1 : 0;
+    return (hidden == H && ((obs_dim == 6 && n_actions == 5) || (obs_dim == 4 && (n_actions == 4 || n_actions == 5)) ||
+                            (obs_dim == 7 && n_actions == 3))) ? 1 : 0;
 }
 
 int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 2 * ((rows + 127) / 128 * 128) * (int64_t)hidden; }
@@ -889,7 +892,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     TMLA_REQUIRE(rows > 0 && global_rows >= rows, "bad row counts");
     TMLA_REQUIRE(!normalize_advantage || adv_sums, "adv_sums required when normalising");
     if (!tmla_ppo_minibatch_supported(obs_dim, hidden, n_actions)) {
-        tmla_set_error("tmla_ppo_minibatch_bf16: fused path covers hidden=256 with (obs_dim, actions) = (6,5), (4,5), (4,4) (got %d/%d/%d)", obs_dim, hidden, n_actions);
+        tmla_set_error("tmla_ppo_minibatch_bf16: fused path covers hidden=256 with (obs_dim, actions) = (6,5), (4,5), (4,4), (7,3) (got %d/%d/%d)", obs_dim, hidden, n_actions);
         return TMLA_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -912,6 +915,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         a.stats = stats_out;
         int rc;
         if (obs_dim == 6) rc = t == 0 ? tower_train_launch_t<6, 5>(a, st) : tower_train_launch_t<6, 1>(a, st);
+        else if (obs_dim == 7) rc = t == 0 ? tower_train_launch_t<7, 3>(a, st) : tower_train_launch_t<7, 1>(a, st);
         else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
         else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st) : tower_train_launch_t<4, 1>(a, st);
         if (rc) return rc;

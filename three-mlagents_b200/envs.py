@@ -101,3 +101,7 @@ def make_walljump_env() -> CudaTaskEnv:     # envs.py:202-213
 
 def make_brick_break_env() -> CudaTaskEnv:  # envs.py:216-227
     return CudaTaskEnv("brickbreak")
+
+
+def make_bicycle_env() -> CudaTaskEnv:      # envs.py:230-241
+    return CudaTaskEnv("bicycle")

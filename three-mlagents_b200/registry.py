@@ -2,7 +2,7 @@
 (`TaskSpec`, `TASKS`, `list_tasks`, `list_task_cards`, `get_task`, `make_env`; registry.py:18-370).
 
 All 19 task cards are kept so `three-mlagents list/inspect` and any caller of `get_task` keep
-working.  Only the four tasks on the hot path (basic, ball3d, gridworld, push) and walljump, brickbreak have a CUDA env
+working.  Only the four tasks on the hot path (basic, ball3d, gridworld, push) and walljump, brickbreak, bicycle have a CUDA env
 factory here; the reference's other Gymnasium tasks are listed with `env_factory=None`, so — by the
 reference's own rule `trainable = interface == "gymnasium" and env_factory is not None`
 (registry.py:41-43) — they report `trainable: false` in this backend and `make_env` raises the same
@@ -75,7 +75,7 @@ _TABLE: list[tuple] = [
      dict(publication_role="small arcade control benchmark before ALE/Procgen", env_factory=envs.make_brick_break_env)),
     ("bicycle", "Bicycle Balance and Navigation", "continuous-control", "gymnasium", "benchmark", "ppo", 500_000, 50, 8, None,
      ("underactuated-control", "stability", "navigation"),
-     dict(publication_role="control-system benchmark", notes=_NO_CUDA)),
+     dict(publication_role="control-system benchmark", env_factory=envs.make_bicycle_env)),
     ("glider", "Dynamic Soaring Glider", "aerospace", "gymnasium", "frontier", "ppo", 1_000_000, 50, 8, None,
      ("aerodynamics", "energy-management", "long-horizon"),
      dict(publication_role="domain-specific continuous physics case study", notes=_NO_CUDA)),

@@ -64,4 +64,6 @@ def spaces_for(task_id: str):
         return Box(-1.0, 1.0, (4,), np.float32), Discrete(4)
     if task_id == "brickbreak":            # envs.py:216-227 (shape probed from BrickBreakEnv().reset(): 2 + 2 + 1 + 40)
         return Box(-np.inf, np.inf, (45,), np.float32), Discrete(3)
+    if task_id == "bicycle":               # envs.py:230-241 (shape probed from BicycleEnv().reset(): 7 floats, bicycle.py:133-145)
+        return Box(-np.inf, np.inf, (7,), np.float32), Discrete(3)
     raise KeyError(task_id)
