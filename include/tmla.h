@@ -40,8 +40,8 @@ extern "C" {
 #define TMLA_ENOMEM       -3
 #define TMLA_EACTION      -4      /* an out-of-range action was seen by a step kernel */
 
-typedef enum { TMLA_BASIC = 0, TMLA_BALL3D = 1, TMLA_GRIDWORLD = 2, TMLA_PUSH = 3, TMLA_WALLJUMP = 4, TMLA_BRICKBREAK = 5, TMLA_BICYCLE = 6 } tmla_task;
-#define TMLA_NUM_TASKS 7
+typedef enum { TMLA_BASIC = 0, TMLA_BALL3D = 1, TMLA_GRIDWORLD = 2, TMLA_PUSH = 3, TMLA_WALLJUMP = 4, TMLA_BRICKBREAK = 5, TMLA_BICYCLE = 6, TMLA_GLIDER = 7 } tmla_task;
+#define TMLA_NUM_TASKS 8
 
 typedef struct tmla_env tmla_env;     /* opaque handle: packed SoA state of n envs on one GPU */
 
@@ -54,13 +54,14 @@ typedef struct { int32_t agent[2], box[2], goal_x, steps; float ep_return; } tml
 typedef struct { int32_t agent_x, in_air, wall, steps; float ep_return; } tmla_walljump_state;                   /* walljump.py:39-45 */
 typedef struct { double pos[2], vel[2], paddle; uint8_t bricks[40]; int32_t steps; float ep_return; } tmla_brickbreak_state; /* brick_break.py:39-46 */
 typedef struct { double x, z, theta, phi, phi_dot, delta, goal[2], dist; int32_t steps; float ep_return; } tmla_bicycle_state; /* bicycle.py:22-36 */
+typedef struct { double pos[3], vel[3], rot[3], ang_vel[3]; int32_t waypoint, steps; float ep_return; int32_t pad_; } tmla_glider_state; /* glider.py:41-52 */
 
 int         tmla_version(void);
 const char *tmla_last_error(void);
 
 /* task metadata — replaces the space declarations in make_*_env (envs.py:38-44,169-199) */
-int tmla_task_from_name(const char *name);            /* "basic"|"ball3d"|"gridworld"|"push"|"walljump"|"brickbreak"|"bicycle" -> tmla_task or TMLA_EINVAL */
-int tmla_task_obs_dim(int task);                      /* 21 / 6 / 4 / 4 / 4 / 45 / 7 */
+int tmla_task_from_name(const char *name);            /* "basic"|"ball3d"|"gridworld"|"push"|"walljump"|"brickbreak"|"bicycle"|"glider" -> tmla_task or TMLA_EINVAL */
+int tmla_task_obs_dim(int task);                      /* 21 / 6 / 4 / 4 / 4 / 45 / 7 / 16 */
 int tmla_task_num_actions(int task);                  /* 3 / 5 / 5 / 5 / 4 / 3 */
 int tmla_task_max_steps(int task);                    /* 50 / 200 / 100 / 120 / 150 / 2000 */
 int tmla_task_state_size(int task);                   /* sizeof(tmla_<task>_state) */

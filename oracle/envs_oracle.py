@@ -16,6 +16,7 @@ Reference anchors (relative to /root/reference/backend):
   walljump   examples/walljump.py:14-98
   brickbreak examples/brick_break.py:11-133
   bicycle    examples/bicycle.py:11-146
+  glider     examples/glider.py:11-265
   adapter    mlagents/envs.py:87-159  (time-limit truncation, terminated/truncated split)
   vec/auto-reset + Monitor: SB3 DummyVecEnv/Monitor semantics, SURVEY.md §8(a) A7
 Reset draws use this repo's Philox streams (oracle/philox.py), not MT19937.
@@ -49,6 +50,7 @@ TASKS = {
     "walljump":  (4, 4, 150),     # walljump.py:14-21 ; envs.py:202-213
     "brickbreak": (45, 3, 2000),  # brick_break.py:14-38 (2 + 2 + 1 + 5*8 obs) ; envs.py:216-227
     "bicycle":   (7, 3, 2000),    # bicycle.py:130-145 ; envs.py:230-241
+    "glider":    (16, 5, 4000),   # glider.py:241-265 (9 + 3 + 3 + 1) ; envs.py:244-255
 }
 
 STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format of get/set_state)
@@ -64,6 +66,8 @@ STATE_DTYPES = {   # identical to the C structs in include/tmla.h (wire format o
                             ("steps", "<i4"), ("ep_return", "<f4")]),
     "bicycle": np.dtype([("x", "<f8"), ("z", "<f8"), ("theta", "<f8"), ("phi", "<f8"), ("phi_dot", "<f8"), ("delta", "<f8"),
                          ("goal", "<f8", (2,)), ("dist", "<f8"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "glider": np.dtype([("pos", "<f8", (3,)), ("vel", "<f8", (3,)), ("rot", "<f8", (3,)), ("ang_vel", "<f8", (3,)),
+                        ("waypoint", "<i4"), ("steps", "<i4"), ("ep_return", "<f4"), ("pad_", "<i4")]),
 }
 
 f32 = np.float32
@@ -75,6 +79,76 @@ BIKE_VLH = 5.0 ** 2 / (1.0 * 0.8)    # self.v**2 / (self.L * self.h)
 BIKE_VL = 5.0 / 1.0                  # self.v / self.L
 BIKE_MAX_PHI = np.pi / 4
 BIKE_MAX_DELTA = np.pi / 6
+
+
+# glider.py:16-50 — constants as the reference's Python expressions evaluate them
+GL_DT, GL_MASS, GL_G, GL_RHO, GL_S = 0.02, 1.5, 9.81, 1.225, 0.5
+GL_CL_ALPHA, GL_CD0, GL_CDK = 2 * np.pi, 0.02, 0.05
+GL_WAYPOINTS = np.array([[-160.0, 0.0, 70.0], [160.0, 0.0, 70.0]])
+GL_F1, GL_F2, GL_C1, GL_MAG1, GL_MAG2, GL_C3 = 1.0 / 250.0, 1.0 / 400.0, 8.0, 1.0, 0.7, 50.0
+GL_MAX_ROLL, GL_MAX_PITCH, GL_MAX_AOA = np.pi / 2, np.pi / 4, np.deg2rad(15)
+GL_TORQUES = np.array([[0.0, 0.0, 0.0], [-15.0, 0.0, 4.0], [15.0, 0.0, -4.0], [0.0, 10.0, 0.0], [0.0, -10.0, 0.0]])  # glider.py:92-103
+
+
+def _glider_step_one(pos, vel, rot, ang_vel, wp, action):
+    """One env, one step of glider.py:87-238 on float64 3-vectors, through the same NumPy entry points as the reference
+    (np.linalg.norm, np.dot, `@` go to this host's BLAS; np.arctan2 / np.sin / np.cos to its libm or SVML) — the restatement is
+    pinned bit for bit on the host that made the fixture and held to a tolerance elsewhere, like the CUDA kernel."""
+    t = GL_TORQUES[action]
+    ang_vel = ang_vel.copy()
+    ang_vel[0] += t[0] * GL_DT                                      # :107-109
+    ang_vel[1] += t[1] * GL_DT
+    ang_vel[2] += t[2] * GL_DT
+    ang_vel = ang_vel * 0.95                                        # :110
+    rot = rot + ang_vel * GL_DT                                     # :111
+    rot[0] = np.clip(rot[0], -GL_MAX_ROLL, GL_MAX_ROLL)             # :114-115
+    rot[1] = np.clip(rot[1], -GL_MAX_PITCH, GL_MAX_PITCH)
+    x, y = pos[0], pos[1]                                           # :55-77 wind at the position before integration
+    up1 = np.sin(x * GL_F1 * 2 * np.pi) * np.cos(y * GL_F1 * 2 * np.pi) * GL_C1 * GL_MAG1
+    up2 = np.sin(x * GL_F2 * 2 * np.pi / 1.5) * np.cos(y * GL_F1 * 2 * np.pi / 1.5) * GL_C1 * GL_MAG2
+    v_air = vel - np.array([1.0, 0.5, up1 + up2])                   # :118-119
+    v_air_mag = np.linalg.norm(v_air)                               # :120
+    aoa = np.arctan2(-v_air[2], v_air[0]) if v_air[0] != 0 else 0   # :123
+    if v_air_mag > 0.1:                                             # :125-160
+        CL = GL_CL_ALPHA * aoa
+        CD = GL_CD0 + GL_CDK * CL**2
+        lift = 0.5 * GL_RHO * v_air_mag**2 * GL_S * CL
+        drag = 0.5 * GL_RHO * v_air_mag**2 * GL_S * CD
+        c0, s0, c1, s1, c2, s2 = np.cos(rot[0]), np.sin(rot[0]), np.cos(rot[1]), np.sin(rot[1]), np.cos(rot[2]), np.sin(rot[2])
+        R_roll = np.array([[1, 0, 0], [0, c0, -s0], [0, s0, c0]])
+        R_pitch = np.array([[c1, 0, s1], [0, 1, 0], [-s1, 0, c1]])
+        R_yaw = np.array([[c2, -s2, 0], [s2, c2, 0], [0, 0, 1]])
+        aero = (R_yaw @ R_pitch @ R_roll) @ (np.array([0, 0, lift]) + np.array([-drag, 0, 0]))
+    else:
+        aero = np.zeros(3)
+        aoa = 0
+    total = aero + np.array([0, 0, -GL_MASS * GL_G])                # :162-163
+    vel = vel + (total / GL_MASS) * GL_DT                           # :166
+    pos = pos + vel * GL_DT                                         # :167
+    vec = GL_WAYPOINTS[wp] - pos                                    # :173-175
+    dist = np.linalg.norm(vec)
+    if dist < 15.0:                                                 # :177-180
+        wp = (wp + 1) % 2
+    vel_dir = vel / (np.linalg.norm(vel) + 1e-8)                    # :183-185
+    heading = np.dot(vel_dir, vec / (dist + 1e-8))
+    H = (heading + 1) / 2                                           # :188
+    E = np.clip(np.linalg.norm(vel) / 30.0, 0, 2.0)                 # :190-192
+    reward = E * (H - E + 1)                                        # :196
+    lateral = abs(pos[1])                                           # :201-206
+    if lateral > 250.0:
+        reward -= 2.0 * (((lateral - 250.0) / 100.0) ** 2)
+    if pos[2] > 250.0:                                              # :209-215
+        reward -= 2.0 * ((pos[2] - 250.0) / 50.0) ** 2
+    elif pos[2] < 25.0:
+        reward -= 0.5
+    done = False
+    if pos[2] < 5.0:                                                # :218-220
+        reward, done = -50.0, True
+    if abs(aoa) > GL_MAX_AOA:                                       # :223-225
+        reward, done = -50.0, True
+    if dist > 500:                                                  # :228-230
+        reward, done = -50.0, True
+    return pos, vel, rot, ang_vel, wp, float(reward), done
 
 
 def dot2(a, b):
@@ -150,6 +224,15 @@ def observe(task, st):
         x = st["agent_x"].astype(np.float64)
         return np.stack([(WJ_WIDTH - 1 - x) / (WJ_WIDTH - 1), (WJ_WALL_X - x) / (WJ_WIDTH - 1), st["wall"].astype(np.float64),
                          (st["in_air"] == 0).astype(np.float64)], axis=1).astype(np.float32)
+    if task == "glider":         # glider.py:241-265 (the target direction uses the waypoint index AFTER a switch)
+        out = np.zeros((n, 16), np.float64)
+        for i in range(n):
+            pos, vel, rot, av = st["pos"][i], st["vel"][i], st["rot"][i], st["ang_vel"][i]
+            vec = GL_WAYPOINTS[st["waypoint"][i]] - pos
+            dist = np.linalg.norm(vec)
+            out[i] = np.concatenate([np.array([vel[2] / 10.0, (pos[2] - GL_C3) / 50.0, rot[0], rot[1], np.sin(rot[2]), np.cos(rot[2]),
+                                               av[0], av[1], av[2]]), vel / 20.0, vec / (dist + 1e-8), [dist / 100.0]])
+        return out.astype(np.float32)
     if task == "bicycle":        # bicycle.py:128-145: the goal direction is re-derived from the state; the adapter casts to f32
         vec = st["goal"] - np.stack([st["x"], st["z"]], 1)
         dist = np.sqrt(dot2(vec, vec))
@@ -309,6 +392,18 @@ def transition(task, st, actions):
         reward = reward.astype(np.float32)
         hit_limit = st["steps"] >= max_steps
         terminated, truncated = done & ~hit_limit, hit_limit
+    elif task == "glider":
+        reward = np.zeros(n, np.float64)
+        done = np.zeros(n, bool)
+        for i in range(n):
+            pos, vel, rot, av, wp, reward[i], done[i] = _glider_step_one(st["pos"][i], st["vel"][i], st["rot"][i], st["ang_vel"][i],
+                                                                         int(st["waypoint"][i]), int(a[i]))
+            st["pos"][i], st["vel"][i], st["rot"][i], st["ang_vel"][i], st["waypoint"][i] = pos, vel, rot, av, wp
+        st["steps"] += 1
+        done |= st["steps"] > 4000                                                                 # glider.py:233-234
+        reward = reward.astype(np.float32)
+        hit_limit = st["steps"] >= max_steps
+        terminated, truncated = done & ~hit_limit, hit_limit
     elif task == "bicycle":
         # bicycle.py:59-126 in the reference's operation order (Python doubles).  np.sin/np.cos are libm; np.tan and `** 0.5`
         # (libm pow, not sqrt) are whatever this host's NumPy dispatches to — the CUDA side is compared within a tolerance.
@@ -399,6 +494,12 @@ def draw_reset(task, seed, env_ids, k, tag=px.TAG_RESET, episode=None):
         st["vel"] = np.stack([-s_ * 1.5, c_ * 1.5], 1)
         st["paddle"] = 20.0
         st["bricks"] = 1
+    elif task == "glider":                                          # glider.py:79-86
+        b = px.stream_block(seed, env_ids, k, tag, 0)
+        st["pos"] = np.array([0.0, 0.0, 60.0])
+        st["vel"] = np.array([15.0, 0.0, -1.0])
+        st["ang_vel"] = np.stack([-0.1 + 0.2 * px.u32_unit(b[j]) for j in range(3)], 1)   # np.random.uniform(-0.1, 0.1, 3)
+        st["waypoint"] = (b[3] >> np.uint32(31)).astype(np.int32)   # np.random.randint(0, 2)
     elif task == "bicycle":                                         # bicycle.py:40-58
         b = px.stream_block(seed, env_ids, k, tag, 0)
         st["phi"] = -0.1 + 0.2 * px.u32_unit(b[0])                  # np.random.uniform(lo, hi) = lo + (hi - lo) * u

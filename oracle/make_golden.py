@@ -30,6 +30,10 @@ OUT_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 E = 32      # environments per task
 T = 1000    # steps per environment (north_star: "over 1,000 steps")
+# glider: the last steps before a stall amplify a 1-ulp libm difference by ~1e8, so its trace also records the reference state
+# after EVERY step (one-step parity: the replay re-injects it) and is kept to 500 steps to bound the fixture size.
+T_TASK = {"glider": 500}
+PER_STEP_STATE = ("glider",)
 SEED = 20261017
 
 
@@ -70,6 +74,10 @@ def _state_of(task, env):
     if task == "brickbreak":
         return {"pos": np.asarray(inner.ball_pos, dtype=np.float64).copy(), "vel": np.asarray(inner.ball_vel, dtype=np.float64).copy(),
                 "paddle": np.float64(inner.paddle_x), "bricks": np.asarray(inner.bricks, dtype=np.uint8).reshape(-1).copy()}
+    if task == "glider":
+        return {"pos": np.asarray(inner.pos, dtype=np.float64).copy(), "vel": np.asarray(inner.vel, dtype=np.float64).copy(),
+                "rot": np.asarray(inner.rot, dtype=np.float64).copy(), "ang_vel": np.asarray(inner.ang_vel, dtype=np.float64).copy(),
+                "waypoint": np.int32(inner.current_waypoint_index)}
     if task == "bicycle":
         return {"x": np.float64(inner.x), "z": np.float64(inner.z), "theta": np.float64(inner.theta), "phi": np.float64(inner.phi),
                 "phi_dot": np.float64(inner.phi_dot), "delta": np.float64(inner.delta),
@@ -79,7 +87,7 @@ def _state_of(task, env):
     raise KeyError(task)
 
 
-def _actions(task, n_actions, rng):
+def _actions(task, n_actions, rng, T):
     """[T, E] action plan: a few constant-action envs (to reach clips, walls and
     time-limit truncation) + uniform-random envs."""
     acts = rng.integers(0, n_actions, size=(T, E), dtype=np.int64)
@@ -96,6 +104,11 @@ def _actions(task, n_actions, rng):
     if task == "brickbreak":
         acts[:, 6] = np.where(np.arange(T) % 5 < 3, 0, 2)       # drifts left, keeps the paddle near the wall clip
         acts[:, 7] = np.where(np.arange(T) % 11 < 6, 2, 0)
+    if task == "glider":
+        acts[:, 0] = 0                                           # hands off: glides until it stalls or lands
+        acts[:, 11] = np.where(np.arange(T) % 40 < 3, 3, 0)     # occasional pitch-up keeps it flying for long episodes
+        acts[:, 12] = np.where(np.arange(T) % 50 < 2, 3, np.where(np.arange(T) % 50 == 25, 1, 0))
+        acts[:, 13] = np.where(np.arange(T) % 60 < 2, 3, np.where(np.arange(T) % 60 == 30, 2, 0))
     if task == "bicycle":
         acts[:, 1] = 1                                           # never steers: falls over from the initial lean
         acts[:, 6] = np.where(np.arange(T) % 6 < 3, 0, 2)       # slow weave
@@ -112,7 +125,8 @@ def record(task, make_env):
     envs = [make_env(task) for _ in range(E)]
     obs_dim = envs[0].observation_space.shape[0]
     n_actions = envs[0].action_space.n
-    acts = _actions(task, n_actions, rng)
+    T = T_TASK.get(task, globals()["T"])
+    acts = _actions(task, n_actions, rng, T)
 
     # seeding as make_vector_env does it: env i <- reset(seed=seed+i)  (training.py:80-84)
     init_states, init_obs = [], []
@@ -132,6 +146,7 @@ def record(task, make_env):
     trunc = np.zeros((T, E), np.bool_)
     reset_obs = np.zeros((T, E, obs_dim), np.float32)
     resets = {k: np.zeros((T, E) + np.shape(init_states[0][k]), np.asarray(init_states[0][k]).dtype) for k in keys}
+    per_step = {k: np.zeros_like(v) for k, v in resets.items()} if task in PER_STEP_STATE else None
 
     for t in range(T):
         for i, env in enumerate(envs):
@@ -142,6 +157,10 @@ def record(task, make_env):
             rew[t, i] = np.float32(r)
             term[t, i] = te
             trunc[t, i] = tr
+            if per_step is not None:
+                st = _state_of(task, env)
+                for k in keys:
+                    per_step[k][t, i] = st[k]
             if te or tr:
                 ro, _ = env.reset()          # DummyVecEnv auto-reset: reset() without seed
                 reset_obs[t, i] = ro
@@ -150,6 +169,8 @@ def record(task, make_env):
                     resets[k][t, i] = st[k]
     out.update(obs=obs, reward=rew, reward64=rew64, terminated=term, truncated=trunc, reset_obs=reset_obs)
     out.update({f"reset_{k}": v for k, v in resets.items()})
+    if per_step is not None:
+        out.update({f"step_{k}": v for k, v in per_step.items()})
     for env in envs:
         env.close()
     return out
@@ -176,7 +197,7 @@ def main():
     make_env = _import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
     only = set(sys.argv[1:])                 # e.g. `python oracle/make_golden.py walljump` regenerates one task
-    for task in ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle"):
+    for task in ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider"):
         if only and task not in only:
             continue
         g = record(task, make_env)
@@ -185,7 +206,7 @@ def main():
         n_ep = int((g["terminated"] | g["truncated"]).sum())
         print(f"{task}: {path}  episodes={n_ep} terminated={int(g['terminated'].sum())} "
               f"truncated={int(g['truncated'].sum())}  size={os.path.getsize(path)/1024:.0f} KiB")
-    for task in ("ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle"):
+    for task in ("ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider"):
         if only and task not in only:
             continue
         s = reset_samples(task, make_env)

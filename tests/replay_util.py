@@ -20,11 +20,12 @@ STATE_KEYS = {
     "walljump": ("agent_x", "in_air", "wall"),
     "brickbreak": ("pos", "vel", "paddle", "bricks"),
     "bicycle": ("x", "z", "theta", "phi", "phi_dot", "delta", "goal", "dist"),
+    "glider": ("pos", "vel", "rot", "ang_vel", "waypoint"),
 }
 # Tasks whose reference arithmetic goes through host-dependent libm / SVML / BLAS routines (np.tan, pow, ddot): compared
 # within a stated tolerance instead of bit for bit.  obs: 2e-6 absolute (|obs| <= ~8, one f32 ulp is <= 4.8e-7);
 # reward: 1e-5 absolute (|reward| <= 50).
-LIBM_TASKS = {"bicycle": {"obs_atol": 2e-6, "reward_atol": 1e-5}}
+LIBM_TASKS = {"bicycle": {"obs_atol": 2e-6, "reward_atol": 1e-5}, "glider": {"obs_atol": 2e-6, "reward_atol": 1e-5}}
 
 
 def load(task):
@@ -36,6 +37,17 @@ def initial_state(task, g, dtype):
     st = np.zeros(E, dtype)
     for k in STATE_KEYS[task]:
         st[k] = g[f"init_{k}"]
+    return st
+
+
+def inject_step_state(task, g, t, st, done):
+    """Traces with per-step reference states (glider): overwrite the state of the envs that are still in their episode with
+    the reference's state after step t, so that every step is compared from identical inputs (one-step parity)."""
+    if f"step_{STATE_KEYS[task][0]}" not in g:
+        return st
+    live = np.nonzero(~done)[0]
+    for k in STATE_KEYS[task]:
+        st[k][live] = g[f"step_{k}"][t][live]
     return st
 
 

@@ -33,14 +33,14 @@ def test_metadata_calls_match_reference_spaces():
     lib = native.lib
     assert lib.tmla_version() == 100
     want = {"basic": (21, 3, 50, 12), "ball3d": (6, 5, 200, 48), "gridworld": (4, 5, 100, 36), "push": (4, 5, 120, 28),
-            "walljump": (4, 4, 150, 20), "brickbreak": (45, 3, 2000, 88), "bicycle": (7, 3, 2000, 80)}
+            "walljump": (4, 4, 150, 20), "brickbreak": (45, 3, 2000, 88), "bicycle": (7, 3, 2000, 80), "glider": (16, 5, 4000, 112)}
     for name, (d, a, m, sz) in want.items():
         t = lib.tmla_task_from_name(name.encode())
         assert t == native.TASK_IDS[name]
         assert (lib.tmla_task_obs_dim(t), lib.tmla_task_num_actions(t), lib.tmla_task_max_steps(t),
                 lib.tmla_task_state_size(t)) == (d, a, m, sz)
-    assert lib.tmla_task_from_name(b"glider") == native.TMLA_EINVAL
-    assert b"glider" in lib.tmla_last_error()
+    assert lib.tmla_task_from_name(b"labyrinth") == native.TMLA_EINVAL
+    assert b"labyrinth" in lib.tmla_last_error()
     # parameter counts of SURVEY.md A8
     assert lib.tmla_mlp_num_params(6, 256, 5) == 136710
     assert lib.tmla_mlp_num_params(4, 256, 5) == 135686
@@ -78,7 +78,7 @@ def test_registry_surface():
     from three_mlagents_b200 import registry
 
     assert len(registry.TASKS) == 19
-    assert registry.CUDA_TASKS == ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
+    assert registry.CUDA_TASKS == ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider")
     assert m.get_task("brick-break").id == "brickbreak"            # tests/test_mlagents.py:47-49
     assert m.get_task("self_driving_car").id == "self-driving-car"
     with pytest.raises(KeyError):
@@ -87,7 +87,7 @@ def test_registry_surface():
         m.make_env("fish")
     card = m.get_task("basic").card()
     assert card["trainable"] is True and "env_factory" not in card
-    assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["brickbreak", "ball3d", "bicycle", "basic", "gridworld", "push", "walljump"]
+    assert [t.id for t in m.list_tasks(include_roadmap=False)] == ["glider", "brickbreak", "ball3d", "bicycle", "basic", "gridworld", "push", "walljump"]
     fams = [(t.family, t.id) for t in m.list_tasks()]
     assert fams == sorted(fams)
 

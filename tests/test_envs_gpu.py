@@ -15,7 +15,7 @@ from oracle import envs_oracle as eo
 
 pytestmark = pytest.mark.gpu
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider")
 # north_star: "ball3d trajectories must stay within a stated float tolerance over 1,000 steps".
 # The only non-bit-exact operation on the device is sin(double) (own polynomial vs libm, <= 1 ulp of
 # f64); everything else follows NumPy's rounding sequence exactly, so 1e-5 absolute is generous.
@@ -59,12 +59,22 @@ def test_golden_replay_matches_reference(task):
         _close(task, obs[live], g["obs"][t][live], f"{task} obs t={t}")
         exact += int((obs[live].view(np.uint32) == g["obs"][t][live].view(np.uint32)).sum())
         total += int(obs[live].size)
+        per_step = "step_" + _replay.STATE_KEYS[task][0] in g
         if done.any():
             tobs = b["tobs"].cpu().numpy()
             _close(task, tobs[done], g["obs"][t][done], f"{task} terminal obs t={t}")
             # Monitor episode length == adapter steps
             assert (b["len"].cpu().numpy()[done] <= env.max_episode_steps).all()
+        if done.any() or per_step:
             st = _replay.inject_resets(task, g, t, env.get_state(), done)
+            if per_step:                 # one-step parity: continue from the reference's state (replay_util.inject_step_state)
+                got = st.copy()
+                st = _replay.inject_step_state(task, g, t, st, done)
+                for k in _replay.STATE_KEYS[task]:
+                    if st[k].dtype.kind == "f":
+                        np.testing.assert_allclose(got[k][live], st[k][live], rtol=1e-12, atol=1e-12, err_msg=f"{task} state {k} t={t}")
+                    else:
+                        assert np.array_equal(got[k][live], st[k][live]), (task, k, t)
             env.set_state(st)
     env.check_actions()
     if task == "ball3d" or task in _replay.LIBM_TASKS:
@@ -76,6 +86,9 @@ def test_golden_replay_matches_reference(task):
 @pytest.mark.parametrize("task", TASKS)
 def test_lockstep_with_oracle_and_philox_resets(task):
     n, steps, seed, base = 4096, 300, 11, 1_000_000
+    resync = task == "glider"     # one-step parity (the pre-stall steps amplify an ulp by ~1e8): CUDA continues from the oracle's state
+    if resync:
+        n, steps = 512, 150       # the glider oracle steps one env at a time through NumPy
     env = _vec(task, n, seed=seed, env_id_base=base)
     ora = eo.OracleVecEnv(task, n, seed=seed, env_id_base=base)
     _close(task, env.reset_tensor().cpu().numpy(), eo.observe(task, ora.state), "reset obs")
@@ -94,6 +107,14 @@ def test_lockstep_with_oracle_and_philox_resets(task):
             _close(task, b["tobs"].cpu().numpy()[done], info["terminal_obs"][done], "terminal obs")
             assert np.array_equal(b["len"].cpu().numpy()[done], info["episode_length"][done])
             np.testing.assert_allclose(b["ret"].cpu().numpy()[done], info["episode_return"][done], rtol=1e-6, atol=1e-6)
+        if resync:
+            got = env.get_state()
+            for k in got.dtype.names:
+                if got[k].dtype.kind == "f" and k != "ep_return":
+                    np.testing.assert_allclose(got[k], ora.state[k], rtol=1e-12, atol=1e-12, err_msg=f"{k} t={t}")
+            nxt = ora.state.copy()
+            nxt["ep_return"] = got["ep_return"]
+            env.set_state(nxt)
     assert n_done > 0
     st = env.get_state()
     if task in _replay.LIBM_TASKS:
@@ -354,4 +375,47 @@ def test_bicycle_goal_fall_and_time_limit_against_oracle():
     got = env.get_state()
     np.testing.assert_allclose(got["delta"][4], ora["delta"][4], rtol=0, atol=1e-15)
     assert (got["steps"][[0, 1, 2, 3, 5]] == 0).all() and got["steps"][4] == 6  # finished envs were re-drawn on the device
+    env.close()
+
+
+def test_glider_penalties_waypoints_and_limits_against_oracle():
+    """Paths of glider.py the golden trace rarely or never reaches — waypoint switch (:177-180), corridor and altitude
+    penalties (:201-215), crash (:218-220), too-far (:228-230), the calm-air branch |v_air| <= 0.1 (:125,158-160) and the
+    adapter's 4000-step truncation (envs.py:141-145) — by state injection, CUDA kernel vs the pinned oracle."""
+    task = "glider"
+    tol = _replay.LIBM_TASKS[task]
+    n = 8
+    st = np.zeros(n, eo.STATE_DTYPES[task])
+    st["pos"] = [0.0, 0.0, 60.0]
+    st["vel"] = [15.0, 0.0, -1.0]
+    st["ang_vel"] = np.random.default_rng(0).uniform(-0.1, 0.1, (n, 3))
+    st["pos"][0] = [-150.0, 2.0, 68.0]                  # 10 m from waypoint 0 -> switches to waypoint 1
+    st["pos"][1] = [0.0, 300.0, 60.0]                   # outside the corridor
+    st["pos"][2] = [0.0, 0.0, 300.0]                    # too high
+    st["pos"][3] = [0.0, 0.0, 20.0]                     # low
+    st["pos"][4] = [0.0, 0.0, 5.01]; st["vel"][4] = [15.0, 0.0, -5.0]     # crashes
+    st["pos"][5] = [700.0, 0.0, 60.0]                   # 860 m from waypoint 0
+    st["steps"][6] = 3999                               # time limit
+    st["vel"][7] = [1.0, 0.5, 0.0]                      # rides the wind: |v_air| = 0 -> no aerodynamic force, aoa = 0
+    env = _vec(task, n, seed=9)
+    env.set_state(st.copy())
+    ora = st.copy()
+    a = np.array([0, 1, 2, 3, 4, 0, 0, 0])
+    b = env.step_tensor(torch.from_numpy(a.astype(np.int32)).cuda())
+    obs, rew, term, trunc = eo.transition(task, ora, a)
+    assert ora["waypoint"][0] == 1 and (ora["waypoint"][1:] == 0).all()
+    assert list(term) == [False, False, False, False, True, True, False, False] and list(trunc) == [False] * 6 + [True, False]
+    assert rew[4] == -50.0 and rew[5] == -50.0 and rew[1] < rew[0] and rew[2] < rew[0] and abs((rew[0] - rew[3]) - 0.5) < 0.05
+    assert np.array_equal(b["done"].cpu().numpy().astype(bool), term | trunc)
+    assert np.array_equal(b["trunc"].cpu().numpy().astype(bool), trunc & ~term)
+    np.testing.assert_allclose(b["rew"].cpu().numpy(), rew, rtol=0, atol=tol["reward_atol"])
+    done = term | trunc
+    np.testing.assert_allclose(b["tobs"].cpu().numpy()[done], obs[done], rtol=0, atol=tol["obs_atol"])
+    np.testing.assert_allclose(b["obs"].cpu().numpy()[~done], obs[~done], rtol=0, atol=tol["obs_atol"])
+    got = env.get_state()
+    for k in ("pos", "vel", "rot", "ang_vel"):
+        np.testing.assert_allclose(got[k][~done], ora[k][~done], rtol=1e-13, atol=1e-13, err_msg=k)
+    assert np.array_equal(got["waypoint"][~done], ora["waypoint"][~done])
+    # env 7: gravity only
+    np.testing.assert_allclose(got["vel"][7], [1.0, 0.5, -9.81 * 0.02], rtol=0, atol=1e-15)
     env.close()

@@ -7,7 +7,7 @@ from oracle import envs_oracle as eo
 from oracle import philox as px
 import replay_util as _replay
 
-TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle")
+TASKS = ("basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider")
 
 
 def test_philox_known_answers():

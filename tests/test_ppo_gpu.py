@@ -15,7 +15,7 @@ from oracle import ppo_oracle as po
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(6, 5), (4, 5), (21, 3), (4, 4), (45, 3), (7, 3)]   # ball3d, gridworld/push, basic, walljump, brickbreak, bicycle
+SHAPES = [(6, 5), (4, 5), (21, 3), (4, 4), (45, 3), (7, 3), (16, 5)]   # ball3d, gridworld/push, basic, walljump, brickbreak, bicycle, glider
 
 
 def _ops():

@@ -5,7 +5,8 @@ Stated tolerances:
   * descriptor probe / wgrad: fp32 accumulation of exact bf16 products -> |d| <= 2e-3 * max(1, |ref|)
   * head outputs (logits, values) fused vs unfused bf16: 5e-3 abs (the fused head GEMM reads H2 rounded to bf16,
     2^-9 relative per element over 256 terms; the unfused head reads the fp32 tanh outputs)
-  * gradients fused vs unfused bf16: cosine > 0.9999, relative L2 error < 1e-2 (one extra bf16 rounding of dH1)
+  * gradients fused vs unfused bf16: cosine > 0.9999, relative L2 error < 1e-2 (one extra bf16 rounding of dH1); per
+    parameter tensor the fused error against fp32 is at most 1.5x the unfused-bf16 error + 0.2 % of the gradient norm
   * gradients fused vs fp32: cosine > 0.999, relative L2 error < 5e-2 (the bf16-path tolerance of test_trainer_gpu)
   * loss statistics: 1e-4 abs/rel
 """
@@ -74,8 +75,9 @@ def _setup(task, n, T, seed=5):
 
     env = CudaVecEnv(task, n, seed=seed)
     m = CudaPPO("MlpPolicy", env, seed=seed, n_steps=T, batch_size=n * T, n_epochs=1, ent_coef=0.01, mlp_impl="bf16")
-    with torch.no_grad():
-        m.params += 0.05 * torch.randn_like(m.params)          # non-trivial biases / heads
+    with torch.no_grad():                                       # non-trivial biases / heads (own generator: reproducible)
+        g = torch.Generator(device=m.params.device).manual_seed(1234 + seed)
+        m.params += 0.05 * torch.randn(m.params.shape, device=m.params.device, generator=g)
     m._repack()
     m.collect_rollouts()
     torch.cuda.synchronize()
@@ -128,11 +130,11 @@ def test_fused_minibatch_matches_unfused(task, n, T, rows):
         names.append((nm, off, off + sz)); off += sz
     assert off == g_f.numel()
     for nm, lo, hi in names:
-        x, y = g_f[lo:hi], g_ref[lo:hi]
-        # per tensor: error relative to that tensor's norm, floored at 10 % of the whole gradient's norm (a slice whose
-        # own gradient nearly cancels — walljump's pi.W2 with its 40 distinct observations — carries only bf16 noise)
-        rel = float((x - y).norm() / max(float(y.norm()), 0.1 * float(g_ref.norm())))
-        assert rel < 2e-2, f"{task} {nm}: fused vs unfused-bf16 relative error {rel}"
+        # per tensor, both bf16 paths against the fp32 gradient: the fused kernel must be as accurate as the three-call path
+        # (1.5x its error plus 0.2 % of the whole gradient's norm).  Comparing fused and unfused directly is meaningless for a
+        # slice whose gradient nearly cancels (walljump's pi.W2 with its 40 distinct observations carries only bf16 noise).
+        err_f, err_u = float((g_f[lo:hi] - g32[lo:hi]).norm()), float((g_ref[lo:hi] - g32[lo:hi]).norm())
+        assert err_f <= 1.5 * err_u + 2e-3 * float(g32.norm()), f"{task} {nm}: fused error {err_f} vs unfused-bf16 error {err_u} (|g| = {float(g32.norm())})"
     cos = float(torch.nn.functional.cosine_similarity(g_f, g_ref, dim=0))
     rel = float((g_f - g_ref).norm() / g_ref.norm())
     cos32 = float(torch.nn.functional.cosine_similarity(g_f, g32, dim=0))

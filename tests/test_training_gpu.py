@@ -62,6 +62,18 @@ def test_train_task_brickbreak_runs_on_the_unfused_path(tmp_path, monkeypatch):
     assert res.algorithm == "ppo" and np.isfinite(res.mean_reward) and res.eval_episodes == 16
 
 
+def test_train_task_glider_runs_on_the_unfused_path(tmp_path, monkeypatch):
+    """glider (16 inputs, 5 actions) trains through the three-call bf16 path (the fused kernel covers obs_dim <= 7) and beats
+    the hands-off return: 5 M steps of PPO must lift the evaluation return well above a stall at -50."""
+    from three_mlagents_b200.training import TrainConfig, train_task
+
+    monkeypatch.chdir(tmp_path)
+    res = train_task(TrainConfig("glider", total_timesteps=5_000_000, n_envs=2048, eval_episodes=64, eval_freq=10**12, verbose=0,
+                                 run_name="gl"), model_kwargs={"n_steps": 128, "batch_size": 32768})
+    print("glider eval mean reward", res.mean_reward)
+    assert res.algorithm == "ppo" and np.isfinite(res.mean_reward) and res.eval_episodes == 64 and res.mean_reward > 0.0
+
+
 def test_train_task_bicycle_learns_to_stay_up(tmp_path, monkeypatch):
     """bicycle (7 inputs, 3 actions; no registry threshold) through the fused update: a random policy falls after ~37 steps
     (tests/golden/bicycle.npz: 863 episodes in 32 000 steps, about -10 + 36 * 0.3 per episode); 20 M steps of PPO must keep the

@@ -1,4 +1,4 @@
-// env_kernels.cu — batched environment stepping for basic / ball3d / gridworld / push / walljump / brickbreak / bicycle (sm_100a).
+// env_kernels.cu — batched environment stepping for basic / ball3d / gridworld / push / walljump / brickbreak / bicycle / glider (sm_100a).
 //
 // Replaces SB3 `DummyVecEnv.step_wait` (a serial Python loop over envs) + `Monitor` + the reference's
 // `LegacySingleAgentGymAdapter.step/reset` (backend/mlagents/envs.py:110-152) and the task dynamics
@@ -446,6 +446,7 @@ __global__ void selftest_arith_kernel(unsigned long long *out) {
         case TMLA_WALLJUMP: { using TaskT = WallJumpTask; CALL; } break;  \
         case TMLA_BRICKBREAK: { using TaskT = BrickBreakTask; CALL; } break; \
         case TMLA_BICYCLE: { using TaskT = BicycleTask; CALL; } break;       \
+        case TMLA_GLIDER: { using TaskT = GliderTask; CALL; } break;         \
         default: tmla_set_error("unknown task %d", task); return TMLA_EINVAL; \
     }
 
@@ -456,13 +457,13 @@ static EnvPtrs ptrs_of(const tmla_env *h) {
 }
 static inline unsigned grid_for(int64_t n) { return (unsigned)ceil_div64(n, kBlock); }
 
-static const int kObsDim[TMLA_NUM_TASKS] = {BasicTask::D, Ball3DTask::D, GridWorldTask::D, PushTask::D, WallJumpTask::D, BrickBreakTask::D, BicycleTask::D};
-static const int kNumActions[TMLA_NUM_TASKS] = {BasicTask::A, Ball3DTask::A, GridWorldTask::A, PushTask::A, WallJumpTask::A, BrickBreakTask::A, BicycleTask::A};
+static const int kObsDim[TMLA_NUM_TASKS] = {BasicTask::D, Ball3DTask::D, GridWorldTask::D, PushTask::D, WallJumpTask::D, BrickBreakTask::D, BicycleTask::D, GliderTask::D};
+static const int kNumActions[TMLA_NUM_TASKS] = {BasicTask::A, Ball3DTask::A, GridWorldTask::A, PushTask::A, WallJumpTask::A, BrickBreakTask::A, BicycleTask::A, GliderTask::A};
 static const int kMaxSteps[TMLA_NUM_TASKS] = {BasicTask::MAX_STEPS, Ball3DTask::MAX_STEPS, GridWorldTask::MAX_STEPS, PushTask::MAX_STEPS,
-                                              WallJumpTask::MAX_STEPS, BrickBreakTask::MAX_STEPS, BicycleTask::MAX_STEPS};
+                                              WallJumpTask::MAX_STEPS, BrickBreakTask::MAX_STEPS, BicycleTask::MAX_STEPS, GliderTask::MAX_STEPS};
 static const int kStateSize[TMLA_NUM_TASKS] = {(int)sizeof(tmla_basic_state), (int)sizeof(tmla_ball3d_state), (int)sizeof(tmla_gridworld_state),
                                                (int)sizeof(tmla_push_state), (int)sizeof(tmla_walljump_state), (int)sizeof(tmla_brickbreak_state),
-                                               (int)sizeof(tmla_bicycle_state)};
+                                               (int)sizeof(tmla_bicycle_state), (int)sizeof(tmla_glider_state)};
 
 // staging layout shared by the device block and its pinned host mirror (16-byte aligned sections):
 //   actions i32[n] | obs f32[n,D] | reward f32[n] | done u8[n] | truncated u8[n] | flags i32[4] {n_done, bad_action}
@@ -501,7 +502,8 @@ int tmla_task_from_name(const char *name) {
     if (!strcmp(name, "walljump")) return TMLA_WALLJUMP;
     if (!strcmp(name, "brickbreak")) return TMLA_BRICKBREAK;
     if (!strcmp(name, "bicycle")) return TMLA_BICYCLE;
-    tmla_set_error("no CUDA backend for task '%s' (have: basic, ball3d, gridworld, push, walljump, brickbreak, bicycle)", name);
+    if (!strcmp(name, "glider")) return TMLA_GLIDER;
+    tmla_set_error("no CUDA backend for task '%s' (have: basic, ball3d, gridworld, push, walljump, brickbreak, bicycle, glider)", name);
     return TMLA_EINVAL;
 }
 #define TASK_META(fn, table)                                                                   \

@@ -715,3 +715,169 @@ struct BicycleTask {
         s.steps = 0; s.ep_ret = 0.0f;
     }
 };
+
+// ---------------------------------------------------------------------------------------- glider
+// examples/glider.py:11-265 behind the legacy adapter (envs.py:244-255): float64 rigid-body glider in a sinusoidal thermal
+// field, 16-float observation, 5 actions, 4000-step limit.  Reference operation order throughout; the BLAS calls of the
+// reference (np.linalg.norm / np.dot on 3-vectors, the 3x3 `@` chain, R @ f) round as forward FMA chains on FMA hosts
+// (measured, see oracle/envs_oracle.py) and are written out that way with the structural zeros and ones of the rotation
+// matrices folded (an FMA with a zero factor is the identity).  Like bicycle the task is held to a stated tolerance:
+// CUDA's f64 sin / cos / atan2 are within 2 ulp of the host's.
+struct GliderTask {
+    static constexpr bool HAS_SPARE = false;
+    typedef NoSpare Spare;
+    typedef NoConsts Consts;
+    static __device__ __forceinline__ Consts load_consts() { return Consts{}; }
+    static constexpr int D = 16, A = 5, MAX_STEPS = 4000, NBUF = 4;
+    typedef tmla_glider_state Wire;
+    struct State { double pos[3], vel[3], rot[3], av[3]; int wp, steps; float ep_ret; };
+    static __host__ __device__ size_t plane_bytes(int b) { return b < 3 ? 32 : 16; }
+
+    static __device__ __forceinline__ State load(void *const *buf, int64_t i) {
+        State s;
+        double v[12];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double2 lo = reinterpret_cast<const double2 *>(buf[b])[2 * i], hi = reinterpret_cast<const double2 *>(buf[b])[2 * i + 1];
+            v[4 * b] = lo.x; v[4 * b + 1] = lo.y; v[4 * b + 2] = hi.x; v[4 * b + 3] = hi.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.pos[k] = v[k]; s.vel[k] = v[3 + k]; s.rot[k] = v[6 + k]; s.av[k] = v[9 + k]; }
+        const int4 m = reinterpret_cast<const int4 *>(buf[3])[i];
+        s.wp = m.x; s.steps = m.y; s.ep_ret = __int_as_float(m.z);
+        return s;
+    }
+    static __device__ __forceinline__ void store(void *const *buf, int64_t i, const State &s) {
+        double v[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[k] = s.pos[k]; v[3 + k] = s.vel[k]; v[6 + k] = s.rot[k]; v[9 + k] = s.av[k]; }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            reinterpret_cast<double2 *>(buf[b])[2 * i] = make_double2(v[4 * b], v[4 * b + 1]);
+            reinterpret_cast<double2 *>(buf[b])[2 * i + 1] = make_double2(v[4 * b + 2], v[4 * b + 3]);
+        }
+        reinterpret_cast<int4 *>(buf[3])[i] = make_int4(s.wp, s.steps, __float_as_int(s.ep_ret), 0);
+    }
+    static __device__ State from_wire(const Wire &w) {
+        State s;
+        for (int k = 0; k < 3; ++k) { s.pos[k] = w.pos[k]; s.vel[k] = w.vel[k]; s.rot[k] = w.rot[k]; s.av[k] = w.ang_vel[k]; }
+        s.wp = w.waypoint & 1; s.steps = w.steps; s.ep_ret = w.ep_return;
+        return s;
+    }
+    static __device__ Wire to_wire(const State &s) {
+        Wire w;
+        for (int k = 0; k < 3; ++k) { w.pos[k] = s.pos[k]; w.vel[k] = s.vel[k]; w.rot[k] = s.rot[k]; w.ang_vel[k] = s.av[k]; }
+        w.waypoint = s.wp; w.steps = s.steps; w.ep_return = s.ep_ret; w.pad_ = 0;
+        return w;
+    }
+    // ddot / dgemm / dgemv on 3-vectors: forward FMA chain
+    static __device__ __forceinline__ double dot3(const double *a, const double *b) {
+        return __fma_rn(a[2], b[2], __fma_rn(a[1], b[1], __dmul_rn(a[0], b[0])));
+    }
+    static __device__ __forceinline__ void to_target(const State &s, double *vec, double &dist) {   // glider.py:173-175 / 243-245
+        vec[0] = __dsub_rn(s.wp ? 160.0 : -160.0, s.pos[0]);
+        vec[1] = __dsub_rn(0.0, s.pos[1]);
+        vec[2] = __dsub_rn(70.0, s.pos[2]);
+        dist = __dsqrt_rn(dot3(vec, vec));
+    }
+    static __device__ __forceinline__ void observe(const State &s, float *o) {   // glider.py:241-265, cast envs.py:150
+        double vec[3], dist, sy, cy;
+        to_target(s, vec, dist);
+        sincos(s.rot[2], &sy, &cy);
+        const double den = __dadd_rn(dist, 1e-8);
+        o[0] = __double2float_rn(__ddiv_rn(s.vel[2], 10.0));
+        o[1] = __double2float_rn(__ddiv_rn(__dsub_rn(s.pos[2], 50.0), 50.0));
+        o[2] = __double2float_rn(s.rot[0]); o[3] = __double2float_rn(s.rot[1]);
+        o[4] = __double2float_rn(sy); o[5] = __double2float_rn(cy);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o[6 + k] = __double2float_rn(s.av[k]);
+            o[9 + k] = __double2float_rn(__ddiv_rn(s.vel[k], 20.0));
+            o[12 + k] = __double2float_rn(__ddiv_rn(vec[k], den));
+        }
+        o[15] = __double2float_rn(__ddiv_rn(dist, 100.0));
+    }
+    static __device__ __forceinline__ void step(const Consts &, State &s, int a, float &reward, bool &term, bool &trunc) {
+        constexpr double PI = 3.141592653589793, DT = 0.02, MASS = 1.5, G = 9.81;
+        constexpr double F1 = 1.0 / 250.0, F2 = 1.0 / 400.0, CL_ALPHA = 2 * PI, MAX_AOA = 0.2617993877991494;   // np.deg2rad(15)
+        const double roll_t = a == 1 ? -15.0 : (a == 2 ? 15.0 : 0.0), pitch_t = a == 3 ? 10.0 : (a == 4 ? -10.0 : 0.0);   // glider.py:92-103
+        const double yaw_t = a == 1 ? 4.0 : (a == 2 ? -4.0 : 0.0);
+        s.av[0] = __dmul_rn(__dadd_rn(s.av[0], __dmul_rn(roll_t, DT)), 0.95);                      // :107-110
+        s.av[1] = __dmul_rn(__dadd_rn(s.av[1], __dmul_rn(pitch_t, DT)), 0.95);
+        s.av[2] = __dmul_rn(__dadd_rn(s.av[2], __dmul_rn(yaw_t, DT)), 0.95);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s.rot[k] = __dadd_rn(s.rot[k], __dmul_rn(s.av[k], DT));       // :111
+        s.rot[0] = fmin(fmax(s.rot[0], -PI / 2), PI / 2);                                          // :114-115
+        s.rot[1] = fmin(fmax(s.rot[1], -PI / 4), PI / 4);
+        // wind at the position before integration (:55-77): ((x * f) * 2) * pi [/ 1.5]
+        const double ax1 = __dmul_rn(__dmul_rn(__dmul_rn(s.pos[0], F1), 2.0), PI), ay1 = __dmul_rn(__dmul_rn(__dmul_rn(s.pos[1], F1), 2.0), PI);
+        const double ax2 = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(s.pos[0], F2), 2.0), PI), 1.5), ay2 = __ddiv_rn(ay1, 1.5);
+        const double up1 = __dmul_rn(__dmul_rn(__dmul_rn(sin(ax1), cos(ay1)), 8.0), 1.0);
+        const double up2 = __dmul_rn(__dmul_rn(__dmul_rn(sin(ax2), cos(ay2)), 8.0), 0.7);
+        const double va[3] = {__dsub_rn(s.vel[0], 1.0), __dsub_rn(s.vel[1], 0.5), __dsub_rn(s.vel[2], __dadd_rn(up1, up2))};   // :118-119
+        const double vam = __dsqrt_rn(dot3(va, va));                                               // :120
+        double aoa = va[0] != 0.0 ? atan2(-va[2], va[0]) : 0.0;                                    // :123
+        double aero[3] = {0.0, 0.0, 0.0};
+        if (vam > 0.1) {                                                                           // :125-160
+            const double CL = __dmul_rn(CL_ALPHA, aoa);
+            const double CD = __dadd_rn(0.02, __dmul_rn(0.05, __dmul_rn(CL, CL)));
+            const double q = __dmul_rn(__dmul_rn(0.5 * 1.225, __dmul_rn(vam, vam)), 0.5);          // ((0.5 * rho) * |v|^2) * S
+            const double lift = __dmul_rn(q, CL), ndrag = -__dmul_rn(q, CD);
+            double s0, c0, s1, c1, s2, c2;
+            sincos(s.rot[0], &s0, &c0); sincos(s.rot[1], &s1, &c1); sincos(s.rot[2], &s2, &c2);
+            // R = (R_yaw @ R_pitch) @ R_roll, columns 0 and 2 (the force [-drag, 0, lift] has no y component)
+            const double r00 = __dmul_rn(c2, c1), r10 = __dmul_rn(s2, c1), r20 = -s1;
+            const double r02 = __fma_rn(__dmul_rn(c2, s1), c0, __dmul_rn(-s2, -s0));
+            const double r12 = __fma_rn(__dmul_rn(s2, s1), c0, __dmul_rn(c2, -s0));
+            const double r22 = __dmul_rn(c1, c0);
+            aero[0] = __fma_rn(r02, lift, __dmul_rn(r00, ndrag));                                  // dgemv: fma(R[i][2], f2, R[i][0] * f0)
+            aero[1] = __fma_rn(r12, lift, __dmul_rn(r10, ndrag));
+            aero[2] = __fma_rn(r22, lift, __dmul_rn(r20, ndrag));
+        } else aoa = 0.0;
+        aero[2] = __dadd_rn(aero[2], -(MASS * G));                                                 // :162-163 (adding 0 to x, y is exact)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s.vel[k] = __dadd_rn(s.vel[k], __dmul_rn(__ddiv_rn(aero[k], MASS), DT));               // :166
+            s.pos[k] = __dadd_rn(s.pos[k], __dmul_rn(s.vel[k], DT));                               // :167
+        }
+        double vec[3], dist;
+        to_target(s, vec, dist);
+        if (dist < 15.0) s.wp ^= 1;                                                                // :177-180
+        const double vmag = __dsqrt_rn(dot3(s.vel, s.vel));
+        const double dv = __dadd_rn(vmag, 1e-8), dt_ = __dadd_rn(dist, 1e-8);
+        const double vd[3] = {__ddiv_rn(s.vel[0], dv), __ddiv_rn(s.vel[1], dv), __ddiv_rn(s.vel[2], dv)};   // :183-185
+        const double td[3] = {__ddiv_rn(vec[0], dt_), __ddiv_rn(vec[1], dt_), __ddiv_rn(vec[2], dt_)};
+        const double Hh = __ddiv_rn(__dadd_rn(dot3(vd, td), 1.0), 2.0);                            // :188
+        const double E = fmin(fmax(__ddiv_rn(vmag, 30.0), 0.0), 2.0);                              // :190-192
+        double r = __dmul_rn(E, __dadd_rn(__dsub_rn(Hh, E), 1.0));                                 // :196
+        const double lateral = fabs(s.pos[1]);                                                     // :201-206
+        if (lateral > 250.0) { const double pr = __ddiv_rn(__dsub_rn(lateral, 250.0), 100.0); r = __dsub_rn(r, __dmul_rn(2.0, __dmul_rn(pr, pr))); }
+        if (s.pos[2] > 250.0) { const double pr = __ddiv_rn(__dsub_rn(s.pos[2], 250.0), 50.0); r = __dsub_rn(r, __dmul_rn(2.0, __dmul_rn(pr, pr))); }   // :209-215
+        else if (s.pos[2] < 25.0) r = __dsub_rn(r, 0.5);
+        bool done = false;
+        if (s.pos[2] < 5.0) { r = -50.0; done = true; }                                            // :218-220
+        if (fabs(aoa) > MAX_AOA) { r = -50.0; done = true; }                                       // :223-225
+        if (dist > 500.0) { r = -50.0; done = true; }                                              // :228-230
+        s.steps += 1;
+        if (s.steps > 4000) done = true;                                                           // :233-234
+        reward = __double2float_rn(r);
+        trunc = s.steps >= MAX_STEPS;                                                              // envs.py:141-145
+        term = done && !trunc;
+    }
+    struct Pending { float r; };
+    static __device__ __forceinline__ void advance(const NoConsts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        step(c, s, a, pend.r, term, trunc);
+    }
+    static __device__ __forceinline__ float finish(const Pending &pend) { return pend.r; }
+    static __device__ __forceinline__ void reset(State &s, uint64_t seed, uint64_t env_id, uint64_t k, uint32_t tag) {
+        const uint4 b = tmla_stream_block(seed, env_id, k, tag, 0);                                // glider.py:79-86
+        s.pos[0] = 0.0; s.pos[1] = 0.0; s.pos[2] = 60.0;
+        s.vel[0] = 15.0; s.vel[1] = 0.0; s.vel[2] = -1.0;
+        s.rot[0] = 0.0; s.rot[1] = 0.0; s.rot[2] = 0.0;
+        s.av[0] = __dadd_rn(-0.1, __dmul_rn(0.2, u32_to_unit(b.x)));                               // np.random.uniform(-0.1, 0.1, 3)
+        s.av[1] = __dadd_rn(-0.1, __dmul_rn(0.2, u32_to_unit(b.y)));
+        s.av[2] = __dadd_rn(-0.1, __dmul_rn(0.2, u32_to_unit(b.z)));
+        s.wp = (int)(b.w >> 31);                                                                   // np.random.randint(0, 2)
+        s.steps = 0; s.ep_ret = 0.0f;
+    }
+};

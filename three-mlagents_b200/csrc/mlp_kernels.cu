@@ -648,9 +648,9 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
         if constexpr (BF) {
             if (obs_dim == 4) l1_forward_bf16_kernel<4><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
             else if (obs_dim == 6) l1_forward_bf16_kernel<6><<<gs, 256, 0, st>>>(params + o.w1[t], params + o.b1[t], x, index, rows, rows_dev, h1);
-            else if (obs_dim == 45) L1F(45); else if (obs_dim == 7) L1F(7); else L1F(21);
+            else if (obs_dim == 45) L1F(45); else if (obs_dim == 7) L1F(7); else if (obs_dim == 16) L1F(16); else L1F(21);
         } else {
-            if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else if (obs_dim == 45) L1F(45); else if (obs_dim == 7) L1F(7); else L1F(21);
+            if (obs_dim == 4) L1F(4); else if (obs_dim == 6) L1F(6); else if (obs_dim == 45) L1F(45); else if (obs_dim == 7) L1F(7); else if (obs_dim == 16) L1F(16); else L1F(21);
         }
 #undef L1F
         TMLA_LAUNCH_CHECK();
@@ -735,9 +735,9 @@ static int mlp_backward_impl(const float *params, const void *wpack, int obs_dim
         if constexpr (BF) {
             if (obs_dim == 4) l1_backward_bf16_kernel<4><<<gr, 256, kPipeSmem, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
             else if (obs_dim == 6) l1_backward_bf16_kernel<6><<<gr, 256, kPipeSmem, st>>>(dz1, x, index, rows, rpb, grads + o.w1[t], grads + o.b1[t]);
-            else if (obs_dim == 45) L1B(45); else if (obs_dim == 7) L1B(7); else L1B(21);
+            else if (obs_dim == 45) L1B(45); else if (obs_dim == 7) L1B(7); else if (obs_dim == 16) L1B(16); else L1B(21);
         } else {
-            if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else if (obs_dim == 45) L1B(45); else if (obs_dim == 7) L1B(7); else L1B(21);
+            if (obs_dim == 4) L1B(4); else if (obs_dim == 6) L1B(6); else if (obs_dim == 45) L1B(45); else if (obs_dim == 7) L1B(7); else if (obs_dim == 16) L1B(16); else L1B(21);
         }
 #undef L1B
         TMLA_LAUNCH_CHECK();
@@ -754,7 +754,7 @@ int64_t tmla_mlp_num_params(int obs_dim, int hidden, int n_actions) {
 
 static int check_shape(int D, int hidden, int A) {
     if (hidden != H) { tmla_set_error("hidden must be 256 (net_arch of training.py:363-365), got %d", hidden); return TMLA_EINVAL; }
-    if (!(D == 4 || D == 6 || D == 7 || D == 21 || D == 45)) { tmla_set_error("obs_dim must be 4, 6, 7, 21 or 45, got %d", D); return TMLA_EINVAL; }
+    if (!(D == 4 || D == 6 || D == 7 || D == 16 || D == 21 || D == 45)) { tmla_set_error("obs_dim must be 4, 6, 7, 16, 21 or 45, got %d", D); return TMLA_EINVAL; }
     if (!(A >= 3 && A <= 5)) { tmla_set_error("n_actions must be 3, 4 or 5, got %d", A); return TMLA_EINVAL; }
     return TMLA_OK;
 }

@@ -105,3 +105,7 @@ def make_brick_break_env() -> CudaTaskEnv:  # envs.py:216-227
 
 def make_bicycle_env() -> CudaTaskEnv:      # envs.py:230-241
     return CudaTaskEnv("bicycle")
+
+
+def make_glider_env() -> CudaTaskEnv:       # envs.py:244-255
+    return CudaTaskEnv("glider")

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtmla.so")
 
 TMLA_OK, TMLA_EINVAL, TMLA_ECUDA, TMLA_ENOMEM, TMLA_EACTION = 0, -1, -2, -3, -4
-TASK_IDS = {"basic": 0, "ball3d": 1, "gridworld": 2, "push": 3, "walljump": 4, "brickbreak": 5, "bicycle": 6}
+TASK_IDS = {"basic": 0, "ball3d": 1, "gridworld": 2, "push": 3, "walljump": 4, "brickbreak": 5, "bicycle": 6, "glider": 7}
 
 
 class TmlaError(RuntimeError):

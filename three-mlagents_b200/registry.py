@@ -2,7 +2,7 @@
 (`TaskSpec`, `TASKS`, `list_tasks`, `list_task_cards`, `get_task`, `make_env`; registry.py:18-370).
 
 All 19 task cards are kept so `three-mlagents list/inspect` and any caller of `get_task` keep
-working.  Only the four tasks on the hot path (basic, ball3d, gridworld, push) and walljump, brickbreak, bicycle have a CUDA env
+working.  Only the four tasks on the hot path (basic, ball3d, gridworld, push) and walljump, brickbreak, bicycle, glider have a CUDA env
 factory here; the reference's other Gymnasium tasks are listed with `env_factory=None`, so — by the
 reference's own rule `trainable = interface == "gymnasium" and env_factory is not None`
 (registry.py:41-43) — they report `trainable: false` in this backend and `make_env` raises the same
@@ -78,7 +78,7 @@ _TABLE: list[tuple] = [
      dict(publication_role="control-system benchmark", env_factory=envs.make_bicycle_env)),
     ("glider", "Dynamic Soaring Glider", "aerospace", "gymnasium", "frontier", "ppo", 1_000_000, 50, 8, None,
      ("aerodynamics", "energy-management", "long-horizon"),
-     dict(publication_role="domain-specific continuous physics case study", notes=_NO_CUDA)),
+     dict(publication_role="domain-specific continuous physics case study", env_factory=envs.make_glider_env)),
     ("labyrinth", "Labyrinth / NetHack-Inspired Navigation", "games", "gymnasium", "frontier", "ppo", 2_000_000, 100, 8, None,
      ("pixels", "maze", "memory", "exploration"),
      dict(observation="image", publication_role="first serious game-like benchmark in this repo", notes=_NO_CUDA)),

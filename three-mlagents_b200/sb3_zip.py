@@ -215,4 +215,4 @@ def read_zip(path: str) -> dict:
             "obs_dim": obs_dim, "n_actions": n_actions}
 
 
-TASK_BY_SHAPE = {(21, 3): "basic", (6, 5): "ball3d", (4, 4): "walljump", (45, 3): "brickbreak", (7, 3): "bicycle"}      # (4,5) is ambiguous (gridworld / push): needs the task id
+TASK_BY_SHAPE = {(21, 3): "basic", (6, 5): "ball3d", (4, 4): "walljump", (45, 3): "brickbreak", (7, 3): "bicycle", (16, 5): "glider"}      # (4,5) is ambiguous (gridworld / push): needs the task id

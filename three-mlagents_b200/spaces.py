@@ -66,4 +66,6 @@ def spaces_for(task_id: str):
         return Box(-np.inf, np.inf, (45,), np.float32), Discrete(3)
     if task_id == "bicycle":               # envs.py:230-241 (shape probed from BicycleEnv().reset(): 7 floats, bicycle.py:133-145)
         return Box(-np.inf, np.inf, (7,), np.float32), Discrete(3)
+    if task_id == "glider":                # envs.py:244-255 (shape probed from GliderEnv().reset(): 9 + 3 + 3 + 1, glider.py:241-265)
+        return Box(-np.inf, np.inf, (16,), np.float32), Discrete(5)
     raise KeyError(task_id)

@@ -35,6 +35,8 @@ STATE_DTYPES = {   # wire structs of include/tmla.h
                             ("steps", "<i4"), ("ep_return", "<f4")]),
     "bicycle": np.dtype([("x", "<f8"), ("z", "<f8"), ("theta", "<f8"), ("phi", "<f8"), ("phi_dot", "<f8"), ("delta", "<f8"),
                          ("goal", "<f8", (2,)), ("dist", "<f8"), ("steps", "<i4"), ("ep_return", "<f4")]),
+    "glider": np.dtype([("pos", "<f8", (3,)), ("vel", "<f8", (3,)), ("rot", "<f8", (3,)), ("ang_vel", "<f8", (3,)),
+                        ("waypoint", "<i4"), ("steps", "<i4"), ("ep_return", "<f4"), ("pad_", "<i4")]),
 }
 
 
