@@ -108,13 +108,14 @@ int tmla_host_views(tmla_env *h, int32_t **actions, float **obs, float **reward,
                     uint8_t **truncated, float **terminal_obs, float **ep_return, int32_t **ep_length);
 int tmla_step_pinned(tmla_env *h, int64_t *n_done);
 /* The same episode-end payload as *n_done compact records in the pinned block, in no particular order:
- * {int32 env index, float ep_return, int32 ep_length, float terminal_obs[D]} = (3 + D) 32-bit words each — what a
+ * {int32 env index, float ep_return, int32 ep_length, float terminal_obs[D], zero padding} = *floats_per_record 32-bit words
+ * each (3 + D rounded up to a multiple of 4, so the kernel writes a record as 128-bit stores) — what a
  * binding should read instead of scanning `done` (Monitor / infos of the finished envs only). */
 int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_record);
 /* Result blocks: pinned host memory a binding hands out to ITS caller, so that the copy engine writes a step's results
  * straight into the arrays the caller receives (no copy out of a staging block).  Layout, as byte offsets from the block:
  * offsets[0..5] = obs f32[n,D], reward f32[n], done u8[n], truncated u8[n], flags i32[4] {n_done, bad_action, -, -},
- * records (3 + D words each, as tmla_host_records); *bytes = size of a block.  tmla_step_block is tmla_step_pinned with the
+ * records (stride as tmla_host_records reports it); *bytes = size of a block.  tmla_step_block is tmla_step_pinned with the
  * results (and the n_done compact records) landing in `block`; the actions still come from the pinned action view.
  * The reference's DummyVecEnv returns fresh copies each step (SB3 dummy_vec_env.py step_wait): a binding keeps a small
  * pool of blocks and reuses one only when its caller has dropped every array over it (vec_env.py does this by refcount). */

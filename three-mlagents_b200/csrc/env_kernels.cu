@@ -97,11 +97,13 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
             float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag,
-            float *__restrict__ compact, int32_t *__restrict__ host_flags) {
+            float *__restrict__ compact, int32_t *__restrict__ host_flags, int host_seq) {
     // compact != NULL (host-facing step): finished envs append one record {env index, ep_return, ep_length, terminal_obs[D]}
     // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays.
-    // host_flags != NULL (zero-copy host step): the last CTA to finish publishes {n_done, bad_action} to mapped host memory
-    // and re-arms the device counters n_done[0..2] (count, bad action, ticket), so the step needs no memset and no flag copy.
+    // host_flags != NULL (zero-copy host step): the last CTA to finish publishes {n_done, bad_action, host_seq} to mapped host
+    // memory and re-arms the device counters n_done[0..2] (count, bad action, ticket): the step needs no memset and no flag
+    // copy, and the host can poll host_flags[2] for host_seq instead of synchronising the stream (every CTA fences its
+    // result stores at system scope before taking its ticket, so the sequence word is the last thing to become visible).
     constexpr int D = Task::D;
     __shared__ __align__(16) float s_obs[kBlock * D];
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
@@ -126,10 +128,17 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             int slot = 0;
             if (n_done) slot = atomicAdd(n_done, 1);
             if (compact) {
-                float *rec = compact + (int64_t)slot * (3 + D);
+                // records are padded to a multiple of 4 words and written as 128-bit stores (they may go over PCIe)
+                constexpr int RW = (3 + D + 3) & ~3;
+                float rec[RW];
                 rec[0] = __int_as_float((int)i); rec[1] = s.ep_ret; rec[2] = __int_as_float(s.steps);
 #pragma unroll
                 for (int j = 0; j < D; ++j) rec[3 + j] = o[j];
+#pragma unroll
+                for (int j = 3 + D; j < RW; ++j) rec[j] = 0.0f;
+                float4 *dst = reinterpret_cast<float4 *>(compact + (int64_t)slot * RW);
+#pragma unroll
+                for (int q = 0; q < RW / 4; ++q) dst[q] = make_float4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
             }
             Task::reset(s, seed, env_base + (uint64_t)i, step_index + 1, TMLA_TAG_RESET);
             Task::observe(s, o);
@@ -140,13 +149,18 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     }
     __syncthreads();
     block_store_obs<D, kBlock, false>(s_obs, obs + i0 * D, (int)min((int64_t)kBlock, n - i0));
-    if (host_flags && threadIdx.x == 0) {        // (the __syncthreads above orders this CTA's atomics before the ticket)
-        __threadfence();
-        if (atomicAdd(n_done + 2, 1) == (int)gridDim.x - 1) {
-            __threadfence();
-            host_flags[0] = *(volatile int32_t *)n_done;
-            host_flags[1] = *(volatile int32_t *)(n_done + 1);
-            n_done[0] = 0; n_done[1] = 0; n_done[2] = 0;
+    if (host_flags) {
+        __syncthreads();                         // every thread's result stores (obs included) precede thread 0's fence
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(n_done + 2, 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                host_flags[0] = *(volatile int32_t *)n_done;
+                host_flags[1] = *(volatile int32_t *)(n_done + 1);
+                n_done[0] = 0; n_done[1] = 0; n_done[2] = 0;
+                __threadfence_system();
+                *(volatile int32_t *)(host_flags + 2) = host_seq;
+            }
         }
     }
 }
@@ -473,6 +487,7 @@ static const int kStateSize[TMLA_NUM_TASKS] = {(int)sizeof(tmla_basic_state), (i
 // so that the copy engine writes a step's results straight into the arrays the caller receives.  The episode-end payload
 // travels as n_done compact records (36 B each for ball3d); the dense terminal_obs/ep_return/ep_length views of
 // tmla_step_pinned are filled from them on the host: only the entries of envs whose `done` flag is set are meaningful.
+static inline int record_words(int D) { return (3 + D + 3) & ~3; }      // {idx, ret, len, tobs[D]} padded to whole 16-byte chunks
 struct StageLayout { size_t act, obs, rew, done, trunc, flags, crec, tobs, ret, len, end; };
 static StageLayout stage_layout(int64_t n, int D) {
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
@@ -484,7 +499,7 @@ static StageLayout stage_layout(int64_t n, int D) {
     L.trunc = L.done + n;
     L.flags = up(L.trunc + n);
     L.crec = L.flags + 16;                      // compact episode-end records {idx, ret, len, tobs[D]}, at most n of them
-    L.tobs = up(L.crec + 4 * n * (3 + D));
+    L.tobs = up(L.crec + 4 * n * record_words(D));
     L.ret = L.tobs + 4 * n * D;
     L.len = L.ret + 4 * n;
     L.end = L.len + 4 * n;
@@ -590,7 +605,7 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
     cudaStream_t st = (cudaStream_t)stream;
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
-                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr)));
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr, 0)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     return TMLA_OK;
@@ -617,13 +632,26 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
         // done / truncated / records over PCIe itself (coalesced 128-byte lines), overlapping the transfer with the step
         // arithmetic and saving the two copy-engine hand-offs; only the 16-byte flag word is copied afterwards.
         char *b = block - L.obs;      // block-relative addressing with stage offsets
+        const int seq = (int)((h->step_count + 1) & 0x3FFFFFFF) | 0x40000000;
+        volatile int32_t *hseq = (volatile int32_t *)(b + L.flags) + 2;
+        *hseq = 0;
         TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                                  ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(p + L.act),
                                  (float *)(b + L.obs), (float *)(b + L.rew), (uint8_t *)(b + L.done), (uint8_t *)(b + L.trunc),
-                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags))));
+                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq)));
         TMLA_LAUNCH_CHECK();
         h->step_count += 1;
-        TMLA_CUDA(cudaStreamSynchronize(st));      // ONE launch + one synchronise per step (the flag word of d_stage is zeroed at create)
+        // ONE launch per step, no stream synchronise: poll the sequence word the last CTA writes after all results
+        // (cudaStreamQuery every 4096 polls catches a failed launch; the flag word of d_stage is zeroed at create)
+        static const bool poll = [] { const char *e = getenv("TMLA_HOST_STEP"); return !(e && !strcmp(e, "sync")); }();
+        if (!poll) TMLA_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t spins = 1; *hseq != seq; ++spins) {
+            if ((spins & 4095u) == 0) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaErrorNotReady) { TMLA_CUDA(q); if (*hseq != seq) { tmla_set_error("step kernel finished without publishing its results"); return TMLA_ECUDA; } }
+            }
+        }
+        __sync_synchronize();
         if (n_done) *n_done = bflags[0];
         if (bflags[1]) {
             tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
@@ -636,10 +664,10 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                              ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
                              (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
-                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr)));
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr, 0)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
-    const size_t rec = (size_t)4 * (3 + D);
+    const size_t rec = (size_t)4 * record_words(D);
     const int64_t head = h->rec_hint < n ? h->rec_hint : n;
     TMLA_CUDA(cudaMemcpyAsync(block, d + L.obs, (L.crec - L.obs) + rec * head, cudaMemcpyDeviceToHost, st));
     TMLA_CUDA(cudaStreamSynchronize(st));
@@ -671,7 +699,7 @@ int tmla_step_pinned(tmla_env *h, int64_t *n_done) {
     const int rc = step_into_block(h, p + L.obs, &nd);
     if (rc != TMLA_OK && rc != TMLA_EACTION) return rc;
     if (nd > 0) {   // episode-end payload: nd compact records, scattered into the dense host arrays
-        const size_t rec = (size_t)4 * (3 + D);
+        const size_t rec = (size_t)4 * record_words(D);
         float *tobs = (float *)(p + L.tobs), *ret = (float *)(p + L.ret);
         int32_t *len = (int32_t *)(p + L.len);
         for (int64_t s = 0; s < nd; ++s) {
@@ -729,7 +757,7 @@ int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_re
     TMLA_REQUIRE(h && records && floats_per_record, "NULL argument");
     const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
     *records = (const float *)((char *)h->h_stage + L.crec);
-    *floats_per_record = 3 + kObsDim[h->task];
+    *floats_per_record = record_words(kObsDim[h->task]);
     return TMLA_OK;
 }
 
@@ -749,7 +777,7 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
     memcpy(reward, p + L.rew, 4 * n);
     memcpy(done, p + L.done, n);
     memcpy(truncated, p + L.trunc, n);
-    const size_t rec = (size_t)4 * (3 + D);
+    const size_t rec = (size_t)4 * record_words(D);
     for (int64_t s = 0; s < nd; ++s) {   // "written only where done": the records of the finished envs, not three dense arrays
         const float *r = (const float *)(p + L.crec + rec * s);
         int32_t i, l;

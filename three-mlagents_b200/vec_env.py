@@ -106,6 +106,9 @@ class _ResultBlocks:
         nbytes = native.i64(0)
         check(lib.tmla_result_block_layout(handle, off, C.byref(nbytes)))
         self.off, self.nbytes = [int(x) for x in off], int(nbytes.value)
+        recp, recw = native.vp(), native.i32(0)
+        check(lib.tmla_host_records(handle, C.byref(recp), C.byref(recw)))
+        self.rec_words = int(recw.value)              # record stride: {idx, ret, len, tobs[d]} padded to a multiple of 4 words
         self._raw, self._ptr = [], []
         self.n, self.d = n, d
         self.scratch = self._alloc()      # never handed out: the fallback copies out of it
@@ -134,7 +137,8 @@ class _ResultBlocks:
         rew = raw[o_rew:o_rew + 4 * n].view(np.float32)
         done = raw[o_done:o_done + n].view(np.bool_)
         trunc = raw[o_trunc:o_trunc + n].view(np.bool_)
-        rec = raw[o_rec:o_rec + 4 * (3 + d) * n_done].view(np.float32).reshape(n_done, 3 + d) if n_done else None
+        rw = self.rec_words
+        rec = raw[o_rec:o_rec + 4 * rw * n_done].view(np.float32).reshape(n_done, rw)[:, :3 + d] if n_done else None
         return obs, rew, done, trunc, rec
 
     def close(self):
