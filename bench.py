@@ -160,6 +160,9 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: three-mlagents_b200 has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
+    from three_mlagents_b200.distributed import bind_to_gpu_numa_node
+
+    numa_cpus = bind_to_gpu_numa_node(local_rank)      # pinned host buffers on the GPU's own NUMA node (host-step e2e)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -269,7 +272,8 @@ def run_cuda(args):
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N_ENVS,
                 "d2h_bytes_per_step": N_ENVS * (4 * OBS_DIM + 4 + 1 + 1),
                 "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_block (H2D actions, kernel, one D2H straight into a pooled pinned "
-                       "result block, sync); the returned NumPy arrays are slices of that block, reused only when dropped", "steps": n_e2e},
+                       "result block, sync); the returned NumPy arrays are slices of that block, reused only when dropped", "steps": n_e2e,
+                "numa_cpus": None if numa_cpus is None else len(numa_cpus)},
         "step_api": {"value": step_api, "unit": "env-steps/s", "us_per_launch": 1e3 * api_ms / n_api,
                      "frac_hbm": (89.0 * N_ENVS / (api_ms / n_api * 1e-3) / 1e9) / peak,
                      "note": "one tmla_step launch per env step on device tensors; 5.8 MB working set, launch-bound"},

@@ -35,6 +35,28 @@ def init_from_env(backend: str = "nccl", device_index: int | None = None):
     return dist_state()
 
 
+def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
+    """Pin the calling thread to the CPUs NVML reports as local to GPU `device_index` (its NUMA node).  Call it BEFORE the
+    first `CudaVecEnv` of the process: the pinned result blocks of the host step are then allocated on the GPU's own node, so
+    the kernel's PCIe stores do not cross the socket interconnect (matters with one process per GPU on a two-socket box).
+    Returns the CPU list, or None when NVML is unavailable (the binding is an optimisation, never a requirement)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - NVML missing, containers without the sysfs topology, ...
+        return None
+
+
 def env_shard(rank: int, world: int, envs_per_rank: int) -> tuple[int, int]:
     """[first, last) global env ids owned by `rank`; the Philox sub-sequence of an env is its global id,
     so trajectories do not depend on `world`."""
