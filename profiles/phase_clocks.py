@@ -46,3 +46,26 @@ tot = sum(buf[i] for i in range(12))
 print(f"cycles per tile (CTA 0, both towers averaged): {tot / tiles:.0f}")
 for i, nm in enumerate(NAMES):
     print(f"  {buf[i] / tiles:8.0f}  {100.0 * buf[i] / tot:5.1f} %  {nm}")
+launches = 2 * reps
+print(f"CTA 0 whole kernels: {buf[25]} cycles in {buf[24]} ns of %globaltimer -> SM clock {1e3 * buf[25] / max(buf[24], 1):.0f} MHz during the tower kernels")
+print(f"whole kernel, CTA 0, cycles per launch: prologue {buf[16] / launches:.0f}  tile loop {buf[17] / launches:.0f}  flush {buf[18] / launches:.0f}")
+print(f"maximum over CTAs and launches: prologue {buf[20]}  tile loop {buf[21]}  flush {buf[22]}  whole kernel {buf[23]}  (1965 cycles = 1 us)")
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(20):
+    ops.ppo_minibatch(params, wpack, obs, D, A, act, adv, logp, ret, index=idx, rows=B, adv_sums=sums)
+t1.record(); torch.cuda.synchronize()
+print(f"ppo_minibatch (2 towers + 2 wgrads, instrumented build): {t0.elapsed_time(t1) / 20 * 1e3:.1f} us")
+cta = (C.c_uint * 512)()
+lib.tmla_debug_phase_cycles(cta, 2)
+import numpy as np
+arr = np.array(list(cta), dtype=np.int64).reshape(256, 2)[:148]
+loop, sm = arr[:, 0], arr[:, 1]
+ntile = np.where(np.arange(148) < 2048 - 148 * 13, 14, 13)
+per = loop / ntile
+print("per-CTA tile-loop cycles of the last launch (value tower): min/median/max", loop.min(), int(np.median(loop)), loop.max())
+print("cycles per tile by CTA: min/median/max", int(per.min()), int(np.median(per)), int(per.max()))
+order = np.argsort(per)
+print("slowest 12 CTAs (cta, sm, tiles, cycles/tile):", [(int(c), int(sm[c]), int(ntile[c]), int(per[c])) for c in order[-12:]])
+print("fastest 6:", [(int(c), int(sm[c]), int(ntile[c]), int(per[c])) for c in order[:6]])
+print("mean cycles/tile SM<74:", int(per[sm < 74].mean()), " SM>=74:", int(per[sm >= 74].mean()))

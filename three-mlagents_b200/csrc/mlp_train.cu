@@ -122,6 +122,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // consecutive marks of the worker tile loop in shared memory; CTA 0 publishes them (profiles/phase_clocks.py)
 #ifdef TMLA_PHASE_CLOCKS
 __device__ unsigned long long g_phase_cycles[32];
+__device__ unsigned int g_cta_loop[512];      // per CTA of the LAST launch: tile-loop cycles, SM id
 #define TMLA_PH(i) do { if (tid == 0) { const long long c__ = clock64(); ph_acc[i] += (unsigned long long)(c__ - ph_clock); ph_clock = c__; } } while (0)
 #else
 #define TMLA_PH(i) do { } while (0)
@@ -181,6 +182,10 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     using L = TrainSmem<D, NOUT>;
     constexpr bool PI = NOUT > 1;
     static_assert(3 * NOUT <= 16 && 2 * D + 1 <= 16, "operand tiles are 16 columns wide");
+#ifdef TMLA_PHASE_CLOCKS
+    const long long ph_t0 = clock64();
+    unsigned long long ph_g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_g0));
+#endif
     // TMEM columns: ACC (Z2 / dH2 / dH1), H1 stash (bf16 pairs), persistent gradient accumulators
     constexpr uint32_t C_ACC = 0, C_H1 = 256, C_GWH = 384, C_GB2 = 416, C_GW1 = 448, C_HEAD = 480;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -329,6 +334,7 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     unsigned long long *ph_acc = reinterpret_cast<unsigned long long *>(smem + L::bar + 64);
     if (tid == 0) for (int i = 0; i < 32; ++i) ph_acc[i] = 0;
     long long ph_clock = clock64();
+    const long long ph_t1 = ph_clock;
 #endif
     if (is_driver) {
         // ================================ driver warp: tensor core + bulk TMA ================================
@@ -634,7 +640,8 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     }
     if (!is_driver) { mbar_wait(bar1, ph1); tc_fence_after(); }   // the last M4
 #ifdef TMLA_PHASE_CLOCKS
-    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 32; ++i) g_phase_cycles[i] += ph_acc[i];
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 16; ++i) g_phase_cycles[i] += ph_acc[i];
+    const long long ph_t2 = clock64();
 #endif
 
     // ---- flush: TMEM gradient accumulators (lane = hidden unit) -> one atomic per value; scalar sums
@@ -674,6 +681,21 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
+#ifdef TMLA_PHASE_CLOCKS
+    if (tid == 0) {      // whole-kernel budget: prologue / tile loop / flush, CTA 0 summed and the maximum over CTAs
+        const long long ph_t3 = clock64();
+        if (blockIdx.x == 0) {
+            unsigned long long ph_g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_g1));
+            g_phase_cycles[24] += ph_g1 - ph_g0; g_phase_cycles[25] += (unsigned long long)(ph_t3 - ph_t0);
+            g_phase_cycles[16] += (unsigned long long)(ph_t1 - ph_t0); g_phase_cycles[17] += (unsigned long long)(ph_t2 - ph_t1);
+            g_phase_cycles[18] += (unsigned long long)(ph_t3 - ph_t2);
+        }
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (blockIdx.x < 256) { g_cta_loop[2 * blockIdx.x] = (unsigned)(ph_t2 - ph_t1); g_cta_loop[2 * blockIdx.x + 1] = smid; }
+        atomicMax(&g_phase_cycles[20], (unsigned long long)(ph_t1 - ph_t0)); atomicMax(&g_phase_cycles[21], (unsigned long long)(ph_t2 - ph_t1));
+        atomicMax(&g_phase_cycles[22], (unsigned long long)(ph_t3 - ph_t2)); atomicMax(&g_phase_cycles[23], (unsigned long long)(ph_t3 - ph_t0));
+    }
+#endif
 }
 
 // --------------------------------------------------------- G[256,256] += X^T . Y  over tile images
@@ -683,20 +705,28 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
 // a 3-stage ring — no per-thread loads, no transposes: the tensor core reads both operands through MN-major
 // descriptors.  Warp-specialised: one producer thread, one MMA-issuing thread, full/empty mbarriers per stage;
 // 256x256 fp32 accumulators in all 512 TMEM columns; split-K over CTAs finished with red.global.add.v4.f32.
+// Two independent problems (the policy and the value tower of one minibatch) can share a launch: even CTAs take
+// problem 0, odd CTAs problem 1 — one kernel boundary and half as many 256 KB atomic epilogues as two launches.
 static constexpr uint32_t kwChunk = 64 * H * 2;               // 32768 B: 64 rows of one operand
 static constexpr uint32_t kwStage = 2 * kwChunk;              // X and Y
 static constexpr int kwStages = 3;
 static constexpr uint32_t kWgradTiledSmem = kwStages * kwStage + 128;   // 196736 (>= the 128 KB epilogue stage)
 
 __global__ void __launch_bounds__(256, 1)
-tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 *__restrict__ Yt, float *__restrict__ G, int64_t nchunks) {
+tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16 *__restrict__ Yt0, float *__restrict__ G0,
+                      const __nv_bfloat16 *__restrict__ Xt1, const __nv_bfloat16 *__restrict__ Yt1, float *__restrict__ G1, int64_t nchunks) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kwStages * kwStage);   // full[3], empty[3], done
     uint64_t *empty = full + kwStages, *done = empty + kwStages;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kwStages * kwStage + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    if ((int64_t)blockIdx.x >= nchunks) return;
+    const bool dual = Xt1 != nullptr;
+    const bool second = dual && (blockIdx.x & 1);
+    const __nv_bfloat16 *Xt = second ? Xt1 : Xt0, *Yt = second ? Yt1 : Yt0;
+    float *G = second ? G1 : G0;
+    const int64_t first = dual ? blockIdx.x >> 1 : blockIdx.x, stride = dual ? gridDim.x >> 1 : gridDim.x;
+    if (first >= nchunks) return;
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
     if (tid == 32) {
@@ -709,15 +739,14 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt, const __nv_bfloat16 
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     const uint32_t s_addr = smem_u32(smem);
-    const int64_t stride = gridDim.x;
-    const int64_t my_chunks = (nchunks - blockIdx.x + stride - 1) / stride;
+    const int64_t my_chunks = (nchunks - first + stride - 1) / stride;
 
     if (tid == 0) {                                        // producer: bulk-TMA loads, one stage ahead of the ring's tail
         uint32_t pe[kwStages] = {0u, 0u, 0u};
         for (int64_t j = 0; j < my_chunks; ++j) {
             const int s = (int)(j % kwStages);
             if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }   // the MMAs of chunk j-3 have read this stage
-            const int64_t c = blockIdx.x + j * stride;
+            const int64_t c = first + j * stride;
             mbar_expect_tx(full + s, kwStage);
             bulk_load(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s);
             bulk_load(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s);
@@ -845,16 +874,19 @@ static int sm_count_train() {
     return n;
 }
 
-// Xt, Yt: tile images covering `rows_padded` rows (a multiple of 128)
-static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64_t rows_padded, cudaStream_t st) {
+// Xt, Yt: tile images covering `rows_padded` rows (a multiple of 128); Xt1/Yt1/G1 = an optional second problem of the same size
+static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64_t rows_padded, cudaStream_t st,
+                                 const void *Xt1 = nullptr, const void *Yt1 = nullptr, float *G1 = nullptr) {
     static int attr_done = 0;
     if (!attr_done) {
         TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradTiledSmem));
         attr_done = 1;
     }
     const int64_t nchunks = rows_padded / 64;
-    const unsigned grid = (unsigned)std::min<int64_t>(nchunks, sm_count_train());
-    tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G, nchunks);
+    unsigned grid = (unsigned)std::min<int64_t>(Xt1 ? 2 * nchunks : nchunks, sm_count_train());
+    if (Xt1) grid &= ~1u;                                  // CTA pairs: even -> problem 0, odd -> problem 1
+    tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G,
+                                                              (const __nv_bfloat16 *)Xt1, (const __nv_bfloat16 *)Yt1, G1, nchunks);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -881,7 +913,7 @@ int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions) {
                             (obs_dim == 7 && n_actions == 3))) ? 1 : 0;
 }
 
-int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 2 * ((rows + 127) / 128 * 128) * (int64_t)hidden; }
+int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows) { return 4 * ((rows + 127) / 128 * 128) * (int64_t)hidden; }
 
 int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *obs,
                             const int32_t *index, int64_t rows, int64_t global_rows, const int32_t *actions,
@@ -900,8 +932,11 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
     TMLA_CUDA(cudaMemsetAsync(stats_out, 0, 8 * sizeof(float), st));
     const int64_t rows_padded = (rows + 127) / 128 * 128;  // whole tile images; rows past `rows` contribute exact zeros (dZ2 = 0)
-    __nv_bfloat16 *h1 = reinterpret_cast<__nv_bfloat16 *>(scratch), *dz2 = h1 + rows_padded * H;
+    // scratch: H1 and dZ2 tile images of both towers (one weight-gradient launch covers the two towers)
+    __nv_bfloat16 *img[2][2];
+    for (int t = 0; t < 2; ++t) for (int q = 0; q < 2; ++q) img[t][q] = reinterpret_cast<__nv_bfloat16 *>(scratch) + (int64_t)(2 * t + q) * rows_padded * H;
     for (int t = 0; t < 2; ++t) {
+        __nv_bfloat16 *h1 = img[t][0], *dz2 = img[t][1];
         TowerTrainArgs a;
         a.W1 = params + o.w1[t]; a.B1 = params + o.b1[t];
         a.W2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H;
@@ -919,10 +954,8 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
         else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st) : tower_train_launch_t<4, 1>(a, st);
         if (rc) return rc;
-        rc = tc_wgrad_tiled_launch(dz2, h1, grads + o.w2[t], rows_padded, st);
-        if (rc) return rc;
     }
-    return TMLA_OK;
+    return tc_wgrad_tiled_launch(img[0][1], img[0][0], grads + o.w2[0], rows_padded, st, img[1][1], img[1][0], grads + o.w2[1]);
 }
 
 int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_padded, void *stream) {
@@ -933,6 +966,7 @@ int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_p
 #ifdef TMLA_PHASE_CLOCKS
 int tmla_debug_phase_cycles(unsigned long long *out32, int reset) {      // debug builds only; not part of include/tmla.h
     if (out32) TMLA_CUDA(cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof(g_phase_cycles)));
+    if (out32 && reset == 2) { TMLA_CUDA(cudaMemcpyFromSymbol(out32, g_cta_loop, sizeof(g_cta_loop))); return TMLA_OK; }
     if (reset) { unsigned long long z[32] = {0}; TMLA_CUDA(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z))); }
     return TMLA_OK;
 }

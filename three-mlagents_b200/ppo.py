@@ -137,7 +137,8 @@ class CudaPPO:
             self.dlogits = torch.empty((B, A), **f32)
             self.dvalues = torch.empty(B, **f32)
             self.cache_mb = torch.empty((4, B, HIDDEN), dtype=self._act_dtype, device=dev)
-        self.scratch_mb = torch.empty(2 * ((B + 127) // 128 * 128) * HIDDEN, dtype=self._act_dtype, device=dev)
+        n_img = 4 if self.fused_update else 2          # fused: H1 and dZ2 tile images of both towers
+        self.scratch_mb = torch.empty(n_img * ((B + 127) // 128 * 128) * HIDDEN, dtype=self._act_dtype, device=dev)
         self.adv_sums = torch.zeros(((total + B - 1) // B, 3), dtype=torch.float64, device=dev)   # one row per minibatch of an epoch
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
