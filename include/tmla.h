@@ -235,6 +235,11 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
 int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
                    float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                    float *norm_out, void *stream);
+/* Same step; zero_grads != 0 also clears `grads` once consumed, so that the next tmla_ppo_minibatch_bf16 call can run with
+ * TMLA_MB_GRADS_ZEROED (no memset launch between minibatches). */
+int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
+                        float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                        float *norm_out, int zero_grads, void *stream);
 
 /* ---- tensor-core building blocks (csrc/mlp_tc.cu: tcgen05.mma, TMEM accumulators), bf16 row-major device
  * buffers.  Used by the bf16 MLP path; exported so the parity tests can exercise them in isolation.
@@ -260,16 +265,20 @@ int tmla_tc_debug(int swap_lbo_sbo);
  *   [T*N] buffers actions/advantages/old_logp/returns;  adv_sums from tmla_adv_stats (all-reduced by the caller
  *   when world_size>1), global_rows = rows summed over ranks;
  *   grads float[num_params] OVERWRITTEN;  scratch bf16[tmla_ppo_minibatch_scratch(hidden, rows)] (tile images);
- *   stats_out float[8] as tmla_ppo_loss;  logits_out float[rows,A] / values_out float[rows]: optional (NULL).
+ *   stats_out float[8] as tmla_ppo_loss;  logits_out float[rows,A] / values_out float[rows]: optional (NULL);
+ *   flags: TMLA_MB_GRADS_ZEROED — the caller guarantees grads is all zeros (tmla_adam_clip_zero left it so): no memset;
+ *          TMLA_MB_ACCUMULATE_STATS — stats_out is added to instead of overwritten (a running sum over minibatches).
  * tmla_ppo_minibatch_supported: 1 when the fused path covers (obs_dim, hidden, n_actions) — ball3d, gridworld,
- * push, walljump; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
+ * push, walljump, bicycle; callers use the three-call sequence otherwise (basic: obs_dim 21, 3 actions). */
+#define TMLA_MB_GRADS_ZEROED 1
+#define TMLA_MB_ACCUMULATE_STATS 2
 int tmla_ppo_minibatch_supported(int obs_dim, int hidden, int n_actions);
 int64_t tmla_ppo_minibatch_scratch(int hidden, int64_t rows);
 int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim, int hidden, int n_actions, const float *obs,
                             const int32_t *index, int64_t rows, int64_t global_rows, const int32_t *actions,
                             const float *advantages, const float *old_logp, const float *returns, const double *adv_sums,
                             int normalize_advantage, float clip_range, float ent_coef, float vf_coef, float *grads,
-                            void *scratch, float *stats_out, float *logits_out, float *values_out, void *stream);
+                            void *scratch, float *stats_out, float *logits_out, float *values_out, int flags, void *stream);
 
 /* test hooks of csrc/mlp_train.cu:
  *   tmla_tc_wgrad_tiled: G[256,256] (fp32, accumulated) += X^T . Y where X and Y are given as TILE IMAGES — per 128

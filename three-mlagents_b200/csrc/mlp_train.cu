@@ -919,7 +919,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
                             const int32_t *index, int64_t rows, int64_t global_rows, const int32_t *actions,
                             const float *advantages, const float *old_logp, const float *returns, const double *adv_sums,
                             int normalize_advantage, float clip_range, float ent_coef, float vf_coef, float *grads,
-                            void *scratch, float *stats_out, float *logits_out, float *values_out, void *stream) {
+                            void *scratch, float *stats_out, float *logits_out, float *values_out, int flags, void *stream) {
     TMLA_REQUIRE(params && wpack && obs && actions && advantages && old_logp && returns && grads && scratch && stats_out, "NULL buffer");
     TMLA_REQUIRE(rows > 0 && global_rows >= rows, "bad row counts");
     TMLA_REQUIRE(!normalize_advantage || adv_sums, "adv_sums required when normalising");
@@ -929,8 +929,8 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     }
     cudaStream_t st = (cudaStream_t)stream;
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
-    TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
-    TMLA_CUDA(cudaMemsetAsync(stats_out, 0, 8 * sizeof(float), st));
+    if (!(flags & TMLA_MB_GRADS_ZEROED)) TMLA_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * o.total, st));
+    if (!(flags & TMLA_MB_ACCUMULATE_STATS)) TMLA_CUDA(cudaMemsetAsync(stats_out, 0, 8 * sizeof(float), st));
     const int64_t rows_padded = (rows + 127) / 128 * 128;  // whole tile images; rows past `rows` contribute exact zeros (dZ2 = 0)
     // scratch: H1 and dZ2 tile images of both towers (one weight-gradient launch covers the two towers)
     __nv_bfloat16 *img[2][2];

@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__
     }
 }
 __global__ void __launch_bounds__(256)
-adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t np,
+adam_kernel(float *__restrict__ p, const float *g, float *__restrict__ m, float *__restrict__ v, int64_t np,
             float scale, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-            const float *__restrict__ partial, float *norm_out) {
+            const float *__restrict__ partial, float *norm_out, int zero_grads) {
     __shared__ float s_norm;
     if (threadIdx.x < 32) {                                // same summation order in every block and on every rank
         float t = 0.0f;
@@ -292,6 +292,7 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
     if (i == 0 && norm_out) *norm_out = norm;
     if (i >= np) return;
     const float gi = g[i] * scale * coef;
+    if (zero_grads) const_cast<float *>(g)[i] = 0.0f;     // the next minibatch accumulates into a clean buffer (no memset launch)
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
@@ -379,8 +380,8 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
     return TMLA_OK;
 }
 
-int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
-                   float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, void *stream) {
+int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                        float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *stream) {
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer (norm_out doubles as scratch)");
     TMLA_REQUIRE(num_params > 0 && step >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -389,9 +390,13 @@ int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_
     TMLA_LAUNCH_CHECK();
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<(unsigned)ceil_div64(num_params, 256), 256, 0, st>>>(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr,
-                                                                      beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), norm_out + 1, norm_out);
+                                                                      beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), norm_out + 1, norm_out, zero_grads);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
+}
+int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                   float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, void *stream) {
+    return tmla_adam_clip_zero(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out, 0, stream);
 }
 
 int tmla_bootstrap_add(float *rew_buf, const int32_t *trunc_count, const int32_t *trunc_index, const float *trunc_values,

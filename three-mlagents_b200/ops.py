@@ -163,8 +163,10 @@ def ppo_minibatch_supported(obs_dim: int, n_actions: int) -> bool:
 
 def ppo_minibatch(params, wpack, obs, obs_dim, n_actions, actions, advantages, old_logp, returns, *, index=None, rows=None,
                   global_rows=None, adv_sums=None, normalize=True, clip_range=0.2, ent_coef=0.01, vf_coef=0.5, grads=None,
-                  scratch=None, stats=None, logits=None, values=None):
-    """One PPO.train minibatch, forward + loss + backward fused (tmla_ppo_minibatch_bf16): returns (grads, stats)."""
+                  scratch=None, stats=None, logits=None, values=None, grads_zeroed=False, accumulate_stats=False):
+    """One PPO.train minibatch, forward + loss + backward fused (tmla_ppo_minibatch_bf16): returns (grads, stats).
+    grads_zeroed: `grads` is known to be all zeros (adam_clip(zero_grads=True) left it so) — skips the memset launch;
+    accumulate_stats: add to `stats` instead of overwriting it."""
     _chk(params, torch.float32, "params"); _chk(wpack, torch.bfloat16, "wpack"); _chk(obs, torch.float32, "obs")
     _chk(index, torch.int32, "index"); _chk(actions, torch.int32, "actions"); _chk(advantages, torch.float32, "advantages")
     _chk(old_logp, torch.float32, "old_logp"); _chk(returns, torch.float32, "returns")
@@ -184,17 +186,18 @@ def ppo_minibatch(params, wpack, obs, obs_dim, n_actions, actions, advantages, o
     check(lib.tmla_ppo_minibatch_bf16(ptr(params), ptr(wpack), obs_dim, HIDDEN, n_actions, ptr(obs), ptr(index), int(rows),
                                       int(global_rows or rows), ptr(actions), ptr(advantages), ptr(old_logp), ptr(returns),
                                       ptr(adv_sums), 1 if normalize else 0, float(clip_range), float(ent_coef),
-                                      float(vf_coef), ptr(grads), ptr(scratch), ptr(stats), ptr(logits), ptr(values), _s()))
+                                      float(vf_coef), ptr(grads), ptr(scratch), ptr(stats), ptr(logits), ptr(values),
+                                      (1 if grads_zeroed else 0) | (2 if accumulate_stats else 0), _s()))
     return grads, stats
 
 
 def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
-              eps=1e-5, norm_out=None):
+              eps=1e-5, norm_out=None, zero_grads=False):
     if norm_out is None:
         norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
-    check(lib.tmla_adam_clip(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
-                             float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
-                             ptr(norm_out), _s()))
+    check(lib.tmla_adam_clip_zero(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
+                                  float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                  ptr(norm_out), 1 if zero_grads else 0, _s()))
     return norm_out
 
 

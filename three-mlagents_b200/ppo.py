@@ -181,6 +181,9 @@ class CudaPPO:
         B = self.mb_rows
         obs_flat = self.obs[:T].reshape(total, D)
         self.stats_acc.zero_()
+        fused = self.fused_update
+        if fused:              # no per-minibatch memsets: Adam clears the gradient it consumed, statistics accumulate in place
+            self.grads.zero_()
         n_mb = 0
         for _ in range(self.n_epochs):
             ops.permutation(self.seed + 7919 * self.rank, self._epoch_counter, T, N, out=self.perm)
@@ -196,7 +199,8 @@ class CudaPPO:
                     ops.ppo_minibatch(self.params, self.wpack, obs_flat, D, A, self.act, self.adv, self.logp, self.ret,
                                       index=idx, rows=rows, global_rows=rows * self.world, adv_sums=sums,
                                       normalize=sums is not None, clip_range=self.clip_range, ent_coef=self.ent_coef,
-                                      vf_coef=self.vf_coef, grads=self.grads, scratch=self.scratch_mb, stats=self.stats)
+                                      vf_coef=self.vf_coef, grads=self.grads, scratch=self.scratch_mb, stats=self.stats_acc,
+                                      grads_zeroed=True, accumulate_stats=True)
                 else:
                     ops.mlp_forward(self.params, obs_flat, D, A, index=idx, rows=rows, logits=self.logits_mb,
                                     values=self.values_mb, act_cache=self.cache_mb, wpack=self.wpack)
@@ -209,9 +213,10 @@ class CudaPPO:
                 allreduce_sum_(self.grads)                # the one collective on the path: NCCL sum over NVLink
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
-                              lr=self.lr, eps=1e-5, norm_out=self.norm_out)
+                              lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused)
                 self._repack()
-                self.stats_acc += self.stats
+                if not fused:
+                    self.stats_acc += self.stats
                 n_mb += 1
             self.n_updates += 1
         return n_mb
