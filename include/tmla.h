@@ -240,6 +240,12 @@ int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_
 int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
                         float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                         float *norm_out, int zero_grads, void *stream);
+/* ... and, with wpack != NULL (the buffer of tmla_mlp_pack_bf16), also refreshes the bf16 OPERAND IMAGES of the two hidden-layer
+ * matrices — all the fused minibatch kernel reads — so no repack launch is needed between minibatches; the row-major bf16
+ * copies the rollout's forward uses are NOT refreshed: call tmla_mlp_pack_bf16 once when the update loop ends. */
+int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
+                         float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                         float *norm_out, int zero_grads, void *wpack, int obs_dim, int hidden, int n_actions, void *stream);
 
 /* ---- tensor-core building blocks (csrc/mlp_tc.cu: tcgen05.mma, TMEM accumulators), bf16 row-major device
  * buffers.  Used by the bf16 MLP path; exported so the parity tests can exercise them in isolation.

@@ -158,6 +158,31 @@ def test_adam_clip_vs_torch():
     np.testing.assert_allclose(P.cpu().numpy(), flat.detach().numpy(), rtol=0, atol=1e-6)
 
 
+def test_adam_zero_grads_and_operand_image_refresh():
+    """tmla_adam_clip_fused: same update as the plain call, the consumed gradient is cleared, and the bf16 operand images of
+    both hidden-layer matrices inside `wpack` equal a full tmla_mlp_pack_bf16 of the new parameters (bit for bit)."""
+    ops = _ops()
+    d, a = 6, 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 136710
+    P = torch.randn(n, device="cuda", generator=g) * 0.1
+    G = torch.randn(n, device="cuda", generator=g) * 0.01
+    P2, G2 = P.clone(), G.clone()
+    m, v, m2, v2 = (torch.zeros_like(P) for _ in range(4))
+    wpack = ops.mlp_pack(P, d, a)
+    stale = wpack.clone()
+    ops.adam_clip(P, G, m, v, 1)
+    ops.adam_clip(P2, G2, m2, v2, 1, zero_grads=True, wpack=wpack, obs_dim=d, n_actions=a)
+    torch.cuda.synchronize()
+    assert torch.equal(P, P2) and torch.equal(m, m2) and torch.equal(v, v2)
+    assert float(G2.abs().max()) == 0.0 and float(G.abs().max()) > 0.0
+    fresh = ops.mlp_pack(P2, d, a)
+    w = wpack.view(6, 256, 256)
+    assert torch.equal(w[4:].view(torch.int16), fresh.view(6, 256, 256)[4:].view(torch.int16))       # the two operand images
+    assert torch.equal(w[:4].view(torch.int16), stale.view(6, 256, 256)[:4].view(torch.int16))       # row-major copies untouched
+    assert not torch.equal(w[4:].view(torch.int16), stale.view(6, 256, 256)[4:].view(torch.int16))
+
+
 def test_step_policy_sampling_and_bootstrap_records():
     """Policy-driven step: sampled actions follow the inverse-CDF twin, log-probs match log_softmax,
     truncation records carry the terminal observation of exactly the time-limit envs."""

@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
+#include "mlp_common.cuh"
+#include <cuda_bf16.h>
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *g, float *__restrict__ m, float *__restrict__ v, int64_t np,
             float scale, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-            const float *__restrict__ partial, float *norm_out, int zero_grads) {
+            const float *__restrict__ partial, float *norm_out, int zero_grads,
+            __nv_bfloat16 *__restrict__ img0, __nv_bfloat16 *__restrict__ img1, int64_t w2_off0, int64_t w2_off1) {
     __shared__ float s_norm;
     if (threadIdx.x < 32) {                                // same summation order in every block and on every rank
         float t = 0.0f;
@@ -297,7 +300,16 @@ adam_kernel(float *__restrict__ p, const float *g, float *__restrict__ m, float 
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;      // torch.optim.Adam (no amsgrad, no weight decay)
-    p[i] -= (lr / bc1) * (mi / denom);
+    const float pn = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pn;
+    if (img0) {      // hidden-layer weight: refresh its bf16 entry of the tensor-core operand image (mlp_tc.cu:pack_w2_kernel layout)
+        const int64_t e0 = i - w2_off0, e1 = i - w2_off1;
+        const bool in0 = e0 >= 0 && e0 < 65536, in1 = e1 >= 0 && e1 < 65536;
+        if (in0 || in1) {
+            const int e = (int)(in0 ? e0 : e1), r = e >> 8, k = e & 255;
+            (in0 ? img0 : img1)[(r >> 3) * 2048 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7)] = __float2bfloat16_rn(pn);
+        }
+    }
 }
 
 __global__ void bootstrap_add_kernel(float *rew, const int32_t *count, const int32_t *idx, const float *vals, float g, int32_t cap) {
@@ -380,19 +392,35 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
     return TMLA_OK;
 }
 
-int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
-                        float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *stream) {
+int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                         float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
+                         void *wpack, int obs_dim, int hidden, int n_actions, void *stream) {
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer (norm_out doubles as scratch)");
     TMLA_REQUIRE(num_params > 0 && step >= 1, "bad arguments");
+    __nv_bfloat16 *img0 = nullptr, *img1 = nullptr;
+    int64_t off0 = 0, off1 = 0;
+    if (wpack) {
+        TMLA_REQUIRE(hidden == 256, "operand images exist for hidden = 256 only");
+        const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+        TMLA_REQUIRE(o.total == num_params, "num_params does not match (obs_dim, n_actions)");
+        img0 = reinterpret_cast<__nv_bfloat16 *>(wpack) + (int64_t)4 * 65536; img1 = img0 + 65536;
+        off0 = o.w2[0]; off1 = o.w2[1];
+    }
     cudaStream_t st = (cudaStream_t)stream;
     // norm_out[0] = norm, norm_out[1 .. 1+kNormBlocks) = per-block partial sums of squares
     gradnorm_kernel<<<kNormBlocks, 256, 0, st>>>(grads, num_params, grad_scale, norm_out + 1);
     TMLA_LAUNCH_CHECK();
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<(unsigned)ceil_div64(num_params, 256), 256, 0, st>>>(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr,
-                                                                      beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), norm_out + 1, norm_out, zero_grads);
+                                                                      beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), norm_out + 1, norm_out, zero_grads,
+                                                                      img0, img1, off0, off1);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
+}
+int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                        float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *stream) {
+    return tmla_adam_clip_fused(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out,
+                                zero_grads, nullptr, 0, 0, 0, stream);
 }
 int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
                    float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, void *stream) {

@@ -192,12 +192,15 @@ def ppo_minibatch(params, wpack, obs, obs_dim, n_actions, actions, advantages, o
 
 
 def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
-              eps=1e-5, norm_out=None, zero_grads=False):
+              eps=1e-5, norm_out=None, zero_grads=False, wpack=None, obs_dim=0, n_actions=0):
+    """clip_grad_norm_ + Adam.step.  zero_grads: clear `grads` once consumed.  wpack (+ obs_dim, n_actions): also refresh the bf16
+    operand images of the hidden-layer weights inside `wpack` (what the fused minibatch kernel reads)."""
     if norm_out is None:
         norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
-    check(lib.tmla_adam_clip_zero(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
-                                  float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
-                                  ptr(norm_out), 1 if zero_grads else 0, _s()))
+    _chk(wpack, torch.bfloat16, "wpack")
+    check(lib.tmla_adam_clip_fused(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
+                                   float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                   ptr(norm_out), 1 if zero_grads else 0, ptr(wpack), int(obs_dim), HIDDEN, int(n_actions), _s()))
     return norm_out
 
 

@@ -213,12 +213,15 @@ class CudaPPO:
                 allreduce_sum_(self.grads)                # the one collective on the path: NCCL sum over NVLink
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
-                              lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused)
-                self._repack()
-                if not fused:
+                              lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused,
+                              wpack=self.wpack if fused else None, obs_dim=D, n_actions=A)
+                if not fused:          # (fused: Adam refreshed the operand images itself; full repack once after the loop)
+                    self._repack()
                     self.stats_acc += self.stats
                 n_mb += 1
             self.n_updates += 1
+        if fused:
+            self._repack()
         return n_mb
 
     def _log_row(self, n_mb: int, t_roll: float, t_train: float, t0: float) -> dict[str, Any]:
