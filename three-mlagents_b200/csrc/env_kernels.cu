@@ -257,8 +257,15 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
 // present, 16-byte aligned rows, 32-bit element offsets.  Same arithmetic as the generic kernel above (the
 // tests compare them bit for bit) with the loop bookkeeping stripped down: shared memory is indexed directly
 // (no generic pointers), offsets are running 32-bit counters, and for tasks with an episode-indexed reset
-// stream (ball3d) the next initial state is drawn ahead of time every 16 steps (`Spare`), so the two Philox
+// stream (ball3d) the next initial state is drawn ahead of time every kSpareEvery steps (`Spare`), so the two Philox
 // blocks of a reset no longer sit inside a divergent branch that ~23 % of the warps enter on every step.
+// Refill period of the ahead-of-time reset draws.  The draw is indexed by the env's episode counter, not by time, so the
+// period changes no result — only how often a warp pays two Philox blocks for its consumed lanes (TMLA_SPARE_EVERY).
+#ifndef TMLA_SPARE_EVERY
+#define TMLA_SPARE_EVERY 64   /* measured on 128-step launches: 16 -> 66.3 us, 32 -> 64.6, 64 -> 63.9, 128 -> 66.7 */
+#endif
+static constexpr int kSpareEvery = TMLA_SPARE_EVERY;
+static_assert((kSpareEvery & (kSpareEvery - 1)) == 0, "power of two");
 template <class Task>
 __global__ void __launch_bounds__(kRollBlock)
 rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uint64_t step0, int T,
@@ -283,7 +290,7 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
 #pragma unroll 2   // measured: 73.2 us (no unroll) / 70.8 us (2) / 72.1 us (4)
     for (int t = 0; t < T; ++t) {
         if constexpr (Task::HAS_SPARE) {
-            if ((t & 15) == 0 && !have_spare) {         // off the critical path: refill consumed spares
+            if ((t & (kSpareEvery - 1)) == 0 && !have_spare) {   // off the critical path: refill consumed spares
                 sp = Task::draw(seed, env_id, Task::next_episode(s), TMLA_TAG_RESET);
                 have_spare = true;
             }
