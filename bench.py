@@ -117,9 +117,28 @@ def _cpu_baseline(seconds_target: float = 12.0):
     t_probe = ref_port.time_random_policy(TASK, n_envs, 500)
     vec_steps = max(1000, int(500 * seconds_target / max(t_probe, 1e-3)))
     dt = ref_port.time_random_policy(TASK, n_envs, vec_steps)
-    return {"value": n_envs * vec_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"ball3d, {n_envs} envs x {vec_steps} serial vec-steps, uniform random actions, "
-                      f"scalar Python port of the reference env + adapter + DummyVecEnv loop ({dt:.1f} s)"}
+    out = {"value": n_envs * vec_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+           "sample": f"ball3d, {n_envs} envs x {vec_steps} serial vec-steps, uniform random actions, "
+                     f"scalar Python port of the reference env + adapter + DummyVecEnv loop ({dt:.1f} s)"}
+    # For scale, the same semantics restated as vectorised NumPy over all 65 536 envs (oracle/envs_oracle.py, the parity
+    # checker): what one host core reaches once the per-env Python objects of the reference are gone.
+    try:
+        import numpy as np
+        from oracle import envs_oracle as eo
+
+        ora = eo.OracleVecEnv(TASK, N_ENVS, seed=1)
+        acts = np.random.default_rng(0).integers(0, 5, size=(8, N_ENVS))
+        ora.step(acts[0])
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < 3.0:
+            ora.step(acts[k % 8])
+            k += 1
+        out["numpy_vectorised"] = {"value": N_ENVS * k / (time.perf_counter() - t0), "unit": "env-steps/s", "cores": 1,
+                                   "sample": f"{k} vec-steps of {N_ENVS} envs (NumPy restatement with Philox auto-reset, 3 s)"}
+    except Exception as e:  # noqa: BLE001
+        out["numpy_vectorised"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def run_reference(args):
