@@ -246,46 +246,20 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             } else cp_async_ca<4>(dst, p.returns + src, ok ? 4u : 0u);
         }
     };
+    // Prologue, ordered so that nothing waits alone: the index fetch of the first two tiles flies while the barriers are set up,
+    // the W2 image load is issued and the constant tiles are built; the observation rows it selects fly while the transposed
+    // layer-1 weights are staged.
     fetch_index(0u, blockIdx.x);
     fetch_index(1u, (int64_t)blockIdx.x + gridDim.x);
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-    fetch_rows(0u);
-    fetch_loss_inputs(0u);
     cp_async_commit();
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
     if (tid == 32) { mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(rdy, 1); mbar_init(bar_st, 1); fence_barrier_init(); }
     if (tid == 32) { mbar_expect_tx(bar0, kWBytes); bulk_load(smem_u32(Ws), p.W2, kWBytes, bar0); }   // W2 image: one bulk-TMA load
-    for (int e = tid; e < H * D; e += blockDim.x) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
-    if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
-    for (int e = tid; e < H * 16; e += blockDim.x) {       // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
-        const int j = e >> 4, c = e & 15;
-        float v = 0.0f;
-        if (c < 3 * NOUT) {
-            const float w = p.Wh[(c % NOUT) * H + j];
-            v = c < 2 * NOUT ? w : w - bf16_round(w);
-        }
-        *reinterpret_cast<__nv_bfloat16 *>(smem + L::wht + (j >> 3) * ksG + (c >> 3) * ksS + (j & 7) * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
-    }
-    cp_async_wait_all();                                   // the first tile's rows
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
-    const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
-    uint32_t ph0 = 0, ph1 = 0, phs = 0;                     // phs: parity of bar_st (workers) / rdy (driver)
-    mbar_wait(bar0, ph0);                                  // the W2 image has landed
-    ph0 ^= 1u;
-
     // advantage normalisation constants (PPO.train: (adv - mean) / (std + 1e-8), std unbiased) and the per-row running
     // sums live in shared memory: registers are the scarce resource of this kernel
     float *racc = reinterpret_cast<float *>(smem + L::racc), *advc = racc + 128 * L::RS;
-    if (tid == 0) {
+    if (tid == 64) {
         float adv_mean = 0.0f, adv_inv_std = 1.0f;
         if (PI && p.normalize) {
             const double cnt = p.adv_sums[2], mu = p.adv_sums[0] / cnt;
@@ -298,7 +272,32 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         advc[0] = adv_mean; advc[1] = adv_inv_std;
     }
     for (int e = tid; e < 128 * (int)L::RS; e += blockDim.x) racc[e] = 0.0f;
+    if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
+    for (int e = tid; e < H * 16; e += blockDim.x) {       // WHT[j][c]: c in [0,NOUT) hi, [NOUT,2NOUT) hi, [2NOUT,3NOUT) lo
+        const int j = e >> 4, c = e & 15;
+        float v = 0.0f;
+        if (c < 3 * NOUT) {
+            const float w = p.Wh[(c % NOUT) * H + j];
+            v = c < 2 * NOUT ? w : w - bf16_round(w);
+        }
+        *reinterpret_cast<__nv_bfloat16 *>(smem + L::wht + (j >> 3) * ksG + (c >> 3) * ksS + (j & 7) * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
+    }
+    cp_async_wait_all();                                   // the index of the first two tiles
     __syncthreads();
+    fetch_rows(0u);
+    fetch_loss_inputs(0u);
+    cp_async_commit();
+    for (int e = tid; e < H * D; e += blockDim.x) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
+    cp_async_wait_all();                                   // the first tile's rows
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_addr = smem_u32(Ts), w_addr = smem_u32(Ws);
+    const uint32_t wht_addr = smem_u32(smem + L::wht), dout_addr = smem_u32(smem + L::dout), xb_addr = smem_u32(smem + L::xb);
+    uint32_t ph0 = 0, ph1 = 0, phs = 0;                     // phs: parity of bar_st (workers) / rdy (driver)
 
     // layer 1, H1 = tanh(x W1^T + b1): this thread computes rows l1row + 8*i (i < 4) x 16 columns from l1col — every
     // weight load then serves four rows (broadcast LDS.128 costs four shared-memory cycles each, and one
@@ -328,6 +327,8 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
         }
     };
     if (!is_driver) layer1();
+    mbar_wait(bar0, ph0);                                  // the W2 image has landed (its load overlapped everything above)
+    ph0 ^= 1u;
 
     uint32_t it = 0;
 #ifdef TMLA_PHASE_CLOCKS
