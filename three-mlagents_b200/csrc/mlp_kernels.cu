@@ -634,7 +634,8 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
         AT *h1 = act_cache + (int64_t)(2 * t) * rows * H, *h2 = act_cache + (int64_t)(2 * t + 1) * rows * H;
         if constexpr (BF) {
             if (obs_dim <= 6) {      // fused tower: gather + layer 1 + tcgen05 layer 2 + head in one persistent kernel
-                const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(2 * t) * H * H;
+                // W2 as its 128 KB operand IMAGE (wpack matrices 4, 5): one bulk-TMA load per CTA instead of a per-thread staging loop
+                const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H;
                 int rc = tc_tower_forward_launch(obs_dim, o.nout[t], params + o.w1[t], params + o.b1[t], w2, params + o.b2[t],
                                                  params + o.wh[t], params + o.bh[t], x, index, rows, rows_dev, out,
                                                  keep_act ? (void *)h1 : nullptr, keep_act ? (void *)h2 : nullptr, st);

@@ -354,8 +354,12 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     prefetch_x(blockIdx.x);
 
     if (warp == 0) tmem_alloc<256>(tmem_holder);
-    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
-    stage_rows<H>(Ws, W2, 0, H);
+    uint64_t *barw = bar + 1;                              // W2 (given as its operand image, mlp_tc.cu:pack_w2_kernel) landing
+    if (tid == 32) {
+        mbar_init(bar, 1); mbar_init(barw, 1); fence_barrier_init();
+        mbar_expect_tx(barw, kWBytes); bulk_load(smem_u32(Ws), W2, kWBytes, barw);   // one bulk-TMA load, overlaps the rest of the prologue
+    }
+    bool w2_pending = true;
     for (int e = tid; e < H * D; e += NT) w1s[e] = W1[e];
     for (int e = tid; e < NOUT * H; e += NT) whs[e] = Wh[e];
     if (tid < H) { b1s[tid] = B1[tid]; b2s[tid] = B2[tid]; }
@@ -400,6 +404,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            if (w2_pending) { mbar_wait(barw, 0); w2_pending = false; }
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < H / 16; ++kk)

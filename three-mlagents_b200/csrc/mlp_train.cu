@@ -91,13 +91,6 @@ __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t b
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc),
-                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 // per-thread asynchronous global -> shared copies (LDGSTS): the prefetched rows never occupy registers
 template <int BYTES>
 __device__ __forceinline__ void cp_async_ca(uint32_t dst, const void *src, uint32_t src_bytes) {   // src_bytes 0 = zero-fill
