@@ -112,9 +112,15 @@ int tmla_step_pinned(tmla_env *h, int64_t *n_done);
  * each (3 + D rounded up to a multiple of 4, so the kernel writes a record as 128-bit stores) — what a
  * binding should read instead of scanning `done` (Monitor / infos of the finished envs only). */
 int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_record);
-/* Result blocks: pinned host memory a binding hands out to ITS caller, so that the copy engine writes a step's results
- * straight into the arrays the caller receives (no copy out of a staging block).  Layout, as byte offsets from the block:
- * offsets[0..5] = obs f32[n,D], reward f32[n], done u8[n], truncated u8[n], flags i32[4] {n_done, bad_action, -, -},
+/* Result blocks: pinned host memory a binding hands out to ITS caller, so that the GPU writes a step's results
+ * straight into the arrays the caller receives (no copy out of a staging block).  How they get there is selected by the
+ * environment variable TMLA_HOST_STEP, read once per process (all tmla_step_host / _pinned / _block calls):
+ *   unset / "poll": the step kernel reads the actions from and stores the results to pinned memory itself (zero-copy over
+ *                   PCIe), the last CTA publishes {n_done, bad_action, sequence} and the host polls the sequence word;
+ *   "sync"        : the same stores, completion by cudaStreamSynchronize;
+ *   "copy"        : H2D actions -> kernel -> ONE D2H of obs..flags + the head of the record area (copy engines).
+ * Layout, as byte offsets from the block:
+ * offsets[0..5] = obs f32[n,D], reward f32[n], done u8[n], truncated u8[n], flags i32[4] {n_done, bad_action, sequence, -},
  * records (stride as tmla_host_records reports it); *bytes = size of a block.  tmla_step_block is tmla_step_pinned with the
  * results (and the n_done compact records) landing in `block`; the actions still come from the pinned action view.
  * The reference's DummyVecEnv returns fresh copies each step (SB3 dummy_vec_env.py step_wait): a binding keeps a small
