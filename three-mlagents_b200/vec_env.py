@@ -109,7 +109,7 @@ class _ResultBlocks:
         recp, recw = native.vp(), native.i32(0)
         check(lib.tmla_host_records(handle, C.byref(recp), C.byref(recw)))
         self.rec_words = int(recw.value)              # record stride: {idx, ret, len, tobs[d]} padded to a multiple of 4 words
-        self._raw, self._ptr = [], []
+        self._raw, self._fixed, self._ptr = [], [], []
         self.n, self.d = n, d
         self.scratch = self._alloc()      # never handed out: the fallback copies out of it
         self._alloc(); self._alloc()      # the usual case — the caller holds one step's results while asking for the next
@@ -118,36 +118,55 @@ class _ResultBlocks:
         q = native.vp()
         check(lib.tmla_result_block_alloc(self._h, C.byref(q)))
         raw = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(q.value))
+        o_obs, o_rew, o_done, o_trunc = self.off[:4]
+        n, d = self.n, self.d
+        # the four fixed-shape slices are made once per block and handed out again with it (5 us per step otherwise)
+        fixed = (raw[o_obs:o_obs + 4 * n * d].view(np.float32).reshape(n, d), raw[o_rew:o_rew + 4 * n].view(np.float32),
+                 raw[o_done:o_done + n].view(np.bool_), raw[o_trunc:o_trunc + n].view(np.bool_))
         self._raw.append(raw)
+        self._fixed.append(fixed)
         self._ptr.append(q)
-        return len(self._raw) - 1
+        k = len(self._raw) - 1
+        del raw, fixed
+        # reference counts of an unused block, measured through the same expressions acquire() evaluates
+        self._idle = (sys.getrefcount(self._raw[k]), sys.getrefcount(self._fixed[k][0]))
+        return k
 
     def acquire(self):
-        """Index of a block nobody references, or None when `cap` blocks are all still in use."""
-        raws = self._raw
+        """Index of a block nobody references, or None when `cap` blocks are all still in use.  A caller can hold a block
+        through one of its four cached slices (their own reference count rises) or through anything derived from them or
+        from the record slice (NumPy makes `raw` the base of every derived view: its count rises)."""
+        raws, fixed = self._raw, self._fixed
+        idle_raw, idle_view = self._idle
         for k in range(1, len(raws)):
-            if sys.getrefcount(raws[k]) == 2:          # the list + getrefcount's argument
-                return k
+            if sys.getrefcount(raws[k]) == idle_raw:
+                f = fixed[k]
+                if (sys.getrefcount(f[0]) == idle_view and sys.getrefcount(f[1]) == idle_view
+                        and sys.getrefcount(f[2]) == idle_view and sys.getrefcount(f[3]) == idle_view):
+                    return k
         return self._alloc() if len(raws) <= self._cap else None
 
     def views(self, k, n_done):
-        raw, (o_obs, o_rew, o_done, o_trunc, _, o_rec) = self._raw[k], self.off[:6]
-        n, d = self.n, self.d
-        obs = raw[o_obs:o_obs + 4 * n * d].view(np.float32).reshape(n, d)
-        rew = raw[o_rew:o_rew + 4 * n].view(np.float32)
-        done = raw[o_done:o_done + n].view(np.bool_)
-        trunc = raw[o_trunc:o_trunc + n].view(np.bool_)
-        rw = self.rec_words
-        rec = raw[o_rec:o_rec + 4 * rw * n_done].view(np.float32).reshape(n_done, rw)[:, :3 + d] if n_done else None
+        obs, rew, done, trunc = self._fixed[k]
+        rec = None
+        if n_done:
+            o_rec, rw = self.off[5], self.rec_words
+            rec = self._raw[k][o_rec:o_rec + 4 * rw * n_done].view(np.float32).reshape(n_done, rw)[:, :3 + self.d]
         return obs, rew, done, trunc, rec
 
     def close(self):
-        raws, self._raw = self._raw, []
+        busy = [k for k in range(len(self._raw)) if not self._is_idle(k)]
+        raws, fixed, ptrs = self._raw, self._fixed, self._ptr
+        self._raw, self._fixed, self._ptr = [], [], []
         for k in range(len(raws)):
-            if sys.getrefcount(raws[k]) == 2:          # `raws` + getrefcount's argument
-                lib.tmla_result_block_free(self._ptr[k])
+            if k not in busy:
+                fixed[k] = None
+                lib.tmla_result_block_free(ptrs[k])
             # else: a caller still holds arrays over this block; leave the pinned memory to process teardown
-        self._ptr = []
+
+    def _is_idle(self, k):
+        idle_raw, idle_view = self._idle
+        return sys.getrefcount(self._raw[k]) == idle_raw and all(sys.getrefcount(self._fixed[k][j]) == idle_view for j in range(4))
 
 
 class CudaVecEnv:
