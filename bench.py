@@ -336,10 +336,17 @@ def main():
     ap.add_argument("--ppo-envs", type=int, default=0, help="envs per GPU for the PPO section (default: 65536 ball3d, 32768 otherwise)")
     ap.add_argument("--quick", action="store_true", help="fused rollout only (for ncu runs)")
     args = ap.parse_args()
+    # Exactly ONE line on stdout: libraries that print there on their own (NCCL's version banner under NCCL_DEBUG, a
+    # stray warning) are sent to stderr at the file-descriptor level; the JSON line goes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
