@@ -25,6 +25,10 @@ int tc_linear_launch(int epi, const void *A, const void *W, const float *bias, c
                      const int32_t *rows_dev, cudaStream_t st);
 int tc_wgrad_launch(const void *X, const void *Y, float *G, int64_t rows, cudaStream_t st);
 int tc_pack_w2_launch(const float *w2, void *w, void *wt, void *img, cudaStream_t st);
+int tc_tower_forward_dual_launch(int D, int n_actions, const float *const *W1, const float *const *B1, const void *const *W2,
+                                 const float *const *B2, const float *const *Wh, const float *const *Bh, const float *x,
+                                 const int32_t *index, int64_t M, const int32_t *rows_dev, float *const *out, void *const *h1,
+                                 void *const *h2, cudaStream_t st);
 int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
                             const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
                             void *h1, void *h2, cudaStream_t st);
@@ -628,6 +632,22 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
     constexpr bool BF = sizeof(AT) == 2;
     if (BF) { int rc = ensure_pipe_attrs(); if (rc) return rc; }
     const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+    if constexpr (BF) {
+        if (obs_dim <= 6 && logits && values) {      // both towers, one launch (even / odd CTAs)
+            const float *W1[2], *B1[2], *B2[2], *Wh[2], *Bh[2];
+            const void *W2[2];
+            float *out[2] = {logits, values};
+            void *h1[2], *h2[2];
+            for (int t = 0; t < 2; ++t) {
+                W1[t] = params + o.w1[t]; B1[t] = params + o.b1[t]; B2[t] = params + o.b2[t]; Wh[t] = params + o.wh[t]; Bh[t] = params + o.bh[t];
+                W2[t] = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H;      // operand images
+                h1[t] = keep_act ? (void *)(act_cache + (int64_t)(2 * t) * rows * H) : nullptr;
+                h2[t] = keep_act ? (void *)(act_cache + (int64_t)(2 * t + 1) * rows * H) : nullptr;
+            }
+            const int rc = tc_tower_forward_dual_launch(obs_dim, n_actions, W1, B1, W2, B2, Wh, Bh, x, index, rows, rows_dev, out, h1, h2, st);
+            if (rc != TMLA_EINVAL) return rc;
+        }
+    }
     for (int t = 0; t < 2; ++t) {
         float *out = t == 0 ? logits : values;
         if (!out) continue;

@@ -315,12 +315,15 @@ struct TowerSmem {
     static constexpr uint32_t total = bar + 64;
 };
 
+// bid / nblk: this CTA's index and the number of CTAs working on THIS tower (the dual launch gives even CTAs to the policy
+// tower and odd CTAs to the value tower)
 template <int D, int NOUT>
-__global__ void __launch_bounds__(kTowerThreads, 1)
-tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ B1, const __nv_bfloat16 *__restrict__ W2,
-                        const float *__restrict__ B2, const float *__restrict__ Wh, const float *__restrict__ Bh,
-                        const float *__restrict__ x, const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev,
-                        float *__restrict__ out, __nv_bfloat16 *__restrict__ h1_out, __nv_bfloat16 *__restrict__ h2_out) {
+__device__ __forceinline__ void
+tower_forward_body(const float *__restrict__ W1, const float *__restrict__ B1, const __nv_bfloat16 *__restrict__ W2,
+                   const float *__restrict__ B2, const float *__restrict__ Wh, const float *__restrict__ Bh,
+                   const float *__restrict__ x, const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev,
+                   float *__restrict__ out, __nv_bfloat16 *__restrict__ h1_out, __nv_bfloat16 *__restrict__ h2_out,
+                   const int64_t bid, const int64_t nblk) {
     using L = TowerSmem<D, NOUT>;
     constexpr int NT = kTowerThreads, NW = NT / 32;        // 16 warps
     constexpr int RPW = 128 / NW;                          // rows per warp in the row-parallel phases (8)
@@ -335,7 +338,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (rows_dev) M = min(M, (int64_t)*rows_dev);
     const int64_t ntiles = (M + 127) / 128;
-    if ((int64_t)blockIdx.x >= ntiles) return;
+    if (bid >= ntiles) return;
 
     float xpre[XPT];
     auto prefetch_x = [&](int64_t tile) {                  // element e = tid + NT*i of the [128][D] obs tile
@@ -351,7 +354,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
             xpre[i] = v;
         }
     };
-    prefetch_x(blockIdx.x);
+    prefetch_x(bid);
 
     if (warp == 0) tmem_alloc<256>(tmem_holder);
     uint64_t *barw = bar + 1;                              // W2 (given as its operand image, mlp_tc.cu:pack_w2_kernel) landing
@@ -379,7 +382,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
         for (int k = 0; k < D; ++k) w1r[c][k] = w1s[(lane * 8 + c) * D + k];
     }
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = bid; tile < ntiles; tile += nblk) {
         const int64_t row0 = tile * 128;
 #pragma unroll
         for (int i = 0; i < XPT; ++i) { const int e = tid + NT * i; if (e < 128 * D) xs[e] = xpre[i]; }
@@ -420,7 +423,7 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
                 if (row0 + r < M) reinterpret_cast<uint4 *>(h1_out + (row0 + r) * H)[lane] = v;
             }
         }
-        if (tile + gridDim.x < ntiles) prefetch_x(tile + gridDim.x);   // dependent index->obs loads, hidden behind the MMAs
+        if (tile + nblk < ntiles) prefetch_x(tile + nblk);   // dependent index->obs loads, hidden behind the MMAs
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
@@ -489,6 +492,29 @@ tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ 
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+template <int D, int NOUT>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+tc_tower_forward_kernel(const float *__restrict__ W1, const float *__restrict__ B1, const __nv_bfloat16 *__restrict__ W2,
+                        const float *__restrict__ B2, const float *__restrict__ Wh, const float *__restrict__ Bh,
+                        const float *__restrict__ x, const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev,
+                        float *__restrict__ out, __nv_bfloat16 *__restrict__ h1_out, __nv_bfloat16 *__restrict__ h2_out) {
+    tower_forward_body<D, NOUT>(W1, B1, W2, B2, Wh, Bh, x, index, M, rows_dev, out, h1_out, h2_out, blockIdx.x, gridDim.x);
+}
+
+// Both towers of a policy step in ONE launch: 2 x 512 tiles over 74 + 74 CTAs are 7 rounds instead of 4 + 4, and one kernel
+// boundary per step less.  Same per-tower code; the branch is uniform per CTA.
+struct TowerFwdArgs {
+    const float *W1, *B1; const __nv_bfloat16 *W2; const float *B2, *Wh, *Bh; float *out; __nv_bfloat16 *h1_out, *h2_out;
+};
+template <int D, int A>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+tc_tower_forward_dual_kernel(const __grid_constant__ TowerFwdArgs pi, const __grid_constant__ TowerFwdArgs vf, const float *__restrict__ x,
+                             const int32_t *__restrict__ index, int64_t M, const int32_t *rows_dev) {
+    const int64_t bid = blockIdx.x >> 1, nblk = gridDim.x >> 1;
+    if (blockIdx.x & 1) tower_forward_body<D, 1>(vf.W1, vf.B1, vf.W2, vf.B2, vf.Wh, vf.Bh, x, index, M, rows_dev, vf.out, vf.h1_out, vf.h2_out, bid, nblk);
+    else tower_forward_body<D, A>(pi.W1, pi.B1, pi.W2, pi.B2, pi.Wh, pi.Bh, x, index, M, rows_dev, pi.out, pi.h1_out, pi.h2_out, bid, nblk);
 }
 
 // ------------------------------------------------------------------------------- small helper kernels
@@ -568,6 +594,34 @@ static int tower_forward_launch_t(const float *W1, const float *B1, const void *
                                                               (__nv_bfloat16 *)h1, (__nv_bfloat16 *)h2);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
+}
+template <int D, int A>
+static int tower_forward_dual_launch_t(const TowerFwdArgs &pi, const TowerFwdArgs &vf, const float *x, const int32_t *index, int64_t M,
+                                       const int32_t *rows_dev, cudaStream_t st) {
+    static int attr_done = 0;
+    constexpr uint32_t smem = TowerSmem<D, A>::total > TowerSmem<D, 1>::total ? TowerSmem<D, A>::total : TowerSmem<D, 1>::total;
+    static_assert(smem <= 232448, "fused tower kernel exceeds the 227 KB shared-memory limit");
+    if (!attr_done) {
+        TMLA_CUDA(cudaFuncSetAttribute(tc_tower_forward_dual_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = 1;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(2 * ((M + 127) / 128), sm_count() & ~1);
+    tc_tower_forward_dual_kernel<D, A><<<grid, kTowerThreads, smem, st>>>(pi, vf, x, index, M, rows_dev);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+// both towers in one launch (policy step of a rollout); W1/B1/W2/B2/Wh/Bh/out/h1/h2 as [2] arrays: policy, value
+int tc_tower_forward_dual_launch(int D, int n_actions, const float *const *W1, const float *const *B1, const void *const *W2,
+                                 const float *const *B2, const float *const *Wh, const float *const *Bh, const float *x,
+                                 const int32_t *index, int64_t M, const int32_t *rows_dev, float *const *out, void *const *h1,
+                                 void *const *h2, cudaStream_t st) {
+    TowerFwdArgs a[2];
+    for (int t = 0; t < 2; ++t)
+        a[t] = TowerFwdArgs{W1[t], B1[t], (const __nv_bfloat16 *)W2[t], B2[t], Wh[t], Bh[t], out[t], (__nv_bfloat16 *)h1[t], (__nv_bfloat16 *)h2[t]};
+#define TFD(DD, AA) if (D == DD && n_actions == AA) return tower_forward_dual_launch_t<DD, AA>(a[0], a[1], x, index, M, rows_dev, st)
+    TFD(6, 5); TFD(4, 5); TFD(4, 4);
+#undef TFD
+    return TMLA_EINVAL;
 }
 // fused tower forward for the shapes of the four tasks; returns TMLA_EINVAL for an unsupported (D, NOUT)
 int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
