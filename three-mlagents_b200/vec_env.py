@@ -6,6 +6,11 @@ NumPy in / NumPy out, `dones = terminated | truncated`, auto-reset with
 `infos[i]["terminal_observation"]`, `infos[i]["TimeLimit.truncated"]` and Monitor's
 `infos[i]["episode"] = {"r","l","t"}`.  All n environments advance in ONE kernel launch
 (`tmla_step`); `step_tensor` is the zero-copy device path the PPO trainer uses.
+
+Host step (`step` / `step_wait`): the GPU writes obs / rewards / dones / episode-end records of a step straight into a pooled
+pinned *result block* (`tmla_step_block`) and the arrays returned to the caller are slices of that block — no host memcpy.
+A block is handed out again only when the caller has dropped every array over it (`_ResultBlocks`), so results stay valid for
+as long as they are referenced, like DummyVecEnv's fresh copies; `infos` is a lazy sequence over the compact records.
 """
 from __future__ import annotations
 
