@@ -101,3 +101,18 @@ def test_sharded_envs_equal_the_unsharded_batch():
             assert np.array_equal(dp, d[k * N:(k + 1) * N])
     with pytest.raises(ValueError):
         env_shard(2, 2, 10)
+
+
+def test_numa_binding_is_optional_and_never_widens_the_affinity():
+    """bench.py pins each rank to the CPUs local to its GPU before allocating pinned host buffers; without NVML (this
+    container) the helper must report None and leave the process alone."""
+    import os
+
+    from three_mlagents_b200.distributed import bind_to_gpu_numa_node
+
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert cpus is None or (set(cpus) <= before and set(cpus) == after)
+    assert after <= before
+    os.sched_setaffinity(0, before)
