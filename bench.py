@@ -12,7 +12,9 @@ rollout of all 65 536 environments (`tmla_rollout_random`, 8 388 608 env-steps, 
              (C ABI `tmla_step_host`): host buffers, H2D + kernel + D2H inside the timed region
   roofline   rollout kernel: algorithmic bytes / measured launch duration vs the measured HBM peak
   cpu_baseline   the scalar reference port (oracle/ref_port.py) timed on this box's host cores
-  ppo        end-to-end PPO samples/s on BASELINE config 3 (ball3d, 64K envs/GPU, T=128, 2x256 MLP)
+  ppo        end-to-end PPO samples/s on BASELINE configs 3/4/5 (ball3d 64K envs/GPU, gridworld and push 32K envs/GPU; T=128,
+             2x256 MLP), each with update TFLOP/s against the measured sustained bf16 peak, the all-reduce cost and a
+             replicas-identical check; `cpu_baseline.ppo` is the CPU restatement of SB3 PPO at the reference defaults
 Multi-GPU: one process per GPU under torchrun; environments shard by global env id, no data-path
 collective for the env-step metric (weak scaling); PPO adds one gradient all-reduce per minibatch.
 """
@@ -39,9 +41,13 @@ OBS_DIM = 6
 BYTES_PER_ENV_STEP = 33.0 + 56.0 / T_ROLLOUT
 
 
+NCU_TRAFFIC_CSV = "profiles/r1_rollout_fast_ncu_raw.csv"
+
+
 def _ncu_traffic():
-    """dram bytes (read+write) per rollout launch from the committed `ncu --set full` capture, or None."""
-    path = os.path.join(ROOT, "profiles", "r1_rollout_fast_ncu_raw.csv")
+    """dram bytes (read+write) per rollout launch from the committed `ncu --set full` capture of the same kernel, or None.
+    (ncu cannot run inside a timed bench; the line names the file the figure comes from as `traffic_source`.)"""
+    path = os.path.join(ROOT, NCU_TRAFFIC_CSV)
     try:
         vals = {}
         with open(path) as f:
@@ -58,12 +64,14 @@ def _ncu_traffic():
 
 
 def _peaks():
+    """(HBM GB/s, sustained bf16 TFLOP/s, source): the driver-measured peaks of this pool, else the recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or 1400.0), "measured (MEASURED_PEAKS.json)"
     except Exception:  # noqa: BLE001
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -138,7 +146,46 @@ def _cpu_baseline(seconds_target: float = 12.0):
                                    "sample": f"{k} vec-steps of {N_ENVS} envs (NumPy restatement with Philox auto-reset, 3 s)"}
     except Exception as e:  # noqa: BLE001
         out["numpy_vectorised"] = {"error": f"{type(e).__name__}: {e}"}
+    # PPO end to end on the CPU at the reference defaults (registry.py:77-80 n_envs=8; training.py:379-389 n_steps=1024,
+    # batch 256, 10 epochs): the CPU figure that stands beside `ppo.*.value`
+    try:
+        from oracle import ppo_cpu_baseline
+
+        out["ppo"] = ppo_cpu_baseline.time_ppo("ball3d", n_envs=8, n_steps=1024, batch_size=256, n_epochs=10, iterations=3)
+    except Exception as e:  # noqa: BLE001
+        out["ppo"] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def _config1_pair():
+    """BASELINE configs[0] — `three-mlagents train basic -a ppo -t 25000 --seed 1` — as a (wall-clock, eval reward) pair on the
+    CPU restatement and through this backend's own `train_task` (same registry defaults: n_envs=1, 50 eval episodes)."""
+    import tempfile
+
+    pair = {}
+    try:
+        from oracle import ppo_cpu_baseline
+
+        pair["cpu"] = ppo_cpu_baseline.train_config1(25_000, seed=1)
+    except Exception as e:  # noqa: BLE001
+        pair["cpu"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        from three_mlagents_b200.training import TrainConfig, train_task
+
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            try:
+                t0 = time.perf_counter()
+                res = train_task(TrainConfig(task_id="basic", total_timesteps=25_000, algorithm="ppo", seed=1, verbose=0))
+                pair["cuda"] = {"wall_s": time.perf_counter() - t0, "timesteps": res.total_timesteps, "eval_mean_reward": res.mean_reward,
+                                "eval_std_reward": res.std_reward, "eval_episodes": res.eval_episodes,
+                                "note": "n_envs=1: launch-latency bound (one env per kernel launch), the reference's own configuration"}
+            finally:
+                os.chdir(cwd)
+    except Exception as e:  # noqa: BLE001
+        pair["cuda"] = {"error": f"{type(e).__name__}: {e}"}
+    return pair
 
 
 def run_reference(args):
@@ -156,6 +203,12 @@ def run_reference(args):
     value = n_envs * vec_steps * args.steps / total
     sample = (f"each step = {n_envs} envs x {vec_steps} serial vec-steps of ball3d with uniform random actions "
               f"(scalar Python port of the reference; DummyVecEnv is single-threaded by construction)")
+    try:      # the other half of BASELINE's metric on the CPU: PPO end to end at the reference defaults (bounded: 2 iterations)
+        from oracle import ppo_cpu_baseline
+
+        ppo = ppo_cpu_baseline.time_ppo("ball3d", n_envs=8, n_steps=1024, batch_size=256, n_epochs=10, iterations=2)
+    except Exception as e:  # noqa: BLE001
+        ppo = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -164,7 +217,7 @@ def run_reference(args):
                    "envs": n_envs, "vec_steps_per_step": vec_steps},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "ppo": {"ball3d": ppo},
     }))
 
 
@@ -237,7 +290,7 @@ def run_cuda(args):
     steps_per_launch = N_ENVS * T_ROLLOUT
     value = world * steps_per_launch * K / (ms * 1e-3)
     launch_ms = ms / K
-    peak, peak_src = _peaks()
+    peak, tensor_sustained, peak_src = _peaks()
     achieved = BYTES_PER_ENV_STEP * steps_per_launch / (launch_ms * 1e-3) / 1e9
     done_rate = float(done.float().mean().item())
 
@@ -285,7 +338,8 @@ def run_cuda(args):
                    "l2": "each step writes 277 MB of rollout rows (> 126 MB L2); no flush needed",
                    "done_rate": done_rate},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _ncu_traffic(), "algorithmic_bytes": BYTES_PER_ENV_STEP * steps_per_launch,
+                     "traffic": _ncu_traffic(), "traffic_source": NCU_TRAFFIC_CSV + " (ncu --set full capture of this kernel, per launch)",
+                     "algorithmic_bytes": BYTES_PER_ENV_STEP * steps_per_launch,
                      "kernel": "rollout_fast_kernel<Ball3DTask>",
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N_ENVS,
@@ -300,20 +354,34 @@ def run_cuda(args):
         "clocks": clocks.summary(),
     }
     if not args.no_ppo:
-        try:
-            from three_mlagents_b200.ppo import bench_ppo
+        # BASELINE configs[2..4]: ball3d 64K envs/GPU, gridworld 32K envs/GPU (256K over 8), push 32K envs/GPU — every one at the
+        # N this run uses, `--ppo-warmup` untimed + `--ppo-iters` timed iterations each
+        from three_mlagents_b200.ppo import bench_ppo
 
-            # BASELINE configs[2] (ball3d, 64K envs/GPU) by default; --ppo-task gridworld|push = configs[3]/[4] (32K envs/GPU)
-            ppo_envs = args.ppo_envs or (N_ENVS if args.ppo_task == "ball3d" else 32768)
-            out["ppo"] = bench_ppo(local_rank, rank, world, iters=args.ppo_iters, task=args.ppo_task, n_envs=ppo_envs)
-            if world == 1 and args.ppo_task == "ball3d":
+        out["ppo"] = {}
+        for task in [t for t in args.ppo_tasks.split(",") if t]:
+            try:
+                ppo_envs = args.ppo_envs or (N_ENVS if task == "ball3d" else 32768)
+                out["ppo"][task] = bench_ppo(local_rank, rank, world, iters=args.ppo_iters, warmup=args.ppo_warmup, task=task,
+                                             n_envs=ppo_envs, sustained_tflops=tensor_sustained)
+            except Exception as e:  # noqa: BLE001 - the env-step headline must still print
+                out["ppo"][task] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and "ball3d" in out["ppo"] and "error" not in out["ppo"]["ball3d"] and not args.no_kernels:
+            try:
                 from three_mlagents_b200.ppo import bench_kernels
 
-                out["ppo"]["kernels"] = bench_kernels(local_rank)
-        except Exception as e:  # noqa: BLE001 - the env-step headline must still print
-            out["ppo"] = {"error": f"{type(e).__name__}: {e}"}
+                out["ppo"]["ball3d"]["kernels"] = bench_kernels(local_rank)
+            except Exception as e:  # noqa: BLE001
+                out["ppo"]["ball3d"]["kernels"] = {"error": f"{type(e).__name__}: {e}"}
+        # the second half of BASELINE's metric, where the driver's parser keeps it (it retains `config` whole)
+        out["config"]["ppo_samples_per_sec"] = {
+            t: ({k: r.get(k) for k in ("value", "update_tflops", "frac_of_sustained", "allreduce_us", "replicas_identical", "rollout_ms", "update_ms")}
+                if "error" not in r else r) for t, r in out["ppo"].items()}
+        out["config"]["ppo_workload"] = "PPO end-to-end samples/s: ball3d 65536 envs/GPU | gridworld 32768 | push 32768; T=128, 2x256 MLP, 10 epochs x 32 minibatches"
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = _cpu_baseline()
+        if not args.no_config1:
+            out["config1_basic_ppo_25k"] = _config1_pair()
     elif rank == 0:
         out["cpu_baseline"] = None
     env.close()
@@ -331,8 +399,11 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ppo-iters", type=int, default=3)
-    ap.add_argument("--ppo-task", default="ball3d", choices=["ball3d", "gridworld", "push"])
+    ap.add_argument("--ppo-iters", type=int, default=5)
+    ap.add_argument("--ppo-warmup", type=int, default=2)
+    ap.add_argument("--ppo-tasks", default="ball3d,gridworld,push", help="comma-separated subset of ball3d,gridworld,push")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel PPO micro-benchmarks")
+    ap.add_argument("--no-config1", action="store_true", help="skip the BASELINE configs[0] wall-clock/eval-reward pair")
     ap.add_argument("--ppo-envs", type=int, default=0, help="envs per GPU for the PPO section (default: 65536 ball3d, 32768 otherwise)")
     ap.add_argument("--quick", action="store_true", help="fused rollout only (for ncu runs)")
     args = ap.parse_args()

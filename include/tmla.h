@@ -125,6 +125,12 @@ int tmla_host_records(tmla_env *h, const float **records, int32_t *floats_per_re
  * results (and the n_done compact records) landing in `block`; the actions still come from the pinned action view.
  * The reference's DummyVecEnv returns fresh copies each step (SB3 dummy_vec_env.py step_wait): a binding keeps a small
  * pool of blocks and reuses one only when its caller has dropped every array over it (vec_env.py does this by refcount). */
+/* Actions of the next host step (tmla_step_pinned / tmla_step_block), range-checked and narrowed in one pass over the caller's
+ * array into the pinned action stage as ONE BYTE per action: a quarter of the PCIe reads of int32, and an out-of-range action
+ * returns TMLA_EACTION before anything is launched — the reference's ACTION_DELTAS[action] (examples/ball3d.py:76) raises
+ * before any state change.  elem_bytes = 4 (int32) or 8 (int64, what SB3 passes to VecEnv.step).  A caller that writes
+ * int32 actions straight into the tmla_host_views action view instead is checked by the kernel (after the step). */
+int tmla_stage_actions(tmla_env *h, const void *actions, int elem_bytes);
 int tmla_result_block_layout(tmla_env *h, int64_t offsets[6], int64_t *bytes);
 int tmla_result_block_alloc(tmla_env *h, void **block);
 int tmla_result_block_free(void *block);
@@ -155,6 +161,11 @@ int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_
                      int32_t *trunc_count, int32_t *trunc_index, float *trunc_obs, int32_t trunc_capacity,
                      float *ep_stats /* [4]: sum return, sum length, episodes, (unused) */,
                      const uint64_t *step_base, void *stream);
+/* Monitor (training.py:83: `Monitor(env, filename=...)` logs {r, l, t} per episode) for the policy-driven device path: while a
+ * log is attached, every episode that ends inside tmla_step_policy / tmla_rollout appends {ep_return, float(ep_length)} at slot
+ * atomicAdd(count); records float[capacity][2] and count int32 are DEVICE memory owned by the caller, who reads and re-zeroes
+ * count between rollouts (slots >= capacity are counted, not written).  records = count = NULL detaches. */
+int tmla_set_episode_log(tmla_env *h, float *records, int32_t capacity, int32_t *count);
 /* advance the handle's host step counter after a graph replay of T tmla_step_policy launches,
  * and the matching device-side counter increment to put at the end of the captured graph */
 int tmla_advance_steps(tmla_env *h, uint64_t n);

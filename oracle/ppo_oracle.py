@@ -143,7 +143,7 @@ def _mix(v):
 
 
 def permutation(seed: int, epoch: int, T: int, n: int) -> np.ndarray:
-    """Twin of csrc/ppo_kernels.cu:permutation_kernel — keyed 4-round Feistel + cycle walking over
+    """Twin of csrc/ppo_kernels.cu:permutation_kernel — keyed 6-round Feistel + cycle walking over
     [0, T*n), mapped from SB3's flat sample index env*T+t (swapaxes(0,1).reshape) to buffer offset t*n+env."""
     from . import philox as px
 
@@ -163,8 +163,8 @@ def permutation(seed: int, epoch: int, T: int, n: int) -> np.ndarray:
     while todo.any():
         xs = x[todo]
         L, R = xs >> np.uint64(half), xs & mask
-        for r in range(4):
-            F = _mix(R ^ key[r]) & mask
+        for r in range(6):                                   # rounds 4, 5 reuse keys 0, 1 with a round constant
+            F = _mix(R ^ key[r & 3] ^ np.uint64(0x9E3779B9 if r >= 4 else 0)) & mask
             L, R = R, L ^ F
         xs = (L << np.uint64(half)) | R
         x[todo] = xs

@@ -108,7 +108,19 @@ def test_model_path_errors_match_reference(tmp_path, monkeypatch):
     assert training._resolve_model_path(task, str(model_path)) == model_path
     assert training._resolve_model_path(task, model_path.name) == model_path
     with pytest.raises(ValueError):
-        training.train_task(training.TrainConfig("basic"))            # default algorithm dqn has no CUDA backend
+        training.train_task(training.TrainConfig("basic", algorithm="dqn"))   # asked for explicitly: no CUDA backend
+    # algorithm=None (what the CLI / REST / websocket pass): the reference's per-task default dqn resolves to PPO with a
+    # warning instead of raising; without a GPU the run then stops at tmla_create (no CPU fallback), not at the algorithm
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        try:
+            training.train_task(training.TrainConfig("basic", total_timesteps=64, verbose=0))
+        except ValueError:
+            raise
+        except Exception:   # noqa: BLE001 - TmlaError without a CUDA device
+            pass
+    assert any("trains it with 'ppo'" in str(w.message) for w in caught)
     with pytest.raises(ValueError):
         training.train_task(training.TrainConfig("fish"))
     with pytest.raises(KeyError):

@@ -102,3 +102,26 @@ def test_ppo_reaches_registry_reward_threshold(task, steps, episodes, tmp_path, 
     res = train_task(TrainConfig(task, total_timesteps=steps, algorithm="ppo", n_envs=4096, eval_episodes=episodes, eval_freq=10**12,
                                  verbose=0, run_name="thr"), model_kwargs={"n_steps": 128, "batch_size": 32768})
     assert res.mean_reward >= get_task(task).reward_threshold, (task, res.mean_reward)
+
+
+@pytest.mark.parametrize("task", ["basic", "ball3d", "gridworld", "push", "walljump", "brickbreak", "bicycle", "glider"])
+def test_train_task_with_the_default_algorithm(task, tmp_path, monkeypatch):
+    """`algorithm=None` is what the CLI, the REST route and the websocket pass by default.  The registry keeps the reference's
+    per-task default (dqn for basic / gridworld / push / walljump, registry.py:61-112); on this backend it resolves to PPO
+    (with a warning for the dqn tasks) instead of raising.  Monitor rows are written from the device path."""
+    import warnings
+
+    from three_mlagents_b200.registry import get_task
+    from three_mlagents_b200.training import TrainConfig, train_task
+
+    monkeypatch.chdir(tmp_path)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        res = train_task(TrainConfig(task, total_timesteps=2 * 64 * 32, n_envs=64, eval_episodes=4, eval_freq=10**12, verbose=0,
+                                     run_name="dflt"), model_kwargs={"n_steps": 32, "batch_size": 1024})
+    assert res.algorithm == "ppo" and np.isfinite(res.mean_reward)
+    assert any("trains it with 'ppo'" in str(w.message) for w in caught) == (get_task(task).default_algorithm != "ppo")
+    rows = open(os.path.join(res.run_dir, "monitor", "0.monitor.csv")).read().splitlines()
+    assert rows[0].startswith("#") and rows[1] == "r,l,t"
+    if task in ("basic", "gridworld", "walljump", "bicycle"):      # short episodes: some finish within 64 steps
+        assert len(rows) > 2 and all(len(r.split(",")) == 3 for r in rows[2:])

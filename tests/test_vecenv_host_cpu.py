@@ -33,7 +33,7 @@ def test_lazy_infos_sorts_on_first_access_and_matches_dense_semantics():
     order = np.argsort(idx)
     assert np.array_equal(ret, rec[order, 1]) and np.array_equal(length, rec.view(np.int32)[order, 2])
     live = int(np.nonzero(~done)[0][0])
-    assert infos[live] == {"TimeLimit.truncated": False}
+    assert infos[live] == {"TimeLimit.truncated": False}         # (no step bookkeeping passed: `steps` only at episode ends)
     assert infos[-1] == infos[n - 1] and len(infos[2:5]) == 3
     # the sorted payload is a copy: overwriting the record block (the pinned block going back to the pool) changes nothing
     want = infos[i]["terminal_observation"].copy()
@@ -87,38 +87,67 @@ class _FakeLib:
 
 def test_result_block_pool_reuses_a_block_only_when_nothing_references_it(monkeypatch):
     """DummyVecEnv hands out fresh arrays every step; the pool must never recycle memory a caller can still see — whether the
-    caller holds one of the cached slices, something derived from them, a buffer export, or the record slice."""
+    caller holds one of the returned arrays, something derived from them, a buffer export, or the record slice.  Every
+    hand-out is a lease (a fresh base array + weakref callback): no reference counts are inspected."""
+    import sys
+
     import three_mlagents_b200.vec_env as ve
 
     fake = _FakeLib(64, 6, 12)
     monkeypatch.setattr(ve, "lib", fake)
     monkeypatch.setattr(ve, "check", lambda rc: None)
     pool = ve._ResultBlocks(None, 64, 6)
-    assert len(pool._raw) == 3                                   # scratch + two pre-allocated blocks
+    assert len(pool._mem) == 3 and sorted(pool._free) == [1, 2]  # scratch + two pre-allocated blocks
+    assert "getrefcount" not in open(ve.__file__).read()
+
+    def busy():
+        return {1, 2, 3, 4, 5, 6, 7, 8}.intersection(range(len(pool._mem))) - set(pool._free)
+
     k = pool.acquire()
-    assert k == 1
     obs, rew, done, trunc, rec = pool.views(k, 5)
     assert obs.shape == (64, 6) and rew.shape == (64,) and done.dtype == np.bool_ and rec.shape == (5, 9)
-    assert pool.acquire() == 2                                   # block 1 is held
+    assert obs.base is rew.base is done.base is trunc.base       # one lease base per hand-out
+    assert busy() == {k}
+    k2 = pool.acquire()
+    assert k2 != k                                               # block k is held
+    pool.release(k2)                                             # (acquired but not handed out: the step failed)
     del obs, rew, done, trunc
-    assert pool.acquire() == 2                                   # ... still, through the record slice
+    assert busy() == {k}                                         # ... still held, through the record slice
     del rec
-    assert pool.acquire() == 1
-    part = pool.views(1, 0)[0][3:5]                              # a derived view keeps the block alive
-    assert pool.acquire() == 2
+    assert busy() == set()
+    extra = [sys.getrefcount]                                    # a tracer-style extra reference only DELAYS the reuse
+    k = pool.acquire()
+    arrs = pool.views(k, 0)
+    extra.append(arrs[0])
+    del arrs
+    assert busy() == {k}
+    extra.pop()
+    assert busy() == set()
+    k = pool.acquire()
+    part = pool.views(k, 0)[0][3:5]                              # a derived view keeps the block alive
+    assert busy() == {k}
     del part
-    export = memoryview(pool.views(1, 0)[2])                     # so does a buffer export (torch.from_numpy, memoryview)
-    assert pool.acquire() == 2
+    assert busy() == set()
+    k = pool.acquire()
+    export = memoryview(pool.views(k, 0)[2])                     # so does a buffer export (torch.from_numpy, memoryview)
+    assert busy() == {k}
     del export
-    assert pool.acquire() == 1
+    assert busy() == set()
     held = []
     for _ in range(12):                                          # a caller that never lets go: the pool grows to its cap, then says no
         k = pool.acquire()
         held.append(None if k is None else pool.views(k, 0)[0])
-    assert [h is not None for h in held] == [True] * 8 + [False] * 4 and len(pool._raw) == 9
+    assert [h is not None for h in held] == [True] * 8 + [False] * 4 and len(pool._mem) == 9
     survivor = held[0]
     del held, k
-    assert pool.acquire() == 2                                   # block 1 is still referenced by `survivor`
+    assert len(busy()) == 1                                      # one block is still referenced by `survivor`
     pool.close()
     assert len(fake.freed) == 8                                  # everything but the block `survivor` still sees
     assert survivor.shape == (64, 6)
+
+
+def test_lazy_infos_reports_steps_of_running_envs():
+    """The reference's `_info` (envs.py:154-159) carries `steps` on every step, not only at episode ends."""
+    last_reset = np.array([0, 3, 5, 5], np.int64)
+    infos = LazyInfos(4, np.zeros(4, bool), np.zeros(4, bool), None, 0.0, step_no=7, last_reset=last_reset)
+    assert [infos[i]["steps"] for i in range(4)] == [7, 4, 2, 2]

@@ -28,7 +28,42 @@ struct tmla_env {
     cudaStream_t own_stream;
     int32_t *d_ndone;         // device counter of finished episodes in the last step
     int64_t rec_hint;         // records fetched with the first D2H of a host step (1.5x the last count + 256)
+    // ordering between the device path (caller's stream) and the host path (own_stream): the last stream a device-path
+    // call launched on, and whether anything was launched there since the host path last waited for it
+    cudaStream_t dev_stream;
+    bool dev_dirty;
+    cudaEvent_t dev_evt;
+    int act_u8;               // the pinned action stage currently holds uint8 actions (tmla_stage_actions)
+    // optional per-episode log of the policy-driven device path (Monitor rows): {ep_return, ep_length} records
+    float2 *ep_log;
+    int32_t ep_log_cap;
+    int32_t *ep_log_count;
 };
+
+// RAII: run an entry point on the handle's device and give the calling thread its previous device back
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+static inline void mark_device_path(tmla_env *h, cudaStream_t st) { h->dev_stream = st; h->dev_dirty = true; }
+// the host path runs on own_stream: make it wait for whatever the device path enqueued on the caller's stream
+static int order_after_device_path(tmla_env *h) {
+    if (!h->dev_dirty) return TMLA_OK;
+    h->dev_dirty = false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(h->dev_stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone ||
+        cudaEventRecord(h->dev_evt, h->dev_stream) != cudaSuccess) {
+        cudaGetLastError();                               // stale / capturing stream: fall back to a device-wide wait
+        TMLA_CUDA(cudaDeviceSynchronize());
+        return TMLA_OK;
+    }
+    TMLA_CUDA(cudaStreamWaitEvent(h->own_stream, h->dev_evt, 0));
+    return TMLA_OK;
+}
 
 struct EnvPtrs { void *buf[4]; };
 
@@ -97,7 +132,7 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
             float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag,
-            float *__restrict__ compact, int32_t *__restrict__ host_flags, int host_seq) {
+            float *__restrict__ compact, int32_t *__restrict__ host_flags, int host_seq, int act_u8) {
     // compact != NULL (host-facing step): finished envs append one record {env index, ep_return, ep_length, terminal_obs[D]}
     // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays.
     // host_flags != NULL (zero-copy host step): the last CTA to finish publishes {n_done, bad_action, host_seq} to mapped host
@@ -110,7 +145,7 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     if (i < n) {
         const typename Task::Consts cst = Task::load_consts();
         typename Task::State s = Task::load(p.buf, i);
-        int a = actions[i];
+        int a = act_u8 ? (int)reinterpret_cast<const uint8_t *>(actions)[i] : actions[i];   // host step: one byte per action on the wire
         if ((unsigned)a >= (unsigned)Task::A) { *err_flag = 1; a = min(max(a, 0), Task::A - 1); }
         float r; bool term, trunc;
         Task::step(cst, s, a, r, term, trunc);
@@ -378,7 +413,7 @@ step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint6
                    int64_t row_index, float *__restrict__ obs_next, int32_t *__restrict__ act, float *__restrict__ logp_out,
                    float *__restrict__ rew, uint8_t *__restrict__ done, int32_t *trunc_count,
                    int32_t *__restrict__ trunc_index, float *__restrict__ trunc_obs, int32_t trunc_capacity,
-                   float *ep_stats) {
+                   float *ep_stats, float2 *__restrict__ ep_log, int32_t ep_log_cap, int32_t *ep_log_count) {
     constexpr int D = Task::D, A = Task::A;
     __shared__ __align__(16) float s_obs[kBlock * D];
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
@@ -416,6 +451,10 @@ step_policy_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint6
                 atomicAdd(ep_stats + 0, s.ep_ret);
                 atomicAdd(ep_stats + 1, (float)s.steps);
                 atomicAdd(ep_stats + 2, 1.0f);
+            }
+            if (ep_log) {                                    // Monitor rows of the device path: one (r, l) record per episode
+                const int slot = atomicAdd(ep_log_count, 1);
+                if (slot < ep_log_cap) ep_log[slot] = make_float2(s.ep_ret, (float)s.steps);
             }
             Task::reset(s, seed, env_id, k + 1, TMLA_TAG_RESET);
             Task::observe(s, o);
@@ -545,7 +584,7 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
     int ndev = 0;
     TMLA_CUDA(cudaGetDeviceCount(&ndev));
     TMLA_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU path)");
-    TMLA_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     tmla_env *h = new (std::nothrow) tmla_env();
     if (!h) { tmla_set_error("out of host memory"); return TMLA_ENOMEM; }
     memset(h, 0, sizeof(*h));
@@ -563,7 +602,8 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
     h->stage_bytes = stage_layout(n_envs, D).end + 64;
     if (cudaMalloc(&h->d_stage, h->stage_bytes) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stage_bytes) != cudaSuccess ||
         cudaMalloc((void **)&h->err_flag, sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->d_ndone, sizeof(int32_t)) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->dev_evt, cudaEventDisableTiming) != cudaSuccess) {
         tmla_set_error("allocating staging buffers: %s", cudaGetErrorString(cudaGetLastError()));
         tmla_destroy(h);
         return TMLA_ENOMEM;
@@ -575,18 +615,20 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
     int rc = tmla_reset(h, nullptr, nullptr);
     if (rc) return rc;
     TMLA_CUDA(cudaStreamSynchronize(nullptr));
+    h->dev_dirty = false;
     return TMLA_OK;
 }
 
 int tmla_destroy(tmla_env *h) {
     if (!h) return TMLA_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     for (int b = 0; b < 4; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->err_flag) cudaFree(h->err_flag);
     if (h->d_ndone) cudaFree(h->d_ndone);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->dev_evt) cudaEventDestroy(h->dev_evt);
     delete h;
     return TMLA_OK;
 }
@@ -598,7 +640,9 @@ int tmla_advance_steps(tmla_env *h, uint64_t n) { TMLA_REQUIRE(h, "handle is NUL
 
 int tmla_reset(tmla_env *h, float *obs, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
+    DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (st != h->own_stream) mark_device_path(h, st);
     TASK_SWITCH(h->task, (reset_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, TMLA_TAG_RESET_ALL, obs)));
     TMLA_LAUNCH_CHECK();
@@ -609,10 +653,12 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
               float *terminal_obs, float *ep_return, int32_t *ep_length, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
     TMLA_REQUIRE(actions && obs && reward && done && truncated, "actions/obs/reward/done/truncated must be non-NULL");
+    DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    mark_device_path(h, st);
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
-                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr, 0)));
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr, 0, 0)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     return TMLA_OK;
@@ -626,7 +672,10 @@ static bool host_step_mapped() {      // TMLA_HOST_STEP=copy selects the copy-en
     return mapped;
 }
 static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
-    TMLA_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    { const int rc = order_after_device_path(h); if (rc) return rc; }
+    const int act_u8 = h->act_u8;                          // set by tmla_stage_actions for exactly one step
+    h->act_u8 = 0;
     const int64_t n = h->n;
     const int D = kObsDim[h->task];
     const StageLayout L = stage_layout(n, D);
@@ -645,7 +694,7 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
         TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                                  ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(p + L.act),
                                  (float *)(b + L.obs), (float *)(b + L.rew), (uint8_t *)(b + L.done), (uint8_t *)(b + L.trunc),
-                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq)));
+                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq, act_u8)));
         TMLA_LAUNCH_CHECK();
         h->step_count += 1;
         // ONE launch per step, no stream synchronise: poll the sequence word the last CTA writes after all results
@@ -666,12 +715,12 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
         }
         return TMLA_OK;
     }
-    TMLA_CUDA(cudaMemcpyAsync(d + L.act, p + L.act, 4 * n, cudaMemcpyHostToDevice, st));
+    TMLA_CUDA(cudaMemcpyAsync(d + L.act, p + L.act, (act_u8 ? 1 : 4) * n, cudaMemcpyHostToDevice, st));
     TMLA_CUDA(cudaMemsetAsync(dflags, 0, 16, st));
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                              ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
                              (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
-                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr, 0)));
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr, 0, act_u8)));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     const size_t rec = (size_t)4 * record_words(D);
@@ -689,6 +738,43 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
         tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
         return TMLA_EACTION;
     }
+    return TMLA_OK;
+}
+
+// Actions of the next host step: range-checked and converted in ONE pass over the caller's array into the pinned action
+// stage, as one byte per action (every task has <= 5 actions) — a quarter of the PCIe reads of int32, and an out-of-range
+// action is reported BEFORE anything is launched, like the reference's ACTION_DELTAS[action] (ball3d.py:76) raising before
+// any state change.  elem_bytes: 4 (int32) or 8 (int64, what SB3 hands to VecEnv.step).
+int tmla_stage_actions(tmla_env *h, const void *actions, int elem_bytes) {
+    TMLA_REQUIRE(h && actions, "handle/actions is NULL");
+    TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
+    const int64_t n = h->n;
+    const uint64_t A = (uint64_t)kNumActions[h->task];
+    uint8_t *dst = (uint8_t *)h->h_stage + stage_layout(n, kObsDim[h->task]).act;
+    uint64_t bad = 0;
+    if (elem_bytes == 4) {
+        const int32_t *src = (const int32_t *)actions;
+        for (int64_t i = 0; i < n; ++i) { const uint32_t a = (uint32_t)src[i]; bad |= (uint64_t)(a >= A); dst[i] = (uint8_t)a; }
+    } else {
+        const int64_t *src = (const int64_t *)actions;
+        for (int64_t i = 0; i < n; ++i) { const uint64_t a = (uint64_t)src[i]; bad |= (uint64_t)(a >= A); dst[i] = (uint8_t)a; }
+    }
+    h->act_u8 = 1;
+    if (bad) {
+        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+        return TMLA_EACTION;
+    }
+    return TMLA_OK;
+}
+
+// Monitor rows for the policy-driven device path (tmla_step_policy / tmla_rollout): every finished episode appends
+// {ep_return, ep_length} at slot atomicAdd(count); records beyond `capacity` are counted but dropped.  NULL detaches.
+int tmla_set_episode_log(tmla_env *h, float *records, int32_t capacity, int32_t *count) {
+    TMLA_REQUIRE(h, "handle is NULL");
+    TMLA_REQUIRE((!records && !count) || (records && count && capacity > 0), "records/count must both be set (capacity > 0) or both NULL");
+    h->ep_log = reinterpret_cast<float2 *>(records);
+    h->ep_log_cap = records ? capacity : 0;
+    h->ep_log_count = count;
     return TMLA_OK;
 }
 
@@ -731,7 +817,7 @@ int tmla_result_block_layout(tmla_env *h, int64_t offsets[6], int64_t *bytes) {
 }
 int tmla_result_block_alloc(tmla_env *h, void **block) {
     TMLA_REQUIRE(h && block, "NULL argument");
-    TMLA_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
     if (cudaMallocHost(block, L.tobs - L.obs) != cudaSuccess) {
         tmla_set_error("cudaMallocHost(result block, %zu bytes): %s", L.tobs - L.obs, cudaGetErrorString(cudaGetLastError()));
@@ -776,7 +862,7 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
     const int D = kObsDim[h->task];
     const StageLayout L = stage_layout(n, D);
     char *p = (char *)h->h_stage;
-    memcpy(p + L.act, actions, 4 * n);
+    { const int rc = tmla_stage_actions(h, actions, 4); if (rc) return rc; }     // range check first: a rejected step changes nothing
     int64_t nd = 0;
     const int rc = step_into_block(h, p + L.obs, &nd);
     if (rc != TMLA_OK && rc != TMLA_EACTION) return rc;
@@ -799,7 +885,8 @@ int tmla_step_host(tmla_env *h, const int32_t *actions, float *obs, float *rewar
 
 int tmla_reset_host(tmla_env *h, float *obs) {
     TMLA_REQUIRE(h && obs, "handle/obs is NULL");
-    TMLA_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    { const int rc = order_after_device_path(h); if (rc) return rc; }
     const size_t bytes = (size_t)4 * h->n * kObsDim[h->task];
     const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
     char *d = (char *)h->d_stage, *p = (char *)h->h_stage;
@@ -813,6 +900,8 @@ int tmla_reset_host(tmla_env *h, float *obs) {
 
 int tmla_get_state(tmla_env *h, void *aos, void *stream) {
     TMLA_REQUIRE(h && aos, "handle/aos is NULL");
+    DeviceGuard guard(h->device);
+    mark_device_path(h, (cudaStream_t)stream);
     TASK_SWITCH(h->task, (get_state_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
                              ptrs_of(h), h->n, (typename TaskT::Wire *)aos)));
     TMLA_LAUNCH_CHECK();
@@ -820,6 +909,8 @@ int tmla_get_state(tmla_env *h, void *aos, void *stream) {
 }
 int tmla_set_state(tmla_env *h, const void *aos, void *stream) {
     TMLA_REQUIRE(h && aos, "handle/aos is NULL");
+    DeviceGuard guard(h->device);
+    mark_device_path(h, (cudaStream_t)stream);
     TASK_SWITCH(h->task, (set_state_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
                              ptrs_of(h), h->n, (const typename TaskT::Wire *)aos)));
     TMLA_LAUNCH_CHECK();
@@ -827,6 +918,7 @@ int tmla_set_state(tmla_env *h, const void *aos, void *stream) {
 }
 int tmla_check_actions(tmla_env *h, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
+    DeviceGuard guard(h->device);
     int err = 0;
     TMLA_CUDA(cudaMemcpyAsync(&err, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     TMLA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -841,6 +933,8 @@ int tmla_check_actions(tmla_env *h, void *stream) {
 int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, float *rew_buf, uint8_t *done_buf, void *stream) {
     TMLA_REQUIRE(h, "handle is NULL");
     TMLA_REQUIRE(T > 0, "T must be positive");
+    DeviceGuard guard(h->device);
+    mark_device_path(h, (cudaStream_t)stream);
     const int D = kObsDim[h->task];
     const bool fast = obs_buf && act_buf && rew_buf && done_buf && (h->n % kRollBlock == 0) &&
                       ((reinterpret_cast<uintptr_t>(obs_buf) & 15u) == 0) && ((int64_t)T * h->n * D / 4 < ((int64_t)1 << 31));
@@ -864,10 +958,12 @@ int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_
     TMLA_REQUIRE(h, "handle is NULL");
     TMLA_REQUIRE(logits && obs_next && rew && done, "logits/obs_next/rew/done must be non-NULL");
     TMLA_REQUIRE(!trunc_count || (trunc_index && trunc_obs && trunc_capacity > 0), "truncation list is incomplete");
+    DeviceGuard guard(h->device);
+    mark_device_path(h, (cudaStream_t)stream);
     TASK_SWITCH(h->task, (step_policy_kernel<TaskT><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, step_base, logits, deterministic,
                              (int64_t)row_index, obs_next, act, logp, rew, done, trunc_count, trunc_index, trunc_obs,
-                             trunc_capacity, ep_stats)));
+                             trunc_capacity, ep_stats, h->ep_log, h->ep_log_cap, h->ep_log_count)));
     TMLA_LAUNCH_CHECK();
     if (!step_base) h->step_count += 1;
     return TMLA_OK;

@@ -97,15 +97,15 @@ __host__ __device__ __forceinline__ uint32_t perm_mix(uint32_t v) {
     v *= 0x9E3779B1u; v ^= v >> 15; v *= 0x85EBCA77u; v ^= v >> 13;
     return v;
 }
-// keyed 4-round Feistel network on 2*half bits + cycle walking = a bijection of [0,total)
+// keyed 6-round Feistel network on 2*half bits + cycle walking = a bijection of [0,total)
 __host__ __device__ __forceinline__ uint64_t perm_index(uint64_t x, uint64_t total, int half, uint4 key) {
     const uint32_t mask = (half >= 32) ? 0xFFFFFFFFu : ((1u << half) - 1u);
     const uint32_t k[4] = {key.x, key.y, key.z, key.w};
     do {
         uint32_t L = (uint32_t)(x >> half), R = (uint32_t)x & mask;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t F = perm_mix(R ^ k[r]) & mask;
+        for (int r = 0; r < 6; ++r) {                       // rounds 4, 5 reuse keys 0, 1 with a round constant
+            const uint32_t F = perm_mix(R ^ k[r & 3] ^ (r >= 4 ? 0x9E3779B9u : 0u)) & mask;
             const uint32_t nl = R;
             R = L ^ F;
             L = nl;

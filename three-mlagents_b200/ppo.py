@@ -21,6 +21,7 @@ from typing import Any
 
 import numpy as np
 import torch
+from torch.cuda import nvtx      # NVTX ranges rollout / gae / update / allreduce (visible in nsys / ncu --nvtx)
 
 from . import ops
 from .distributed import allreduce_sum_, dist_state
@@ -30,6 +31,20 @@ HIDDEN = 256
 
 
 _dist = dist_state
+
+
+def _on_device(fn):
+    """Run a CudaPPO method with the model's GPU as the current CUDA device: the C entry points enqueue on torch's current
+    stream, which is per device — without this a model on cuda:1 called from a thread whose current device is cuda:0 would
+    launch on the wrong GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
 
 
 def orthogonal_init(obs_dim: int, n_actions: int, seed: int) -> torch.Tensor:
@@ -91,6 +106,8 @@ class CudaPPO:
             self._repack()
         self._buffers_ready = False
         self._last_obs_valid = False
+        self.allreduce_impl = "nccl" if self.world > 1 else "none"
+        self.rollout_impl = "per-step launches (tmla_mlp_forward_bf16 + tmla_step_policy)"
         self.logger_rows: list[dict[str, Any]] = []
 
     def _repack(self):
@@ -143,12 +160,16 @@ class CudaPPO:
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
         self.norm_out = torch.zeros(129, **f32)
+        if getattr(self.env, "_monitor", None) is not None and self.env._ep_log is None:
+            self.env.attach_episode_log(N * T)          # Monitor rows for the device path (flushed after every rollout)
         self._buffers_ready = True
 
     # ------------------------------------------------------------------------------------- rollout
+    @_on_device
     def collect_rollouts(self):
         """OnPolicyAlgorithm.collect_rollouts + compute_returns_and_advantage, no host round-trip per step."""
         self._alloc()
+        nvtx.range_push("rollout")
         T, N, D, A = self.n_steps, self.n_envs, self.obs_dim, self.n_actions
         if not self._last_obs_valid:
             self.obs[0].copy_(self.env.reset_tensor())
@@ -170,16 +191,21 @@ class CudaPPO:
         ops.mlp_forward(self.params, self.trunc_obs, D, A, rows=cap, rows_dev=self.trunc_count, want_logits=False,
                         values=self.trunc_values, act_cache=self.cache_trunc, wpack=self.wpack, keep_act=False)
         ops.bootstrap_add(self.rew, self.trunc_count, self.trunc_index, self.trunc_values, self.gamma)
+        nvtx.range_pop()
+        nvtx.range_push("gae")
         ops.gae(self.rew, self.val, self.done, self.last_values, self.gamma, self.gae_lambda, self.adv, self.ret)
+        nvtx.range_pop()
         self.num_timesteps += T * N * self.world
 
     # -------------------------------------------------------------------------------------- update
+    @_on_device
     def train(self):
         """PPO.train: n_epochs passes over the rollout in minibatches of batch_size."""
         T, N, D, A = self.n_steps, self.n_envs, self.obs_dim, self.n_actions
         total = T * N
         B = self.mb_rows
         obs_flat = self.obs[:T].reshape(total, D)
+        nvtx.range_push("update")
         self.stats_acc.zero_()
         fused = self.fused_update
         if fused:              # no per-minibatch memsets: Adam clears the gradient it consumed, statistics accumulate in place
@@ -210,7 +236,10 @@ class CudaPPO:
                                  dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
                     ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
                                      rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
-                allreduce_sum_(self.grads)                # the one collective on the path: NCCL sum over NVLink
+                if self.world > 1:
+                    nvtx.range_push("allreduce")
+                    self._allreduce_grads(self.grads)     # the one collective on the path: sum over NVLink
+                    nvtx.range_pop()
                 self._adam_step += 1
                 ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
                               lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused,
@@ -222,7 +251,11 @@ class CudaPPO:
             self.n_updates += 1
         if fused:
             self._repack()
+        nvtx.range_pop()
         return n_mb
+
+    def _allreduce_grads(self, grads: torch.Tensor) -> None:
+        allreduce_sum_(grads)
 
     def _log_row(self, n_mb: int, t_roll: float, t_train: float, t0: float) -> dict[str, Any]:
         s = (self.stats_acc / max(n_mb, 1)).cpu().numpy()
@@ -251,6 +284,7 @@ class CudaPPO:
         }
         return row
 
+    @_on_device
     def learn(self, total_timesteps: int, callback=None, progress_bar: bool = False, log_interval: int = 1):
         t0 = time.time()
         target = self.num_timesteps + int(total_timesteps)
@@ -259,6 +293,8 @@ class CudaPPO:
             ts = time.time()
             self.collect_rollouts()
             torch.cuda.synchronize(self.device)
+            if getattr(self.env, "_monitor", None) is not None:
+                self.env.flush_episode_log()             # Monitor rows of the episodes that ended in this rollout
             tr = time.time()
             n_mb = self.train()
             torch.cuda.synchronize(self.device)
@@ -281,12 +317,14 @@ class CudaPPO:
         return self
 
     # ------------------------------------------------------------------------- predict / evaluate
+    @_on_device
     def policy_logits(self, obs_dev: torch.Tensor) -> torch.Tensor:
         rows = obs_dev.shape[0]
         logits, _, _ = ops.mlp_forward(self.params, obs_dev.contiguous(), self.obs_dim, self.n_actions, rows=rows,
                                        want_values=False, wpack=self.wpack, keep_act=False)
         return logits
 
+    @_on_device
     def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
         obs = np.asarray(observation, dtype=np.float32)
         single = obs.ndim == 1
@@ -370,10 +408,19 @@ class CudaPPO:
 
 
 # ---------------------------------------------------------------------------------------- bench / smoke
-def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: int = 65536, n_steps: int = 128,
-              minibatches: int = 32, task: str = "ball3d", mlp_impl: str = "bf16", fused_update: bool = True) -> dict[str, Any]:
-    """BASELINE config 3: ball3d PPO end-to-end, 64K envs/GPU, 128-step rollouts, 2x256 MLP, 10 epochs,
-    32 minibatches per epoch (262 144 samples per GPU per optimizer step)."""
+def params_hash(params: torch.Tensor) -> int:
+    """64-bit position-weighted checksum of the parameter BITS (wrap-around int64 arithmetic, deterministic)."""
+    w = params.detach().contiguous().view(torch.int32).to(torch.int64)
+    k = torch.arange(1, w.numel() + 1, dtype=torch.int64, device=w.device) * 0x9E3779B1
+    return int(((w + 0x7F4A7C15) * k).sum().item())
+
+
+def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 5, warmup: int = 2, n_envs: int = 65536, n_steps: int = 128,
+              minibatches: int = 32, task: str = "ball3d", mlp_impl: str = "bf16", fused_update: bool = True,
+              sustained_tflops: float | None = None) -> dict[str, Any]:
+    """BASELINE configs 3/4/5: PPO end-to-end (rollout + GAE + update), `n_envs` envs per GPU, 128-step rollouts, 2x256 MLP,
+    10 epochs x 32 minibatches: `warmup` untimed iterations, then `iters` timed ones (CUDA events, max over
+    ranks).  With world > 1 every rank's parameters are hashed after the timed iterations and compared (`replicas_identical`)."""
     dist, _, _ = _dist()
     env = CudaVecEnv(task, n_envs, seed=1, device=local_rank, env_id_base=rank * n_envs)
     model = CudaPPO("MlpPolicy", env, seed=1, n_steps=n_steps, batch_size=n_envs * n_steps // minibatches, n_epochs=10,
@@ -385,7 +432,8 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    model.collect_rollouts(); model.train()           # warm-up iteration (allocations, NCCL setup)
+    for _ in range(max(1, warmup)):                   # allocations, NCCL setup, graph capture
+        model.collect_rollouts(); model.train()
     sync()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     roll_ms = train_ms = 0.0
@@ -397,14 +445,41 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
     if dist is not None:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     tot_ms, roll_ms, train_ms = (float(x) for x in tot)
+    # replicas must hold bit-identical parameters (the gradient sum and the norm reduction have a fixed order)
+    h = torch.tensor([params_hash(model.params)], dtype=torch.int64, device=dev)
+    replicas_identical = True
+    if dist is not None:
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        replicas_identical = all(int(x.item()) == int(hs[0].item()) for x in hs)
+    # cost of the one collective on the path, measured alone: the gradient all-reduce of one minibatch
+    allreduce_us = 0.0
+    if dist is not None:
+        g = torch.zeros_like(model.grads)
+        for _ in range(5):
+            model._allreduce_grads(g)
+        sync()
+        e[0].record()
+        for _ in range(50):
+            model._allreduce_grads(g)
+        e[1].record()
+        sync()
+        t = torch.tensor([e[0].elapsed_time(e[1]) * 1e3 / 50], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_us = float(t.item())
     samples = world * n_envs * n_steps * iters
     flop_sample = 807936.0 if env.obs_dim == 6 else 803840.0      # fwd+bwd per sample (ball3d | gridworld, push)
     flop_update = flop_sample * n_envs * n_steps * 10 * iters
     row = model._log_row(10 * minibatches, roll_ms / 1e3 / iters, train_ms / 1e3 / iters, time.time())
-    env.close()
-    return {
+    update_tflops = flop_update / (train_ms * 1e-3) / 1e12
+    out = {
         "value": samples / (tot_ms * 1e-3), "unit": "samples/s (env-steps consumed per second, rollout+GAE+update)",
-        "iters": iters, "ms_per_iter": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": train_ms / iters,
+        "iters": iters, "warmup": max(1, warmup), "ms_per_iter": tot_ms / iters, "rollout_ms": roll_ms / iters,
+        "update_ms": train_ms / iters, "update_us_per_minibatch": train_ms / iters * 1e3 / (10 * minibatches),
+        "update_tflops": update_tflops,
+        "frac_of_sustained": (update_tflops / sustained_tflops) if sustained_tflops else None,
+        "allreduce_us": allreduce_us, "allreduce_impl": model.allreduce_impl, "replicas_identical": replicas_identical,
+        "rollout_impl": model.rollout_impl,
         "config": {"task": task, "envs_per_gpu": n_envs, "n_steps": n_steps, "epochs": 10, "minibatches_per_epoch": minibatches,
                    "minibatch_rows_per_gpu": n_envs * n_steps // minibatches,
                    "mlp": f"{env.obs_dim}-256-256-{{{env.n_actions},1}} tanh, separate towers",
@@ -412,9 +487,12 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 3, n_envs: in
                                 else "fp32 CUDA-core SGEMM (csrc/mlp_kernels.cu)"),
                    "update": ("fused forward+loss+backward kernel per tower + MN-major wgrad (csrc/mlp_train.cu)"
                               if model.fused_update else "unfused (forward, loss, backward kernels)")},
-        "update_tflops": flop_update / (train_ms * 1e-3) / 1e12,
         "ep_rew_mean": row["rollout/ep_rew_mean"], "approx_kl": row["train/approx_kl"],
     }
+    env.close()
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_kernels(device: int = 0, n_envs: int = 65536, n_steps: int = 128) -> dict[str, Any]:

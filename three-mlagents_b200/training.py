@@ -15,6 +15,7 @@ from __future__ import annotations
 import json
 import platform
 import uuid
+import warnings
 from dataclasses import asdict, dataclass
 from datetime import datetime, timezone
 from pathlib import Path
@@ -112,6 +113,12 @@ def train_task(config: TrainConfig, *, callback=None, model_kwargs: dict[str, An
     if not task.trainable:
         raise ValueError(f"Task '{task.id}' is not trainable through Gymnasium/SB3 yet.")
     algorithm_name = (config.algorithm or task.default_algorithm).lower()
+    if config.algorithm is None and algorithm_name not in ALGORITHMS and algorithm_name in _REFERENCE_ALGORITHMS:
+        # the registry keeps the reference's per-task default (dqn for basic / gridworld / push / walljump, registry.py:61-112);
+        # this backend trains every CUDA task with PPO, so an unspecified algorithm resolves to it
+        warnings.warn(f"task '{task.id}' defaults to '{algorithm_name}' in the reference; three-mlagents_b200 has a CUDA backend "
+                      f"for PPO only and trains it with 'ppo'", stacklevel=2)
+        algorithm_name = "ppo"
     if algorithm_name not in ALGORITHMS:
         if algorithm_name in _REFERENCE_ALGORITHMS:
             raise ValueError(f"Algorithm '{algorithm_name}' has no CUDA backend in three-mlagents_b200 "

@@ -17,8 +17,8 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
-import sys
 import time
+import weakref
 from typing import Any, Sequence
 
 import numpy as np
@@ -26,6 +26,8 @@ import numpy as np
 from . import native
 from .native import lib, check, ptr
 from .spaces import spaces_for
+
+_F32, _BOOL = np.dtype(np.float32), np.dtype(np.bool_)
 
 STATE_DTYPES = {   # wire structs of include/tmla.h
     "basic": np.dtype([("pos", "<i4"), ("steps", "<i4"), ("ep_return", "<f4")]),
@@ -51,9 +53,12 @@ class LazyInfos(Sequence):
     compact records the step kernel wrote ({env index, ep_return, ep_length, terminal_obs[D]}, unordered); they are
     sorted by env index on first access."""
 
-    def __init__(self, n, done, truncated, records, t_elapsed):
+    def __init__(self, n, done, truncated, records, t_elapsed, step_no=0, last_reset=None):
         self._n, self._done, self._trunc, self._rec, self._t = n, done, truncated, records, t_elapsed
         self._idx = None
+        # `steps` of a running env (the reference's `_info`, envs.py:154-159, reports it every step) = vec-steps since its last
+        # reset; `last_reset` is the env's live bookkeeping array, so the value is exact until the NEXT step() call
+        self._step_no, self._last_reset = step_no, last_reset
 
     def _sort(self):
         if self._idx is None:
@@ -85,6 +90,8 @@ class LazyInfos(Sequence):
             info["terminal_observation"] = self._tobs[k]
             info["episode"] = {"r": round(float(self._ret[k]), 6), "l": int(self._len[k]), "t": round(self._t, 6)}
             info["steps"] = int(self._len[k])
+        elif self._last_reset is not None:
+            info["steps"] = max(0, int(self._step_no - self._last_reset[i]))
         return info
 
     def finished(self):
@@ -99,11 +106,13 @@ class LazyInfos(Sequence):
 
 
 class _ResultBlocks:
-    """Pool of pinned result blocks (include/tmla.h `tmla_result_block_*`).  A step's D2H copy lands directly in the block
-    whose slices are returned to the caller as obs / rewards / dones / infos.  DummyVecEnv returns fresh copies every step
-    (SB3 dummy_vec_env.py `step_wait`), so a block is handed out again only when no array over it is alive — every view of
-    a block holds a reference to its `raw` array, and `sys.getrefcount(raw)` says when they are all gone.  A caller that
-    keeps more than `cap` steps' results alive gets ordinary NumPy copies from then on."""
+    """Pool of pinned result blocks (include/tmla.h `tmla_result_block_*`).  A step's results land directly in a block whose
+    slices are returned to the caller as obs / rewards / dones / infos.  DummyVecEnv returns fresh copies every step (SB3
+    dummy_vec_env.py `step_wait`), so a block is handed out again only when no array over it is alive.  Every hand-out is a
+    LEASE: a fresh base ndarray over the block's memory that all returned arrays (and anything sliced from them) keep alive
+    through `.base`; a `weakref` callback on that base returns the block to the free list when the last of them is dropped.
+    No reference counts are inspected, so a debugger or tracer holding extra references only delays the reuse.  A caller
+    that keeps more than `cap` steps' results alive gets ordinary NumPy copies from then on."""
 
     def __init__(self, handle, n, d, cap=8):
         self._h, self._cap = handle, cap
@@ -114,64 +123,62 @@ class _ResultBlocks:
         recp, recw = native.vp(), native.i32(0)
         check(lib.tmla_host_records(handle, C.byref(recp), C.byref(recw)))
         self.rec_words = int(recw.value)              # record stride: {idx, ret, len, tobs[d]} padded to a multiple of 4 words
-        self._raw, self._fixed, self._ptr = [], [], []
+        self._mem, self._ptr, self._lease, self._release = [], [], [], []
+        self._free: list[int] = []
         self.n, self.d = n, d
         self.scratch = self._alloc()      # never handed out: the fallback copies out of it
+        self._free.clear()
         self._alloc(); self._alloc()      # the usual case — the caller holds one step's results while asking for the next
 
     def _alloc(self):
         q = native.vp()
         check(lib.tmla_result_block_alloc(self._h, C.byref(q)))
-        raw = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(q.value))
-        o_obs, o_rew, o_done, o_trunc = self.off[:4]
-        n, d = self.n, self.d
-        # the four fixed-shape slices are made once per block and handed out again with it (5 us per step otherwise)
-        fixed = (raw[o_obs:o_obs + 4 * n * d].view(np.float32).reshape(n, d), raw[o_rew:o_rew + 4 * n].view(np.float32),
-                 raw[o_done:o_done + n].view(np.bool_), raw[o_trunc:o_trunc + n].view(np.bool_))
-        self._raw.append(raw)
-        self._fixed.append(fixed)
+        k = len(self._mem)
+        self._mem.append((C.c_uint8 * self.nbytes).from_address(q.value))
         self._ptr.append(q)
-        k = len(self._raw) - 1
-        del raw, fixed
-        # reference counts of an unused block, measured through the same expressions acquire() evaluates
-        self._idle = (sys.getrefcount(self._raw[k]), sys.getrefcount(self._fixed[k][0]))
+        self._lease.append(None)
+        free = self._free
+        self._release.append(lambda _ref, k=k: free.append(k))
+        free.append(k)
         return k
 
     def acquire(self):
-        """Index of a block nobody references, or None when `cap` blocks are all still in use.  A caller can hold a block
-        through one of its four cached slices (their own reference count rises) or through anything derived from them or
-        from the record slice (NumPy makes `raw` the base of every derived view: its count rises)."""
-        raws, fixed = self._raw, self._fixed
-        idle_raw, idle_view = self._idle
-        for k in range(1, len(raws)):
-            if sys.getrefcount(raws[k]) == idle_raw:
-                f = fixed[k]
-                if (sys.getrefcount(f[0]) == idle_view and sys.getrefcount(f[1]) == idle_view
-                        and sys.getrefcount(f[2]) == idle_view and sys.getrefcount(f[3]) == idle_view):
-                    return k
-        return self._alloc() if len(raws) <= self._cap else None
+        """Index of a block no live array refers to, or None when `cap` blocks are all still in use."""
+        if not self._free:
+            if len(self._mem) > self._cap:
+                return None
+            self._alloc()
+        return self._free.pop()
 
-    def views(self, k, n_done):
-        obs, rew, done, trunc = self._fixed[k]
+    def release(self, k):
+        """Give back a block acquired but never handed out (the step failed)."""
+        self._free.append(k)
+
+    def views(self, k, n_done, lease=True):
+        """(obs, rew, done, trunc, records) over block k.  With `lease`, the arrays share one fresh base whose death
+        (the caller dropped them all) puts the block back on the free list."""
+        raw = np.frombuffer(self._mem[k], dtype=np.uint8)
+        if lease:
+            self._lease[k] = weakref.ref(raw, self._release[k])
+        n, d = self.n, self.d
+        o_obs, o_rew, o_done, o_trunc = self.off[:4]
+        obs = np.ndarray((n, d), _F32, raw, o_obs)
+        rew = np.ndarray((n,), _F32, raw, o_rew)
+        done = np.ndarray((n,), _BOOL, raw, o_done)
+        trunc = np.ndarray((n,), _BOOL, raw, o_trunc)
         rec = None
         if n_done:
-            o_rec, rw = self.off[5], self.rec_words
-            rec = self._raw[k][o_rec:o_rec + 4 * rw * n_done].view(np.float32).reshape(n_done, rw)[:, :3 + self.d]
+            rec = np.ndarray((n_done, self.rec_words), _F32, raw, self.off[5])[:, :3 + self.d]
         return obs, rew, done, trunc, rec
 
     def close(self):
-        busy = [k for k in range(len(self._raw)) if not self._is_idle(k)]
-        raws, fixed, ptrs = self._raw, self._fixed, self._ptr
-        self._raw, self._fixed, self._ptr = [], [], []
-        for k in range(len(raws)):
-            if k not in busy:
-                fixed[k] = None
+        free = set(self._free) | {self.scratch}
+        mem, ptrs = self._mem, self._ptr
+        self._mem, self._ptr, self._lease, self._free = [], [], [], []
+        for k in range(len(mem)):
+            if k in free:
                 lib.tmla_result_block_free(ptrs[k])
             # else: a caller still holds arrays over this block; leave the pinned memory to process teardown
-
-    def _is_idle(self, k):
-        idle_raw, idle_view = self._idle
-        return sys.getrefcount(self._raw[k]) == idle_raw and all(sys.getrefcount(self._fixed[k][j]) == idle_view for j in range(4))
 
 
 class CudaVecEnv:
@@ -190,13 +197,12 @@ class CudaVecEnv:
         check(lib.tmla_create(native.TASK_IDS[task_id], self.num_envs, int(seed) & (2**64 - 1), int(env_id_base),
                               self.device_index, C.byref(self._h)))
         n, d = self.num_envs, self.obs_dim
-        # NumPy view of the handle's pinned action buffer (tmla_host_views); results land in pooled pinned result blocks
-        q = native.vp()
-        check(lib.tmla_host_views(self._h, C.byref(q), None, None, None, None, None, None, None))
-        self._pin_act = np.ctypeslib.as_array((C.c_int32 * n).from_address(q.value))
-        self._blocks = _ResultBlocks(self._h, n, d)
+        self._blocks = _ResultBlocks(self._h, n, d)      # results land in pooled pinned result blocks
         self._actions = None
         self._t0 = time.time()
+        self._vec_step = 0                               # host-path vec-steps taken (for infos[i]["steps"])
+        self._last_reset = np.zeros(n, np.int64)         # vec-step index at which env i last (auto-)reset
+        self._ep_log = None                              # device episode log of the policy-driven path (Monitor rows)
         self._dev = None      # device-side buffers for step_tensor, allocated lazily
         self._monitor = None
         if monitor_dir is not None:
@@ -206,39 +212,55 @@ class CudaVecEnv:
 
     # ------------------------------------------------------------------ SB3 VecEnv surface (NumPy)
     def seed(self, seed: int | None = None):
-        if seed is not None:
-            check(lib.tmla_seed(self._h, int(seed) & (2**64 - 1)))
-        return [None if seed is None else seed + i for i in range(min(self.num_envs, 1))]
+        """SB3 `VecEnv.seed`: env i gets seed + i; returns the num_envs seeds (a random base seed when None).  Here the base
+        seed keys the Philox streams and the env's global id is the sub-sequence, which is the same separation."""
+        if seed is None:
+            seed = int(np.random.randint(0, np.iinfo(np.uint32).max, dtype=np.uint32))
+        check(lib.tmla_seed(self._h, int(seed) & (2**64 - 1)))
+        return [int(seed) + i for i in range(self.num_envs)]
 
     def reset(self) -> np.ndarray:
         obs = np.empty((self.num_envs, self.obs_dim), np.float32)
         check(lib.tmla_reset_host(self._h, ptr(obs)))
+        self._last_reset[:] = self._vec_step
         return obs
 
     def step_async(self, actions) -> None:
         a = np.asarray(actions).reshape(-1)
         if a.shape[0] != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions, got {a.shape[0]}")
-        np.copyto(self._pin_act, a, casting="unsafe")      # int64 -> int32 straight into pinned memory
-        self._actions = self._pin_act
+        if a.dtype not in (np.int32, np.int64) or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=np.int64)
+        # one C pass: range check (IndexError BEFORE anything is launched, like the reference's ACTION_DELTAS[action]) and
+        # narrowing to one byte per action in the pinned stage the step kernel reads over PCIe
+        check(lib.tmla_stage_actions(self._h, a.ctypes.data, a.dtype.itemsize))
+        self._actions = a
 
     def step_wait(self):
         blocks = self._blocks
         k = blocks.acquire()
         nd = native.i64(0)
-        check(lib.tmla_step_block(self._h, blocks._ptr[blocks.scratch if k is None else k], C.byref(nd)))
+        try:
+            check(lib.tmla_step_block(self._h, blocks._ptr[blocks.scratch if k is None else k], C.byref(nd)))
+        except BaseException:
+            if k is not None:
+                blocks.release(k)
+            raise
+        n_done = int(nd.value)
         if k is None:     # the caller holds every pooled block: ordinary copies out of the scratch block
-            obs, rew, done, trunc, rec = (None if v is None else v.copy() for v in blocks.views(blocks.scratch, int(nd.value)))
+            obs, rew, done, trunc, rec = (None if v is None else v.copy() for v in blocks.views(blocks.scratch, n_done, lease=False))
         else:
-            obs, rew, done, trunc, rec = blocks.views(k, int(nd.value))
+            obs, rew, done, trunc, rec = blocks.views(k, n_done)
+        self._vec_step += 1
         if rec is not None:
-            infos = LazyInfos(self.num_envs, done, trunc, rec, time.time() - self._t0)
+            infos = LazyInfos(self.num_envs, done, trunc, rec, time.time() - self._t0, self._vec_step, self._last_reset)
+            self._last_reset[rec[:, 0].view(np.int32)] = self._vec_step
             if self._monitor is not None:
                 t = round(time.time() - self._t0, 6)
                 for r, l in zip(*infos.episode_stats()):
                     self._monitor.write(f"{round(float(r), 6)},{int(l)},{t}\n")
         else:
-            infos = LazyInfos(self.num_envs, done, trunc, None, 0.0)
+            infos = LazyInfos(self.num_envs, done, trunc, None, 0.0, self._vec_step, self._last_reset)
         return obs, rew, done, infos
 
     def step(self, actions):
@@ -247,6 +269,7 @@ class CudaVecEnv:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
+            self._ep_log = None
             self._blocks.close()
             lib.tmla_destroy(self._h)
             self._h = native.vp()
@@ -305,32 +328,67 @@ class CudaVecEnv:
             }
         return self._dev
 
+    def _stream(self) -> int:
+        """torch's current stream ON THIS ENV'S DEVICE (not the thread's current device)."""
+        import torch
+
+        return torch.cuda.current_stream(self.device_index).cuda_stream
+
     def reset_tensor(self):
         b = self._device_buffers()
-        check(lib.tmla_reset(self._h, ptr(b["obs"]), native.current_stream()))
+        check(lib.tmla_reset(self._h, ptr(b["obs"]), self._stream()))
         return b["obs"]
+
+    def attach_episode_log(self, capacity: int) -> None:
+        """Monitor for the policy-driven device path (`tmla_step_policy` / `tmla_rollout`): finished episodes append
+        (return, length) records to a device buffer that `flush_episode_log` turns into monitor.csv rows."""
+        import torch
+
+        dev = torch.device("cuda", self.device_index)
+        cap = int(max(1, min(capacity, 1 << 22)))
+        self._ep_log = {"rec": torch.zeros((cap, 2), dtype=torch.float32, device=dev),
+                        "count": torch.zeros(1, dtype=torch.int32, device=dev), "cap": cap, "dropped": 0}
+        check(lib.tmla_set_episode_log(self._h, ptr(self._ep_log["rec"]), cap, ptr(self._ep_log["count"])))
+
+    def flush_episode_log(self):
+        """(returns, lengths) of the episodes logged since the last flush (order within a rollout is arbitrary); writes
+        them to monitor.csv when this env has a monitor file.  Synchronises the env's stream."""
+        log = self._ep_log
+        if log is None:
+            return np.zeros(0, np.float32), np.zeros(0, np.int64)
+        count = int(log["count"].item())
+        k = min(count, log["cap"])
+        log["dropped"] += count - k
+        rec = log["rec"][:k].cpu().numpy()
+        log["count"].zero_()
+        rets, lens = rec[:, 0].copy(), rec[:, 1].astype(np.int64)
+        if self._monitor is not None and k:
+            t = round(time.time() - self._t0, 6)
+            self._monitor.write("".join(f"{round(float(r), 6)},{int(l)},{t}\n" for r, l in zip(rets, lens)))
+            self._monitor.flush()
+        return rets, lens
 
     def step_tensor(self, actions, out: dict | None = None):
         """actions: int32 CUDA tensor [n].  Returns the dict of device tensors
         obs / rew / done / trunc / tobs / ret / len (overwritten by the next call)."""
         b = out or self._device_buffers()
         check(lib.tmla_step(self._h, ptr(actions), ptr(b["obs"]), ptr(b["rew"]), ptr(b["done"]), ptr(b["trunc"]),
-                            ptr(b.get("tobs")), ptr(b.get("ret")), ptr(b.get("len")), native.current_stream()))
+                            ptr(b.get("tobs")), ptr(b.get("ret")), ptr(b.get("len")), self._stream()))
         return b
 
     def check_actions(self) -> None:
-        check(lib.tmla_check_actions(self._h, native.current_stream()))
+        check(lib.tmla_check_actions(self._h, self._stream()))
 
     def rollout_random(self, T: int, obs=None, act=None, rew=None, done=None) -> None:
         """Fused T-step random-policy rollout into [T,n,...] CUDA tensors (any may be None)."""
-        check(lib.tmla_rollout_random(self._h, int(T), ptr(obs), ptr(act), ptr(rew), ptr(done), native.current_stream()))
+        check(lib.tmla_rollout_random(self._h, int(T), ptr(obs), ptr(act), ptr(rew), ptr(done), self._stream()))
 
     def get_state(self) -> np.ndarray:
         import torch
 
         dt = STATE_DTYPES[self.task_id]
         buf = torch.empty(self.num_envs * dt.itemsize, dtype=torch.uint8, device=torch.device("cuda", self.device_index))
-        check(lib.tmla_get_state(self._h, ptr(buf), native.current_stream()))
+        check(lib.tmla_get_state(self._h, ptr(buf), self._stream()))
         return buf.cpu().numpy().view(dt).copy()
 
     def set_state(self, state: np.ndarray) -> None:
@@ -341,5 +399,6 @@ class CudaVecEnv:
         if st.shape != (self.num_envs,):
             raise ValueError(f"state must have shape ({self.num_envs},)")
         buf = torch.from_numpy(st.view(np.uint8).copy()).to(torch.device("cuda", self.device_index))
-        check(lib.tmla_set_state(self._h, ptr(buf), native.current_stream()))
-        torch.cuda.current_stream().synchronize()
+        check(lib.tmla_set_state(self._h, ptr(buf), self._stream()))
+        torch.cuda.current_stream(self.device_index).synchronize()
+        self._last_reset[:] = self._vec_step - np.asarray(st["steps"], np.int64)
