@@ -161,6 +161,33 @@ int tmla_step_policy(tmla_env *h, const float *logits, int deterministic, int32_
                      int32_t *trunc_count, int32_t *trunc_index, float *trunc_obs, int32_t trunc_capacity,
                      float *ep_stats /* [4]: sum return, sum length, episodes, (unused) */,
                      const uint64_t *step_base, void *stream);
+/* The whole PPO rollout as ONE call — OnPolicyAlgorithm.collect_rollouts + RolloutBuffer.compute_returns_and_advantage of
+ * SB3 2.9.0, the loop the reference enters from backend/mlagents/training.py:166 (§8(b) `tmla_rollout`):
+ *   for t in [0, n_steps): logits, values[t] = policy(obs[t]); a ~ Categorical(logits) (TAG_SAMPLE Philox stream);
+ *                          obs[t+1], rewards[t], dones[t] = VecEnv.step(a) with auto-reset; timeouts recorded in trunc_*
+ *   last_values = V(obs[n_steps]);  rewards[idx] += gamma * V(terminal_obs) for the timeouts;  GAE -> advantages, returns.
+ * The launches (tower forward on tcgen05 + step_policy_kernel per step, value forwards, bootstrap, GAE scan) are recorded
+ * once per (handle, argument block) into a CUDA graph and replayed with one cudaGraphLaunch per call: no host round trip
+ * per step.  A call is bit-identical to n_steps x {tmla_mlp_forward[_bf16] + tmla_step_policy} + tmla_bootstrap_add +
+ * tmla_gae issued one by one (environment variable TMLA_ROLLOUT=launch does exactly that, for debugging).
+ * Every pointer is DEVICE memory owned by the caller; the struct has no padding (it is compared bytewise to reuse the graph).
+ *   params/wpack/act_cache  as tmla_mlp_forward_bf16 (wpack NULL = fp32 CUDA-core path, act_cache then float); act_cache holds
+ *                           4 x max(n, trunc_capacity) x hidden elements, NULL allowed where tmla_mlp_forward_bf16 allows it
+ *   obs [n_steps+1,n,D]     row 0 = current observations (input), rows 1.. written
+ *   actions/log_probs/rewards/values/dones/advantages/returns [n_steps,n];  last_values [n];  logits [n,A] scratch
+ *   trunc_count int32[1], trunc_index int32[cap], trunc_obs float[cap,D], trunc_values float[cap]: timeout records
+ *   ep_stats float[4] (sum return, sum length, episodes, -) or NULL;  step_counter: device uint64 scratch */
+typedef struct {
+    const float *params; const void *wpack; void *act_cache;
+    float *obs; int32_t *actions; float *log_probs; float *rewards; float *values; uint8_t *dones;
+    float *last_values; float *advantages; float *returns; float *logits;
+    int32_t *trunc_count; int32_t *trunc_index; float *trunc_obs; float *trunc_values;
+    float *ep_stats; uint64_t *step_counter;
+    double gamma, gae_lambda;
+    int32_t obs_dim, hidden, n_actions, n_steps, deterministic, trunc_capacity;
+} tmla_rollout_args;
+int tmla_rollout(tmla_env *h, const tmla_rollout_args *args, void *stream);
+
 /* Monitor (training.py:83: `Monitor(env, filename=...)` logs {r, l, t} per episode) for the policy-driven device path: while a
  * log is attached, every episode that ends inside tmla_step_policy / tmla_rollout appends {ep_return, float(ep_length)} at slot
  * atomicAdd(count); records float[capacity][2] and count int32 are DEVICE memory owned by the caller, who reads and re-zeroes

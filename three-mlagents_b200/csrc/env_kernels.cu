@@ -13,43 +13,8 @@
 #include <string.h>
 #include <new>
 #include "envs.cuh"
+#include "env_handle.cuh"
 
-// ------------------------------------------------------------------------------------------ handle
-struct tmla_env {
-    int task;
-    int64_t n;
-    uint64_t seed, env_id_base, step_count;
-    int device;
-    void *buf[4];             // packed SoA planes (device)
-    int *err_flag;            // device: set when a kernel saw an out-of-range action
-    // staging for the *_host entry points
-    void *d_stage, *h_stage;  // device / pinned host, same layout
-    size_t stage_bytes;
-    cudaStream_t own_stream;
-    int32_t *d_ndone;         // device counter of finished episodes in the last step
-    int64_t rec_hint;         // records fetched with the first D2H of a host step (1.5x the last count + 256)
-    // ordering between the device path (caller's stream) and the host path (own_stream): the last stream a device-path
-    // call launched on, and whether anything was launched there since the host path last waited for it
-    cudaStream_t dev_stream;
-    bool dev_dirty;
-    cudaEvent_t dev_evt;
-    int act_u8;               // the pinned action stage currently holds uint8 actions (tmla_stage_actions)
-    // optional per-episode log of the policy-driven device path (Monitor rows): {ep_return, ep_length} records
-    float2 *ep_log;
-    int32_t ep_log_cap;
-    int32_t *ep_log_count;
-};
-
-// RAII: run an entry point on the handle's device and give the calling thread its previous device back
-struct DeviceGuard {
-    int prev = -1;
-    bool switched = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
-};
-static inline void mark_device_path(tmla_env *h, cudaStream_t st) { h->dev_stream = st; h->dev_dirty = true; }
 // the host path runs on own_stream: make it wait for whatever the device path enqueued on the caller's stream
 static int order_after_device_path(tmla_env *h) {
     if (!h->dev_dirty) return TMLA_OK;
@@ -629,6 +594,7 @@ int tmla_destroy(tmla_env *h) {
     if (h->d_ndone) cudaFree(h->d_ndone);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->dev_evt) cudaEventDestroy(h->dev_evt);
+    if (h->rollout_plan && h->rollout_plan_free) h->rollout_plan_free(h->rollout_plan);
     delete h;
     return TMLA_OK;
 }

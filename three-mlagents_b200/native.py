@@ -33,6 +33,15 @@ lib = _load()
 vp, i32, i64, u64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 _i = C.c_int
 
+class RolloutArgs(C.Structure):
+    """`tmla_rollout_args` of include/tmla.h, field for field."""
+    _fields_ = ([(k, C.c_void_p) for k in ("params", "wpack", "act_cache", "obs", "actions", "log_probs", "rewards", "values", "dones",
+                                            "last_values", "advantages", "returns", "logits", "trunc_count", "trunc_index", "trunc_obs",
+                                            "trunc_values", "ep_stats", "step_counter")]
+                + [("gamma", C.c_double), ("gae_lambda", C.c_double)]
+                + [(k, C.c_int32) for k in ("obs_dim", "hidden", "n_actions", "n_steps", "deterministic", "trunc_capacity")])
+
+
 # name -> (restype, argtypes); mirrors include/tmla.h declaration by declaration
 SIGNATURES = {
     "tmla_version": (_i, []),
@@ -65,6 +74,7 @@ SIGNATURES = {
     "tmla_check_actions": (_i, [vp, vp]),
     "tmla_rollout_random": (_i, [vp, _i, vp, vp, vp, vp, vp]),
     "tmla_step_policy": (_i, [vp, vp, _i, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "tmla_rollout": (_i, [vp, C.POINTER(RolloutArgs), vp]),
     "tmla_advance_steps": (_i, [vp, u64]),
     "tmla_counter_add": (_i, [vp, u64, vp]),
     "tmla_selftest_arith": (_i, [vp, vp]),

@@ -23,7 +23,8 @@ import numpy as np
 import torch
 from torch.cuda import nvtx      # NVTX ranges rollout / gae / update / allreduce (visible in nsys / ncu --nvtx)
 
-from . import ops
+from . import native, ops
+from .native import ptr
 from .distributed import allreduce_sum_, dist_state
 from .vec_env import CudaVecEnv
 
@@ -69,7 +70,7 @@ class CudaPPO:
                  batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  normalize_advantage: bool = True, policy_kwargs: dict | None = None, tensorboard_log: str | None = None,
-                 verbose: int = 0, mlp_impl: str = "auto", fused_update: bool = True,
+                 verbose: int = 0, mlp_impl: str = "auto", fused_update: bool = True, rollout_impl: str = "fused",
                  _params: torch.Tensor | None = None):
         if policy != "MlpPolicy":
             raise ValueError("CudaPPO supports 'MlpPolicy' (vector observations) only")
@@ -106,8 +107,11 @@ class CudaPPO:
             self._repack()
         self._buffers_ready = False
         self._last_obs_valid = False
+        self._rollout_args = None
         self.allreduce_impl = "nccl" if self.world > 1 else "none"
-        self.rollout_impl = "per-step launches (tmla_mlp_forward_bf16 + tmla_step_policy)"
+        if rollout_impl not in ("fused", "steps"):
+            raise ValueError("rollout_impl must be 'fused' (tmla_rollout: one call per rollout) or 'steps' (one call per step)")
+        self.rollout_impl = rollout_impl
         self.logger_rows: list[dict[str, Any]] = []
 
     def _repack(self):
@@ -130,6 +134,7 @@ class CudaPPO:
         self.logp = torch.empty((T, N), **f32)
         self.rew = torch.empty((T, N), **f32)
         self.val = torch.empty((T, N), **f32)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.adv = torch.empty((T, N), **f32)
         self.ret = torch.empty((T, N), **f32)
         self.done = torch.empty((T, N), dtype=torch.uint8, device=dev)
@@ -176,6 +181,24 @@ class CudaPPO:
             self._last_obs_valid = True
         else:
             self.obs[0].copy_(self.obs[T])
+        if self.rollout_impl == "fused":
+            # ONE call: T x {tower forward, sample + env step}, last-value and timeout-bootstrap forwards, GAE — a CUDA graph
+            # recorded once per buffer set inside libtmla.so and replayed here (include/tmla.h tmla_rollout)
+            if self._rollout_args is None:
+                keep = self.cache_trunc if self.cache_trunc.numel() >= self.cache_roll.numel() else self.cache_roll
+                need_cache = not (self.mlp_impl == "bf16" and D <= 6)
+                self._rollout_args = native.RolloutArgs(
+                    params=ptr(self.params), wpack=ptr(self.wpack), act_cache=ptr(keep) if need_cache else None,
+                    obs=ptr(self.obs), actions=ptr(self.act), log_probs=ptr(self.logp), rewards=ptr(self.rew), values=ptr(self.val),
+                    dones=ptr(self.done), last_values=ptr(self.last_values), advantages=ptr(self.adv), returns=ptr(self.ret),
+                    logits=ptr(self.logits_roll), trunc_count=ptr(self.trunc_count), trunc_index=ptr(self.trunc_index),
+                    trunc_obs=ptr(self.trunc_obs), trunc_values=ptr(self.trunc_values), ep_stats=ptr(self.ep_stats),
+                    step_counter=ptr(self.step_counter), gamma=self.gamma, gae_lambda=self.gae_lambda, obs_dim=D, hidden=HIDDEN,
+                    n_actions=A, n_steps=T, deterministic=0, trunc_capacity=self.trunc_index.numel())
+            native.check(native.lib.tmla_rollout(self.env.handle, self._rollout_args, native.current_stream()))
+            nvtx.range_pop()
+            self.num_timesteps += T * N * self.world
+            return
         self.trunc_count.zero_()
         self.ep_stats.zero_()
         for t in range(T):
