@@ -419,3 +419,29 @@ def test_glider_penalties_waypoints_and_limits_against_oracle():
     # env 7: gravity only
     np.testing.assert_allclose(got["vel"][7], [1.0, 0.5, -9.81 * 0.02], rtol=0, atol=1e-15)
     env.close()
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+@pytest.mark.parametrize("n", [1, 31, 32, 1000, 4099])
+def test_out_of_range_action_is_rejected_before_any_state_change(n, dtype):
+    """The reference's `ACTION_DELTAS[action]` (examples/ball3d.py:76) raises before the env changes; the host step checks the
+    whole batch while staging it (one SIMD pass, tmla_stage_actions) and launches nothing when an action is out of range."""
+    from three_mlagents_b200.vec_env import CudaVecEnv
+
+    env = CudaVecEnv("ball3d", n, seed=3)
+    env.reset()
+    rng = np.random.default_rng(n)
+    good = rng.integers(0, env.n_actions, n).astype(dtype)
+    env.step(good)
+    before, count = env.get_state(), env.step_count
+    for pos in sorted({0, n // 2, n - 1}):
+        for bad_value in (env.n_actions, 7, 8, 255, 256, -1, np.iinfo(dtype).max, np.iinfo(dtype).min):
+            a = good.copy()
+            a[pos] = bad_value
+            with pytest.raises(IndexError):
+                env.step(a)
+    after = env.get_state()
+    assert env.step_count == count and before.tobytes() == after.tobytes()
+    obs, rew, done, infos = env.step(good)                       # and the env is still usable
+    assert obs.shape == (n, 6) and infos[0]["steps"] >= 1
+    env.close()

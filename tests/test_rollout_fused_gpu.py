@@ -38,7 +38,8 @@ def test_fused_rollout_is_bit_identical_to_per_step_calls(task, n, T, impl):
             assert torch.equal(a.view(torch.uint8) if a.dtype == torch.uint8 else a.view(torch.int32),
                                b.view(torch.uint8) if b.dtype == torch.uint8 else b.view(torch.int32)), (task, it, name)
         assert int(fused.trunc_count.item()) == int(steps.trunc_count.item())
-        assert torch.equal(fused.ep_stats, steps.ep_stats)
+        # episode statistics are float atomicAdd sums: same addends, order not fixed
+        assert torch.allclose(fused.ep_stats, steps.ep_stats, rtol=1e-5, atol=0) and fused.ep_stats[2] == steps.ep_stats[2]
         assert fused.env.step_count == steps.env.step_count == (it + 1) * T
         if it == 1:                                            # an update between rollouts: the graph reads the parameters in place
             for m in (fused, steps):

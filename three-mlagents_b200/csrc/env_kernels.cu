@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "envs.cuh"
 #include "env_handle.cuh"
 
@@ -106,7 +109,13 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     // result stores at system scope before taking its ticket, so the sequence word is the last thing to become visible).
     constexpr int D = Task::D;
     __shared__ __align__(16) float s_obs[kBlock * D];
+    __shared__ __align__(16) float s_rew[kBlock];
+    __shared__ __align__(16) uint8_t s_flag[2 * kBlock];          // done[kBlock] | truncated[kBlock]
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    // full block with 16-byte aligned rows: reward / done / truncated leave as 128-bit stores too (40 per CTA instead of 384
+    // scalar ones — they may travel over PCIe to a pinned result block, where a 1-byte store per lane is a 32-byte write)
+    const bool wide = (n - i0 >= kBlock) && (((reinterpret_cast<uintptr_t>(reward + i0) | reinterpret_cast<uintptr_t>(done + i0) |
+                                               reinterpret_cast<uintptr_t>(truncated + i0)) & 15u) == 0);
     if (i < n) {
         const typename Task::Consts cst = Task::load_consts();
         typename Task::State s = Task::load(p.buf, i);
@@ -116,9 +125,15 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
         Task::step(cst, s, a, r, term, trunc);
         s.ep_ret = __fadd_rn(s.ep_ret, r);                       // Monitor: episode return
         const bool d = term || trunc;
-        reward[i] = r;
-        done[i] = d ? 1 : 0;
-        truncated[i] = (trunc && !term) ? 1 : 0;                 // infos["TimeLimit.truncated"]
+        if (wide) {
+            s_rew[threadIdx.x] = r;
+            s_flag[threadIdx.x] = d ? 1 : 0;
+            s_flag[kBlock + threadIdx.x] = (trunc && !term) ? 1 : 0;
+        } else {
+            reward[i] = r;
+            done[i] = d ? 1 : 0;
+            truncated[i] = (trunc && !term) ? 1 : 0;             // infos["TimeLimit.truncated"]
+        }
         float o[D];
         Task::observe(s, o);
         if (d) {                                                 // DummyVecEnv: keep terminal obs, auto-reset
@@ -149,6 +164,12 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     }
     __syncthreads();
     block_store_obs<D, kBlock, false>(s_obs, obs + i0 * D, (int)min((int64_t)kBlock, n - i0));
+    if (wide) {
+        const int t = threadIdx.x;
+        if (t < kBlock / 4) reinterpret_cast<float4 *>(reward + i0)[t] = reinterpret_cast<const float4 *>(s_rew)[t];
+        else if (t < kBlock / 4 + kBlock / 16) reinterpret_cast<uint4 *>(done + i0)[t - kBlock / 4] = reinterpret_cast<const uint4 *>(s_flag)[t - kBlock / 4];
+        else if (t < kBlock / 4 + kBlock / 8) reinterpret_cast<uint4 *>(truncated + i0)[t - kBlock / 4 - kBlock / 16] = reinterpret_cast<const uint4 *>(s_flag + kBlock)[t - kBlock / 4 - kBlock / 16];
+    }
     if (host_flags) {
         __syncthreads();                         // every thread's result stores (obs included) precede thread 0's fence
         if (threadIdx.x == 0) {
@@ -517,6 +538,55 @@ static StageLayout stage_layout(int64_t n, int D) {
     return L;
 }
 
+
+#if defined(__x86_64__)
+// host-side action staging (tmla_stage_actions): AVX2 bodies, selected at run time; they return how many elements they handled
+__attribute__((target("avx2"))) static int64_t stage_actions32_avx2(const int32_t *src, uint8_t *dst, int64_t n, uint64_t *ored, uint32_t *mx) {
+    __m256i acc = _mm256_setzero_si256(), vmx = _mm256_setzero_si256();
+    const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    int64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 8));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 16)), d = _mm256_loadu_si256((const __m256i *)(src + i + 24));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+        __m256i p = _mm256_packus_epi16(_mm256_packs_epi32(a, b), _mm256_packs_epi32(c, d));   // per 128-bit lane: a b c d quarters
+        p = _mm256_permutevar8x32_epi32(p, perm);
+        vmx = _mm256_max_epu8(vmx, p);
+        _mm256_storeu_si256((__m256i *)(dst + i), p);
+    }
+    uint64_t t[4]; uint8_t m8[32];
+    _mm256_storeu_si256((__m256i *)t, acc); _mm256_storeu_si256((__m256i *)m8, vmx);
+    const uint64_t o = t[0] | t[1] | t[2] | t[3];
+    *ored |= (o | (o >> 32)) & 0xFFFFFFFFull;
+    for (int k = 0; k < 32; ++k) *mx = m8[k] > *mx ? m8[k] : *mx;
+    return i;
+}
+__attribute__((target("avx2"))) static int64_t stage_actions64_avx2(const int64_t *src, uint8_t *dst, int64_t n, uint64_t *ored, uint32_t *mx) {
+    __m256i acc = _mm256_setzero_si256(), vmx = _mm256_setzero_si256();
+    const __m256i lo = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6), perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    int64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        __m256i w[4];
+        for (int k = 0; k < 4; ++k) {
+            const __m256i x = _mm256_loadu_si256((const __m256i *)(src + i + 8 * k)), y = _mm256_loadu_si256((const __m256i *)(src + i + 8 * k + 4));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(x, y));
+            const __m256i xl = _mm256_permutevar8x32_epi32(x, lo), yl = _mm256_permutevar8x32_epi32(y, lo);   // low dwords -> low half
+            w[k] = _mm256_inserti128_si256(xl, _mm256_castsi256_si128(yl), 1);
+        }
+        __m256i p = _mm256_packus_epi16(_mm256_packs_epi32(w[0], w[1]), _mm256_packs_epi32(w[2], w[3]));
+        p = _mm256_permutevar8x32_epi32(p, perm);
+        vmx = _mm256_max_epu8(vmx, p);
+        _mm256_storeu_si256((__m256i *)(dst + i), p);
+    }
+    uint64_t t[4]; uint8_t m8[32];
+    _mm256_storeu_si256((__m256i *)t, acc); _mm256_storeu_si256((__m256i *)m8, vmx);
+    const uint64_t o = t[0] | t[1] | t[2] | t[3];
+    *ored |= (o & ~7ull) ? 0xFFFFFFFFull : (o & 7ull);
+    for (int k = 0; k < 32; ++k) *mx = m8[k] > *mx ? m8[k] : *mx;
+    return i;
+}
+#endif
+
 extern "C" {
 
 int tmla_task_from_name(const char *name) {
@@ -715,16 +785,26 @@ int tmla_stage_actions(tmla_env *h, const void *actions, int elem_bytes) {
     TMLA_REQUIRE(h && actions, "handle/actions is NULL");
     TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
     const int64_t n = h->n;
-    const uint64_t A = (uint64_t)kNumActions[h->task];
+    const uint32_t A = (uint32_t)kNumActions[h->task];                 // <= 8 for every task
     uint8_t *dst = (uint8_t *)h->h_stage + stage_layout(n, kObsDim[h->task]).act;
-    uint64_t bad = 0;
-    if (elem_bytes == 4) {
-        const int32_t *src = (const int32_t *)actions;
-        for (int64_t i = 0; i < n; ++i) { const uint32_t a = (uint32_t)src[i]; bad |= (uint64_t)(a >= A); dst[i] = (uint8_t)a; }
-    } else {
-        const int64_t *src = (const int64_t *)actions;
-        for (int64_t i = 0; i < n; ++i) { const uint64_t a = (uint64_t)src[i]; bad |= (uint64_t)(a >= A); dst[i] = (uint8_t)a; }
+    // one pass, 32 actions per AVX2 iteration: OR of the raw lanes catches negatives and anything >= 8, a byte-wise running
+    // maximum of the packed actions catches A..7 (a plain scalar loop costs ~0.5 ns per action)
+    uint64_t ored = 0;
+    uint32_t mx = 0;
+    int64_t i = 0;
+#if defined(__x86_64__)
+    static const bool has_avx2 = __builtin_cpu_supports("avx2");
+    if (has_avx2)
+        i = elem_bytes == 4 ? stage_actions32_avx2((const int32_t *)actions, dst, n, &ored, &mx)
+                            : stage_actions64_avx2((const int64_t *)actions, dst, n, &ored, &mx);
+#endif
+    for (; i < n; ++i) {
+        const uint64_t a = elem_bytes == 4 ? (uint64_t)(uint32_t)((const int32_t *)actions)[i] : (uint64_t)((const int64_t *)actions)[i];
+        ored |= (a | (a >> 32)) & 0xFFFFFFFFull;
+        mx = (uint32_t)(a & 7u) > mx ? (uint32_t)(a & 7u) : mx;
+        dst[i] = (uint8_t)a;
     }
+    const bool bad = (ored & ~7ull) != 0 || mx >= A;
     h->act_u8 = 1;
     if (bad) {
         tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);

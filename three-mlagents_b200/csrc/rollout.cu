@@ -90,11 +90,18 @@ int tmla_rollout(tmla_env *h, const tmla_rollout_args *args, void *stream) {
     if (!plan || memcmp(&plan->key, &a, sizeof(a)) != 0 || plan->ep_log != h->ep_log || plan->ep_log_count != h->ep_log_count ||
         plan->seed != h->seed) {
         if (plan) { plan_free(plan); h->rollout_plan = nullptr; }
-        TMLA_CUDA(cudaStreamSynchronize(st));
+        // recorded on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+        // instantiated graph is then launched on the caller's stream
+        cudaStream_t cap = nullptr;
+        TMLA_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
-        TMLA_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        const int rc = enqueue(h, a, st);
-        const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+        cudaError_t ec = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+        int rc = TMLA_OK;
+        if (ec == cudaSuccess) {
+            rc = enqueue(h, a, cap);
+            ec = cudaStreamEndCapture(cap, &graph);
+        }
+        cudaStreamDestroy(cap);
         if (rc || ec != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             if (!rc) tmla_set_error("tmla_rollout: stream capture failed: %s", cudaGetErrorString(ec));
