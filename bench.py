@@ -41,7 +41,7 @@ OBS_DIM = 6
 BYTES_PER_ENV_STEP = 33.0 + 56.0 / T_ROLLOUT
 
 
-NCU_TRAFFIC_CSV = "profiles/r1_rollout_fast_ncu_raw.csv"
+NCU_TRAFFIC_CSV = "profiles/r2_rollout_fast_ncu_raw.csv"
 
 
 def _ncu_traffic():

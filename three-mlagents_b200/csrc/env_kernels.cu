@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <type_traits>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -286,8 +287,12 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
 #define TMLA_SPARE_EVERY 64   /* measured on 128-step launches: 16 -> 66.3 us, 32 -> 64.6, 64 -> 63.9, 128 -> 66.7 */
 #endif
 static constexpr int kSpareEvery = TMLA_SPARE_EVERY;
+// tasks that split a step into an independent "plan" half (Task::Tilt, Task::plan, Task::advance_planned — ball3d) run the
+// fused rollout software-pipelined: the plan of step t+1 is computed beside the integration / reward chain of step t
+template <class T, class = void> struct is_pipelined { static constexpr bool value = false; };
+template <class T> struct is_pipelined<T, std::void_t<typename T::Tilt>> { static constexpr bool value = true; };
 static_assert((kSpareEvery & (kSpareEvery - 1)) == 0, "power of two");
-template <class Task>
+template <class Task, bool PIPE_ON = false>
 __global__ void __launch_bounds__(kRollBlock)
 rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uint64_t step0, int T,
                     float4 *__restrict__ obs4, int32_t *__restrict__ act_buf, float *__restrict__ rew_buf,
@@ -308,6 +313,12 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
     uint32_t sb = 0;                                    // stage buffer toggle: 0 / BLOCK*D
     [[maybe_unused]] typename Task::Spare sp;
     [[maybe_unused]] bool have_spare = false;
+    constexpr bool PIPE = PIPE_ON && is_pipelined<Task>::value;
+    [[maybe_unused]] int a_next = 0;
+    [[maybe_unused]] auto tilt = [&] {
+        if constexpr (PIPE) { a_next = as.next(seed, env_id, step0, 0u, Task::A); return Task::template plan<true>(cst, s, a_next); }
+        else return 0;
+    }();
 #pragma unroll 2   // measured: 73.2 us (no unroll) / 70.8 us (2) / 72.1 us (4)
     for (int t = 0; t < T; ++t) {
         if constexpr (Task::HAS_SPARE) {
@@ -330,9 +341,21 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
         } else {
             st_stream_f4(obs4 + off, make_float4(o[0], o[1], o[2], o[3]));
         }
-        const int a = as.next(seed, env_id, step0, (uint32_t)t, Task::A);
+        int a;
         float r; bool term, trunc;
-        Task::step(cst, s, a, r, term, trunc);
+        if constexpr (PIPE) {
+            // step t: apply the tilt planned one iteration ago, integrate; meanwhile plan step t+1 from the rotation just applied
+            // (steps >= 1 here, so the after-reset float32 round trip cannot apply; a reset below re-plans with it)
+            a = a_next;
+            typename Task::Pending pend;
+            Task::advance_planned(cst, s, tilt, pend, term, trunc);
+            a_next = as.next(seed, env_id, step0, (uint32_t)t + 1u, Task::A);      // (one action past the end on the last step: unused)
+            tilt = Task::template plan<false>(cst, s, a_next);
+            r = Task::finish(pend);
+        } else {
+            a = as.next(seed, env_id, step0, (uint32_t)t, Task::A);
+            Task::step(cst, s, a, r, term, trunc);
+        }
         s.ep_ret = __fadd_rn(s.ep_ret, r);
         const bool d = term || trunc;
         __stcs(act_buf + off, a);
@@ -347,6 +370,7 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
             } else {
                 Task::reset(s, seed, env_id, step0 + (uint64_t)t + 1, TMLA_TAG_RESET);
             }
+            if constexpr (PIPE) tilt = Task::template plan<true>(cst, s, a_next);  // new episode: plan again from its rotation
         }
         if constexpr (STAGED) {
             if constexpr (BLOCK == 32) __syncwarp(); else __syncthreads();   // one warp per CTA: no CTA barrier needed
@@ -985,7 +1009,15 @@ int tmla_rollout_random(tmla_env *h, int T, float *obs_buf, int32_t *act_buf, fl
     const bool fast = obs_buf && act_buf && rew_buf && done_buf && (h->n % kRollBlock == 0) &&
                       ((reinterpret_cast<uintptr_t>(obs_buf) & 15u) == 0) && ((int64_t)T * h->n * D / 4 < ((int64_t)1 << 31));
     const unsigned grid = (unsigned)ceil_div64(h->n, kRollBlock);
-    if (fast) {
+    // TMLA_ROLLOUT_PIPE=1: the software-pipelined ball3d loop (plan of step t+1 beside the integration chain of step t).  Measured
+    // on B200 (profiles/r2_rollout_fast_ncu.txt): 63.52 vs 63.54 us per launch — fixed-latency wait stalls drop 38.6 -> 33.0 %
+    // of the samples and issue slots rise 58.7 -> 62.9 %, but the re-plan inside the reset branch costs 4.8 % more
+    // instructions; the plain loop stays the default.
+    static const bool pipe = [] { const char *e = getenv("TMLA_ROLLOUT_PIPE"); return e && !strcmp(e, "1"); }();
+    if (fast && pipe && h->task == TMLA_BALL3D) {
+        rollout_fast_kernel<Ball3DTask, true><<<grid, kRollBlock, 0, (cudaStream_t)stream>>>(
+            ptrs_of(h), (uint32_t)h->n, h->seed, h->env_id_base, h->step_count, T, reinterpret_cast<float4 *>(obs_buf), act_buf, rew_buf, done_buf);
+    } else if (fast) {
         TASK_SWITCH(h->task, (rollout_fast_kernel<TaskT><<<grid, kRollBlock, 0, (cudaStream_t)stream>>>(
                                  ptrs_of(h), (uint32_t)h->n, h->seed, h->env_id_base, h->step_count, T,
                                  reinterpret_cast<float4 *>(obs_buf), act_buf, rew_buf, done_buf)));

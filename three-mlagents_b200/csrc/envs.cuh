@@ -182,26 +182,37 @@ struct Ball3DTask {
         o[0] = s.orx; o[1] = s.orz;
         o[2] = s.px; o[3] = s.pz; o[4] = s.vx; o[5] = s.vz;
     }
-    // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding below is
-    // explicit (`__*_rn` never contracts into FMA) so the result does not depend on compiler flags.
     struct Pending { float sq; uint32_t flags; };
-    static __device__ __forceinline__ void advance(const Consts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+    // The tilt half of a step (ball3d.py:76-84): the new rotation of the ONE axis action `a` touches, with the products that
+    // depend on it.  It reads only rx/rz (and, right after a reset, `steps == 0`), never pos/vel — so the fused rollout kernel
+    // computes the tilt of step t+1 while the velocity/position/reward chain of step t is still in flight (two independent
+    // dependency chains per thread instead of one; `PIPELINED`).
+    struct Tilt { double rot, adt; float orot; bool x; };
+    static constexpr bool PIPELINED = true;
+    template <bool MAYBE_FIRST>
+    static __device__ __forceinline__ Tilt plan(const Consts &c, const State &s, int a) {
         // ACTION_DELTAS (ball3d.py:31-37): 0:+x 1:-x 2:+z 3:-z 4:none, each +-np.deg2rad(3.0).  The sign is
         // XOR-ed into the high word; adding the 0.0 entries is the identity (rot is never -0.0) and is skipped.
         const int td_hi = __double2hiint(c.tilt_delta), td_lo = __double2loint(c.tilt_delta);
         // a odd -> -delta; action 4 adds (0, 0): it runs through the z axis with a zero delta (rot + 0, the clip and the f32
         // round trip of an f32 value are identities, the cached products are recomputed to the same bits) — no divergent branch
         const double sd = __hiloint2double(a < 4 ? td_hi ^ (int)((unsigned)a << 31) : 0, a < 4 ? td_lo : 0);
-        const bool tilt_x = a < 2;
-        double rot = __dadd_rn(tilt_x ? s.rx : s.rz, sd);                            // ball3d.py:77
-        if (s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back (the untouched
-            asm volatile("");     // axis is already an f32 value); kept a branch: conversions for <1 % of the lanes
+        Tilt tl;
+        tl.x = a < 2;
+        double rot = __dadd_rn(tl.x ? s.rx : s.rz, sd);                              // ball3d.py:77
+        if (MAYBE_FIRST && s.steps == 0) {   // first step after reset(): rot is still the float32 array, `+=` casts back (the
+            asm volatile("");     // untouched axis is already an f32 value); kept a branch: conversions for <1 % of the lanes
             rot = (double)__double2float_rn(rot);
         }
         rot = clip_sym(rot, c.max_tilt);                                             // ball3d.py:78 (float64 from here)
-        const double adt = __dmul_rn(__dmul_rn(c.g, sin_small_c(c, rot)), c.dt);     // ball3d.py:81-84
-        const float orot = __double2float_rn(rot);
-        if (tilt_x) { s.rx = rot; s.axdt = adt; s.orx = orot; } else { s.rz = rot; s.azdt = adt; s.orz = orot; }
+        tl.rot = rot;
+        tl.adt = __dmul_rn(__dmul_rn(c.g, sin_small_c(c, rot)), c.dt);               // ball3d.py:81-84
+        tl.orot = __double2float_rn(rot);
+        return tl;
+    }
+    // the rest of the step: apply the planned tilt, integrate velocity and position, flags
+    static __device__ __forceinline__ void advance_planned(const Consts &, State &s, const Tilt &tl, Pending &pend, bool &term, bool &trunc) {
+        if (tl.x) { s.rx = tl.rot; s.axdt = tl.adt; s.orx = tl.orot; } else { s.rz = tl.rot; s.azdt = tl.adt; s.orz = tl.orot; }
         float vx = __double2float_rn(__dadd_rn((double)s.vx, s.axdt));              // ball3d.py:83-84
         float vz = __double2float_rn(__dadd_rn((double)s.vz, s.azdt));
         vx = __fmul_rn(vx, 0.98f);                                                  // ball3d.py:87
@@ -217,6 +228,12 @@ struct Ball3DTask {
         pend.flags = (done ? 1u : 0u) | ((timeout && !off) ? 2u : 0u);
         trunc = s.steps >= MAX_STEPS;                                               // envs.py:141-145
         term = done && !trunc;
+    }
+    // NumPy-2 promotion makes this a mixed f64/f32 computation; every rounding is explicit (`__*_rn` never
+    // contracts into FMA) so the result does not depend on compiler flags.
+    static __device__ __forceinline__ void advance(const Consts &c, State &s, int a, Pending &pend, bool &term, bool &trunc) {
+        const Tilt tl = plan<true>(c, s, a);
+        advance_planned(c, s, tl, pend, term, trunc);
     }
     // second half of step(): the reward (ball3d.py:103-111).  It depends only on `Pending`, so the fused rollout
     // kernel evaluates it one iteration late, interleaved with the next step's physics (more ILP per warp).
