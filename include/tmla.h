@@ -291,6 +291,28 @@ int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_
                          float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                          float *norm_out, int zero_grads, void *wpack, int obs_dim, int hidden, int n_actions, void *stream);
 
+/* ---- the one collective of the path, fused with the optimizer step (csrc/comm.cu) -------------------------------------
+ * Data-parallel PPO (one process per GPU) sums the flat gradient over the ranks once per minibatch.  The reference
+ * is single-process (no collective anywhere in backend/); this replaces the `torch.distributed.all_reduce(grads)` +
+ * tmla_adam_clip_fused pair with a one-shot all-reduce over NVLink peer memory inside the clip + Adam launches: every rank
+ * publishes its gradient in an IPC-exported slot, waits on flags the peers store into ITS memory, reads all slots directly and
+ * sums them in rank order (replicas stay bit-identical), producing clip_grad_norm_'s partial sums in the same pass.
+ *   tmla_comm_create : allocates this rank's exchange memory on `device` (num_floats >= num_params); handle_out receives the
+ *                      64-byte CUDA IPC handle the caller gathers from all ranks (any transport: torch.distributed, MPI, files)
+ *   tmla_comm_connect: all_handles = world x 64 bytes, rank-major; maps every peer's exchange memory
+ *   tmla_adam_clip_allreduce: arguments as tmla_adam_clip_fused; `step` doubles as the exchange sequence number, so all ranks
+ *                      must call it the same number of times with the same step.  Waits are bounded (TMLA_COMM_TIMEOUT_MS, default
+ *                      5000): a rank that never shows up sets an error word instead of hanging the GPU — tmla_comm_check
+ *                      (synchronises `stream`) turns it into TMLA_ECUDA. */
+typedef struct tmla_comm tmla_comm;
+int tmla_comm_create(int rank, int world, int device, int64_t num_floats, tmla_comm **out, void *handle_out);
+int tmla_comm_connect(tmla_comm *c, const void *all_handles);
+int tmla_comm_destroy(tmla_comm *c);
+int tmla_comm_check(tmla_comm *c, void *stream);
+int tmla_adam_clip_allreduce(tmla_comm *c, float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
+                             float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out,
+                             int zero_grads, void *wpack, int obs_dim, int hidden, int n_actions, void *stream);
+
 /* ---- tensor-core building blocks (csrc/mlp_tc.cu: tcgen05.mma, TMEM accumulators), bf16 row-major device
  * buffers.  Used by the bf16 MLP path; exported so the parity tests can exercise them in isolation.
  *   tmla_tc_linear: out[M,256] = tanh(A . W^T + bias)            (epi 0; layer-2 forward of a tower)

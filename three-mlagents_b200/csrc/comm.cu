@@ -1,0 +1,267 @@
+// comm.cu — the one collective of the hot path, fused with the optimizer step: a one-shot gradient all-reduce over
+// NVLink peer memory inside the clip_grad_norm_ + Adam launch pair (sm_100a, one process per GPU on one NVSwitch box).
+//
+// Data-parallel PPO sums the flat fp32 gradient (547 KB for ball3d) over the ranks once per minibatch, 320 times per
+// iteration, with the next minibatch waiting for the updated weights: the transfer is latency-bound and fully exposed
+// (SB3 has no counterpart — the reference trains in one process; this replaces the `dist.all_reduce(grads)` +
+// `tmla_adam_clip_fused` pair of the NCCL path).  Here every rank owns an IPC-exported exchange buffer:
+//     reduce_norm_kernel   (1) copy the local gradient into the rank's own exchange slot (double-buffered by step parity),
+//                          (2) the last CTA to finish publishes the step number into every peer's flag word (st.release.sys),
+//                          (3) every CTA waits until all peers' flags for this step have arrived in LOCAL memory,
+//                          (4) reads its slice of every rank's slot straight over NVLink (ld.relaxed.sys, 128-bit), sums
+//                              them in RANK ORDER — identical on every rank, so replicas stay bit-identical — writes the
+//                              sum back into the local gradient and emits the squared-norm partials of clip_grad_norm_;
+//     adam_kernel          (ppo_kernels.cu, unchanged) clips, steps, clears the gradient, refreshes the bf16 operand images.
+// No NCCL launch, no extra pass over the gradient for the norm.  Slot reuse is safe with two slots: a rank publishes step
+// s+2 only after its wait of step s+1, i.e. after every peer has published s+1, which each peer does only after it has
+// finished reading the slots of step s (stream order).  Spins are bounded (TMLA_COMM_TIMEOUT_MS, default 5000): a missing
+// peer sets an error word instead of hanging the GPU; tmla_comm_check reports it.
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "common.cuh"
+#include "mlp_common.cuh"
+
+static constexpr int kMaxRanks = 16;
+static constexpr int kReduceBlocks = TMLA_NORM_BLOCKS;      // the Adam kernel sums exactly this many partials
+static constexpr int kReduceThreads = 256;
+
+struct tmla_comm {
+    int rank, world, device;
+    int64_t capacity;                // floats per slot
+    size_t bytes;                    // allocation: flags page + 2 slots
+    char *local;                     // this rank's allocation
+    char *peer[kMaxRanks];           // every rank's allocation as mapped here (peer[rank] == local)
+    uint32_t *ticket;                // device: CTA ticket counter
+    int *err;                        // device: set when a spin timed out
+    long long timeout_ns;
+    bool connected;
+};
+
+// layout of one rank's allocation: [0, 4096): flags uint32[2][kMaxRanks] ; then slot 0, slot 1 (each capacity floats, 16-byte aligned)
+static constexpr size_t kFlagBytes = 4096;
+__host__ __device__ inline size_t slot_offset(int64_t capacity, int parity) {
+    return kFlagBytes + (size_t)parity * (((size_t)capacity * 4 + 255) & ~(size_t)255);
+}
+
+struct CommPtrs { char *peer[kMaxRanks]; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum_comm(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(kReduceThreads)
+reduce_norm_kernel(CommPtrs cp, int rank, int world_rt, int64_t capacity, float *__restrict__ grads, int64_t np, float scale,
+                   uint32_t step, uint32_t *ticket, int *err, long long timeout_ns, float *__restrict__ partial) {
+    const int world = WORLD > 0 ? WORLD : world_rt;
+    const int parity = (int)(step & 1u);
+    char *mine = cp.peer[rank];
+    float *my_slot = reinterpret_cast<float *>(mine + slot_offset(capacity, parity));
+    __shared__ float sh[kReduceThreads / 32];
+    __shared__ int s_last;
+    const int64_t nvec = np >> 2;                          // float4 body + scalar tail; slices are contiguous per CTA
+    const int64_t per = (nvec + gridDim.x - 1) / gridDim.x, v0 = (int64_t)blockIdx.x * per, v1 = min(nvec, v0 + per);
+    // (1) publish: local gradient -> own slot
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) reinterpret_cast<float4 *>(my_slot)[i] = reinterpret_cast<const float4 *>(grads)[i];
+    if (blockIdx.x == gridDim.x - 1) for (int64_t i = (nvec << 2) + threadIdx.x; i < np; i += blockDim.x) my_slot[i] = grads[i];
+    __threadfence_system();
+    __syncthreads();
+    // (2) the last CTA to get here tells every peer (and itself) that this rank's slot holds step `step`
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0u;                           // re-armed for the next launch (stream order)
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<uint32_t *>(cp.peer[threadIdx.x]) + parity * kMaxRanks + rank, step);
+    }
+    // (3) wait for every rank's flag of this step in local memory (bounded spin)
+    if (threadIdx.x < world) {
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine) + parity * kMaxRanks + threadIdx.x;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        uint32_t spins = 0;
+        while (ld_acquire_sys(flag) != step) {
+            if ((++spins & 1023u) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if ((long long)(t1 - t0) > timeout_ns) { *err = 1 + threadIdx.x; break; }
+            }
+        }
+    }
+    __syncthreads();
+    // (4) sum the slices of all ranks in rank order (identical on every rank), write back, squared-norm partial
+    float ss = 0.0f;
+    const size_t off = slot_offset(capacity, parity);
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+        float4 acc = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(cp.peer[0] + off) + i);
+#pragma unroll
+        for (int q = 1; q < (WORLD > 0 ? WORLD : kMaxRanks); ++q) {
+            if (q >= world) break;
+            const float4 x = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(cp.peer[q] + off) + i);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        reinterpret_cast<float4 *>(grads)[i] = acc;
+        const float a = acc.x * scale, b = acc.y * scale, c = acc.z * scale, d = acc.w * scale;
+        ss += (a * a + b * b) + (c * c + d * d);
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int64_t i = (nvec << 2) + threadIdx.x; i < np; i += blockDim.x) {
+            float acc = 0.0f;
+            for (int q = 0; q < world; ++q) acc += *reinterpret_cast<const volatile float *>(cp.peer[q] + off + (size_t)i * 4);
+            grads[i] = acc;
+            const float a = acc * scale;
+            ss += a * a;
+        }
+    }
+    ss = warp_sum_comm(ss);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kReduceThreads / 32; ++w) t += sh[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+extern "C" {
+
+int tmla_comm_create(int rank, int world, int device, int64_t num_floats, tmla_comm **out, void *handle_out) {
+    TMLA_REQUIRE(out && handle_out, "out/handle_out is NULL");
+    TMLA_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank/world out of range (at most 16 ranks)");
+    TMLA_REQUIRE(num_floats > 0, "num_floats must be positive");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    TMLA_CUDA(cudaSetDevice(device));
+    tmla_comm *c = new (std::nothrow) tmla_comm();
+    if (!c) { tmla_set_error("out of host memory"); return TMLA_ENOMEM; }
+    memset(c, 0, sizeof(*c));
+    c->rank = rank; c->world = world; c->device = device; c->capacity = num_floats;
+    c->bytes = slot_offset(num_floats, 2);
+    const char *e = getenv("TMLA_COMM_TIMEOUT_MS");
+    c->timeout_ns = (long long)(e ? atoll(e) : 5000) * 1000000ll;
+    if (cudaMalloc((void **)&c->local, c->bytes) != cudaSuccess || cudaMalloc((void **)&c->ticket, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&c->err, sizeof(int)) != cudaSuccess) {
+        tmla_set_error("tmla_comm_create: cudaMalloc: %s", cudaGetErrorString(cudaGetLastError()));
+        tmla_comm_destroy(c);
+        if (prev >= 0) cudaSetDevice(prev);
+        return TMLA_ENOMEM;
+    }
+    TMLA_CUDA(cudaMemset(c->local, 0, c->bytes));
+    TMLA_CUDA(cudaMemset(c->ticket, 0, sizeof(uint32_t)));
+    TMLA_CUDA(cudaMemset(c->err, 0, sizeof(int)));
+    TMLA_CUDA(cudaDeviceSynchronize());
+    c->peer[rank] = c->local;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+    cudaIpcMemHandle_t hnd;
+    TMLA_CUDA(cudaIpcGetMemHandle(&hnd, c->local));
+    memcpy(handle_out, &hnd, sizeof(hnd));
+    *out = c;
+    if (prev >= 0) cudaSetDevice(prev);
+    return TMLA_OK;
+}
+
+// all_handles: world x 64 bytes, rank-major (what every rank's tmla_comm_create returned, gathered by the caller)
+int tmla_comm_connect(tmla_comm *c, const void *all_handles) {
+    TMLA_REQUIRE(c && all_handles, "comm/handles is NULL");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    TMLA_CUDA(cudaSetDevice(c->device));
+    for (int q = 0; q < c->world; ++q) {
+        if (q == c->rank) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const char *)all_handles + (size_t)q * 64, 64);
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            tmla_set_error("tmla_comm_connect: cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+            cudaGetLastError();
+            if (prev >= 0) cudaSetDevice(prev);
+            return TMLA_ECUDA;
+        }
+        c->peer[q] = (char *)p;
+    }
+    c->connected = true;
+    if (prev >= 0) cudaSetDevice(prev);
+    return TMLA_OK;
+}
+
+int tmla_comm_destroy(tmla_comm *c) {
+    if (!c) return TMLA_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < c->world; ++q)
+        if (q != c->rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
+    if (c->local) cudaFree(c->local);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->err) cudaFree(c->err);
+    delete c;
+    if (prev >= 0) cudaSetDevice(prev);
+    return TMLA_OK;
+}
+
+// reads the error word (synchronises `stream`): TMLA_ECUDA when a peer's flag did not arrive within the timeout
+int tmla_comm_check(tmla_comm *c, void *stream) {
+    TMLA_REQUIRE(c, "comm is NULL");
+    int err = 0;
+    TMLA_CUDA(cudaMemcpyAsync(&err, c->err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TMLA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err) {
+        tmla_set_error("gradient exchange: rank %d never published its gradient (waited %lld ms on rank %d)", err - 1,
+                       c->timeout_ns / 1000000ll, c->rank);
+        return TMLA_ECUDA;
+    }
+    return TMLA_OK;
+}
+
+// grads <- sum over ranks of grads (rank order), then clip_grad_norm_ + Adam exactly as tmla_adam_clip_fused.
+// `step` (the 1-based Adam step) doubles as the exchange sequence number: every rank must call with the same step.
+int tmla_adam_clip_allreduce(tmla_comm *c, float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
+                             float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out,
+                             int zero_grads, void *wpack, int obs_dim, int hidden, int n_actions, void *stream) {
+    TMLA_REQUIRE(c && c->connected, "comm is NULL or not connected (tmla_comm_connect)");
+    TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer");
+    TMLA_REQUIRE(num_params > 0 && num_params <= c->capacity && step >= 1, "bad arguments (num_params exceeds the comm's capacity?)");
+    TMLA_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15u) == 0, "grads must be 16-byte aligned");
+    CommPtrs cp;
+    for (int q = 0; q < kMaxRanks; ++q) cp.peer[q] = q < c->world ? c->peer[q] : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t seq = (uint32_t)(step & 0x7FFFFFFF) | 0x80000000u;     // never 0 (the cleared flag value)
+#define RN(W) reduce_norm_kernel<W><<<kReduceBlocks, kReduceThreads, 0, st>>>(cp, c->rank, c->world, c->capacity, grads, num_params, grad_scale, \
+                                                                               seq, c->ticket, c->err, c->timeout_ns, norm_out + 1)
+    switch (c->world) {
+        case 2: RN(2); break;
+        case 4: RN(4); break;
+        case 8: RN(8); break;
+        default: RN(0); break;
+    }
+#undef RN
+    TMLA_LAUNCH_CHECK();
+    return adam_clip_launch(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out, zero_grads,
+                            wpack, obs_dim, hidden, n_actions, stream, true);
+}
+
+}  // extern "C"

@@ -24,3 +24,10 @@ static inline MlpOffsets mlp_offsets(int D, int A) {
     return o;
 }
 
+
+// squared-norm partials of clip_grad_norm_: one per CTA of the norm pass, summed in a fixed order by every CTA of the Adam kernel
+#define TMLA_NORM_BLOCKS 128
+// ppo_kernels.cu: clip + Adam launch shared with the fused all-reduce (comm.cu)
+int adam_clip_launch(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                     float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
+                     void *wpack, int obs_dim, int hidden, int n_actions, void *stream, bool partials_ready);

@@ -257,7 +257,7 @@ ppo_loss_kernel(const float *__restrict__ logits, const float *__restrict__ valu
 // ----------------------------------------------------------------- clip_grad_norm_ + Adam (fused)
 // The squared norm is reduced in a FIXED order (per-block partials, then every block of the Adam kernel sums
 // the partials identically), so data-parallel replicas that all-reduced the same gradient stay bit-identical.
-static constexpr int kNormBlocks = 128;
+static constexpr int kNormBlocks = TMLA_NORM_BLOCKS;     // mlp_common.cuh: comm.cu writes the same number of partials
 __global__ void __launch_bounds__(256) gradnorm_kernel(const float *__restrict__ g, int64_t np, float scale, float *partial) {
     __shared__ float sh[8];
     float s = 0.0f;
@@ -392,9 +392,13 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
     return TMLA_OK;
 }
 
-int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
-                         float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
-                         void *wpack, int obs_dim, int hidden, int n_actions, void *stream) {
+}  // extern "C"
+
+// clip + Adam with the squared-norm partials either computed here (partials_ready = false) or already in norm_out[1..] (the
+// fused all-reduce of comm.cu); shared by tmla_adam_clip_fused and tmla_adam_clip_allreduce
+int adam_clip_launch(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                     float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
+                     void *wpack, int obs_dim, int hidden, int n_actions, void *stream, bool partials_ready) {
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer (norm_out doubles as scratch)");
     TMLA_REQUIRE(num_params > 0 && step >= 1, "bad arguments");
     __nv_bfloat16 *img0 = nullptr, *img1 = nullptr;
@@ -408,14 +412,25 @@ int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_
     }
     cudaStream_t st = (cudaStream_t)stream;
     // norm_out[0] = norm, norm_out[1 .. 1+kNormBlocks) = per-block partial sums of squares
-    gradnorm_kernel<<<kNormBlocks, 256, 0, st>>>(grads, num_params, grad_scale, norm_out + 1);
-    TMLA_LAUNCH_CHECK();
+    if (!partials_ready) {                                 // (comm.cu's reduce_norm_kernel has written them already)
+        gradnorm_kernel<<<kNormBlocks, 256, 0, st>>>(grads, num_params, grad_scale, norm_out + 1);
+        TMLA_LAUNCH_CHECK();
+    }
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<(unsigned)ceil_div64(num_params, 256), 256, 0, st>>>(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr,
                                                                       beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), norm_out + 1, norm_out, zero_grads,
                                                                       img0, img1, off0, off1);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
+}
+
+extern "C" {
+
+int tmla_adam_clip_fused(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                         float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
+                         void *wpack, int obs_dim, int hidden, int n_actions, void *stream) {
+    return adam_clip_launch(params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out, zero_grads,
+                            wpack, obs_dim, hidden, n_actions, stream, false);
 }
 int tmla_adam_clip_zero(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
                         float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *stream) {

@@ -86,3 +86,65 @@ def adv_mean_std(sums):
     mean = s / n
     var = max((ss - s * mean) / (n - 1.0), 0.0)
     return mean, var ** 0.5
+
+
+class PeerComm:
+    """Gradient exchange over NVLink peer memory (include/tmla.h `tmla_comm_*`, csrc/comm.cu): every rank's exchange slot is
+    IPC-mapped into every other rank, and the all-reduce runs inside the clip + Adam launches (`tmla_adam_clip_allreduce`).
+    `create` is collective: it returns None on EVERY rank when any rank could not set the mapping up (ranks on different
+    hosts, no peer access, a single process) — callers then stay on NCCL."""
+
+    def __init__(self, handle, rank: int, world: int):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    @classmethod
+    def create(cls, device_index: int, num_floats: int):
+        import ctypes as C
+
+        import torch
+
+        from . import native
+
+        dist, rank, world = dist_state()
+        if world == 1 or os.environ.get("TMLA_ALLREDUCE", "peer").lower() == "nccl":
+            return None
+        h = native.vp()
+        mine = (C.c_uint8 * 64)()
+        ok, err = 1, ""
+        try:
+            native.check(native.lib.tmla_comm_create(rank, world, int(device_index), int(num_floats), C.byref(h), mine))
+        except Exception as e:  # noqa: BLE001
+            ok, err = 0, str(e)
+        dev = torch.device("cuda", int(device_index))
+        handles = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(handles, torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).to(dev))
+        if ok:
+            blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in handles)
+            try:
+                native.check(native.lib.tmla_comm_connect(h, blob))
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if h:
+                native.lib.tmla_comm_destroy(h)
+            if err and rank == 0:
+                import warnings
+
+                warnings.warn(f"peer-memory gradient exchange unavailable ({err}); using NCCL all-reduce", stacklevel=2)
+            return None
+        dist.barrier()
+        return cls(h, rank, world)
+
+    def check(self) -> None:
+        from . import native
+
+        native.check(native.lib.tmla_comm_check(self.handle, native.current_stream()))
+
+    def close(self) -> None:
+        from . import native
+
+        if self.handle:
+            native.lib.tmla_comm_destroy(self.handle)
+            self.handle = None

@@ -98,6 +98,11 @@ SIGNATURES = {
     "tmla_adam_clip": (_i, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i64, vp, vp]),
     "tmla_adam_clip_zero": (_i, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i64, vp, _i, vp]),
     "tmla_adam_clip_fused": (_i, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i64, vp, _i, vp, _i, _i, _i, vp]),
+    "tmla_comm_create": (_i, [_i, _i, _i, i64, C.POINTER(vp), vp]),
+    "tmla_comm_connect": (_i, [vp, vp]),
+    "tmla_comm_destroy": (_i, [vp]),
+    "tmla_comm_check": (_i, [vp, vp]),
+    "tmla_adam_clip_allreduce": (_i, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i64, vp, _i, vp, _i, _i, _i, vp]),
     "tmla_ppo_minibatch_supported": (_i, [_i, _i, _i]),
     "tmla_ppo_minibatch_scratch": (i64, [_i, i64]),
     "tmla_ppo_minibatch_bf16": (_i, [vp, vp, _i, _i, _i, vp, vp, i64, i64, vp, vp, vp, vp, vp, _i, f32, f32, f32, vp, vp, vp,

@@ -204,6 +204,18 @@ def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, l
     return norm_out
 
 
+def adam_clip_allreduce(comm, params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, lr=3e-4, beta1=0.9, beta2=0.999,
+                        eps=1e-5, norm_out=None, zero_grads=False, wpack=None, obs_dim=0, n_actions=0):
+    """grads <- sum over ranks (one-shot all-reduce over NVLink peer memory, rank order), then adam_clip — two launches, no NCCL."""
+    if norm_out is None:
+        norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
+    _chk(wpack, torch.bfloat16, "wpack"); _chk(grads, torch.float32, "grads")
+    check(lib.tmla_adam_clip_allreduce(comm.handle, ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
+                                       float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                       ptr(norm_out), 1 if zero_grads else 0, ptr(wpack), int(obs_dim), HIDDEN, int(n_actions), _s()))
+    return norm_out
+
+
 def bootstrap_add(rew_buf, trunc_count, trunc_index, trunc_values, gamma: float):
     check(lib.tmla_bootstrap_add(ptr(rew_buf), ptr(trunc_count), ptr(trunc_index), ptr(trunc_values), float(gamma),
                                  int(trunc_index.numel()), _s()))

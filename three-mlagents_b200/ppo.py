@@ -25,7 +25,7 @@ from torch.cuda import nvtx      # NVTX ranges rollout / gae / update / allreduc
 
 from . import native, ops
 from .native import ptr
-from .distributed import allreduce_sum_, dist_state
+from .distributed import PeerComm, allreduce_sum_, dist_state
 from .vec_env import CudaVecEnv
 
 HIDDEN = 256
@@ -108,7 +108,9 @@ class CudaPPO:
         self._buffers_ready = False
         self._last_obs_valid = False
         self._rollout_args = None
-        self.allreduce_impl = "nccl" if self.world > 1 else "none"
+        # the gradient all-reduce: fused into clip + Adam over NVLink peer memory when every rank can map its peers, else NCCL
+        self._comm = PeerComm.create(env.device_index, self.params.numel()) if self.world > 1 else None
+        self.allreduce_impl = "none" if self.world == 1 else ("peer-memory one-shot, fused with clip+Adam (csrc/comm.cu)" if self._comm else "nccl")
         if rollout_impl not in ("fused", "steps"):
             raise ValueError("rollout_impl must be 'fused' (tmla_rollout: one call per rollout) or 'steps' (one call per step)")
         self.rollout_impl = rollout_impl
@@ -259,14 +261,21 @@ class CudaPPO:
                                  dlogits=self.dlogits, dvalues=self.dvalues, stats=self.stats)
                     ops.mlp_backward(self.params, obs_flat, D, A, self.cache_mb, self.dlogits, self.dvalues, index=idx,
                                      rows=rows, grads=self.grads, scratch=self.scratch_mb, wpack=self.wpack)
-                if self.world > 1:
-                    nvtx.range_push("allreduce")
-                    self._allreduce_grads(self.grads)     # the one collective on the path: sum over NVLink
-                    nvtx.range_pop()
                 self._adam_step += 1
-                ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
-                              lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused,
-                              wpack=self.wpack if fused else None, obs_dim=D, n_actions=A)
+                if self._comm is not None:                # the one collective on the path, inside the optimizer launches
+                    nvtx.range_push("allreduce+adam")
+                    ops.adam_clip_allreduce(self._comm, self.params, self.grads, self.m, self.v, self._adam_step,
+                                            max_grad_norm=self.max_grad_norm, lr=self.lr, eps=1e-5, norm_out=self.norm_out,
+                                            zero_grads=fused, wpack=self.wpack if fused else None, obs_dim=D, n_actions=A)
+                    nvtx.range_pop()
+                else:
+                    if self.world > 1:
+                        nvtx.range_push("allreduce")
+                        self._allreduce_grads(self.grads) # NCCL sum over NVLink
+                        nvtx.range_pop()
+                    ops.adam_clip(self.params, self.grads, self.m, self.v, self._adam_step, max_grad_norm=self.max_grad_norm,
+                                  lr=self.lr, eps=1e-5, norm_out=self.norm_out, zero_grads=fused,
+                                  wpack=self.wpack if fused else None, obs_dim=D, n_actions=A)
                 if not fused:          # (fused: Adam refreshed the operand images itself; full repack once after the loop)
                     self._repack()
                     self.stats_acc += self.stats
@@ -274,11 +283,25 @@ class CudaPPO:
             self.n_updates += 1
         if fused:
             self._repack()
+        if self._comm is not None:
+            self._comm.check()                            # a rank that never showed up (bounded waits) surfaces here
         nvtx.range_pop()
         return n_mb
 
     def _allreduce_grads(self, grads: torch.Tensor) -> None:
         allreduce_sum_(grads)
+
+    def close(self) -> None:
+        """Release the peer-memory gradient exchange (collective-free; safe to call more than once)."""
+        if getattr(self, "_comm", None) is not None:
+            self._comm.close()
+            self._comm = None
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def _log_row(self, n_mb: int, t_roll: float, t_train: float, t0: float) -> dict[str, Any]:
         s = (self.stats_acc / max(n_mb, 1)).cpu().numpy()
@@ -479,17 +502,40 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 5, warmup: in
     allreduce_us = 0.0
     if dist is not None:
         g = torch.zeros_like(model.grads)
-        for _ in range(5):
-            model._allreduce_grads(g)
+        if model._comm is None:
+            def exchange(k):
+                model._allreduce_grads(g)
+            base_us = 0.0
+        else:                                             # fused path: cost of the exchange = fused launch pair minus the local one
+            p2, m2, v2 = model.params.clone(), model.m.clone(), model.v.clone()
+            seq = [model._adam_step]
+
+            def exchange(k):
+                seq[0] += 1
+                ops.adam_clip_allreduce(model._comm, p2, g, m2, v2, seq[0], norm_out=model.norm_out)
+            for k in range(5):
+                ops.adam_clip(p2, g, m2, v2, 1 + k, norm_out=model.norm_out)
+            sync()
+            e[0].record()
+            for k in range(50):
+                ops.adam_clip(p2, g, m2, v2, 6 + k, norm_out=model.norm_out)
+            e[1].record()
+            sync()
+            base_us = e[0].elapsed_time(e[1]) * 1e3 / 50
+        for k in range(5):
+            exchange(k)
         sync()
         e[0].record()
-        for _ in range(50):
-            model._allreduce_grads(g)
+        for k in range(50):
+            exchange(k)
         e[1].record()
         sync()
-        t = torch.tensor([e[0].elapsed_time(e[1]) * 1e3 / 50], dtype=torch.float64, device=dev)
+        t = torch.tensor([e[0].elapsed_time(e[1]) * 1e3 / 50 - base_us], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allreduce_us = float(t.item())
+        if model._comm is not None:
+            model._adam_step = seq[0]
+            model._comm.check()
     samples = world * n_envs * n_steps * iters
     flop_sample = 807936.0 if env.obs_dim == 6 else 803840.0      # fwd+bwd per sample (ball3d | gridworld, push)
     flop_update = flop_sample * n_envs * n_steps * 10 * iters
@@ -512,6 +558,9 @@ def bench_ppo(local_rank: int, rank: int, world: int, iters: int = 5, warmup: in
                               if model.fused_update else "unfused (forward, loss, backward kernels)")},
         "ep_rew_mean": row["rollout/ep_rew_mean"], "approx_kl": row["train/approx_kl"],
     }
+    if dist is not None:
+        dist.barrier()                                    # nobody unmaps its exchange memory while a peer may still read it
+    model.close()
     env.close()
     del model
     torch.cuda.empty_cache()
