@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtmla.so")
+# TMLA_LIB selects another build of the same library (A/B runs of kernel variants: profiles/train_variants.py)
+LIB_PATH = os.environ.get("TMLA_LIB") or os.path.join(_HERE, "lib", "libtmla.so")
 
 TMLA_OK, TMLA_EINVAL, TMLA_ECUDA, TMLA_ENOMEM, TMLA_EACTION = 0, -1, -2, -3, -4
 TASK_IDS = {"basic": 0, "ball3d": 1, "gridworld": 2, "push": 3, "walljump": 4, "brickbreak": 5, "bicycle": 6, "glider": 7}
