@@ -361,6 +361,10 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
  *                     mode 0 out[128,256] = A.B^T | mode 1 out[128,256] = A.B | mode 2 out[256,256] = A^T.B[0:128] */
 int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_padded, void *stream);
 int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream);
+/* measurement hook: do tcgen05.ld reads of TMEM columns [256,512) overlap tcgen05.mma (M128 N=n K16) already queued on columns
+ * [0,n)?  out8 = DEVICE uint64[8] cycle counts {MMAs alone, loads alone, MMAs with loads running, loads under queued MMAs,
+ * cycles the issuing lane spent inside the tcgen05.mma instructions, -, -, -}  (profiles/tc_overlap.py) */
+int tmla_tc_overlap_probe(uint64_t *out8, int n, int n_mma, int n_ld, void *stream);
 
 #ifdef __cplusplus
 }

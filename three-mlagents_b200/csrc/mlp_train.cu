@@ -861,6 +861,96 @@ tc_probe_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__rest
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------ tensor pipe / TMEM overlap probe (measurement hook)
+// One CTA.  Warp 4 issues `n_mma` x (M128 N=`n` K16) MMAs into TMEM columns [0, n); warps 0..3 read `n_ld` x 16 columns of
+// columns [256, 512) with tcgen05.ld.  clock64 around each role, alone and together:
+//   out[0] MMAs alone (issue -> commit observed)   out[1] loads alone   out[2] MMAs with the loads running   out[3] loads while the
+//   MMAs are in flight (started after the MMAs were issued)   out[4] cycles the issuing lane spent inside the tcgen05.mma instructions
+// Answers whether a TMEM-reading CUDA-core phase can overlap MMAs that are already queued.
+__global__ void __launch_bounds__(160, 1)
+tc_overlap_probe_kernel(unsigned long long *out, int n, int n_mma, int n_ld) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *Ws = smem, *As = smem + kWBytes;                       // operands: whatever the shared memory holds (timing only)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kWBytes + 128 * 512);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bar + 4);
+    volatile int *go = reinterpret_cast<volatile int *>(bar + 6);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (int)(kWBytes + 128 * 512) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (warp == 0) tmem_alloc<512>(tmem_holder);
+    if (tid == 32) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); *go = 0; }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t a_addr = smem_u32(As), w_addr = smem_u32(Ws);
+    const uint32_t idesc = make_idesc_major(128, n, 0, 0);
+    auto issue = [&](uint64_t *b) {
+        long long inside = 0;
+        for (int i = 0; i < n_mma; ++i) {
+            const int kk = i & 15;
+            const long long c0 = clock64();
+            umma_bf16(tmem_base, make_desc_raw(a_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO), idesc, i > 0 ? 1u : 0u);
+            inside += clock64() - c0;
+        }
+        umma_commit(b);
+        return inside;
+    };
+    auto loads = [&]() {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 256u;
+        uint32_t acc[16], sink = 0;
+        for (int i = 0; i < n_ld; ++i) {
+            tmem_ld16(taddr + (i & 15) * 16, acc);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sink ^= acc[j];
+        }
+        return sink;
+    };
+    // (a) MMAs alone
+    if (warp == 4 && elect_one()) {
+        const long long t0 = clock64();
+        const long long inside = issue(bar);
+        mbar_wait(bar, 0);
+        out[0] = (unsigned long long)(clock64() - t0);
+        out[4] = (unsigned long long)inside;
+    }
+    __syncthreads();
+    // (b) loads alone
+    if (warp < 4) {
+        const long long t0 = clock64();
+        const uint32_t sink = loads();
+        const long long t1 = clock64();
+        if (tid == 0) out[1] = (unsigned long long)(t1 - t0);
+        if (sink == 0x12345678u) out[7] = sink;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // (c) together: the loads start once the issuing lane has issued its first MMA
+    if (warp == 4) {
+        if (elect_one()) {
+            const long long t0 = clock64();
+            umma_bf16(tmem_base, make_desc_raw(a_addr, kLBO, kSBO), make_desc_raw(w_addr, kLBO, kSBO), idesc, 0u);
+            *go = 1;
+            issue(bar + 1);
+            mbar_wait(bar + 1, 0);
+            out[2] = (unsigned long long)(clock64() - t0);
+        }
+        __syncwarp();
+    } else {
+        while (*go == 0) { }
+        const long long t0 = clock64();
+        const uint32_t sink = loads();
+        const long long t1 = clock64();
+        if (tid == 0) out[3] = (unsigned long long)(t1 - t0);
+        if (sink == 0x12345678u) out[7] = sink;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------ host side
 static int sm_count_train() {
     static int n = 0;
@@ -965,6 +1055,20 @@ int tmla_debug_phase_cycles(unsigned long long *out32, int reset) {      // debu
     return TMLA_OK;
 }
 #endif
+
+int tmla_tc_overlap_probe(uint64_t *out8, int n, int n_mma, int n_ld, void *stream) {
+    TMLA_REQUIRE(out8 && n >= 16 && n <= 256 && n % 16 == 0 && n_mma > 0 && n_ld > 0, "bad arguments");
+    static int attr_done = 0;
+    const int smem = (int)(kWBytes + 128 * 512 + 128);
+    if (!attr_done) {
+        TMLA_CUDA(cudaFuncSetAttribute(tc_overlap_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = 1;
+    }
+    TMLA_CUDA(cudaMemsetAsync(out8, 0, 8 * sizeof(uint64_t), (cudaStream_t)stream));
+    tc_overlap_probe_kernel<<<1, 160, smem, (cudaStream_t)stream>>>((unsigned long long *)out8, n, n_mma, n_ld);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
 
 int tmla_tc_probe(const void *A, const void *B, float *out, int mode, void *stream) {
     TMLA_REQUIRE(A && B && out && mode >= 0 && mode <= 2, "bad arguments");

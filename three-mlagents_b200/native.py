@@ -110,6 +110,7 @@ SIGNATURES = {
                                      vp, vp, _i, vp]),
     "tmla_tc_wgrad_tiled": (_i, [vp, vp, vp, i64, vp]),
     "tmla_tc_probe": (_i, [vp, vp, vp, _i, vp]),
+    "tmla_tc_overlap_probe": (_i, [vp, _i, _i, _i, vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
