@@ -114,13 +114,17 @@ reduce_norm_kernel(CommPtrs cp, int rank, int world_rt, int64_t capacity, float 
     float ss = 0.0f;
     const size_t off = slot_offset(capacity, parity);
     for (int64_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
-        float4 acc = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(cp.peer[0] + off) + i);
+        // all peers' loads are issued before the first sum: ONE NVLink round trip per element instead of `world` dependent ones
+        // (measured at 8 ranks: 30 us per exchange with load-add-load-add, the same as NCCL)
+        constexpr int NQ = WORLD > 0 ? WORLD : kMaxRanks;
+        float4 x[NQ];
 #pragma unroll
-        for (int q = 1; q < (WORLD > 0 ? WORLD : kMaxRanks); ++q) {
-            if (q >= world) break;
-            const float4 x = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(cp.peer[q] + off) + i);
-            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-        }
+        for (int q = 0; q < NQ; ++q)
+            if (q < world) x[q] = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(cp.peer[q] + off) + i);
+        float4 acc = x[0];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q)
+            if (q < world) { acc.x += x[q].x; acc.y += x[q].y; acc.z += x[q].z; acc.w += x[q].w; }
         reinterpret_cast<float4 *>(grads)[i] = acc;
         const float a = acc.x * scale, b = acc.y * scale, c = acc.z * scale, d = acc.w * scale;
         ss += (a * a + b * b) + (c * c + d * d);
