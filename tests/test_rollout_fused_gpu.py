@@ -49,7 +49,7 @@ def test_fused_rollout_is_bit_identical_to_per_step_calls(task, n, T, impl):
             assert torch.allclose(fused.params, steps.params, rtol=0, atol=2e-5)
             steps.params.copy_(fused.params)                   # keep the two policies in lockstep for the next rollout
             steps._repack()
-    if task != "ball3d":
+    if task not in ("ball3d", "bicycle"):                      # (time limits 200 / 2000 steps: no timeout inside these rollouts)
         assert int(fused.trunc_count.item()) > 0               # the timeout-bootstrap branch ran
     for m in (fused, steps):
         m.env.close()
