@@ -16,11 +16,15 @@
 // s+2 only after its wait of step s+1, i.e. after every peer has published s+1, which each peer does only after it has
 // finished reading the slots of step s (stream order).  Spins are bounded (TMLA_COMM_TIMEOUT_MS, default 5000): a missing
 // peer sets an error word instead of hanging the GPU; tmla_comm_check reports it.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
+namespace cg = cooperative_groups;
 
 static constexpr int kMaxRanks = 16;
 static constexpr int kReduceBlocks = TMLA_NORM_BLOCKS;      // the Adam kernel sums exactly this many partials
@@ -149,6 +153,211 @@ reduce_norm_kernel(CommPtrs cp, int rank, int world_rt, int64_t capacity, float 
     }
 }
 
+// ------------------------------------------------------------------ the whole optimizer step in ONE cooperative launch
+// gradient exchange (WORLD > 1, as reduce_norm_kernel) -> squared-norm partials -> grid barrier -> clip + Adam + zero_grad +
+// refresh of the bf16 operand images, with the (summed) gradient held in registers across the barrier: one launch per minibatch
+// instead of gradnorm + adam (single GPU) or reduce_norm + adam (data parallel), and one pass over the gradient instead of two.
+// Arithmetic per element is adam_kernel's (ppo_kernels.cu); the norm is the fixed-order sum of TMLA_NORM_BLOCKS partials.
+struct OptStepArgs {
+    CommPtrs cp; int rank, world; int64_t capacity; uint32_t seq; uint32_t *ticket; int *err; long long timeout_ns;   // exchange (WORLD > 1)
+    float *p, *g, *m, *v; int64_t np;
+    float scale, max_norm, lr, b1, b2, eps, bc1, bc2_sqrt;
+    float *norm_out;                 // [0] = norm, [1 .. 1+TMLA_NORM_BLOCKS) = partials
+    int zero_grads;
+    __nv_bfloat16 *img0, *img1; int64_t w2_off0, w2_off1;
+};
+static constexpr int kOptVecPerThread = 2;       // float4 per thread: 128 CTAs x 256 threads x 2 x 4 = 262 144 parameters
+
+template <int WORLD>
+__global__ void __launch_bounds__(kReduceThreads)
+opt_step_kernel(const __grid_constant__ OptStepArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[kReduceThreads / 32];
+    __shared__ int s_last;
+    __shared__ float s_norm;
+    const int64_t nvec = a.np >> 2;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tail0 = nvec << 2;                       // scalar tail [tail0, np): threads 0.. of the last CTA
+    const bool tail_owner = blockIdx.x == gridDim.x - 1 && tail0 + threadIdx.x < a.np;
+    float4 g[kOptVecPerThread];
+    float gt = 0.0f;
+    if constexpr (WORLD > 1) {
+        const int parity = (int)(a.seq & 1u);
+        char *mine = a.cp.peer[a.rank];
+        const size_t off = slot_offset(a.capacity, parity);
+        float *my_slot = reinterpret_cast<float *>(mine + off);
+#pragma unroll
+        for (int j = 0; j < kOptVecPerThread; ++j) {
+            const int64_t i = gtid + j * gsize;
+            if (i < nvec) reinterpret_cast<float4 *>(my_slot)[i] = reinterpret_cast<const float4 *>(a.g)[i];
+        }
+        if (tail_owner) my_slot[tail0 + threadIdx.x] = a.g[tail0 + threadIdx.x];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t t = atomicAdd(a.ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+            if (s_last) *a.ticket = 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence_system();
+            if (threadIdx.x < WORLD) st_release_sys(reinterpret_cast<uint32_t *>(a.cp.peer[threadIdx.x]) + parity * kMaxRanks + a.rank, a.seq);
+        }
+        if (threadIdx.x < WORLD) {
+            const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine) + parity * kMaxRanks + threadIdx.x;
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            uint32_t spins = 0;
+            while (ld_acquire_sys(flag) != a.seq) {
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if ((long long)(t1 - t0) > a.timeout_ns) { *a.err = 1 + threadIdx.x; break; }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kOptVecPerThread; ++j) {
+            const int64_t i = gtid + j * gsize;
+            g[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (i < nvec) {
+                float4 x[WORLD];
+#pragma unroll
+                for (int q = 0; q < WORLD; ++q) x[q] = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(a.cp.peer[q] + off) + i);
+                float4 acc = x[0];
+#pragma unroll
+                for (int q = 1; q < WORLD; ++q) { acc.x += x[q].x; acc.y += x[q].y; acc.z += x[q].z; acc.w += x[q].w; }
+                g[j] = acc;
+            }
+        }
+        if (tail_owner)
+            for (int q = 0; q < WORLD; ++q) gt += *reinterpret_cast<const volatile float *>(a.cp.peer[q] + off + (size_t)(tail0 + threadIdx.x) * 4);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kOptVecPerThread; ++j) {
+            const int64_t i = gtid + j * gsize;
+            g[j] = i < nvec ? reinterpret_cast<const float4 *>(a.g)[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        if (tail_owner) gt = a.g[tail0 + threadIdx.x];
+    }
+    // optimizer state of this thread's elements: in flight across the norm reduction and the grid barrier
+    float4 p4[kOptVecPerThread], m4[kOptVecPerThread], v4[kOptVecPerThread];
+#pragma unroll
+    for (int j = 0; j < kOptVecPerThread; ++j) {
+        const int64_t i = gtid + j * gsize;
+        if (i < nvec) { p4[j] = reinterpret_cast<const float4 *>(a.p)[i]; m4[j] = reinterpret_cast<const float4 *>(a.m)[i]; v4[j] = reinterpret_cast<const float4 *>(a.v)[i]; }
+    }
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kOptVecPerThread; ++j) {
+        const float x0 = g[j].x * a.scale, x1 = g[j].y * a.scale, x2 = g[j].z * a.scale, x3 = g[j].w * a.scale;
+        ss += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+    }
+    { const float xt = gt * a.scale; ss += xt * xt; }
+    ss = warp_sum_comm(ss);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kReduceThreads / 32; ++w) t += sh[w];
+        a.norm_out[1 + blockIdx.x] = t;
+    }
+    grid.sync();
+    if (threadIdx.x < 32) {                                // same summation order in every CTA and on every rank
+        float t = 0.0f;
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) t += __ldcg(a.norm_out + 1 + j);
+        t = warp_sum_comm(t);
+        if (threadIdx.x == 0) s_norm = sqrtf(t);
+    }
+    __syncthreads();
+    const float norm = s_norm;
+    const float coef = a.max_norm > 0.0f ? fminf(a.max_norm / (norm + 1e-6f), 1.0f) : 1.0f;   // torch clip_grad_norm_
+    if (gtid == 0) a.norm_out[0] = norm;
+    auto step1 = [&](float gi_raw, float &pp, float &mm, float &vv, int64_t idx) {
+        const float gi = gi_raw * a.scale * coef;
+        const float mi = a.b1 * mm + (1.0f - a.b1) * gi;
+        const float vi = a.b2 * vv + (1.0f - a.b2) * gi * gi;
+        mm = mi; vv = vi;
+        const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+        const float pn = pp - (a.lr / a.bc1) * (mi / denom);
+        pp = pn;
+        if (a.img0) {                                       // hidden-layer weight: refresh its bf16 operand-image entry
+            const int64_t e0 = idx - a.w2_off0, e1 = idx - a.w2_off1;
+            const bool in0 = e0 >= 0 && e0 < 65536, in1 = e1 >= 0 && e1 < 65536;
+            if (in0 || in1) {
+                const int e = (int)(in0 ? e0 : e1), r = e >> 8, k = e & 255;
+                (in0 ? a.img0 : a.img1)[(r >> 3) * 2048 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7)] = __float2bfloat16_rn(pn);
+            }
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kOptVecPerThread; ++j) {
+        const int64_t i = gtid + j * gsize;
+        if (i < nvec) {
+            step1(g[j].x, p4[j].x, m4[j].x, v4[j].x, 4 * i + 0); step1(g[j].y, p4[j].y, m4[j].y, v4[j].y, 4 * i + 1);
+            step1(g[j].z, p4[j].z, m4[j].z, v4[j].z, 4 * i + 2); step1(g[j].w, p4[j].w, m4[j].w, v4[j].w, 4 * i + 3);
+            reinterpret_cast<float4 *>(a.p)[i] = p4[j]; reinterpret_cast<float4 *>(a.m)[i] = m4[j]; reinterpret_cast<float4 *>(a.v)[i] = v4[j];
+            reinterpret_cast<float4 *>(a.g)[i] = a.zero_grads ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : g[j];
+        }
+    }
+    if (tail_owner) {
+        const int64_t i = tail0 + threadIdx.x;
+        float pp = a.p[i], mm = a.m[i], vv = a.v[i];
+        step1(gt, pp, mm, vv, i);
+        a.p[i] = pp; a.m[i] = mm; a.v[i] = vv;
+        a.g[i] = a.zero_grads ? 0.0f : gt;
+    }
+}
+
+// one cooperative launch; returns TMLA_EINVAL (without an error message) when the shape does not fit so that callers fall back
+template <int WORLD>
+static int opt_step_launch_t(OptStepArgs &a, cudaStream_t st) {
+    void *args[] = {(void *)&a};
+    TMLA_CUDA(cudaLaunchCooperativeKernel((const void *)opt_step_kernel<WORLD>, dim3(kReduceBlocks), dim3(kReduceThreads), args, 0, st));
+    return TMLA_OK;
+}
+static bool opt_step_enabled() {      // TMLA_ADAM=split keeps the two-launch path (A/B runs)
+    static const bool on = [] { const char *e = getenv("TMLA_ADAM"); return !(e && !strcmp(e, "split")); }();
+    return on;
+}
+int opt_step_launch(tmla_comm *c, float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                    float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *wpack, int obs_dim,
+                    int hidden, int n_actions, void *stream) {
+    if (!opt_step_enabled() || (num_params >> 2) > (int64_t)kReduceBlocks * kReduceThreads * kOptVecPerThread || (num_params & 3) >= kReduceThreads ||
+        (reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u)
+        return TMLA_EINVAL;
+    OptStepArgs a;
+    memset(&a, 0, sizeof(a));
+    if (c) {
+        for (int q = 0; q < kMaxRanks; ++q) a.cp.peer[q] = q < c->world ? c->peer[q] : nullptr;
+        a.rank = c->rank; a.world = c->world; a.capacity = c->capacity; a.ticket = c->ticket; a.err = c->err; a.timeout_ns = c->timeout_ns;
+        a.seq = (uint32_t)(step & 0x7FFFFFFF) | 0x80000000u;
+    }
+    a.p = params; a.g = grads; a.m = m; a.v = v; a.np = num_params;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.scale = grad_scale; a.max_norm = max_grad_norm; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.bc1 = (float)bc1; a.bc2_sqrt = (float)sqrt(bc2);
+    a.norm_out = norm_out; a.zero_grads = zero_grads;
+    if (wpack) {
+        if (hidden != 256) return TMLA_EINVAL;
+        const MlpOffsets o = mlp_offsets(obs_dim, n_actions);
+        if (o.total != num_params) return TMLA_EINVAL;
+        a.img0 = reinterpret_cast<__nv_bfloat16 *>(wpack) + (int64_t)4 * 65536; a.img1 = a.img0 + 65536;
+        a.w2_off0 = o.w2[0]; a.w2_off1 = o.w2[1];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int world = c ? c->world : 1;
+    switch (world) {
+        case 1: return opt_step_launch_t<1>(a, st);
+        case 2: return opt_step_launch_t<2>(a, st);
+        case 4: return opt_step_launch_t<4>(a, st);
+        case 8: return opt_step_launch_t<8>(a, st);
+        default: return TMLA_EINVAL;
+    }
+}
+
 extern "C" {
 
 int tmla_comm_create(int rank, int world, int device, int64_t num_floats, tmla_comm **out, void *handle_out) {
@@ -250,6 +459,11 @@ int tmla_adam_clip_allreduce(tmla_comm *c, float *params, float *grads, float *m
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer");
     TMLA_REQUIRE(num_params > 0 && num_params <= c->capacity && step >= 1, "bad arguments (num_params exceeds the comm's capacity?)");
     TMLA_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15u) == 0, "grads must be 16-byte aligned");
+    {   // one cooperative launch for exchange + clip + Adam when the shape fits (2, 4, 8 ranks)
+        const int rc = opt_step_launch(c, params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out,
+                                       zero_grads, wpack, obs_dim, hidden, n_actions, stream);
+        if (rc != TMLA_EINVAL) return rc;
+    }
     CommPtrs cp;
     for (int q = 0; q < kMaxRanks; ++q) cp.peer[q] = q < c->world ? c->peer[q] : nullptr;
     cudaStream_t st = (cudaStream_t)stream;

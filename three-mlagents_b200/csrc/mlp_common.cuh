@@ -31,3 +31,9 @@ static inline MlpOffsets mlp_offsets(int D, int A) {
 int adam_clip_launch(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
                      float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads,
                      void *wpack, int obs_dim, int hidden, int n_actions, void *stream, bool partials_ready);
+// comm.cu: the whole optimizer step (optional gradient exchange + clip + Adam) as one cooperative launch; TMLA_EINVAL = shape
+// does not fit / disabled, callers fall back to the two-launch path
+struct tmla_comm;
+int opt_step_launch(tmla_comm *c, float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale, float max_grad_norm,
+                    float lr, float beta1, float beta2, float eps, int64_t step, float *norm_out, int zero_grads, void *wpack, int obs_dim,
+                    int hidden, int n_actions, void *stream);

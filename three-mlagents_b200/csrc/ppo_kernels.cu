@@ -401,6 +401,11 @@ int adam_clip_launch(float *params, float *grads, float *m, float *v, int64_t nu
                      void *wpack, int obs_dim, int hidden, int n_actions, void *stream, bool partials_ready) {
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer (norm_out doubles as scratch)");
     TMLA_REQUIRE(num_params > 0 && step >= 1, "bad arguments");
+    if (!partials_ready) {      // norm pass + clip + Adam in ONE cooperative launch when the shape fits (comm.cu:opt_step_kernel<1>)
+        const int rc = opt_step_launch(nullptr, params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step,
+                                       norm_out, zero_grads, wpack, obs_dim, hidden, n_actions, stream);
+        if (rc != TMLA_EINVAL) return rc;
+    }
     __nv_bfloat16 *img0 = nullptr, *img1 = nullptr;
     int64_t off0 = 0, off1 = 0;
     if (wpack) {
