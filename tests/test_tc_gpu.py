@@ -83,3 +83,29 @@ def test_tc_linear_device_row_count():
     ref = torch.tanh(A[:300].float() @ W.float().t())
     assert float((out[:300].float() - ref).abs().max()) < 2e-2
     assert bool((out[300:] == 7.0).all())
+
+
+@pytest.mark.parametrize("task_shape,rows", [((6, 5), 65536), ((6, 5), 128 * 74 * 3 + 77), ((4, 5), 32768), ((4, 4), 1000), ((6, 5), 100)])
+def test_pipelined_rollout_forward_is_bit_identical_to_the_classic_kernel(task_shape, rows):
+    """csrc/mlp_fwd_pipe.cu (inference: double-buffered TMEM accumulator, driver warp, MMAs of tile k+1 under the epilogue of
+    tile k) against csrc/mlp_tc.cu's tower kernel (one tile at a time; selected here by keeping the activations): same FMA order,
+    same tanh, same K-step order, same head summation tree -> logits and values bit for bit, full and ragged tile counts."""
+    from three_mlagents_b200 import ops
+    from three_mlagents_b200.ppo import orthogonal_init
+
+    d, a = task_shape
+    g = torch.Generator(device="cuda").manual_seed(rows + d)
+    params = orthogonal_init(d, a, 3).cuda()
+    params += 0.05 * torch.randn(params.shape, device="cuda", generator=g)
+    wpack = ops.mlp_pack(params, d, a)
+    x = torch.randn((rows, d), device="cuda", generator=g)
+    l_pipe, v_pipe, _ = ops.mlp_forward(params, x, d, a, wpack=wpack, keep_act=False)
+    l_ref, v_ref, _ = ops.mlp_forward(params, x, d, a, wpack=wpack, keep_act=True)
+    torch.cuda.synchronize()
+    assert torch.equal(l_pipe.view(torch.int32), l_ref.view(torch.int32))
+    assert torch.equal(v_pipe.view(torch.int32), v_ref.view(torch.int32))
+    idx = torch.randperm(rows, device="cuda", generator=g)[: max(rows // 3, 1)].to(torch.int32).contiguous()   # gathered rows
+    l_pipe, v_pipe, _ = ops.mlp_forward(params, x, d, a, index=idx, wpack=wpack, keep_act=False)
+    l_ref, v_ref, _ = ops.mlp_forward(params, x, d, a, index=idx, wpack=wpack, keep_act=True)
+    torch.cuda.synchronize()
+    assert torch.equal(l_pipe, l_ref) and torch.equal(v_pipe, v_ref)

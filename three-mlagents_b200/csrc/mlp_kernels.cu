@@ -9,6 +9,8 @@
 // Layout: flat fp32 parameter vector in policy.parameters() order (include/tmla.h), PyTorch Linear
 // weights [out,in].  Activations are [rows,256] row-major.
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -29,6 +31,9 @@ int tc_tower_forward_dual_launch(int D, int n_actions, const float *const *W1, c
                                  const float *const *B2, const float *const *Wh, const float *const *Bh, const float *x,
                                  const int32_t *index, int64_t M, const int32_t *rows_dev, float *const *out, void *const *h1,
                                  void *const *h2, cudaStream_t st);
+int tc_tower_forward_pipe_dual_launch(int D, int n_actions, const float *const *W1, const float *const *B1, const void *const *W2,
+                                      const float *const *B2, const float *const *Wh, const float *const *Bh, const float *x,
+                                      const int32_t *index, int64_t M, const int32_t *rows_dev, float *const *out, cudaStream_t st);
 int tc_tower_forward_launch(int D, int nout, const float *W1, const float *B1, const void *W2, const float *B2, const float *Wh,
                             const float *Bh, const float *x, const int32_t *index, int64_t M, const int32_t *rows_dev, float *out,
                             void *h1, void *h2, cudaStream_t st);
@@ -643,6 +648,13 @@ static int mlp_forward_impl(const float *params, const void *wpack, int obs_dim,
                 W2[t] = reinterpret_cast<const __nv_bfloat16 *>(wpack) + (int64_t)(4 + t) * H * H;      // operand images
                 h1[t] = keep_act ? (void *)(act_cache + (int64_t)(2 * t) * rows * H) : nullptr;
                 h2[t] = keep_act ? (void *)(act_cache + (int64_t)(2 * t + 1) * rows * H) : nullptr;
+            }
+            if (!keep_act) {      // inference (rollout step): the pipelined kernel — double-buffered TMEM accumulator, driver warp
+                static const bool classic = [] { const char *e = getenv("TMLA_FWD"); return e && !strcmp(e, "classic"); }();
+                if (!classic) {
+                    const int rcp = tc_tower_forward_pipe_dual_launch(obs_dim, n_actions, W1, B1, W2, B2, Wh, Bh, x, index, rows, rows_dev, out, st);
+                    if (rcp != TMLA_EINVAL) return rcp;
+                }
             }
             const int rc = tc_tower_forward_dual_launch(obs_dim, n_actions, W1, B1, W2, B2, Wh, Bh, x, index, rows, rows_dev, out, h1, h2, st);
             if (rc != TMLA_EINVAL) return rc;
