@@ -14,7 +14,10 @@ tests/test_train_fused_gpu.py::test_wgrad_tiled_matches_torch[1024]
 tests/test_train_fused_gpu.py::test_fused_minibatch_matches_unfused[ball3d-64-8-100]
 tests/test_train_fused_gpu.py::test_fused_minibatch_matches_unfused[ball3d-512-32-4096]
 tests/test_rollout_fused_gpu.py::test_fused_rollout_is_bit_identical_to_per_step_calls[ball3d-512-32-bf16]
-tests/test_envs_gpu.py::test_host_step_contract'
+tests/test_envs_gpu.py::test_host_step_contract
+tests/test_tc_gpu.py::test_pipelined_rollout_forward_is_bit_identical_to_the_classic_kernel
+tests/test_ppo_gpu.py::test_adam_clip_vs_torch
+tests/test_ppo_gpu.py::test_adam_zero_grads_and_operand_image_refresh'
 for tool in $TOOLS; do
   out=gpurun_out/sanitizer_${tool}.log
   timeout 1500 compute-sanitizer --tool "$tool" --print-limit 20 --error-exitcode 0 \
