@@ -37,6 +37,8 @@
 // along K) — cute::UMMA "((1,n),(8,k)):((X,SBO),(1,LBO))" in uint128 units.  So one staged tile serves as the
 // K-major A operand of one GEMM and the MN-major A/B operand of the next, and W2 needs no transposed copy.
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -87,6 +89,16 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // tracked by an mbarrier transaction count
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+// the same load with an L2 eviction-priority hint (createpolicy): image chunks are read exactly once
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(sdst), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -708,18 +720,25 @@ static constexpr uint32_t kWgradTiledSmem = kwStages * kwStage + 128;   // 19673
 
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16 *__restrict__ Yt0, float *__restrict__ G0,
-                      const __nv_bfloat16 *__restrict__ Xt1, const __nv_bfloat16 *__restrict__ Yt1, float *__restrict__ G1, int64_t nchunks) {
+                      const __nv_bfloat16 *__restrict__ Xt1, const __nv_bfloat16 *__restrict__ Yt1, float *__restrict__ G1, int64_t nchunks,
+                      int reverse, int n1, int hint) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kwStages * kwStage);   // full[3], empty[3], done
     uint64_t *empty = full + kwStages, *done = empty + kwStages;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kwStages * kwStage + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    // dual launch: n1 CTAs work on problem 1, the rest on problem 0.  n1 = grid/2 interleaves them (even / odd CTAs); a smaller
+    // n1 hands problem 1 — whose image tail is still L2-resident when read back to front — fewer CTAs: its CTAs are
+    // spread over the grid (every CTA with blockIdx % period == period - 1 ... see `second`)
     const bool dual = Xt1 != nullptr;
-    const bool second = dual && (blockIdx.x & 1);
+    const int n0 = (int)gridDim.x - n1;
+    // problem-1 CTAs are spread evenly over the grid: CTA b belongs to problem 1 iff floor((b+1)*n1/grid) > floor(b*n1/grid)
+    const int before1 = dual ? (int)(((int64_t)blockIdx.x * n1) / gridDim.x) : 0;          // problem-1 CTAs with a smaller index
+    const bool second = dual && (int)(((int64_t)(blockIdx.x + 1) * n1) / gridDim.x) > before1;
     const __nv_bfloat16 *Xt = second ? Xt1 : Xt0, *Yt = second ? Yt1 : Yt0;
     float *G = second ? G1 : G0;
-    const int64_t first = dual ? blockIdx.x >> 1 : blockIdx.x, stride = dual ? gridDim.x >> 1 : gridDim.x;
+    const int64_t first = dual ? (second ? before1 : (int64_t)blockIdx.x - before1) : blockIdx.x, stride = dual ? (second ? n1 : n0) : gridDim.x;
     if (first >= nchunks) return;
 
     if (warp == 0) tmem_alloc<512>(tmem_holder);
@@ -737,13 +756,21 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16
 
     if (tid == 0) {                                        // producer: bulk-TMA loads, one stage ahead of the ring's tail
         uint32_t pe[kwStages] = {0u, 0u, 0u};
+        const uint64_t pol = l2_policy_evict_first();
         for (int64_t j = 0; j < my_chunks; ++j) {
             const int s = (int)(j % kwStages);
             if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }   // the MMAs of chunk j-3 have read this stage
-            const int64_t c = first + j * stride;
+            // reverse: walk the images from their END — the tower kernel wrote them front to back, so the tail is what the
+            // 126 MB L2 still holds when this kernel starts
+            const int64_t c = reverse ? nchunks - 1 - (first + j * stride) : first + j * stride;
             mbar_expect_tx(full + s, kwStage);
-            bulk_load(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s);
-            bulk_load(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s);
+            if (hint) {       // read-once data: do not let it push the not-yet-read tail of the images out of L2
+                bulk_load_hint(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s, pol);
+                bulk_load_hint(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s, pol);
+            } else {
+                bulk_load(s_addr + s * kwStage, Xt + c * (64 * H), kwChunk, full + s);
+                bulk_load(s_addr + s * kwStage + kwChunk, Yt + c * (64 * H), kwChunk, full + s);
+            }
         }
     } else if (warp_u == 1 && elect_one()) {               // MMA issuer
         uint32_t pf[kwStages] = {0u, 0u, 0u};
@@ -959,6 +986,10 @@ static int sm_count_train() {
 }
 
 // Xt, Yt: tile images covering `rows_padded` rows (a multiple of 128); Xt1/Yt1/G1 = an optional second problem of the same size
+static int wgrad_reverse() {      // TMLA_WGRAD_REV=0 restores front-to-back reads (A/B)
+    static const int r = [] { const char *e = getenv("TMLA_WGRAD_REV"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+    return r;
+}
 static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64_t rows_padded, cudaStream_t st,
                                  const void *Xt1 = nullptr, const void *Yt1 = nullptr, float *G1 = nullptr) {
     static int attr_done = 0;
@@ -968,9 +999,13 @@ static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64
     }
     const int64_t nchunks = rows_padded / 64;
     unsigned grid = (unsigned)std::min<int64_t>(Xt1 ? 2 * nchunks : nchunks, sm_count_train());
-    if (Xt1) grid &= ~1u;                                  // CTA pairs: even -> problem 0, odd -> problem 1
+    if (Xt1) grid &= ~1u;
+    // share of the CTAs given to problem 1 (the tower that ran LAST: its image tail is L2-resident): TMLA_WGRAD_N1 per 148 CTAs
+    static const int n1_of_148 = [] { const char *e = getenv("TMLA_WGRAD_N1"); return e ? atoi(e) : 74; }();
+    static const int wgrad_hint = [] { const char *e = getenv("TMLA_WGRAD_HINT"); return e ? atoi(e) : 1; }();
+    int n1 = Xt1 ? std::max(1, std::min((int)grid - 1, (int)((int64_t)grid * n1_of_148 / 148))) : 0;
     tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G,
-                                                              (const __nv_bfloat16 *)Xt1, (const __nv_bfloat16 *)Yt1, G1, nchunks);
+                                                              (const __nv_bfloat16 *)Xt1, (const __nv_bfloat16 *)Yt1, G1, nchunks, wgrad_reverse(), n1, wgrad_hint);
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -1019,6 +1054,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     // scratch: H1 and dZ2 tile images of both towers (one weight-gradient launch covers the two towers)
     __nv_bfloat16 *img[2][2];
     for (int t = 0; t < 2; ++t) for (int q = 0; q < 2; ++q) img[t][q] = reinterpret_cast<__nv_bfloat16 *>(scratch) + (int64_t)(2 * t + q) * rows_padded * H;
+    static const bool interleave = [] { const char *e = getenv("TMLA_WGRAD"); return e && !strcmp(e, "interleave"); }();   // A/B: wgrad right after each tower
     for (int t = 0; t < 2; ++t) {
         __nv_bfloat16 *h1 = img[t][0], *dz2 = img[t][1];
         TowerTrainArgs a;
@@ -1038,7 +1074,9 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
         else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st) : tower_train_launch_t<4, 1>(a, st);
         if (rc) return rc;
+        if (interleave) { rc = tc_wgrad_tiled_launch(img[t][1], img[t][0], grads + o.w2[t], rows_padded, st); if (rc) return rc; }
     }
+    if (interleave) return TMLA_OK;
     return tc_wgrad_tiled_launch(img[0][1], img[0][0], grads + o.w2[0], rows_padded, st, img[1][1], img[1][0], grads + o.w2[1]);
 }
 
