@@ -445,3 +445,37 @@ def test_out_of_range_action_is_rejected_before_any_state_change(n, dtype):
     obs, rew, done, infos = env.step(good)                       # and the env is still usable
     assert obs.shape == (n, 6) and infos[0]["steps"] >= 1
     env.close()
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_chunked_host_step_matches_device_path_and_rolls_back(task):
+    """From 16 384 envs on `CudaVecEnv.step` launches the step kernel first and releases the batch chunk by chunk
+    (tmla_step_block_begin: the staging of chunk c overlaps the PCIe traffic of chunk c-1; 20 000 envs = 157 CTAs = seven chunks
+    of 2 560 envs and a ragged one of 2 080).  The results must equal the plain device path bit for bit, and an out-of-range
+    action in a LATER chunk — found after the first chunks have stepped — must leave every env in its pre-step state (the
+    reference's ACTION_DELTAS[action] raises before any change)."""
+    n = 20000
+    env, dev = _vec(task, n, seed=11), _vec(task, n, seed=11)
+    assert np.array_equal(env.reset(), dev.reset_tensor().cpu().numpy())
+    rng = np.random.default_rng(2)
+    for t in range(24):
+        a = rng.integers(0, env.n_actions, n)
+        obs, rew, dones, infos = env.step(a)
+        b = dev.step_tensor(torch.from_numpy(a.astype(np.int32)).cuda())
+        assert np.array_equal(obs, b["obs"].cpu().numpy()) and np.array_equal(rew, b["rew"].cpu().numpy())
+        assert np.array_equal(dones, b["done"].cpu().numpy().astype(bool))
+        fin = infos.finished()
+        assert np.array_equal(fin, np.nonzero(b["done"].cpu().numpy())[0])
+        if len(fin):
+            ret, length = infos.episode_stats()
+            assert np.array_equal(ret, b["ret"].cpu().numpy()[fin]) and np.array_equal(length, b["len"].cpu().numpy()[fin])
+        if t % 8 == 7:
+            before, count = env.get_state(), env.step_count
+            for pos in (0, 2559, 2560, n // 2, n - 1):
+                bad = a.copy()
+                bad[pos] = env.n_actions
+                with pytest.raises(IndexError):
+                    env.step(bad)
+            assert env.step_count == count and env.get_state().tobytes() == before.tobytes()
+    assert env.get_state().tobytes() == dev.get_state().tobytes()
+    env.close(); dev.close()

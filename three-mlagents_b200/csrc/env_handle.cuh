@@ -21,6 +21,10 @@ struct tmla_env {
     bool dev_dirty;
     cudaEvent_t dev_evt;
     int act_u8;               // the pinned action stage currently holds uint8 actions (tmla_stage_actions)
+    // chunked host step (tmla_step_block_begin / _end): pre-step copy of the state planes (allocated on first use) for the
+    // roll-back of a batch whose later chunk is rejected; sequence word of the step in flight (0 = none, -1 = staged only)
+    void *shadow[4];
+    int pend_seq;
     // optional per-episode log of the policy-driven device path (Monitor rows): {ep_return, ep_length} records
     float2 *ep_log;
     int32_t ep_log_cap;

@@ -101,7 +101,13 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
             const int32_t *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
             float *__restrict__ ep_return, int32_t *__restrict__ ep_length, int32_t *n_done, int *err_flag,
-            float *__restrict__ compact, int32_t *__restrict__ host_flags, int host_seq, int act_u8) {
+            float *__restrict__ compact, int32_t *__restrict__ host_flags, int host_seq, int act_u8,
+            const int32_t *ready, int32_t *dev_ready, int chunk_ctas, EnvPtrs shadow) {
+    // ready != NULL (chunked host step, tmla_step_block_begin): the kernel is launched BEFORE the host has staged the actions;
+    // the CTAs of chunk c = blockIdx.x / chunk_ctas wait until the host publishes ready[c] == host_seq in mapped pinned memory
+    // (its range check + narrowing of that chunk is done; the chunk's first CTA polls it and republishes it in dev_ready[c])
+    // and leave without touching anything on ready[c] == ~host_seq (a chunk was rejected) or after a bounded wait.  shadow.buf[0] != NULL: the state every env had BEFORE this step is kept in
+    // the shadow planes, so that the chunks already stepped can be rolled back.
     // compact != NULL (host-facing step): finished envs append one record {env index, ep_return, ep_length, terminal_obs[D]}
     // at slot atomicAdd(n_done): the host then fetches n_done records instead of three dense [n] arrays.
     // host_flags != NULL (zero-copy host step): the last CTA to finish publishes {n_done, bad_action, host_seq} to mapped host
@@ -113,6 +119,29 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     __shared__ __align__(16) float s_rew[kBlock];
     __shared__ __align__(16) uint8_t s_flag[2 * kBlock];          // done[kBlock] | truncated[kBlock]
     const int64_t i0 = (int64_t)blockIdx.x * kBlock, i = i0 + threadIdx.x;
+    if (ready) {
+        // ONE CTA per chunk polls the host word over PCIe and republishes it in device memory for the others (512 CTAs polling
+        // pinned memory directly saturate the non-posted PCIe reads: 400-540 us per step instead of 80)
+        __shared__ int s_go;
+        if (threadIdx.x == 0) {
+            const int c = blockIdx.x / chunk_ctas;
+            const bool leader = blockIdx.x == (unsigned)(c * chunk_ctas);
+            const volatile int32_t *f = leader ? ready + c : dev_ready + c;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            int v;
+            while ((v = *f) != host_seq && v != ~host_seq) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) { v = ~host_seq; break; }      // 2 s: the host never finished staging
+                if (leader) __nanosleep(100);
+            }
+            if (leader) { __threadfence_system(); *(volatile int32_t *)(dev_ready + c) = v; }
+            __threadfence_system();                                          // the staged actions are read after the flag
+            s_go = v == host_seq;
+        }
+        __syncthreads();
+        if (!s_go) return;
+    }
     // full block with 16-byte aligned rows: reward / done / truncated leave as 128-bit stores too (40 per CTA instead of 384
     // scalar ones — they may travel over PCIe to a pinned result block, where a 1-byte store per lane is a 32-byte write)
     const bool wide = (n - i0 >= kBlock) && (((reinterpret_cast<uintptr_t>(reward + i0) | reinterpret_cast<uintptr_t>(done + i0) |
@@ -120,6 +149,7 @@ step_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, uint64_t ste
     if (i < n) {
         const typename Task::Consts cst = Task::load_consts();
         typename Task::State s = Task::load(p.buf, i);
+        if (shadow.buf[0]) Task::store(shadow.buf, i, s);
         int a = act_u8 ? (int)reinterpret_cast<const uint8_t *>(actions)[i] : actions[i];   // host step: one byte per action on the wire
         if ((unsigned)a >= (unsigned)Task::A) { *err_flag = 1; a = min(max(a, 0), Task::A - 1); }
         float r; bool term, trunc;
@@ -771,7 +801,9 @@ int tmla_create(int task, int64_t n_envs, uint64_t seed, uint64_t env_id_base, i
         return TMLA_ENOMEM;
     }
     TMLA_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+    memset((char *)h->h_stage + stage_layout(n_envs, D).end, 0, 64);      // ready[] words of the chunked host step
     TMLA_CUDA(cudaMemset((char *)h->d_stage + stage_layout(n_envs, D).flags, 0, 16));
+    TMLA_CUDA(cudaMemset((char *)h->d_stage + stage_layout(n_envs, D).end, 0, 64));      // device copies of the ready[] words
     TMLA_CUDA(cudaMemset(h->d_ndone, 0, sizeof(int32_t)));
     *out = h;
     int rc = tmla_reset(h, nullptr, nullptr);
@@ -789,6 +821,7 @@ int tmla_destroy(tmla_env *h) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->err_flag) cudaFree(h->err_flag);
     if (h->d_ndone) cudaFree(h->d_ndone);
+    for (int b = 0; b < 4; ++b) if (h->shadow[b]) cudaFree(h->shadow[b]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->dev_evt) cudaEventDestroy(h->dev_evt);
     if (h->rollout_plan && h->rollout_plan_free) h->rollout_plan_free(h->rollout_plan);
@@ -821,7 +854,7 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
     mark_device_path(h, st);
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(h->n), kBlock, 0, st>>>(
                              ptrs_of(h), h->n, h->seed, h->env_id_base, h->step_count, actions, obs, reward, done,
-                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr, 0, 0)));
+                             truncated, terminal_obs, ep_return, ep_length, nullptr, h->err_flag, nullptr, nullptr, 0, 0, nullptr, nullptr, 1, EnvPtrs{})));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     return TMLA_OK;
@@ -833,6 +866,30 @@ int tmla_step(tmla_env *h, const int32_t *actions, float *obs, float *reward, ui
 static bool host_step_mapped() {      // TMLA_HOST_STEP=copy selects the copy-engine path (default: zero-copy mapped writes)
     static const bool mapped = [] { const char *e = getenv("TMLA_HOST_STEP"); return !(e && !strcmp(e, "copy")); }();
     return mapped;
+}
+// Waits until the last CTA of a mapped host step has published {n_done, bad_action, seq} in the block's flag words: ONE launch
+// (or one launch per chunk) per step and no stream synchronise — the host polls the sequence word, which the kernel writes
+// after all results (cudaStreamQuery every 4096 polls catches a failed launch; the flag word of d_stage is zeroed at create).
+static int wait_block_published(tmla_env *h, const char *block, int seq, int64_t *n_done) {
+    const StageLayout L = stage_layout(h->n, kObsDim[h->task]);
+    const int32_t *bflags = (const int32_t *)(block + (L.flags - L.obs));
+    volatile const int32_t *hseq = (volatile const int32_t *)bflags + 2;
+    cudaStream_t st = h->own_stream;
+    static const bool poll = [] { const char *e = getenv("TMLA_HOST_STEP"); return !(e && !strcmp(e, "sync")); }();
+    if (!poll) TMLA_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t spins = 1; *hseq != seq; ++spins) {
+        if ((spins & 4095u) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaErrorNotReady) { TMLA_CUDA(q); if (*hseq != seq) { tmla_set_error("step kernel finished without publishing its results"); return TMLA_ECUDA; } }
+        }
+    }
+    __sync_synchronize();
+    if (n_done) *n_done = bflags[0];
+    if (bflags[1]) {
+        tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+        return TMLA_EACTION;
+    }
+    return TMLA_OK;
 }
 static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
     DeviceGuard guard(h->device);
@@ -857,33 +914,19 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
         TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                                  ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(p + L.act),
                                  (float *)(b + L.obs), (float *)(b + L.rew), (uint8_t *)(b + L.done), (uint8_t *)(b + L.trunc),
-                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq, act_u8)));
+                                 nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq, act_u8, nullptr, nullptr, 1, EnvPtrs{})));
         TMLA_LAUNCH_CHECK();
         h->step_count += 1;
         // ONE launch per step, no stream synchronise: poll the sequence word the last CTA writes after all results
         // (cudaStreamQuery every 4096 polls catches a failed launch; the flag word of d_stage is zeroed at create)
-        static const bool poll = [] { const char *e = getenv("TMLA_HOST_STEP"); return !(e && !strcmp(e, "sync")); }();
-        if (!poll) TMLA_CUDA(cudaStreamSynchronize(st));
-        for (uint32_t spins = 1; *hseq != seq; ++spins) {
-            if ((spins & 4095u) == 0) {
-                const cudaError_t q = cudaStreamQuery(st);
-                if (q != cudaErrorNotReady) { TMLA_CUDA(q); if (*hseq != seq) { tmla_set_error("step kernel finished without publishing its results"); return TMLA_ECUDA; } }
-            }
-        }
-        __sync_synchronize();
-        if (n_done) *n_done = bflags[0];
-        if (bflags[1]) {
-            tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
-            return TMLA_EACTION;
-        }
-        return TMLA_OK;
+        return wait_block_published(h, block, seq, n_done);
     }
     TMLA_CUDA(cudaMemcpyAsync(d + L.act, p + L.act, (act_u8 ? 1 : 4) * n, cudaMemcpyHostToDevice, st));
     TMLA_CUDA(cudaMemsetAsync(dflags, 0, 16, st));
     TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
                              ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(d + L.act),
                              (float *)(d + L.obs), (float *)(d + L.rew), (uint8_t *)(d + L.done), (uint8_t *)(d + L.trunc),
-                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr, 0, act_u8)));
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(d + L.crec), nullptr, 0, act_u8, nullptr, nullptr, 1, EnvPtrs{})));
     TMLA_LAUNCH_CHECK();
     h->step_count += 1;
     const size_t rec = (size_t)4 * record_words(D);
@@ -908,32 +951,37 @@ static int step_into_block(tmla_env *h, char *block, int64_t *n_done) {
 // stage, as one byte per action (every task has <= 5 actions) — a quarter of the PCIe reads of int32, and an out-of-range
 // action is reported BEFORE anything is launched, like the reference's ACTION_DELTAS[action] (ball3d.py:76) raising before
 // any state change.  elem_bytes: 4 (int32) or 8 (int64, what SB3 hands to VecEnv.step).
-int tmla_stage_actions(tmla_env *h, const void *actions, int elem_bytes) {
-    TMLA_REQUIRE(h && actions, "handle/actions is NULL");
-    TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
-    const int64_t n = h->n;
-    const uint32_t A = (uint32_t)kNumActions[h->task];                 // <= 8 for every task
-    uint8_t *dst = (uint8_t *)h->h_stage + stage_layout(n, kObsDim[h->task]).act;
-    // one pass, 32 actions per AVX2 iteration: OR of the raw lanes catches negatives and anything >= 8, a byte-wise running
-    // maximum of the packed actions catches A..7 (a plain scalar loop costs ~0.5 ns per action)
-    uint64_t ored = 0;
-    uint32_t mx = 0;
+// range [i0, i0 + m) of the caller's action array -> one byte per action in the pinned stage; accumulates the evidence of an
+// out-of-range value (OR of the raw lanes: negatives and anything >= 8; running maximum of the narrowed bytes: A..7)
+static void stage_action_range(tmla_env *h, const void *actions, int elem_bytes, int64_t i0, int64_t m, uint64_t *ored, uint32_t *mx) {
+    uint8_t *dst = (uint8_t *)h->h_stage + stage_layout(h->n, kObsDim[h->task]).act + i0;
+    const char *src = (const char *)actions + i0 * elem_bytes;
     int64_t i = 0;
 #if defined(__x86_64__)
     static const bool has_avx2 = __builtin_cpu_supports("avx2");
     if (has_avx2)
-        i = elem_bytes == 4 ? stage_actions32_avx2((const int32_t *)actions, dst, n, &ored, &mx)
-                            : stage_actions64_avx2((const int64_t *)actions, dst, n, &ored, &mx);
+        i = elem_bytes == 4 ? stage_actions32_avx2((const int32_t *)src, dst, m, ored, mx)
+                            : stage_actions64_avx2((const int64_t *)src, dst, m, ored, mx);
 #endif
-    for (; i < n; ++i) {
-        const uint64_t a = elem_bytes == 4 ? (uint64_t)(uint32_t)((const int32_t *)actions)[i] : (uint64_t)((const int64_t *)actions)[i];
-        ored |= (a | (a >> 32)) & 0xFFFFFFFFull;
-        mx = (uint32_t)(a & 7u) > mx ? (uint32_t)(a & 7u) : mx;
+    for (; i < m; ++i) {       // (a plain scalar loop costs ~0.5 ns per action)
+        const uint64_t a = elem_bytes == 4 ? (uint64_t)(uint32_t)((const int32_t *)src)[i] : (uint64_t)((const int64_t *)src)[i];
+        *ored |= (a | (a >> 32)) & 0xFFFFFFFFull;
+        *mx = (uint32_t)(a & 7u) > *mx ? (uint32_t)(a & 7u) : *mx;
         dst[i] = (uint8_t)a;
     }
-    const bool bad = (ored & ~7ull) != 0 || mx >= A;
+}
+static inline bool staged_actions_bad(const tmla_env *h, uint64_t ored, uint32_t mx) {
+    return (ored & ~7ull) != 0 || mx >= (uint32_t)kNumActions[h->task];        // every task has <= 8 actions
+}
+
+int tmla_stage_actions(tmla_env *h, const void *actions, int elem_bytes) {
+    TMLA_REQUIRE(h && actions, "handle/actions is NULL");
+    TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
+    uint64_t ored = 0;
+    uint32_t mx = 0;
+    stage_action_range(h, actions, elem_bytes, 0, h->n, &ored, &mx);
     h->act_u8 = 1;
-    if (bad) {
+    if (staged_actions_bad(h, ored, mx)) {
         tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
         return TMLA_EACTION;
     }
@@ -954,6 +1002,106 @@ int tmla_set_episode_log(tmla_env *h, float *records, int32_t capacity, int32_t 
 int tmla_step_block(tmla_env *h, void *block, int64_t *n_done) {
     TMLA_REQUIRE(h && block, "handle/block is NULL");
     return step_into_block(h, (char *)block, n_done);
+}
+
+// VecEnv.step_async / step_wait on the caller's own action array.  Above 16 384 envs the step kernel is launched FIRST and
+// the batch is cut into chunks (TMLA_HOST_CHUNKS, default 8): the host range-checks and narrows chunk c, then publishes
+// ready[c] in mapped pinned memory; the CTAs of that chunk, already resident and polling the word over PCIe, step their envs
+// and write the results into the block while the host stages chunk c+1.  Launch latency and the staging pass (14.5 us for
+// 65 536 int32 actions) disappear behind the 1.9 MB of result traffic.  (One launch PER chunk was measured first: every extra
+// launch costs ~7 us on the stream — 80 / 88 / 93 / 124 / 185 us per step with 1 / 2 / 4 / 8 / 16 launches.)
+// "A rejected step changes nothing" still holds: the kernel keeps the pre-step state in shadow planes, and when a later chunk
+// holds an out-of-range action the remaining chunks are told to leave and the envs already stepped are put back before the
+// error returns.
+static int host_chunks(const tmla_env *h) {
+    static const int req = [] { const char *e = getenv("TMLA_HOST_CHUNKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    if (h->n < 16384 || req == 1) return 1;
+    // every CTA must be resident at once (a waiting CTA never yields its slot)
+    static int resident[TMLA_NUM_TASKS];
+    static int sms = 0;
+    if (!sms) { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, h->device) != cudaSuccess) return 1; sms = pr.multiProcessorCount; }
+    if (!resident[h->task]) {
+        int per_sm = 0;
+        TASK_SWITCH(h->task, if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<TaskT>, kBlock, 0) != cudaSuccess) per_sm = 0);
+        resident[h->task] = per_sm > 0 ? per_sm : -1;
+    }
+    if (resident[h->task] < 0 || (int64_t)grid_for(h->n) > (int64_t)resident[h->task] * sms) return 1;
+    return req;
+}
+int tmla_step_block_begin(tmla_env *h, const void *actions, int elem_bytes, void *block) {
+    TMLA_REQUIRE(h && actions && block, "handle/actions/block is NULL");
+    TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
+    TMLA_REQUIRE(h->pend_seq == 0, "a host step is already in flight (call tmla_step_block_end first)");
+    DeviceGuard guard(h->device);
+    const int nchunks = host_step_mapped() ? host_chunks(h) : 1;
+    if (nchunks == 1) {                                      // small batches / copy-engine variant: stage now, run the step in _end
+        const int rc = tmla_stage_actions(h, actions, elem_bytes);
+        if (rc == TMLA_OK) h->pend_seq = -1;
+        return rc;
+    }
+    { const int rc = order_after_device_path(h); if (rc) return rc; }
+    const int64_t n = h->n;
+    const int D = kObsDim[h->task];
+    const StageLayout L = stage_layout(n, D);
+    const int chunk_ctas = (int)ceil_div64(grid_for(n), nchunks);
+    const int64_t chunk = (int64_t)chunk_ctas * kBlock;
+    int nbuf = 0;
+    size_t pb[4] = {0, 0, 0, 0};
+    TASK_SWITCH(h->task, nbuf = TaskT::NBUF; for (int b = 0; b < nbuf; ++b) pb[b] = TaskT::plane_bytes(b));
+    EnvPtrs shadow{};
+    for (int b = 0; b < nbuf; ++b) {
+        if (!h->shadow[b] && cudaMalloc(&h->shadow[b], pb[b] * (size_t)n) != cudaSuccess) {
+            tmla_set_error("cudaMalloc(shadow state plane %d): %s", b, cudaGetErrorString(cudaGetLastError()));
+            return TMLA_ENOMEM;
+        }
+        shadow.buf[b] = h->shadow[b];
+    }
+    char *d = (char *)h->d_stage, *p = (char *)h->h_stage, *b = (char *)block - L.obs;
+    cudaStream_t st = h->own_stream;
+    int32_t *dflags = (int32_t *)(d + L.flags);
+    volatile int32_t *ready = (volatile int32_t *)(p + L.end);          // 16 words after the layout (stage_bytes = end + 64)
+    const int seq = (int)((h->step_count + 1) & 0x3FFFFFFF) | 0x40000000;
+    *((volatile int32_t *)(b + L.flags) + 2) = 0;
+    TASK_SWITCH(h->task, (step_kernel<TaskT><<<grid_for(n), kBlock, 0, st>>>(
+                             ptrs_of(h), n, h->seed, h->env_id_base, h->step_count, (const int32_t *)(p + L.act),
+                             (float *)(b + L.obs), (float *)(b + L.rew), (uint8_t *)(b + L.done), (uint8_t *)(b + L.trunc),
+                             nullptr, nullptr, nullptr, dflags, dflags + 1, (float *)(b + L.crec), (int32_t *)(b + L.flags), seq, 1,
+                             (const int32_t *)ready, (int32_t *)(d + L.end), chunk_ctas, shadow)));
+    TMLA_LAUNCH_CHECK();
+    uint64_t ored = 0;
+    uint32_t mx = 0;
+    int c = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += chunk, ++c) {
+        const int64_t m = n - i0 < chunk ? n - i0 : chunk;
+        stage_action_range(h, actions, elem_bytes, i0, m, &ored, &mx);
+        if (staged_actions_bad(h, ored, mx)) {
+            // tell the chunks not yet released to leave, wait, and put the envs already stepped back: state planes, device counters
+            for (int q = c; q < nchunks; ++q) ready[q] = ~seq;
+            __sync_synchronize();
+            TMLA_CUDA(cudaStreamSynchronize(st));
+            for (int q = 0; q < nbuf && i0 > 0; ++q) TMLA_CUDA(cudaMemcpyAsync(h->buf[q], h->shadow[q], pb[q] * (size_t)i0, cudaMemcpyDeviceToDevice, st));
+            TMLA_CUDA(cudaMemsetAsync(dflags, 0, 16, st));
+            TMLA_CUDA(cudaMemsetAsync(d + L.end, 0, 64, st));
+            TMLA_CUDA(cudaStreamSynchronize(st));
+            for (int q = 0; q < 16; ++q) ready[q] = 0;       // the next attempt reuses this sequence number
+            tmla_set_error("an action outside [0,%d) was passed to step()", kNumActions[h->task]);
+            return TMLA_EACTION;
+        }
+        __sync_synchronize();                                // the narrowed actions are visible before the flag
+        ready[c] = seq;
+    }
+    h->step_count += 1;
+    h->pend_seq = seq;
+    return TMLA_OK;
+}
+
+int tmla_step_block_end(tmla_env *h, void *block, int64_t *n_done) {
+    TMLA_REQUIRE(h && block, "handle/block is NULL");
+    TMLA_REQUIRE(h->pend_seq != 0, "no host step in flight (call tmla_step_block_begin first)");
+    const int seq = h->pend_seq;
+    h->pend_seq = 0;
+    if (seq == -1) return step_into_block(h, (char *)block, n_done);
+    return wait_block_published(h, (const char *)block, seq, n_done);
 }
 
 int tmla_step_pinned(tmla_env *h, int64_t *n_done) {

@@ -350,8 +350,10 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
                 // M1: Z2 = H1 . W2^T -> ACC, and the H1 tile image -> HBM.  The store is issued FIRST: tcgen05.mma issue
                 // blocks while the tensor core's queue is full, the bulk copy then runs beside the MMAs
                 wait_ready();
-                bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2);
-                bulk_commit();
+                if (p.h1_out) {                            // (NULL: the weight-gradient kernel recomputes H1, nothing to write)
+                    bulk_store(p.h1_out + tile * (128 * H), t_addr, 128 * H * 2);
+                    bulk_commit();
+                }
 #pragma unroll
                 for (int kk = 0; kk < H / 16; ++kk)
                     umma_bf16(tmem_base + C_ACC, make_desc_raw(t_addr + kk * 2 * kLBO, kLBO, kSBO), make_desc_raw(w_addr + kk * 2 * kLBO, kLBO, kSBO),
@@ -832,6 +834,208 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// --------------------------------------------------------- G[256,256] += dZ2^T . H1 with H1 RECOMPUTED, not read back
+// The weight-gradient GEMM is HBM-bound on its operand images (1 KB per row).  H1 = tanh(x W1^T + b1) costs 24 B of x per row and
+// ~1.5 K CUDA-core cycles per 64-row chunk to recompute — this kernel's CUDA cores are idle — so only dZ2 travels through HBM:
+// the tower kernel no longer writes an H1 image, and the bytes this kernel reads halve (and what is left is the image whose
+// tail is L2-resident).  Layer 1 is the tower kernel's, instruction for instruction (same FFMA2 order, tanh.approx, bf16 packing):
+// the recomputed operand is bit-identical to the H1 the forward pass used.
+//   warps 0..15 compute H1 of chunk j into the Y half of stage j % 3 (obs rows gathered through the minibatch index, two
+//               chunks of register prefetch), warps 0..7 then run the epilogue;   warp 16: bulk-TMA producer of the dZ2 chunks;
+//   warp 17: MMA issuer.  full[s] counts the producer's expect_tx arrive + one arrive per compute warp.
+// An experiment kept behind TMLA_WGRAD_H1=recompute (bit-identical gradients, but slower than reading the image back: see
+// tmla_ppo_minibatch_bf16).
+struct WgradH1Problem { const __nv_bfloat16 *dz2; const float *W1, *B1; float *G; };
+template <int D>
+struct WgradH1Smem {
+    static constexpr uint32_t bars = kwStages * kwStage;                 // full[3], empty[3], done, tmem holder
+    static constexpr uint32_t w1t = bars + 128;                          // float [D][256]
+    static constexpr uint32_t b1 = w1t + D * H * 4;
+    static constexpr uint32_t xs = b1 + H * 4;                           // float [64][D]
+    static constexpr uint32_t total = xs + 64 * D * 4 + 16;
+};
+static constexpr int kWgradH1Compute = 512;                // 16 compute warps: 2 rows x 16 columns of H1 per thread and chunk
+static constexpr int kWgradH1Threads = kWgradH1Compute + 64;
+
+template <int D>
+__global__ void __launch_bounds__(kWgradH1Threads, 1)
+tc_wgrad_h1_kernel(const __grid_constant__ WgradH1Problem p0, const __grid_constant__ WgradH1Problem p1, const float *__restrict__ x,
+                   const int32_t *__restrict__ index, int64_t M, int64_t nchunks) {
+    using L = WgradH1Smem<D>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bars);
+    uint64_t *empty = full + kwStages, *done = empty + kwStages;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::bars + 64);
+    float *w1t = reinterpret_cast<float *>(smem + L::w1t), *b1s = reinterpret_cast<float *>(smem + L::b1);
+    float *xs = reinterpret_cast<float *>(smem + L::xs);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const bool second = blockIdx.x & 1;
+    const WgradH1Problem &P = second ? p1 : p0;
+    const int64_t first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+    if (first >= nchunks) return;
+
+    if (warp == 0) tmem_alloc<512>(tmem_holder);
+    if (tid == 32) {
+        for (int s = 0; s < kwStages; ++s) { mbar_init(full + s, 1 + kWgradH1Compute / 32); mbar_init(empty + s, 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (tid < kWgradH1Compute) {
+        for (int e = tid; e < H * D; e += kWgradH1Compute) { const int k = e / H, j = e - k * H; w1t[e] = P.W1[j * D + k]; }
+        if (tid < H) b1s[tid] = P.B1[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+    const uint32_t s_addr = smem_u32(smem);
+    const int64_t my_chunks = (nchunks - first + stride - 1) / stride;
+    auto chunk_of = [&](int64_t j) { return nchunks - 1 - (first + j * stride); };     // back to front: the image tail is in L2
+
+    if (warp_u == kWgradH1Compute / 32) {
+        if (lane == 0) {                                   // producer: dZ2 chunks
+            uint32_t pe[kwStages] = {0u, 0u, 0u};
+            const uint64_t pol = l2_policy_evict_first();
+            for (int64_t j = 0; j < my_chunks; ++j) {
+                const int s = (int)(j % kwStages);
+                if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }
+                mbar_expect_tx(full + s, kwChunk);
+                bulk_load_hint(s_addr + s * kwStage, P.dz2 + chunk_of(j) * (64 * H), kwChunk, full + s, pol);
+            }
+        }
+        __syncwarp();
+    } else if (warp_u == kWgradH1Compute / 32 + 1) {
+        if (elect_one()) {                                 // MMA issuer
+            uint32_t pf[kwStages] = {0u, 0u, 0u};
+            const uint32_t idesc = make_idesc_major(128, 256, 1, 1);
+            for (int64_t j = 0; j < my_chunks; ++j) {
+                const int s = (int)(j % kwStages);
+                mbar_wait(full + s, pf[s]);
+                pf[s] ^= 1u;
+                tc_fence_after();
+                const uint32_t x_addr = s_addr + s * kwStage, y_addr = x_addr + kwChunk;
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + mh * 256, make_desc_raw(x_addr + mh * 16 * kLBO + kk * 2 * kSBO, kSBO, kLBO),
+                                  make_desc_raw(y_addr + kk * 2 * kSBO, kSBO, kLBO), idesc, (j == 0 && kk == 0) ? 0u : 1u);
+                umma_commit(empty + s);
+            }
+            umma_commit(done);
+        }
+        __syncwarp();
+    } else {
+        // ---- compute warps 0..15: H1 of chunk j -> Y half of stage j % 3
+        constexpr int PIECES = (D + 1) / 2;                // float2 pieces per observation row (D = 7: the last piece is one float)
+        const int prow = tid & 63, ppiece = tid >> 6;      // prefetch role: row of the chunk, piece index (0..7, the first PIECES load)
+        const int l1row = (warp & 3) * 16 + (lane & 7), l1col = (warp >> 2) * 64 + (lane >> 3) * 16;   // rows l1row, l1row + 8
+        auto load_idx = [&](int64_t j) -> int32_t {        // buffer row of chunk j's row `prow` (-1 past the end)
+            if (j >= my_chunks) return -1;
+            const int64_t r = chunk_of(j) * 64 + prow;
+            if (r >= M) return -1;
+            return index ? __ldg(index + r) : (int32_t)r;
+        };
+        auto load_x = [&](int32_t src) -> float2 {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (src >= 0 && ppiece < PIECES) {
+                const float *q = x + (int64_t)src * D + 2 * ppiece;
+                v.x = __ldg(q);
+                if (2 * ppiece + 1 < D) v.y = __ldg(q + 1);
+            }
+            return v;
+        };
+        int32_t idx1 = load_idx(1);
+        float2 xv = load_x(load_idx(0));
+        uint32_t pe[kwStages] = {0u, 0u, 0u};
+        for (int64_t j = 0; j < my_chunks; ++j) {
+            const int s = (int)(j % kwStages);
+            if (ppiece < PIECES) {
+                xs[prow * D + 2 * ppiece] = xv.x;
+                if (2 * ppiece + 1 < D) xs[prow * D + 2 * ppiece + 1] = xv.y;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWgradH1Compute) : "memory");
+            xv = load_x(idx1);                             // rows of chunk j+1, index of chunk j+2: in flight during layer 1
+            idx1 = load_idx(j + 2);
+            uint32_t h1p[16];
+            {
+                float xr[2][D];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int k = 0; k < D; ++k) xr[i][k] = xs[(l1row + 8 * i) * D + k];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int col = l1col + g * 2;
+                    const float2 bb = *reinterpret_cast<const float2 *>(b1s + col);
+                    float2 ww[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) ww[k] = *reinterpret_cast<const float2 *>(w1t + k * H + col);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float2 v = bb;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) v = __ffma2_rn(make_float2(xr[i][k], xr[i][k]), ww[k], v);
+                        h1p[i * 8 + g] = pack_bf16(tanh_fast(v.x), tanh_fast(v.y));
+                    }
+                }
+            }
+            if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }      // the MMAs of chunk j-3 have read this stage
+            uint8_t *Ys = smem + s * kwStage + kwChunk;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                uint8_t *dst = Ys + ((l1row + 8 * i) >> 3) * kSBO + (l1col >> 3) * kLBO + (lane & 7) * 16;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(h1p[i * 8], h1p[i * 8 + 1], h1p[i * 8 + 2], h1p[i * 8 + 3]);
+                *reinterpret_cast<uint4 *>(dst + kLBO) = make_uint4(h1p[i * 8 + 4], h1p[i * 8 + 5], h1p[i * 8 + 6], h1p[i * 8 + 7]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + s);
+            asm volatile("bar.sync 1, %0;" ::"n"(kWgradH1Compute) : "memory");   // xs is rewritten at the top of the next iteration
+        }
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    // epilogue (warps 0..7): TMEM -> registers -> smem stage (fp32 [128][256], XOR-swizzled 16-byte chunks) -> red.global.add.v4.f32
+#pragma unroll 1
+    for (int mh = 0; mh < 2; ++mh) {
+        __syncthreads();
+        if (warp < 8) {
+            const int rt = (warp & 3) * 32 + lane;
+            const int colbase = (warp >> 2) * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mh * 256 + colbase);
+            uint8_t *srow = smem + rt * 1024;
+#pragma unroll 2
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + c0, acc);
+                const int ch = (colbase + c0) >> 2;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4 *>(srow + (((ch + q) ^ (rt & 7)) << 4)) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        __syncthreads();
+        if (warp < 8) {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp + 8 * i;
+                float *grow = P.G + (int64_t)(mh * 128 + r) * H;
+#pragma unroll
+                for (int hseg = 0; hseg < 2; ++hseg) {
+                    const int ch = hseg * 32 + lane;
+                    const float4 v = *reinterpret_cast<const float4 *>(smem + r * 1024 + ((ch ^ (r & 7)) << 4));
+                    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + ch * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------ descriptor probe (tests only)
 // One CTA, A bf16 [128][256], B bf16 [256][256] staged exactly like the production tiles:
 //   mode 0: out[128][256] = A . B^T   (both K-major)
@@ -1010,6 +1214,23 @@ static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64
     return TMLA_OK;
 }
 
+template <int D>
+static int wgrad_h1_launch_t(const WgradH1Problem &a, const WgradH1Problem &b, const float *x, const int32_t *index, int64_t M, int64_t rows_padded,
+                             cudaStream_t st) {
+    static int attr_done = 0;
+    constexpr uint32_t smem = WgradH1Smem<D>::total;
+    static_assert(smem <= 232448, "wgrad (recomputed H1) exceeds the 227 KB shared-memory limit");
+    if (!attr_done) {
+        TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_h1_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = 1;
+    }
+    const int64_t nchunks = rows_padded / 64;
+    unsigned grid = (unsigned)std::min<int64_t>(2 * nchunks, sm_count_train()) & ~1u;
+    tc_wgrad_h1_kernel<D><<<grid, kWgradH1Threads, smem, st>>>(a, b, x, index, M, nchunks);
+    TMLA_LAUNCH_CHECK();
+    return TMLA_OK;
+}
+
 template <int D, int NOUT>
 static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
     static int attr_done = 0;
@@ -1055,6 +1276,12 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     __nv_bfloat16 *img[2][2];
     for (int t = 0; t < 2; ++t) for (int q = 0; q < 2; ++q) img[t][q] = reinterpret_cast<__nv_bfloat16 *>(scratch) + (int64_t)(2 * t + q) * rows_padded * H;
     static const bool interleave = [] { const char *e = getenv("TMLA_WGRAD"); return e && !strcmp(e, "interleave"); }();   // A/B: wgrad right after each tower
+    // TMLA_WGRAD_H1=recompute: the weight-gradient kernel recomputes H1 from the observations, so that no H1 image is written
+    // or read (tc_wgrad_h1_kernel).  Measured on B200, one 262 144-row ball3d minibatch (2 towers + wgrad): 413.5 us with 8
+    // compute warps, 431.6 us with 16, against 407-410 us for the default (both operands as tile images): the image read it
+    // saves (134 MB per tower, mostly L2 hits on the tail) is cheaper than 2 x 262 144 x 256 tanh on this kernel's CUDA cores.
+    static const bool h1_recompute = [] { const char *e = getenv("TMLA_WGRAD_H1"); return e && !strcmp(e, "recompute"); }();
+    const bool recompute = h1_recompute && !interleave;
     for (int t = 0; t < 2; ++t) {
         __nv_bfloat16 *h1 = img[t][0], *dz2 = img[t][1];
         TowerTrainArgs a;
@@ -1065,7 +1292,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         a.actions = actions; a.adv = advantages; a.old_logp = old_logp; a.returns = returns;
         a.adv_sums = adv_sums; a.normalize = normalize_advantage;
         a.clip = clip_range; a.ent_coef = ent_coef; a.vf_coef = vf_coef; a.inv_rows = (float)(1.0 / (double)global_rows);
-        a.h1_out = h1; a.dz2_out = dz2; a.out = t == 0 ? logits_out : values_out;
+        a.h1_out = recompute ? nullptr : h1; a.dz2_out = dz2; a.out = t == 0 ? logits_out : values_out;
         a.gW1 = grads + o.w1[t]; a.gB1 = grads + o.b1[t]; a.gB2 = grads + o.b2[t]; a.gWh = grads + o.wh[t]; a.gBh = grads + o.bh[t];
         a.stats = stats_out;
         int rc;
@@ -1077,6 +1304,12 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         if (interleave) { rc = tc_wgrad_tiled_launch(img[t][1], img[t][0], grads + o.w2[t], rows_padded, st); if (rc) return rc; }
     }
     if (interleave) return TMLA_OK;
+    if (recompute) {
+        const WgradH1Problem pa{img[0][1], params + o.w1[0], params + o.b1[0], grads + o.w2[0]}, pb{img[1][1], params + o.w1[1], params + o.b1[1], grads + o.w2[1]};
+        if (obs_dim == 6) return wgrad_h1_launch_t<6>(pa, pb, obs, index, rows, rows_padded, st);
+        if (obs_dim == 7) return wgrad_h1_launch_t<7>(pa, pb, obs, index, rows, rows_padded, st);
+        return wgrad_h1_launch_t<4>(pa, pb, obs, index, rows, rows_padded, st);
+    }
     return tc_wgrad_tiled_launch(img[0][1], img[0][0], grads + o.w2[0], rows_padded, st, img[1][1], img[1][0], grads + o.w2[1]);
 }
 

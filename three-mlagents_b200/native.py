@@ -69,6 +69,8 @@ SIGNATURES = {
     "tmla_result_block_free": (_i, [vp]),
     "tmla_step_block": (_i, [vp, vp, C.POINTER(i64)]),
     "tmla_stage_actions": (_i, [vp, vp, _i]),
+    "tmla_step_block_begin": (_i, [vp, vp, _i, vp]),
+    "tmla_step_block_end": (_i, [vp, vp, C.POINTER(i64)]),
     "tmla_set_episode_log": (_i, [vp, vp, i32, vp]),
     "tmla_get_state": (_i, [vp, vp, vp]),
     "tmla_set_state": (_i, [vp, vp, vp]),

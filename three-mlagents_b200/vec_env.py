@@ -199,6 +199,7 @@ class CudaVecEnv:
         n, d = self.num_envs, self.obs_dim
         self._blocks = _ResultBlocks(self._h, n, d)      # results land in pooled pinned result blocks
         self._actions = None
+        self._pending = None                             # result block of the step in flight (None: the scratch block)
         self._t0 = time.time()
         self._vec_step = 0                               # host-path vec-steps taken (for infos[i]["steps"])
         self._last_reset = np.zeros(n, np.int64)         # vec-step index at which env i last (auto-)reset
@@ -231,17 +232,25 @@ class CudaVecEnv:
             raise ValueError(f"expected {self.num_envs} actions, got {a.shape[0]}")
         if a.dtype not in (np.int32, np.int64) or not a.flags.c_contiguous:
             a = np.ascontiguousarray(a, dtype=np.int64)
-        # one C pass: range check (IndexError BEFORE anything is launched, like the reference's ACTION_DELTAS[action]) and
-        # narrowing to one byte per action in the pinned stage the step kernel reads over PCIe
-        check(lib.tmla_stage_actions(self._h, a.ctypes.data, a.dtype.itemsize))
-        self._actions = a
+        # chunk by chunk: range check + narrowing to one byte per action in the pinned stage, then that chunk's step kernel —
+        # the staging of chunk c runs while chunk c-1's results already travel over PCIe.  An out-of-range action raises
+        # IndexError with every env in its pre-step state (like the reference's ACTION_DELTAS[action]).
+        blocks = self._blocks
+        k = blocks.acquire()
+        try:
+            check(lib.tmla_step_block_begin(self._h, a.ctypes.data, a.dtype.itemsize, blocks._ptr[blocks.scratch if k is None else k]))
+        except BaseException:
+            if k is not None:
+                blocks.release(k)
+            raise
+        self._actions, self._pending = a, k
 
     def step_wait(self):
         blocks = self._blocks
-        k = blocks.acquire()
+        k = self._pending
         nd = native.i64(0)
         try:
-            check(lib.tmla_step_block(self._h, blocks._ptr[blocks.scratch if k is None else k], C.byref(nd)))
+            check(lib.tmla_step_block_end(self._h, blocks._ptr[blocks.scratch if k is None else k], C.byref(nd)))
         except BaseException:
             if k is not None:
                 blocks.release(k)
