@@ -136,13 +136,13 @@ int tmla_result_block_alloc(tmla_env *h, void **block);
 int tmla_result_block_free(void *block);
 int tmla_step_block(tmla_env *h, void *block, int64_t *n_done);
 /* VecEnv.step_async / step_wait (SB3 vec_env/base_vec_env.py; what DummyVecEnv.step_wait does serially over
- * backend/mlagents/envs.py:123-152) on the CALLER'S action array.  Above 16 384 envs _begin launches the step kernel first and
- * then, chunk by chunk (TMLA_HOST_CHUNKS, default 8), range-checks + narrows the actions and publishes a ready word in mapped
- * pinned memory that the chunk's CTAs poll: the host's staging pass and the launch latency run while the earlier chunks'
- * results already travel over PCIe into `block`.  _end waits for the sequence word of the batch and returns n_done /
- * TMLA_EACTION like tmla_step_block.  An out-of-range action in ANY chunk makes _begin return TMLA_EACTION with every env in
- * its pre-step state (chunks not yet released leave untouched, chunks already stepped are rolled back from shadow state
- * planes) — the reference's ACTION_DELTAS[action] raises before any state change.  One step in flight per handle. */
+ * backend/mlagents/envs.py:123-152) on the CALLER'S action array.  For int64 actions above 16 384 envs _begin launches the step
+ * kernel first and then, chunk by chunk (TMLA_HOST_CHUNKS; default 4 for int64, 1 = stage-then-launch for int32), range-checks +
+ * narrows the actions and publishes a ready word in mapped pinned memory that the chunk's first CTA polls: the host's staging
+ * pass runs behind the launch latency and the earlier chunks' PCIe traffic.  _end waits for the sequence word of the batch and
+ * returns n_done / TMLA_EACTION like tmla_step_block.  An out-of-range action in ANY chunk makes _begin return TMLA_EACTION
+ * with every env in its pre-step state (chunks not yet released leave untouched, chunks already stepped are rolled back from
+ * shadow state planes) — the reference's ACTION_DELTAS[action] raises before any state change.  One step in flight per handle. */
 int tmla_step_block_begin(tmla_env *h, const void *actions, int elem_bytes, void *block);
 int tmla_step_block_end(tmla_env *h, void *block, int64_t *n_done);
 

@@ -449,9 +449,9 @@ def test_out_of_range_action_is_rejected_before_any_state_change(n, dtype):
 
 @pytest.mark.parametrize("task", TASKS)
 def test_chunked_host_step_matches_device_path_and_rolls_back(task):
-    """From 16 384 envs on `CudaVecEnv.step` launches the step kernel first and releases the batch chunk by chunk
-    (tmla_step_block_begin: the staging of chunk c overlaps the PCIe traffic of chunk c-1; 20 000 envs = 157 CTAs = seven chunks
-    of 2 560 envs and a ragged one of 2 080).  The results must equal the plain device path bit for bit, and an out-of-range
+    """From 16 384 envs on `CudaVecEnv.step` with int64 actions launches the step kernel first and releases the batch chunk by
+    chunk (tmla_step_block_begin: the staging of chunk c overlaps the PCIe traffic of chunk c-1; 20 000 envs = 157 CTAs = three
+    chunks of 5 120 envs and a ragged one of 4 640).  The results must equal the plain device path bit for bit, and an out-of-range
     action in a LATER chunk — found after the first chunks have stepped — must leave every env in its pre-step state (the
     reference's ACTION_DELTAS[action] raises before any change)."""
     n = 20000
@@ -471,7 +471,7 @@ def test_chunked_host_step_matches_device_path_and_rolls_back(task):
             assert np.array_equal(ret, b["ret"].cpu().numpy()[fin]) and np.array_equal(length, b["len"].cpu().numpy()[fin])
         if t % 8 == 7:
             before, count = env.get_state(), env.step_count
-            for pos in (0, 2559, 2560, n // 2, n - 1):
+            for pos in (0, 5119, 5120, n // 2, n - 1):
                 bad = a.copy()
                 bad[pos] = env.n_actions
                 with pytest.raises(IndexError):

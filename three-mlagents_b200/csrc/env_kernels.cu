@@ -1004,17 +1004,23 @@ int tmla_step_block(tmla_env *h, void *block, int64_t *n_done) {
     return step_into_block(h, (char *)block, n_done);
 }
 
-// VecEnv.step_async / step_wait on the caller's own action array.  Above 16 384 envs the step kernel is launched FIRST and
-// the batch is cut into chunks (TMLA_HOST_CHUNKS, default 8): the host range-checks and narrows chunk c, then publishes
-// ready[c] in mapped pinned memory; the CTAs of that chunk, already resident and polling the word over PCIe, step their envs
-// and write the results into the block while the host stages chunk c+1.  Launch latency and the staging pass (14.5 us for
-// 65 536 int32 actions) disappear behind the 1.9 MB of result traffic.  (One launch PER chunk was measured first: every extra
-// launch costs ~7 us on the stream — 80 / 88 / 93 / 124 / 185 us per step with 1 / 2 / 4 / 8 / 16 launches.)
+// VecEnv.step_async / step_wait on the caller's own action array.  For int64 actions above 16 384 envs (what SB3 passes) the
+// step kernel is launched FIRST and the batch is cut into chunks (TMLA_HOST_CHUNKS; default 4 for int64, 1 for int32): the host
+// range-checks and narrows chunk c, then publishes ready[c] in mapped pinned memory; the CTAs of that chunk, already resident,
+// step their envs and write the results into the block while the host stages chunk c+1, so that the staging pass hides behind
+// the launch latency and the first chunks' PCIe traffic.  Measured on B200 at 65 536 ball3d envs (profiles/e2e_chunks.py, C
+// level, begin + end): int64 89.5 us unchunked -> 82.6 (4 chunks) / 85.2 (8); int32 70.7 -> 73.5 / 75.1 — the GPU side of a step
+// is 17 us of fixed latency + 0.65 ns per env of PCIe (46 GB/s), and only the staging of int64 (29.8 us for 512 KB of cache-cold
+// actions against 11.1 us for int32) is long enough to be worth hiding; staging beside the incoming PCIe writes is itself
+// ~50 % slower.  (One launch PER chunk was measured first: every extra launch costs ~7 us on the stream — 80 / 88 / 93 / 124 /
+// 185 us per step with 1 / 2 / 4 / 8 / 16 launches; and letting every CTA poll the host word saturated the non-posted PCIe
+// reads: 400-540 us per step.)
 // "A rejected step changes nothing" still holds: the kernel keeps the pre-step state in shadow planes, and when a later chunk
 // holds an out-of-range action the remaining chunks are told to leave and the envs already stepped are put back before the
 // error returns.
-static int host_chunks(const tmla_env *h) {
-    static const int req = [] { const char *e = getenv("TMLA_HOST_CHUNKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+static int host_chunks(const tmla_env *h, int elem_bytes) {
+    static const int env_req = [] { const char *e = getenv("TMLA_HOST_CHUNKS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+    const int req = env_req ? env_req : (elem_bytes == 8 ? 4 : 1);
     if (h->n < 16384 || req == 1) return 1;
     // every CTA must be resident at once (a waiting CTA never yields its slot)
     static int resident[TMLA_NUM_TASKS];
@@ -1033,7 +1039,7 @@ int tmla_step_block_begin(tmla_env *h, const void *actions, int elem_bytes, void
     TMLA_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (int32) or 8 (int64)");
     TMLA_REQUIRE(h->pend_seq == 0, "a host step is already in flight (call tmla_step_block_end first)");
     DeviceGuard guard(h->device);
-    const int nchunks = host_step_mapped() ? host_chunks(h) : 1;
+    const int nchunks = host_step_mapped() ? host_chunks(h, elem_bytes) : 1;
     if (nchunks == 1) {                                      // small batches / copy-engine variant: stage now, run the step in _end
         const int rc = tmla_stage_actions(h, actions, elem_bytes);
         if (rc == TMLA_OK) h->pend_seq = -1;
