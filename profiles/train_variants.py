@@ -29,5 +29,6 @@ def run(rows, reps):
     return e0.elapsed_time(e1) * 1e3 / reps, float(grads.norm())
 print(os.environ.get("TMLA_LIB", "default"), "rows=100 ok", run(100, 1), flush=True)
 print("rows=4096 ok", run(4096, 1), flush=True)
-us, gn = run(262144, 20)
-print(f"rows=262144: {us:.1f} us per minibatch (2 towers + wgrad), |g| {gn:.5f}", flush=True)
+for rows in [int(a) for a in sys.argv[1:]] or [262144]:
+    us, gn = run(rows, 20)
+    print(f"rows={rows}: {us:.1f} us per minibatch (2 towers + wgrad), |g| {gn:.5f}", flush=True)

@@ -92,9 +92,19 @@ tower_forward_pipe_body(const PipeTowerArgs &p, const float *__restrict__ x, con
         mbar_expect_tx(barw, kWBytes); bulk_load(smem_u32(Ws), p.W2, kWBytes, barw);     // one bulk-TMA load of the W2 image
     }
     if (!is_driver) {
-        for (int e = tid; e < H * D; e += NT) { const int k = e / H, j = e - k * H; w1t[e] = p.W1[j * D + k]; }
-        for (int e = tid; e < NOUT * H; e += NT) whs[e] = p.Wh[e];
-        if (tid < H) { b1s[tid] = p.B1[tid]; b2s[tid] = p.B2[tid]; }
+        // all of a thread's parameter loads are issued before the first store (one global latency instead of one per element)
+        constexpr int NW1 = (H * D + NT - 1) / NT, NWH = (NOUT * H + NT - 1) / NT;
+        float w1v[NW1], whv[NWH], bv1 = 0.0f, bv2 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NW1; ++q) { const int e = tid + q * NT; if (e < H * D) { const int k = e / H, j = e - k * H; w1v[q] = __ldg(p.W1 + j * D + k); } }
+#pragma unroll
+        for (int q = 0; q < NWH; ++q) { const int e = tid + q * NT; if (e < NOUT * H) whv[q] = __ldg(p.Wh + e); }
+        if (tid < H) { bv1 = __ldg(p.B1 + tid); bv2 = __ldg(p.B2 + tid); }
+#pragma unroll
+        for (int q = 0; q < NW1; ++q) { const int e = tid + q * NT; if (e < H * D) w1t[e] = w1v[q]; }
+#pragma unroll
+        for (int q = 0; q < NWH; ++q) { const int e = tid + q * NT; if (e < NOUT * H) whs[e] = whv[q]; }
+        if (tid < H) { b1s[tid] = bv1; b2s[tid] = bv2; }
     }
     tc_fence_before();
     __syncthreads();
