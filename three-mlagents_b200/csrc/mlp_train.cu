@@ -187,6 +187,10 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
     using L = TrainSmem<D, NOUT>;
     constexpr bool PI = NOUT > 1;
     static_assert(3 * NOUT <= 16 && 2 * D + 1 <= 16, "operand tiles are 16 columns wide");
+    // the next launch of the minibatch is a programmatic dependent (the value tower, which needs none of the policy tower's
+    // results; then the weight-gradient kernel, which waits for the grids before its first image load): let its CTAs take
+    // over every SM this kernel's CTA leaves (a no-op when the next launch is an ordinary one)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef TMLA_PHASE_CLOCKS
     const long long ph_t0 = clock64();
     unsigned long long ph_g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_g0));
@@ -701,6 +705,9 @@ tc_tower_train_kernel(const __grid_constant__ TowerTrainArgs p) {
             }
         }
     }
+    // a programmatic dependent must not COMPLETE before its primary: the weight-gradient launch that follows waits for this
+    // grid only, and needs the policy tower's images too (returns at once: the primary finished ~150 us ago; a no-op otherwise)
+    if (!PI) asm volatile("griddepcontrol.wait;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
@@ -774,6 +781,9 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16
     if (tid == 0) {                                        // producer: bulk-TMA loads, one stage ahead of the ring's tail
         uint32_t pe[kwStages] = {0u, 0u, 0u};
         const uint64_t pol = l2_policy_evict_first();
+        // launched as a programmatic dependent of the tower kernels: everything above ran beside their last CTAs; the images
+        // are complete (and visible) once the prerequisite grids have finished (returns at once after an ordinary launch)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int64_t j = 0; j < my_chunks; ++j) {
             const int s = (int)(j % kwStages);
             if (j >= kwStages) { mbar_wait(empty + s, pe[s]); pe[s] ^= 1u; }   // the MMAs of chunk j-3 have read this stage
@@ -1210,7 +1220,7 @@ static int wgrad_reverse() {      // TMLA_WGRAD_REV=0 restores front-to-back rea
     return r;
 }
 static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64_t rows_padded, cudaStream_t st,
-                                 const void *Xt1 = nullptr, const void *Yt1 = nullptr, float *G1 = nullptr) {
+                                 const void *Xt1 = nullptr, const void *Yt1 = nullptr, float *G1 = nullptr, bool overlap_prev = false) {
     static int attr_done = 0;
     if (!attr_done) {
         TMLA_CUDA(cudaFuncSetAttribute(tc_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradTiledSmem));
@@ -1223,8 +1233,20 @@ static int tc_wgrad_tiled_launch(const void *Xt, const void *Yt, float *G, int64
     static const int n1_of_148 = [] { const char *e = getenv("TMLA_WGRAD_N1"); return e ? atoi(e) : 74; }();
     static const int wgrad_hint = [] { const char *e = getenv("TMLA_WGRAD_HINT"); return e ? atoi(e) : 1; }();
     int n1 = Xt1 ? std::max(1, std::min((int)grid - 1, (int)((int64_t)grid * n1_of_148 / 148))) : 0;
-    tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G,
-                                                              (const __nv_bfloat16 *)Xt1, (const __nv_bfloat16 *)Yt1, G1, nchunks, wgrad_reverse(), n1, wgrad_hint);
+    if (overlap_prev) {                                    // programmatic dependent of the tower kernel before it (see tower_train_launch_t)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kWgradTiledSmem; cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        TMLA_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_tiled_kernel, (const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G, (const __nv_bfloat16 *)Xt1,
+                                     (const __nv_bfloat16 *)Yt1, G1, nchunks, wgrad_reverse(), n1, wgrad_hint));
+    } else {
+        tc_wgrad_tiled_kernel<<<grid, 256, kWgradTiledSmem, st>>>((const __nv_bfloat16 *)Xt, (const __nv_bfloat16 *)Yt, G,
+                                                                  (const __nv_bfloat16 *)Xt1, (const __nv_bfloat16 *)Yt1, G1, nchunks, wgrad_reverse(), n1, wgrad_hint);
+    }
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -1247,7 +1269,7 @@ static int wgrad_h1_launch_t(const WgradH1Problem &a, const WgradH1Problem &b, c
 }
 
 template <int D, int NOUT>
-static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
+static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st, bool overlap_prev) {
     static int attr_done = 0;
     constexpr uint32_t smem = TrainSmem<D, NOUT>::total;
     static_assert(smem <= 232448, "fused tower training kernel exceeds the 227 KB shared-memory limit");
@@ -1256,7 +1278,21 @@ static int tower_train_launch_t(const TowerTrainArgs &a, cudaStream_t st) {
         attr_done = 1;
     }
     const unsigned grid = (unsigned)std::min<int64_t>((a.M + 127) / 128, sm_count_train());
-    tc_tower_train_kernel<D, NOUT><<<grid, kTrainThreads + 32, smem, st>>>(a);
+    if (overlap_prev) {
+        // programmatic dependent launch: this kernel needs nothing the previous launch on the stream (the other tower of the
+        // same minibatch, which triggers at its start) produces, so its CTAs may start on every SM the previous kernel's CTA has
+        // left — the launch gap, the prologue and the previous kernel's last-round imbalance overlap instead of adding up
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTrainThreads + 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        TMLA_CUDA(cudaLaunchKernelEx(&cfg, tc_tower_train_kernel<D, NOUT>, a));
+    } else {
+        tc_tower_train_kernel<D, NOUT><<<grid, kTrainThreads + 32, smem, st>>>(a);
+    }
     TMLA_LAUNCH_CHECK();
     return TMLA_OK;
 }
@@ -1297,6 +1333,10 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
     // saves (134 MB per tower, mostly L2 hits on the tail) is cheaper than 2 x 262 144 x 256 tanh on this kernel's CUDA cores.
     static const bool h1_recompute = [] { const char *e = getenv("TMLA_WGRAD_H1"); return e && !strcmp(e, "recompute"); }();
     const bool recompute = h1_recompute && !interleave;
+    static const bool pdl_on = [] { const char *e = getenv("TMLA_PDL"); return !(e && !strcmp(e, "0")); }();   // TMLA_PDL=0: ordinary launches (A/B)
+    const bool pdl = pdl_on && !interleave;
+    static const bool pdl_w = [] { const char *e = getenv("TMLA_PDL"); return !(e && !strcmp(e, "1")); }();   // TMLA_PDL=1: towers only
+    const bool pdl_wgrad = pdl && pdl_w;
     for (int t = 0; t < 2; ++t) {
         __nv_bfloat16 *h1 = img[t][0], *dz2 = img[t][1];
         TowerTrainArgs a;
@@ -1311,10 +1351,10 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         a.gW1 = grads + o.w1[t]; a.gB1 = grads + o.b1[t]; a.gB2 = grads + o.b2[t]; a.gWh = grads + o.wh[t]; a.gBh = grads + o.bh[t];
         a.stats = stats_out;
         int rc;
-        if (obs_dim == 6) rc = t == 0 ? tower_train_launch_t<6, 5>(a, st) : tower_train_launch_t<6, 1>(a, st);
-        else if (obs_dim == 7) rc = t == 0 ? tower_train_launch_t<7, 3>(a, st) : tower_train_launch_t<7, 1>(a, st);
-        else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st) : tower_train_launch_t<4, 1>(a, st);
-        else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st) : tower_train_launch_t<4, 1>(a, st);
+        if (obs_dim == 6) rc = t == 0 ? tower_train_launch_t<6, 5>(a, st, false) : tower_train_launch_t<6, 1>(a, st, pdl);
+        else if (obs_dim == 7) rc = t == 0 ? tower_train_launch_t<7, 3>(a, st, false) : tower_train_launch_t<7, 1>(a, st, pdl);
+        else if (n_actions == 5) rc = t == 0 ? tower_train_launch_t<4, 5>(a, st, false) : tower_train_launch_t<4, 1>(a, st, pdl);
+        else rc = t == 0 ? tower_train_launch_t<4, 4>(a, st, false) : tower_train_launch_t<4, 1>(a, st, pdl);
         if (rc) return rc;
         if (interleave) { rc = tc_wgrad_tiled_launch(img[t][1], img[t][0], grads + o.w2[t], rows_padded, st); if (rc) return rc; }
     }
@@ -1325,7 +1365,7 @@ int tmla_ppo_minibatch_bf16(const float *params, const void *wpack, int obs_dim,
         if (obs_dim == 7) return wgrad_h1_launch_t<7>(pa, pb, obs, index, rows, rows_padded, st);
         return wgrad_h1_launch_t<4>(pa, pb, obs, index, rows, rows_padded, st);
     }
-    return tc_wgrad_tiled_launch(img[0][1], img[0][0], grads + o.w2[0], rows_padded, st, img[1][1], img[1][0], grads + o.w2[1]);
+    return tc_wgrad_tiled_launch(img[0][1], img[0][0], grads + o.w2[0], rows_padded, st, img[1][1], img[1][0], grads + o.w2[1], pdl_wgrad);
 }
 
 int tmla_tc_wgrad_tiled(const void *Xt, const void *Yt, float *G, int64_t rows_padded, void *stream) {
