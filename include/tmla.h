@@ -283,9 +283,10 @@ int tmla_ppo_loss(const float *logits, const float *values, const int32_t *actio
 
 /* clip_grad_norm_(max_norm) + Adam.step fused (after the gradient all-reduce).
  *   grad_scale multiplies the gradient first; state m,v float[np]; step is the 1-based Adam step;
- *   norm_out float[TMLA_ADAM_SCRATCH]: [0] receives the pre-clip global norm, the rest is scratch for the
- *   fixed-order (bit-reproducible across data-parallel replicas) reduction of the squared norm. */
-#define TMLA_ADAM_SCRATCH 129
+ *   norm_out float[TMLA_ADAM_SCRATCH]: [0] receives the pre-clip global norm, [1, 129) is scratch for the
+ *   fixed-order (bit-reproducible across data-parallel replicas) reduction of the squared norm, [129, 131) are the two words of
+ *   the one-launch optimizer step's grid barrier — the caller zeroes the buffer ONCE when it allocates it. */
+#define TMLA_ADAM_SCRATCH 132
 int tmla_adam_clip(float *params, float *grads, float *m, float *v, int64_t num_params, float grad_scale,
                    float max_grad_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                    float *norm_out, void *stream);

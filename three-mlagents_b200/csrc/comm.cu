@@ -23,11 +23,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
-namespace cg = cooperative_groups;
 
 static constexpr int kMaxRanks = 16;
 static constexpr int kReduceBlocks = TMLA_NORM_BLOCKS;      // the Adam kernel sums exactly this many partials
@@ -166,7 +164,7 @@ reduce_norm_kernel(CommPtrs cp, int rank, int world_rt, int64_t capacity, float 
     }
 }
 
-// ------------------------------------------------------------------ the whole optimizer step in ONE cooperative launch
+// ------------------------------------------------------------------ the whole optimizer step in ONE launch
 // gradient exchange (WORLD > 1, as reduce_norm_kernel) -> squared-norm partials -> grid barrier -> clip + Adam + zero_grad +
 // refresh of the bf16 operand images, with the (summed) gradient held in registers across the barrier: one launch per minibatch
 // instead of gradnorm + adam (single GPU) or reduce_norm + adam (data parallel), and one pass over the gradient instead of two.
@@ -181,10 +179,39 @@ struct OptStepArgs {
 };
 static constexpr int kOptVecPerThread = 2;       // float4 per thread: 128 CTAs x 256 threads x 2 x 4 = 262 144 parameters
 
+// Grid barrier for an ORDINARY launch of at most one small CTA per SM (128 x 256 threads: every CTA is resident as soon as the
+// grid starts, also beside the weight-gradient kernel when launched as its programmatic dependent).  bar[0] counts arrivals and
+// is reset by the last one, bar[1] is the generation the waiters watch; both live in the caller's zero-initialised scratch.
+// A cooperative launch + grid.sync() does the same but costs ~10 us more per launch on the stream (measured below).
+__device__ __forceinline__ void opt_grid_barrier(uint32_t *bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile uint32_t *gen = bar + 1;
+        const uint32_t g0 = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            *(volatile uint32_t *)bar = 0u;
+            __threadfence();
+            *gen = g0 + 1u;
+        } else {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            uint32_t spins = 0;
+            while (*gen == g0) {
+                if ((++spins & 4095u) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 5000000000ull) __trap();         // 5 s: a CTA of this grid never became resident
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 template <int WORLD>
 __global__ void __launch_bounds__(kReduceThreads)
 opt_step_kernel(const __grid_constant__ OptStepArgs a) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ float sh[kReduceThreads / 32];
     __shared__ int s_last;
     __shared__ float s_norm;
@@ -194,6 +221,16 @@ opt_step_kernel(const __grid_constant__ OptStepArgs a) {
     const bool tail_owner = blockIdx.x == gridDim.x - 1 && tail0 + threadIdx.x < a.np;
     float4 g[kOptVecPerThread];
     float gt = 0.0f;
+    // optimizer state of this thread's elements: in flight across the wait for the gradient, the norm reduction and the grid barrier
+    float4 p4[kOptVecPerThread], m4[kOptVecPerThread], v4[kOptVecPerThread];
+#pragma unroll
+    for (int j = 0; j < kOptVecPerThread; ++j) {
+        const int64_t i = gtid + j * gsize;
+        if (i < nvec) { p4[j] = reinterpret_cast<const float4 *>(a.p)[i]; m4[j] = reinterpret_cast<const float4 *>(a.m)[i]; v4[j] = reinterpret_cast<const float4 *>(a.v)[i]; }
+    }
+    // launched as a programmatic dependent of the weight-gradient kernel: everything above ran beside its last CTAs; the
+    // gradient is complete once the prerequisite grids have finished (returns at once after an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (WORLD > 1) {
         const int parity = (int)(a.seq & 1u);
         char *mine = a.cp.peer[a.rank];
@@ -264,13 +301,6 @@ opt_step_kernel(const __grid_constant__ OptStepArgs a) {
         }
         if (tail_owner) gt = a.g[tail0 + threadIdx.x];
     }
-    // optimizer state of this thread's elements: in flight across the norm reduction and the grid barrier
-    float4 p4[kOptVecPerThread], m4[kOptVecPerThread], v4[kOptVecPerThread];
-#pragma unroll
-    for (int j = 0; j < kOptVecPerThread; ++j) {
-        const int64_t i = gtid + j * gsize;
-        if (i < nvec) { p4[j] = reinterpret_cast<const float4 *>(a.p)[i]; m4[j] = reinterpret_cast<const float4 *>(a.m)[i]; v4[j] = reinterpret_cast<const float4 *>(a.v)[i]; }
-    }
     float ss = 0.0f;
 #pragma unroll
     for (int j = 0; j < kOptVecPerThread; ++j) {
@@ -287,7 +317,7 @@ opt_step_kernel(const __grid_constant__ OptStepArgs a) {
         for (int w = 0; w < kReduceThreads / 32; ++w) t += sh[w];
         a.norm_out[1 + blockIdx.x] = t;
     }
-    grid.sync();
+    opt_grid_barrier(reinterpret_cast<uint32_t *>(a.norm_out + 1 + TMLA_NORM_BLOCKS), gridDim.x);
     if (threadIdx.x < 32) {                                // same summation order in every CTA and on every rank
         float t = 0.0f;
         for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) t += __ldcg(a.norm_out + 1 + j);
@@ -334,11 +364,18 @@ opt_step_kernel(const __grid_constant__ OptStepArgs a) {
     }
 }
 
-// one cooperative launch; returns TMLA_EINVAL (without an error message) when the shape does not fit so that callers fall back
+// one launch (ordinary or programmatic dependent; own grid barrier); returns TMLA_EINVAL (without an error message) when the shape does not fit so that callers fall back
 template <int WORLD>
 static int opt_step_launch_t(OptStepArgs &a, cudaStream_t st) {
-    void *args[] = {(void *)&a};
-    TMLA_CUDA(cudaLaunchCooperativeKernel((const void *)opt_step_kernel<WORLD>, dim3(kReduceBlocks), dim3(kReduceThreads), args, 0, st));
+    static const int mode = [] { const char *e = getenv("TMLA_OPT_PDL"); return e ? atoi(e) : 1; }();   // 0: ordinary launch, 1: programmatic dependent
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kReduceBlocks); cfg.blockDim = dim3(kReduceThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = mode ? 1 : 0;
+    TMLA_CUDA(cudaLaunchKernelEx(&cfg, opt_step_kernel<WORLD>, a));
     return TMLA_OK;
 }
 static bool opt_step_enabled() {      // TMLA_ADAM=split keeps the two-launch path (A/B runs)
@@ -481,7 +518,7 @@ int tmla_adam_clip_allreduce(tmla_comm *c, float *params, float *grads, float *m
     TMLA_REQUIRE(params && grads && m && v && norm_out, "NULL buffer");
     TMLA_REQUIRE(num_params > 0 && num_params <= c->capacity && step >= 1, "bad arguments (num_params exceeds the comm's capacity?)");
     TMLA_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15u) == 0, "grads must be 16-byte aligned");
-    {   // one cooperative launch for exchange + clip + Adam when the shape fits (2, 4, 8 ranks)
+    {   // one launch for exchange + clip + Adam when the shape fits (2, 4, 8 ranks)
         const int rc = opt_step_launch(c, params, grads, m, v, num_params, grad_scale, max_grad_norm, lr, beta1, beta2, eps, step, norm_out,
                                        zero_grads, wpack, obs_dim, hidden, n_actions, stream);
         if (rc != TMLA_EINVAL) return rc;

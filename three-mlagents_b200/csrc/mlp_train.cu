@@ -752,6 +752,9 @@ tc_wgrad_tiled_kernel(const __nv_bfloat16 *__restrict__ Xt0, const __nv_bfloat16
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + kwStages * kwStage + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    // the optimizer step that follows is a programmatic dependent: its small CTAs may become resident now, fetch their slice of
+    // the parameters and the Adam state, and wait for this grid before touching the gradient (a no-op after an ordinary launch)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // dual launch: n1 CTAs work on problem 1, the rest on problem 0.  n1 = grid/2 interleaves them (even / odd CTAs); a smaller
     // n1 hands problem 1 — whose image tail is still L2-resident when read back to front — fewer CTAs: its CTAs are
     // spread over the grid (every CTA with blockIdx % period == period - 1 ... see `second`)

@@ -196,7 +196,7 @@ def adam_clip(params, grads, m, v, step, *, grad_scale=1.0, max_grad_norm=0.5, l
     """clip_grad_norm_ + Adam.step.  zero_grads: clear `grads` once consumed.  wpack (+ obs_dim, n_actions): also refresh the bf16
     operand images of the hidden-layer weights inside `wpack` (what the fused minibatch kernel reads)."""
     if norm_out is None:
-        norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
+        norm_out = torch.zeros(132, dtype=torch.float32, device=params.device)
     _chk(wpack, torch.bfloat16, "wpack")
     check(lib.tmla_adam_clip_fused(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
                                    float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),
@@ -208,7 +208,7 @@ def adam_clip_allreduce(comm, params, grads, m, v, step, *, grad_scale=1.0, max_
                         eps=1e-5, norm_out=None, zero_grads=False, wpack=None, obs_dim=0, n_actions=0):
     """grads <- sum over ranks (one-shot all-reduce over NVLink peer memory, rank order), then adam_clip — two launches, no NCCL."""
     if norm_out is None:
-        norm_out = torch.empty(129, dtype=torch.float32, device=params.device)
+        norm_out = torch.zeros(132, dtype=torch.float32, device=params.device)
     _chk(wpack, torch.bfloat16, "wpack"); _chk(grads, torch.float32, "grads")
     check(lib.tmla_adam_clip_allreduce(comm.handle, ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(grad_scale),
                                        float(max_grad_norm), float(lr), float(beta1), float(beta2), float(eps), int(step),

@@ -166,7 +166,7 @@ class CudaPPO:
         self.adv_sums = torch.zeros(((total + B - 1) // B, 3), dtype=torch.float64, device=dev)   # one row per minibatch of an epoch
         self.stats = torch.zeros(8, **f32)
         self.stats_acc = torch.zeros(8, **f32)
-        self.norm_out = torch.zeros(129, **f32)
+        self.norm_out = torch.zeros(132, **f32)      # TMLA_ADAM_SCRATCH: norm, 128 partials, grid-barrier words (zeroed once)
         if getattr(self.env, "_monitor", None) is not None and self.env._ep_log is None:
             self.env.attach_episode_log(N * T)          # Monitor rows for the device path (flushed after every rollout)
         self._buffers_ready = True
