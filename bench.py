@@ -344,8 +344,10 @@ def run_cuda(args):
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N_ENVS,
                 "d2h_bytes_per_step": N_ENVS * (4 * OBS_DIM + 4 + 1 + 1),
-                "api": "CudaVecEnv.step(np.ndarray) -> tmla_step_block (H2D actions, kernel, one D2H straight into a pooled pinned "
-                       "result block, sync); the returned NumPy arrays are slices of that block, reused only when dropped", "steps": n_e2e,
+                "api": "CudaVecEnv.step(np.ndarray int32) -> tmla_step_block_begin / _end (range check + narrowing of the actions into pinned "
+                       "memory, ONE kernel that reads them and writes obs/reward/done/truncated/records over PCIe into a pooled pinned "
+                       "result block, host polls the sequence word); the returned NumPy arrays are slices of that block, reused only "
+                       "when dropped", "steps": n_e2e,
                 "numa_cpus": None if numa_cpus is None else len(numa_cpus)},
         "step_api": {"value": step_api, "unit": "env-steps/s", "us_per_launch": 1e3 * api_ms / n_api,
                      "frac_hbm": (89.0 * N_ENVS / (api_ms / n_api * 1e-3) / 1e9) / peak,
