@@ -1,7 +1,8 @@
 #!/bin/bash
 # compute-sanitizer passes over the kernels that use mbarriers, bulk async copies, system-scope fences and a host-polled flag
 # (SURVEY.md §5): small-N GPU tests of the fused tower-train kernel, the tiled wgrad, the tensor-core forward, the host step
-# with mapped result blocks and the fused policy rollout.  Run under gpurun; summaries land in gpurun_out/ and are copied to
+# with mapped result blocks (incl. the chunk-released variant whose CTAs poll host memory, and its rollback), the dependent
+# launches of the fused update with the optimizer step's own grid barrier, and the fused policy rollout.  Run under gpurun; summaries land in gpurun_out/ and are copied to
 # profiles/r2_sanitizer_{memcheck,racecheck,synccheck}.txt.
 #   bash profiles/sanitizer.sh [tool ...]        (default: memcheck racecheck synccheck)
 set -u
@@ -15,6 +16,8 @@ tests/test_train_fused_gpu.py::test_fused_minibatch_matches_unfused[ball3d-64-8-
 tests/test_train_fused_gpu.py::test_fused_minibatch_matches_unfused[ball3d-512-32-4096]
 tests/test_rollout_fused_gpu.py::test_fused_rollout_is_bit_identical_to_per_step_calls[ball3d-512-32-bf16]
 tests/test_envs_gpu.py::test_host_step_contract
+tests/test_envs_gpu.py::test_chunked_host_step_matches_device_path_and_rolls_back[ball3d]
+tests/test_envs_gpu.py::test_chunked_host_step_matches_device_path_and_rolls_back[gridworld]
 tests/test_tc_gpu.py::test_pipelined_rollout_forward_is_bit_identical_to_the_classic_kernel
 tests/test_ppo_gpu.py::test_adam_clip_vs_torch
 tests/test_ppo_gpu.py::test_adam_zero_grads_and_operand_image_refresh'
