@@ -172,3 +172,62 @@ def test_fused_training_tracks_unfused_and_learns():
     print("ball3d ep_rew_mean:", [round(r["rollout/ep_rew_mean"], 2) for r in rows])
     assert rows[-1]["rollout/ep_rew_mean"] > rows[0]["rollout/ep_rew_mean"] + 5.0
     env.close()
+
+
+_VARIANT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from three_mlagents_b200 import ops
+from three_mlagents_b200.ppo import orthogonal_init
+D, A, rows = {D}, {A}, {rows}
+g = torch.Generator(device="cuda").manual_seed(5)
+params = orthogonal_init(D, A, 1).cuda()
+wpack = ops.mlp_pack(params, D, A)
+T, N = 8, rows // 4
+obs = torch.randn((T * N, D), device="cuda", generator=g)
+act = torch.randint(0, A, (T, N), device="cuda", dtype=torch.int32, generator=g)
+adv = torch.randn((T, N), device="cuda", generator=g); ret = torch.randn((T, N), device="cuda", generator=g)
+logp = -torch.rand((T, N), device="cuda", generator=g)
+idx = torch.randperm(T * N, device="cuda", generator=g)[:rows].to(torch.int32).contiguous()
+grads = torch.zeros_like(params); stats = torch.zeros(8, device="cuda")
+scratch = torch.empty(4 * ((rows + 127) // 128 * 128) * 256, dtype=torch.bfloat16, device="cuda")
+sums = ops.adv_stats(adv, idx, rows)
+m = torch.zeros_like(params); v = torch.zeros_like(params)
+for step in (1, 2, 3):                         # three minibatches with the optimizer step between them (exercises every boundary)
+    ops.ppo_minibatch(params, wpack, obs, D, A, act, adv, logp, ret, index=idx, rows=rows, adv_sums=sums, grads=grads, scratch=scratch,
+                      stats=stats, grads_zeroed=True, accumulate_stats=True)
+    if step == 1:
+        g1 = grads.clone()
+    ops.adam_clip(params, grads, m, v, step, max_grad_norm=0.5, lr=3e-4, eps=1e-5, zero_grads=True, wpack=wpack, obs_dim=D, n_actions=A)
+torch.cuda.synchronize()
+torch.save({{"g1": g1.cpu(), "params": params.cpu(), "stats": stats.cpu()}}, {out!r})
+"""
+
+
+@pytest.mark.parametrize("env", [{"TMLA_PDL": "0", "TMLA_OPT_PDL": "0"}, {"TMLA_PDL": "1"}, {"TMLA_WGRAD_H1": "recompute"}, {"TMLA_ADAM": "split"}],
+                         ids=["ordinary-launches", "dependent-towers-only", "wgrad-recomputes-h1", "two-launch-optimizer"])
+def test_launch_and_wgrad_variants_agree_with_the_default(env, tmp_path):
+    """The A/B switches kept in the library (read once per process, hence subprocesses): ordinary launches instead of programmatic
+    dependent ones, the weight-gradient kernel that recomputes H1, the two-launch optimizer step.  Same seeded minibatch, three
+    update steps: the first gradient and the parameters after three steps must agree with the default build of the path
+    (float atomics reorder sums, hence 2e-5 of the gradient norm, and all but a handful of parameters within 1e-6, not bit equality)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, extra in (("default", {}), ("variant", env)):
+        out = str(tmp_path / f"{name}.pt")
+        script = _VARIANT_SCRIPT.format(root=root, D=6, A=5, rows=128 * 148 + 77, out=out)
+        e = {k: v for k, v in os.environ.items() if not k.startswith("TMLA_")}
+        e.update(extra)
+        r = subprocess.run([sys.executable, "-c", script], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = torch.load(out)
+    a, b = outs["default"], outs["variant"]
+    gn = float(a["g1"].norm())
+    assert gn > 0 and float((a["g1"] - b["g1"]).norm()) <= 2e-5 * gn
+    dp = (a["params"] - b["params"]).abs()      # Adam's first steps move a weight by ~lr whatever its gradient: a near-zero gradient
+    assert float((dp > 1e-6).float().mean()) < 1e-3 and float(dp.norm()) <= 1e-4 * float(a["params"].norm())   # may flip sign
+    assert torch.allclose(a["stats"], b["stats"], rtol=1e-4, atol=1e-5)
