@@ -188,6 +188,13 @@ def test_host_step_contract(task):
         env.step(np.full(n, env.n_actions))            # the reference's ACTION_DELTAS[a] raises IndexError
     with pytest.raises(ValueError):
         env.step(np.zeros(n + 1, np.int64))
+    with pytest.raises(RuntimeError):
+        env.step_wait()                                # no step_async in flight
+    env.step_async(np.zeros(n, np.int64))
+    with pytest.raises(Exception):
+        env.step_async(np.zeros(n, np.int64))          # one step in flight per env
+    obs, _, _, _ = env.step_wait()
+    assert obs.shape == (n, env.obs_dim)
     env.close(); dev.close()
 
 

@@ -200,6 +200,7 @@ class CudaVecEnv:
         self._blocks = _ResultBlocks(self._h, n, d)      # results land in pooled pinned result blocks
         self._actions = None
         self._pending = None                             # result block of the step in flight (None: the scratch block)
+        self._in_flight = False
         self._t0 = time.time()
         self._vec_step = 0                               # host-path vec-steps taken (for infos[i]["steps"])
         self._last_reset = np.zeros(n, np.int64)         # vec-step index at which env i last (auto-)reset
@@ -243,9 +244,12 @@ class CudaVecEnv:
             if k is not None:
                 blocks.release(k)
             raise
-        self._actions, self._pending = a, k
+        self._actions, self._pending, self._in_flight = a, k, True
 
     def step_wait(self):
+        if not self._in_flight:
+            raise RuntimeError("step_wait() without a step_async() in flight")
+        self._in_flight = False
         blocks = self._blocks
         k = self._pending
         nd = native.i64(0)
