@@ -314,7 +314,7 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
 // Refill period of the ahead-of-time reset draws.  The draw is indexed by the env's episode counter, not by time, so the
 // period changes no result — only how often a warp pays two Philox blocks for its consumed lanes (TMLA_SPARE_EVERY).
 #ifndef TMLA_SPARE_EVERY
-#define TMLA_SPARE_EVERY 64   /* measured on 128-step launches: 16 -> 66.3 us, 32 -> 64.6, 64 -> 63.9, 128 -> 66.7 */
+#define TMLA_SPARE_EVERY 64   /* measured on 128-step launches: 16 -> 66.3 us, 32 -> 64.6, 64 -> 63.9, 128 -> 66.7; with the spare carrying its sin products: 32 -> 61.5, 64 -> 61.4, 128 -> 63.9 */
 #endif
 static constexpr int kSpareEvery = TMLA_SPARE_EVERY;
 // tasks that split a step into an independent "plan" half (Task::Tilt, Task::plan, Task::advance_planned — ball3d) run the
