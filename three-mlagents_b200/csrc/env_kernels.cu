@@ -317,6 +317,10 @@ rollout_random_kernel(EnvPtrs p, int64_t n, uint64_t seed, uint64_t env_base, ui
 #define TMLA_SPARE_EVERY 64   /* measured on 128-step launches: 16 -> 66.3 us, 32 -> 64.6, 64 -> 63.9, 128 -> 66.7; with the spare carrying its sin products: 32 -> 61.5, 64 -> 61.4, 128 -> 63.9 */
 #endif
 static constexpr int kSpareEvery = TMLA_SPARE_EVERY;
+#ifndef TMLA_ROLLOUT_UNROLL
+#define TMLA_ROLLOUT_UNROLL 2
+#endif
+static constexpr int kRollUnroll = TMLA_ROLLOUT_UNROLL;
 // tasks that split a step into an independent "plan" half (Task::Tilt, Task::plan, Task::advance_planned — ball3d) run the
 // fused rollout software-pipelined: the plan of step t+1 is computed beside the integration / reward chain of step t
 template <class T, class = void> struct is_pipelined { static constexpr bool value = false; };
@@ -349,7 +353,7 @@ rollout_fast_kernel(EnvPtrs p, uint32_t n, uint64_t seed, uint64_t env_base, uin
         if constexpr (PIPE) { a_next = as.next(seed, env_id, step0, 0u, Task::A); return Task::template plan<true>(cst, s, a_next); }
         else return 0;
     }();
-#pragma unroll 2   // measured: 73.2 us (no unroll) / 70.8 us (2) / 72.1 us (4)
+#pragma unroll kRollUnroll   // round 1: 73.2 us (no unroll) / 70.8 us (2) / 72.1 us (4); end of round 2: 63.6 (1) / 61.5-61.8 (2) / 64.2 (3) / 61.6-62.5 (4)
     for (int t = 0; t < T; ++t) {
         if constexpr (Task::HAS_SPARE) {
             if ((t & (kSpareEvery - 1)) == 0 && !have_spare) {   // off the critical path: refill consumed spares
